@@ -1,0 +1,225 @@
+"""ctypes access to the CPU oracles.  TEST INFRASTRUCTURE ONLY.
+
+Two interchangeable back ends expose the same flat C interface (oracle/ref_harness.h):
+
+* ``ref``  - oracle/_ref/libspandsp_ref_{strict,fast}.so : the reference's OWN sources
+             (compiled in place from /root/reference/src by oracle/Makefile) behind
+             oracle/ref_harness.c.  ``strict`` is the pinned oracle, ``fast`` is the
+             reference's default flag set and serves as the CPU baseline.
+* ``port`` - oracle/libtonebank_oracle.so : our plain-C restatement of the algorithm
+             (oracle/tonebank_oracle.c), buildable anywhere.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  Nothing in spandsp_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+DET_DTMF, DET_BELL_MF, DET_R2_MF, DET_SUPER_TONE = 0, 1, 2, 3
+MODE_DIGITS_CB, MODE_REALTIME, MODE_POLL, MODE_SEGMENTS = 0, 1, 2, 3
+EV_DIGIT, EV_TONE, EV_SEGMENT = 1, 2, 5
+
+MAX_ST_TONES = 32
+MAX_ST_ELEMENTS = 128
+
+
+class RefEvent(C.Structure):
+    _fields_ = [("chunk", C.c_int32), ("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32)]
+
+
+EVENT_DTYPE = np.dtype([("chunk", "<i4"), ("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4")])
+
+
+class RefParams(C.Structure):
+    _fields_ = [
+        ("detector", C.c_int32),
+        ("mode", C.c_int32),
+        ("chunk", C.c_int32),
+        ("fillin_every", C.c_int32),
+        ("dtmf_set_parms", C.c_int32),
+        ("dtmf_filter_dialtone", C.c_int32),
+        ("dtmf_twist", C.c_float),
+        ("dtmf_reverse_twist", C.c_float),
+        ("dtmf_threshold", C.c_float),
+        ("r2_fwd", C.c_int32),
+        ("st_tones", C.c_int32),
+        ("st_tone_segs", C.c_int32 * MAX_ST_TONES),
+        ("st_elements", C.c_int32 * (4 * MAX_ST_ELEMENTS)),
+    ]
+
+
+class RefFinal(C.Structure):
+    _fields_ = [("status", C.c_int32), ("ndigits", C.c_int32), ("digits", C.c_char * 256)]
+
+
+FINAL_DTYPE = np.dtype([("status", "<i4"), ("ndigits", "<i4"), ("digits", "S256")])
+
+
+def make_params(detector, mode=MODE_DIGITS_CB, chunk=160, fillin_every=0, dtmf_parms=None, r2_fwd=1, tones=None):
+    """tones: list of tones, each a list of (f1, f2, min_ms, max_ms) elements (super-tone)."""
+    p = RefParams()
+    p.detector = detector
+    p.mode = mode
+    p.chunk = chunk
+    p.fillin_every = fillin_every
+    if dtmf_parms is not None:
+        p.dtmf_set_parms = 1
+        p.dtmf_filter_dialtone = int(dtmf_parms.get("filter_dialtone", -1))
+        p.dtmf_twist = float(dtmf_parms.get("twist", -1.0))
+        p.dtmf_reverse_twist = float(dtmf_parms.get("reverse_twist", -1.0))
+        p.dtmf_threshold = float(dtmf_parms.get("threshold", -99.0))
+    p.r2_fwd = int(r2_fwd)
+    if tones:
+        assert len(tones) <= MAX_ST_TONES
+        k = 0
+        p.st_tones = len(tones)
+        for t, elements in enumerate(tones):
+            p.st_tone_segs[t] = len(elements)
+            for e in elements:
+                assert k < MAX_ST_ELEMENTS
+                for i in range(4):
+                    p.st_elements[4 * k + i] = int(e[i])
+                k += 1
+    return p
+
+
+def build(ref=True, port=True, quiet=True):
+    """Compile the oracles (make -C oracle).  The _ref part is skipped where /root/reference is absent."""
+    targets = []
+    if port:
+        targets.append("port")
+    if ref and os.path.exists("/root/reference/src/dtmf.c"):
+        targets.append("ref")
+    if targets:
+        subprocess.run(["make", "-C", HERE] + targets, check=True,
+                       stdout=subprocess.DEVNULL if quiet else None)
+
+
+class Oracle:
+    """One loaded oracle library."""
+
+    def __init__(self, path, name):
+        self.name = name
+        self.path = path
+        self.lib = C.CDLL(path, mode=os.RTLD_LOCAL)
+        L = self.lib
+        L.ref_run.restype = C.c_double
+        L.ref_run.argtypes = [C.POINTER(RefParams), C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.ref_abi_version.restype = C.c_int
+        for fn in ("ref_dtmf_generate", "ref_bell_mf_generate", "ref_r2_mf_generate", "ref_cadence_generate"):
+            if hasattr(L, fn):
+                getattr(L, fn).restype = C.c_int
+        if hasattr(L, "ref_goertzel_fac"):
+            L.ref_goertzel_fac.restype = C.c_float
+            L.ref_goertzel_fac.argtypes = [C.c_float, C.c_int]
+            L.ref_goertzel_blocks.restype = C.c_int
+            L.ref_goertzel_blocks.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+
+    # ---- detectors -------------------------------------------------------------------
+    def run(self, params, amp, nthreads=1, ev_cap=None, want_events=True):
+        """amp: int16 [channels, n] (C-contiguous rows, row stride may exceed n via slicing of a 2-D array).
+
+        Returns (events list per channel as structured arrays, final structured array, seconds)."""
+        amp = np.asarray(amp)
+        assert amp.dtype == np.int16 and amp.ndim == 2 and amp.strides[1] == 2
+        channels, n = amp.shape
+        stride = amp.strides[0] // 2
+        if ev_cap is None:
+            ev_cap = max(16, n // 100 + 16)
+        fin = np.zeros(channels, dtype=FINAL_DTYPE)
+        if want_events:
+            ev = np.zeros((channels, ev_cap), dtype=EVENT_DTYPE)
+            cnt = np.zeros(channels, dtype=np.int64)
+            secs = self.lib.ref_run(C.byref(params), amp.ctypes.data, stride, channels, n, nthreads,
+                                    ev.ctypes.data, ev_cap, cnt.ctypes.data, fin.ctypes.data)
+            if (cnt > ev_cap).any():
+                raise RuntimeError("oracle event capacity exceeded: %d > %d" % (cnt.max(), ev_cap))
+            events = [ev[c, :cnt[c]] for c in range(channels)]
+        else:
+            secs = self.lib.ref_run(C.byref(params), amp.ctypes.data, stride, channels, n, nthreads,
+                                    None, 0, None, fin.ctypes.data)
+            events = None
+        return events, fin, secs
+
+    # ---- generators (reference back end only) ----------------------------------------
+    def dtmf_generate(self, digits, n, level=-10, twist=0, on_ms=-1, off_ms=-1, noise_seed=0, noise_dbm0=-100.0):
+        out = np.zeros(n, dtype=np.int16)
+        self.lib.ref_dtmf_generate(C.c_void_p(out.ctypes.data), C.c_int(n), digits.encode(), C.c_int(level), C.c_int(twist),
+                                   C.c_int(on_ms), C.c_int(off_ms), C.c_int(noise_seed), C.c_float(noise_dbm0))
+        return out
+
+    def bell_mf_generate(self, digits, n, noise_seed=0, noise_dbm0=-100.0):
+        out = np.zeros(n, dtype=np.int16)
+        self.lib.ref_bell_mf_generate(C.c_void_p(out.ctypes.data), C.c_int(n), digits.encode(),
+                                      C.c_int(noise_seed), C.c_float(noise_dbm0))
+        return out
+
+    def r2_mf_generate(self, digits, n, fwd=True, on_samples=800, off_samples=800, noise_seed=0, noise_dbm0=-100.0):
+        out = np.zeros(n, dtype=np.int16)
+        self.lib.ref_r2_mf_generate(C.c_void_p(out.ctypes.data), C.c_int(n), digits.encode(), C.c_int(int(fwd)),
+                                    C.c_int(on_samples), C.c_int(off_samples), C.c_int(noise_seed), C.c_float(noise_dbm0))
+        return out
+
+    def cadence_generate(self, steps, n, noise_seed=0, noise_dbm0=-100.0):
+        """steps: list of (f1_hz, f2_hz, level_dbm0, length_ms)."""
+        flat = np.asarray(steps, dtype=np.int32).reshape(-1)
+        out = np.zeros(n, dtype=np.int16)
+        self.lib.ref_cadence_generate(C.c_void_p(out.ctypes.data), C.c_int(n), C.c_void_p(flat.ctypes.data),
+                                      C.c_int(len(steps)), C.c_int(noise_seed), C.c_float(noise_dbm0))
+        return out
+
+    def awgn_add(self, amp, seed, level_dbm0):
+        assert amp.dtype == np.int16 and amp.flags.c_contiguous
+        self.lib.ref_awgn_add(C.c_void_p(amp.ctypes.data), C.c_int(amp.size), C.c_int(seed), C.c_float(level_dbm0))
+        return amp
+
+    def goertzel_fac(self, freq, samples):
+        return float(self.lib.ref_goertzel_fac(freq, samples))
+
+    def goertzel_blocks(self, freq, samples, amp):
+        amp = np.ascontiguousarray(amp, dtype=np.int16)
+        out = np.zeros(len(amp) // samples + 1, dtype=np.float32)
+        nb = self.lib.ref_goertzel_blocks(freq, samples, amp.ctypes.data, len(amp), out.ctypes.data)
+        return out[:nb]
+
+    def super_tone_bins(self, params):
+        fac = np.zeros(64, dtype=np.float32)
+        self.lib.ref_super_tone_bins.restype = C.c_int
+        n = self.lib.ref_super_tone_bins(C.byref(params), C.c_void_p(fac.ctypes.data), C.c_int(64))
+        return fac[:n]
+
+
+_cache = {}
+
+
+def _path(kind):
+    if kind == "port":
+        return os.path.join(HERE, "libtonebank_oracle.so")
+    return os.path.join(HERE, "_ref", "libspandsp_ref_%s.so" % kind)
+
+
+def available(kind):
+    return os.path.exists(_path(kind))
+
+
+def load(kind="strict"):
+    """kind: 'strict' (pinned reference build), 'fast' (reference default flags) or 'port'."""
+    if kind not in _cache:
+        p = _path(kind)
+        if not os.path.exists(p):
+            raise FileNotFoundError("oracle library %s is not built (run `make -C oracle`)" % p)
+        _cache[kind] = Oracle(p, kind)
+    return _cache[kind]
+
+
+def events_tuple(ev, with_chunk=False):
+    """Structured event array -> list of plain tuples for easy comparison."""
+    if with_chunk:
+        return [(int(e["chunk"]), int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])) for e in ev]
+    return [(int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])) for e in ev]
