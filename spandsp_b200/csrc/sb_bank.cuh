@@ -1,0 +1,500 @@
+// sb_bank.cuh - the Goertzel filter-bank kernels.
+//
+// One thread owns one channel for a time slice.  Each thread keeps the 2*NPAIRS resonators of
+// its channel in registers and streams the channel's int16 samples through them:
+//
+//      v1 = v2; v2 = v3; v3 = fac*v2 - v1 + x          (reference: src/spandsp/tone_detect.h:184-190)
+//
+// and at every block boundary pushes one zero sample, forms 2*(v3*v3 + v2*v2 - v2*v3*fac)
+// (src/tone_detect.c:174-203), runs the detector's block decision and writes one code per
+// (block, channel).  The sequential per-channel state machines (debounce, cadence, digit
+// history) run afterwards in the sequencer kernels (sb_detectors.cuh) over those codes.  That
+// split is what lets the time axis be cut into independent slices: a slice always starts on a
+// block boundary, where the resonators are zero by definition.
+//
+// Memory path (bank_kernel_staged): input is channel-major [channel][sample] int16.  A warp
+// (32 channels) cooperatively copies SEG_VEC*16 contiguous bytes of each of its 32 rows per
+// stage with 16-byte cp.async (LDGSTS) - each group of SEG_VEC lanes reads one contiguous,
+// 16-byte-aligned run of a row, so every DRAM sector that is fetched is fully used - into a
+// per-warp shared-memory ring of NSTAGE stages.  Row r of the ring starts at r*ROW_BYTES with
+// ROW_BYTES = 16 (mod 128), so when the 32 lanes then read "their" row with one 128-bit
+// ld.shared per 8 samples, every quarter-warp touches 32 distinct banks (conflict-free).
+// Warps are fully independent: no __syncthreads, only __syncwarp + cp.async groups.
+//
+// The generic kernel (bank_kernel_direct) handles what the staged path does not: per-channel
+// block phases that differ inside a bank, and rows that are not 16-byte aligned.
+#pragma once
+
+#include <type_traits>
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+template <class DET>
+struct BankArgs
+{
+    const int16_t *amp;             // [channel][sample], row stride in samples
+    long long stride;
+    int n;                          // samples per channel in this call
+    int channels;
+    int cs0;                        // uniform block phase at entry (samples already in the open block)
+    int slice_blocks;               // blocks per time slice (staged kernel)
+    int nslices;
+    int nblocks;                    // complete blocks produced per channel (uniform phase)
+    float *v2;                      // carried resonator state, [2*NPAIRS][channels]
+    float *v3;
+    float *energy;                  // carried block energy, [channels]
+    const int *cs;                  // block phase at entry, [channels] (direct kernel; the sequencer advances it)
+    typename DET::code_t *code;     // [block][channel] decisions of this call
+    float *eout;                    // [block][channel] block energy (only where DET::ENERGY_OUT)
+    float *raw;                     // [block][bin][channel] bin energies (only where DET::RAW)
+    long long raw_capacity;         // floats
+    int block_rt;                   // block length where DET::BLOCK == 0 (raw Goertzel banks)
+    typename DET::Params det;
+};
+
+template <class DET>
+__device__ __forceinline__ int block_len(const BankArgs<DET> &a)
+{
+    return (DET::BLOCK > 0)  ?  DET::BLOCK  :  a.block_rt;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-thread channel runner
+template <class DET, bool PACKED>
+struct Runner
+{
+    static constexpr int NP = DET::NPAIRS;
+
+    pair_t v2[NP];
+    pair_t v3[NP];
+    pair_t fac[NP];
+    float energy;
+    float z[4];                     // DTMF dial-tone notch state: z350[0], z350[1], z440[0], z440[1]
+    int cs;                         // samples in the open block
+    int blk;                        // index of the next block decision to write
+    int c;                          // channel
+    int channels;
+    bool active;
+    bool filt;
+    typename DET::Local loc;
+
+    __device__ __forceinline__ void zero_state()
+    {
+#pragma unroll
+        for (int p = 0;  p < NP;  p++)
+        {
+            v2[p].x = v2[p].y = 0.0f;
+            v3[p].x = v3[p].y = 0.0f;
+        }
+        energy = 0.0f;
+    }
+
+    __device__ __forceinline__ void load_carry(const BankArgs<DET> &a)
+    {
+#pragma unroll
+        for (int p = 0;  p < NP;  p++)
+        {
+            v2[p].x = a.v2[(size_t) (2*p)*channels + c];
+            v2[p].y = a.v2[(size_t) (2*p + 1)*channels + c];
+            v3[p].x = a.v3[(size_t) (2*p)*channels + c];
+            v3[p].y = a.v3[(size_t) (2*p + 1)*channels + c];
+        }
+        energy = (DET::ENERGY)  ?  a.energy[c]  :  0.0f;
+    }
+
+    __device__ __forceinline__ void store_carry(const BankArgs<DET> &a)
+    {
+        if (!active)
+            return;
+#pragma unroll
+        for (int p = 0;  p < NP;  p++)
+        {
+            a.v2[(size_t) (2*p)*channels + c] = v2[p].x;
+            a.v2[(size_t) (2*p + 1)*channels + c] = v2[p].y;
+            a.v3[(size_t) (2*p)*channels + c] = v3[p].x;
+            a.v3[(size_t) (2*p + 1)*channels + c] = v3[p].y;
+        }
+        if (DET::ENERGY)
+            a.energy[c] = energy;
+        // The block phase cs[] is advanced by the sequencer kernel, which still needs the
+        // entry value to reproduce the reference's duration arithmetic.
+    }
+
+    // src/dtmf.c:167-183.  Both biquads, strict left-to-right evaluation.
+    __device__ __forceinline__ float notch(float famp)
+    {
+        float v1;
+
+        v1 = fsub(fadd(fmul(0.98356f, famp), fmul(1.8954426f, z[0])), fmul(0.9691396f, z[1]));
+        famp = fadd(fsub(v1, fmul(1.9251480f, z[0])), z[1]);
+        z[1] = z[0];
+        z[0] = v1;
+        v1 = fsub(fadd(fmul(0.98456f, famp), fmul(1.8529543f, z[2])), fmul(0.9691396f, z[3]));
+        famp = fadd(fsub(v1, fmul(1.8819938f, z[2])), z[3]);
+        z[3] = z[2];
+        z[2] = v1;
+        return famp;
+    }
+
+    template <bool FILT>
+    __device__ __forceinline__ void step(float x)
+    {
+        if (DET::FILTER  &&  FILT)
+        {
+            const float f = notch(x);
+            x = (filt)  ?  f  :  x;
+        }
+        if (DET::ENERGY)
+            energy = fadd(energy, fmul(x, x));              // src/dtmf.c:189, super_tone_rx.c:477
+#pragma unroll
+        for (int p = 0;  p < NP;  p++)
+        {
+            const pair_t v1 = v2[p];
+            v2[p] = v3[p];
+            v3[p] = padd_scalar<PACKED>(psub<PACKED>(pmul(fac[p], v2[p]), v1), x);
+        }
+    }
+
+    // End of a detection block: finish the bins, decide, emit, reset.
+    __device__ __forceinline__ void block_end(const BankArgs<DET> &a)
+    {
+        float e[2*NP];
+
+#pragma unroll
+        for (int p = 0;  p < NP;  p++)
+        {
+            // src/tone_detect.c:174-203
+            pair_t v1 = v2[p];
+            pair_t w2 = v3[p];
+            pair_t w3 = psub<false>(pmul(fac[p], w2), v1);
+            e[2*p] = fmul(fsub(fadd(fmul(w3.x, w3.x), fmul(w2.x, w2.x)), fmul(fmul(w2.x, w3.x), fac[p].x)), 2.0f);
+            e[2*p + 1] = fmul(fsub(fadd(fmul(w3.y, w3.y), fmul(w2.y, w2.y)), fmul(fmul(w2.y, w3.y), fac[p].y)), 2.0f);
+        }
+        if constexpr (DET::RAW)
+        {
+            if (active)
+            {
+#pragma unroll
+                for (int i = 0;  i < 2*NP;  i++)
+                {
+                    const long long idx = ((long long) blk*loc.bins + i)*channels + c;
+                    if (i < loc.bins  &&  idx < a.raw_capacity)
+                        a.raw[idx] = e[i];
+                }
+            }
+        }
+        else
+        {
+            const int code = DET::decide(e, energy, loc);
+            if (active)
+            {
+                a.code[(size_t) blk*channels + c] = (typename DET::code_t) code;
+                if (DET::ENERGY_OUT  &&  code != 0)
+                    a.eout[(size_t) blk*channels + c] = energy;
+            }
+        }
+        blk++;
+        cs = 0;
+    }
+
+    // Eight samples of one 16-byte vector, no block boundary inside.
+    template <bool FILT>
+    __device__ __forceinline__ void fast8(const uint4 &v)
+    {
+        step<FILT>(sample_of<0>(v));
+        step<FILT>(sample_of<1>(v));
+        step<FILT>(sample_of<2>(v));
+        step<FILT>(sample_of<3>(v));
+        step<FILT>(sample_of<4>(v));
+        step<FILT>(sample_of<5>(v));
+        step<FILT>(sample_of<6>(v));
+        step<FILT>(sample_of<7>(v));
+    }
+
+    // What "reset" means at a block end: goertzel_result()/goertzel_reset() clear the bins
+    // (src/tone_detect.c:110-120,203) and the detectors clear their energy sum.
+    __device__ __forceinline__ void zero_after_block()
+    {
+#pragma unroll
+        for (int p = 0;  p < NP;  p++)
+        {
+            v2[p].x = v2[p].y = 0.0f;
+            v3[p].x = v3[p].y = 0.0f;
+        }
+        energy = 0.0f;
+    }
+
+    // Samples [lo, hi) of one 16-byte vector.  The common case - a whole vector that does not
+    // cross a block boundary - takes the unrolled path; everything else goes sample by sample.
+    // All conditions are warp-uniform in the staged kernel.
+    template <bool FILT>
+    __device__ __forceinline__ void vector(uint4 v, int lo, int hi, const BankArgs<DET> &a)
+    {
+        const int B = block_len(a);
+        if (lo == 0  &&  hi == 8  &&  cs + 8 <= B)
+        {
+            fast8<FILT>(v);
+            cs += 8;
+            if (cs == B)
+            {
+                block_end(a);
+                zero_after_block();
+            }
+        }
+        else
+        {
+            shift_vec_n(v, lo);
+#pragma unroll 1
+            for (int e = lo;  e < hi;  e++)
+            {
+                const float x = (float) (short) (v.x & 0xFFFFu);
+                shift_vec(v);
+                step<FILT>(x);
+                if (++cs == B)
+                {
+                    block_end(a);
+                    zero_after_block();
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Staged kernel: uniform block phase across the bank, 16-byte aligned rows.
+template <int SEG_VEC, int NSTAGE>
+struct StageCfg
+{
+    static constexpr int ROW_BYTES = NSTAGE*SEG_VEC*16 + 16;
+    static constexpr int WARP_BYTES = 32*ROW_BYTES;
+    static_assert((NSTAGE*SEG_VEC) % 8 == 0, "ring must be a multiple of 128 bytes so that ROW_BYTES = 16 mod 128");
+    static_assert(SEG_VEC == 8  ||  SEG_VEC == 16  ||  SEG_VEC == 32, "SEG_VEC lanes copy one row segment");
+};
+
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, bool PACKED>
+__global__ void __launch_bounds__(WARPS*32) bank_kernel_staged(const BankArgs<DET> a)
+{
+    typedef StageCfg<SEG_VEC, NSTAGE> cfg;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int ngroups = (a.channels + 31) >> 5;
+    const long long item = (long long) blockIdx.x*WARPS + warp;
+    const int group = (int) (item % ngroups);
+    const int slice = (int) (item / ngroups);
+    if (slice >= a.nslices)
+        return;
+
+    // ---- sample range of this slice (block geometry: see DESIGN.md "time slicing") ----
+    const int B = block_len(a);
+    const bool last = (slice == a.nslices - 1);
+    long long s0 = (long long) slice*a.slice_blocks*B - a.cs0;
+    if (s0 < 0)
+        s0 = 0;
+    long long s1 = (last)  ?  (long long) a.n  :  ((long long) (slice + 1)*a.slice_blocks*B - a.cs0);
+    if (s1 > a.n)
+        s1 = a.n;
+    const int start = (int) s0;
+    const int end = (int) s1;
+
+    Runner<DET, PACKED> r;
+    r.channels = a.channels;
+    r.c = group*32 + lane;
+    r.active = (r.c < a.channels);
+    if (!r.active)
+        r.c = a.channels - 1;           // shadow the last channel; never writes
+    DET::load_local(a.det, r.c, r.loc);
+#pragma unroll
+    for (int p = 0;  p < DET::NPAIRS;  p++)
+        r.fac[p] = DET::fac(a.det, p);
+    r.blk = slice*a.slice_blocks;
+    r.filt = false;
+    if (slice == 0  &&  a.cs0 > 0)
+    {
+        r.load_carry(a);
+        r.cs = a.cs0;
+    }
+    else
+    {
+        r.zero_state();
+        r.cs = 0;
+    }
+    bool any_filter = false;
+    if (DET::FILTER)
+    {
+        r.filt = DET::filter_on(a.det, r.c);
+        any_filter = __any_sync(0xFFFFFFFFu, r.filt);
+        if (any_filter)
+            DET::load_filter(a.det, r.c, a.channels, r.z);
+    }
+
+    // ---- staging geometry ----
+    const uint32_t warp_smem = (uint32_t) __cvta_generic_to_shared(smem_raw) + warp*cfg::WARP_BYTES;
+    const uint32_t my_row = warp_smem + lane*cfg::ROW_BYTES;
+    const int v_lo = start >> 3;
+    const int v_hi = (end + 7) >> 3;
+    const int g_lo = v_lo/SEG_VEC;
+    const int g_hi = (v_hi + SEG_VEC - 1)/SEG_VEC;
+    const long long row_bytes = (long long) a.n*2;
+
+    // copy role of this lane: SEG_VEC lanes cover one row segment; 32/SEG_VEC rows per instruction
+    constexpr int RPI = 32/SEG_VEC;
+    const int cp_vec = lane % SEG_VEC;
+    const int cp_row0 = lane/SEG_VEC;
+
+    // Row pointer of this lane's first copy and the byte step between its successive copies.
+    const bool full_group = (group*32 + 32 <= a.channels);
+    const char *cp_src0 = (const char *) (a.amp + (long long) (group*32 + cp_row0)*a.stride) + (long long) cp_vec*16;
+    const long long cp_step = (long long) RPI*a.stride*2;
+    const uint32_t cp_dst0 = warp_smem + cp_row0*cfg::ROW_BYTES + cp_vec*16;
+
+    auto issue = [&](int g)
+    {
+        if (g < g_hi)
+        {
+            const int V = g*SEG_VEC + cp_vec;
+            const long long off = (long long) g*(SEG_VEC*16);
+            long long nbytes = row_bytes - (off + cp_vec*16);
+            int sb = (nbytes >= 16)  ?  16  :  (nbytes > 0)  ?  (int) nbytes  :  0;
+            if (V < v_lo  ||  V >= v_hi)
+                sb = 0;
+            uint32_t dst = cp_dst0 + (g % NSTAGE)*(SEG_VEC*16);
+            if (full_group)
+            {
+                const char *src = cp_src0 + off;
+#pragma unroll
+                for (int i = 0;  i < SEG_VEC;  i++)
+                {
+                    cp_async_16(dst, src, sb);
+                    src += cp_step;
+                    dst += RPI*cfg::ROW_BYTES;
+                }
+            }
+            else
+            {
+#pragma unroll 1
+                for (int i = 0;  i < SEG_VEC;  i++)
+                {
+                    int ch = group*32 + i*RPI + cp_row0;
+                    if (ch >= a.channels)
+                        ch = a.channels - 1;
+                    const char *src = (const char *) (a.amp + (long long) ch*a.stride) + off + cp_vec*16;
+                    cp_async_16(dst, src, sb);
+                    dst += RPI*cfg::ROW_BYTES;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (int s = 0;  s < NSTAGE - 1;  s++)
+        issue(g_lo + s);
+
+    auto consume = [&](auto filt_tag)
+    {
+        constexpr bool FILT = decltype(filt_tag)::value;
+        for (int g = g_lo;  g < g_hi;  g++)
+        {
+            cp_async_wait<NSTAGE - 2>();
+            __syncwarp();
+            issue(g + NSTAGE - 1);
+            const uint32_t stage = my_row + (g % NSTAGE)*SEG_VEC*16;
+            const int Vbase = g*SEG_VEC;
+            int j0 = (v_lo > Vbase)  ?  (v_lo - Vbase)  :  0;
+            int j1 = (v_hi < Vbase + SEG_VEC)  ?  (v_hi - Vbase)  :  SEG_VEC;
+            if (j0 < j1)
+            {
+                uint4 cur = lds128(stage + j0*16);
+                for (int j = j0;  j < j1;  j++)
+                {
+                    const uint4 v = cur;
+                    if (j + 1 < j1)
+                        cur = lds128(stage + (j + 1)*16);
+                    const int V = Vbase + j;
+                    const int lo = (V == v_lo)  ?  (start & 7)  :  0;
+                    const int hi = (V == v_hi - 1)  ?  (((end - 1) & 7) + 1)  :  8;
+                    r.template vector<FILT>(v, lo, hi, a);
+                }
+            }
+        }
+    };
+    if (DET::FILTER  &&  any_filter)
+        consume(std::true_type());
+    else
+        consume(std::false_type());
+    cp_async_wait<0>();
+
+    if (last  &&  !DET::RAW)
+    {
+        r.store_carry(a);
+        if (DET::FILTER  &&  any_filter  &&  r.active)
+            DET::store_filter(a.det, r.c, a.channels, r.z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct kernel: any block phase per channel, any alignment.  One thread per channel over the
+// whole call; samples are read with 16-bit loads through L1.
+template <class DET, bool PACKED>
+__global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
+{
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= a.channels)
+        return;
+
+    Runner<DET, PACKED> r;
+    r.channels = a.channels;
+    r.c = c;
+    r.active = true;
+    DET::load_local(a.det, c, r.loc);
+#pragma unroll
+    for (int p = 0;  p < DET::NPAIRS;  p++)
+        r.fac[p] = DET::fac(a.det, p);
+    r.blk = 0;
+    r.cs = (DET::RAW)  ?  0  :  a.cs[c];
+    if (r.cs > 0)
+        r.load_carry(a);
+    else
+        r.zero_state();
+    r.filt = false;
+    if (DET::FILTER)
+    {
+        r.filt = DET::filter_on(a.det, c);
+        DET::load_filter(a.det, c, a.channels, r.z);
+    }
+    const int16_t *row = a.amp + (long long) c*a.stride;
+    if (DET::FILTER  &&  r.filt)
+    {
+#pragma unroll 1
+        for (int i = 0;  i < a.n;  i++)
+        {
+            r.template step<true>((float) __ldg(row + i));
+            if (++r.cs == block_len(a))
+            {
+                r.block_end(a);
+                r.zero_after_block();
+            }
+        }
+        DET::store_filter(a.det, c, a.channels, r.z);
+    }
+    else
+    {
+#pragma unroll 1
+        for (int i = 0;  i < a.n;  i++)
+        {
+            r.template step<false>((float) __ldg(row + i));
+            if (++r.cs == block_len(a))
+            {
+                r.block_end(a);
+                r.zero_after_block();
+            }
+        }
+    }
+    if (!DET::RAW)
+        r.store_carry(a);
+}
+
+}  // namespace sb

@@ -1,0 +1,857 @@
+// sb_detectors.cuh - per-detector block decisions (device) and the per-channel sequencers.
+//
+// Block decisions run inside the bank kernel, once per (channel, block); they are pure
+// functions of the block's bin energies.  Sequencers are the reference's small per-channel
+// state machines (debounce, hit history, cadence tracking); they run as a second, tiny pass
+// over the [block][channel] decision codes and turn them into callback-equivalent event
+// records.  Events are produced with a count -> exclusive-scan -> emit scheme, so the event
+// buffer is compact, ordered by (channel, time) and written without atomics.
+#pragma once
+
+#include <limits.h>
+
+#include "sb_bank.cuh"
+#include "../../include/spandsp_b200.h"
+
+namespace sb {
+
+
+struct SeqCommon
+{
+    int channels;
+    int n;                      // samples per channel in this call
+    int cs0;                    // uniform entry phase, or -1: per channel from cs[]
+    int *cs;                    // [channels] block phase, advanced by the emit pass
+    const unsigned int *offsets;    // exclusive scan of counts (emit pass)
+    unsigned int *counts;       // per-channel event counts (count pass)
+    span_b200_event_t *events;
+    long long capacity;
+};
+
+__device__ __forceinline__ void put_event(const SeqCommon &q, unsigned int pos, int c, int blk, int kind, int a, int b, int cc)
+{
+    if ((long long) pos < q.capacity)
+    {
+        span_b200_event_t e;
+        e.channel = c;
+        e.block = blk;
+        e.kind = kind;
+        e.a = a;
+        e.b = b;
+        e.c = cc;
+        q.events[pos] = e;
+    }
+}
+
+// ==========================================================================================
+// DTMF  (reference: src/dtmf.c)
+__constant__ float c_dtmf_fac[8];       // row0, col0, row1, col1, ... (src/dtmf.c:114-121)
+__constant__ char c_dtmf_positions[17]; // "123A456B789C*0#D" (src/dtmf.c:123)
+
+struct DtmfParams
+{
+    const float *threshold;             // per channel (dtmf_rx_parms, src/dtmf.c:421-445)
+    const float *normal_twist;
+    const float *reverse_twist;
+    const unsigned char *flags;         // SB_DTMF_FLAG_*
+    float *z;                           // [4][channels] dial-tone notch state
+};
+
+#define SB_DTMF_FLAG_FILTER     1
+#define SB_DTMF_FLAG_REALTIME   2
+
+struct DtmfLocal
+{
+    float threshold;
+    float normal_twist;
+    float reverse_twist;
+};
+
+struct DtmfDet
+{
+    static constexpr int NPAIRS = 4;
+    static constexpr int BLOCK = 102;               // src/dtmf.c:71
+    static constexpr bool ENERGY = true;
+    static constexpr bool ENERGY_OUT = true;
+    static constexpr bool FILTER = true;
+    static constexpr bool RAW = false;
+    typedef unsigned char code_t;
+    typedef DtmfParams Params;
+    typedef DtmfLocal Local;
+
+    __device__ static __forceinline__ pair_t fac(const Params &, int p)
+    {
+        pair_t f;
+        f.x = c_dtmf_fac[2*p];
+        f.y = c_dtmf_fac[2*p + 1];
+        return f;
+    }
+
+    __device__ static __forceinline__ void load_local(const Params &d, int c, Local &l)
+    {
+        l.threshold = d.threshold[c];
+        l.normal_twist = d.normal_twist[c];
+        l.reverse_twist = d.reverse_twist[c];
+    }
+
+    __device__ static __forceinline__ bool filter_on(const Params &d, int c)
+    {
+        return (d.flags[c] & SB_DTMF_FLAG_FILTER) != 0;
+    }
+
+    __device__ static __forceinline__ void load_filter(const Params &d, int c, int channels, float (&z)[4])
+    {
+#pragma unroll
+        for (int i = 0;  i < 4;  i++)
+            z[i] = d.z[(size_t) i*channels + c];
+    }
+
+    __device__ static __forceinline__ void store_filter(const Params &d, int c, int channels, const float (&z)[4])
+    {
+#pragma unroll
+        for (int i = 0;  i < 4;  i++)
+            d.z[(size_t) i*channels + c] = z[i];
+    }
+
+    // src/dtmf.c:211-258.  e[2i] = row i, e[2i+1] = col i.
+    __device__ static __forceinline__ int decide(const float (&e)[8], float energy, const Local &l)
+    {
+        float rbest = e[0];
+        float cbest = e[1];
+        int best_row = 0;
+        int best_col = 0;
+#pragma unroll
+        for (int i = 1;  i < 4;  i++)
+        {
+            if (e[2*i] > rbest)
+            {
+                rbest = e[2*i];
+                best_row = i;
+            }
+            if (e[2*i + 1] > cbest)
+            {
+                cbest = e[2*i + 1];
+                best_col = i;
+            }
+        }
+        bool ok = (rbest >= l.threshold)  &&  (cbest >= l.threshold);
+        ok = ok  &&  (cbest < fmul(rbest, l.reverse_twist))  &&  (fmul(cbest, l.normal_twist) > rbest);
+#pragma unroll
+        for (int i = 0;  i < 4;  i++)
+        {
+            if ((i != best_col  &&  fmul(e[2*i + 1], 6.309f) > cbest)
+                ||
+                (i != best_row  &&  fmul(e[2*i], 6.309f) > rbest))
+                ok = false;
+        }
+        ok = ok  &&  (fadd(rbest, cbest) > fmul(83.868f, energy));
+        const int ch = (int) c_dtmf_positions[(best_row << 2) + best_col];        // src/dtmf.c:123,256
+        return (ok)  ?  ch  :  0;
+    }
+};
+
+struct DtmfSeqArgs
+{
+    SeqCommon q;
+    const unsigned char *code;          // [block][channel]
+    const float *eout;                  // [block][channel]
+    const unsigned char *flags;
+    unsigned char *last_hit;
+    unsigned char *in_digit;
+    int *duration;
+    // level(energy) = (int) (10*log10f(energy) - 107.255f) (src/dtmf.c:110,314) is a monotone
+    // step function of the float energy.  The host tabulates its steps once with its own libm
+    // (the same one the CPU oracle uses) so that the device reproduces it exactly:
+    // level = level_min + #{k : level_thr[k] <= energy}.
+    const float *level_thr;
+    int level_n;
+    int level_min;
+};
+
+__device__ __forceinline__ int dtmf_level(const DtmfSeqArgs &s, float energy)
+{
+    int lo = 0;
+    int hi = s.level_n;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (s.level_thr[mid] <= energy)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return s.level_min + lo;
+}
+
+// src/dtmf.c:201-207 (duration) and 304-347 (two-block debounce).
+template <bool EMIT>
+__global__ void dtmf_sequencer(const DtmfSeqArgs s)
+{
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= s.q.channels)
+        return;
+    const int B = DtmfDet::BLOCK;
+    const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
+    const int nb = (cs_old + s.q.n)/B;
+    const bool realtime = (s.flags[c] & SB_DTMF_FLAG_REALTIME) != 0;
+    int in_digit = s.in_digit[c];
+    int last_hit = s.last_hit[c];
+    int dur = s.duration[c];
+    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
+    unsigned int count = 0;
+
+    for (int b = 0;  b < nb;  b++)
+    {
+        const int len = (b == 0)  ?  (B - cs_old)  :  B;
+        if (dur < INT_MAX - len)
+            dur += len;
+        int hit = s.code[(size_t) b*s.q.channels + c];
+        if (hit != in_digit  &&  last_hit != in_digit)
+        {
+            hit = (hit  &&  hit == last_hit)  ?  hit  :  0;
+            if (realtime)
+            {
+                if (in_digit  ||  hit)
+                {
+                    if (EMIT)
+                    {
+                        if (in_digit  &&  !hit)
+                            put_event(s.q, pos, c, b, SPAN_B200_EV_TONE, hit, -99, dur);
+                        else
+                            put_event(s.q, pos, c, b, SPAN_B200_EV_TONE, hit, dtmf_level(s, s.eout[(size_t) b*s.q.channels + c]), dur);
+                    }
+                    pos++;
+                    count++;
+                    dur = 0;
+                }
+            }
+            else if (hit)
+            {
+                if (EMIT)
+                    put_event(s.q, pos, c, b, SPAN_B200_EV_DIGIT, hit, 0, 0);
+                pos++;
+                count++;
+            }
+            in_digit = hit;
+        }
+        last_hit = hit;
+    }
+    if (EMIT)
+    {
+        const int tail = (nb == 0)  ?  s.q.n  :  (cs_old + s.q.n - nb*B);
+        if (dur < INT_MAX - tail)
+            dur += tail;
+        s.in_digit[c] = (unsigned char) in_digit;
+        s.last_hit[c] = (unsigned char) last_hit;
+        s.duration[c] = dur;
+        s.q.cs[c] = cs_old + s.q.n - nb*B;
+    }
+    else
+    {
+        s.q.counts[c] = count;
+    }
+}
+
+// ==========================================================================================
+// Bell MF and MFC/R2  (reference: src/bell_r2_mf.c)
+__constant__ float c_bell_mf_fac[6];    // 700 ... 1700 Hz   (src/bell_r2_mf.c:251-254)
+__constant__ float c_r2_fwd_fac[6];     // 1380 ... 1980 Hz  (src/bell_r2_mf.c:264-267)
+__constant__ float c_r2_back_fac[6];    // 1140 ... 540 Hz   (src/bell_r2_mf.c:269-272)
+__constant__ char c_bell_mf_positions[26];      // "1247C-358A--69*---0B----#"
+__constant__ char c_r2_mf_positions[26];        // "1247B-358C--69D---0E----F"
+
+struct MfParams
+{
+    int fwd;
+};
+
+struct MfLocal
+{
+};
+
+// src/bell_r2_mf.c:554-628 / 793-863: returns index into the 25-character position table, or -1.
+__device__ __forceinline__ int mf_pick(const float (&e)[6], float threshold, float twist, float relative_peak)
+{
+    int best;
+    int second;
+    float ebest;
+    float esecond;
+
+    if (e[0] > e[1])
+    {
+        best = 0;
+        second = 1;
+        ebest = e[0];
+        esecond = e[1];
+    }
+    else
+    {
+        best = 1;
+        second = 0;
+        ebest = e[1];
+        esecond = e[0];
+    }
+#pragma unroll
+    for (int i = 2;  i < 6;  i++)
+    {
+        if (e[i] >= ebest)
+        {
+            second = best;
+            esecond = ebest;
+            best = i;
+            ebest = e[i];
+        }
+        else if (e[i] >= esecond)
+        {
+            second = i;
+            esecond = e[i];
+        }
+    }
+    bool ok = (ebest >= threshold)  &&  (esecond >= threshold)
+              &&  (ebest < fmul(esecond, twist))  &&  (fmul(ebest, twist) > esecond);
+#pragma unroll
+    for (int i = 0;  i < 6;  i++)
+    {
+        if (i != best  &&  i != second  &&  fmul(e[i], relative_peak) >= esecond)
+            ok = false;
+    }
+    if (second < best)
+    {
+        const int t = best;
+        best = second;
+        second = t;
+    }
+    return (ok)  ?  (best*5 + second - 1)  :  -1;
+}
+
+struct BellMfDet
+{
+    static constexpr int NPAIRS = 3;
+    static constexpr int BLOCK = 120;               // src/bell_r2_mf.c:204
+    static constexpr bool ENERGY = false;
+    static constexpr bool ENERGY_OUT = false;
+    static constexpr bool FILTER = false;
+    static constexpr bool RAW = false;
+    typedef unsigned char code_t;
+    typedef MfParams Params;
+    typedef MfLocal Local;
+
+    __device__ static __forceinline__ pair_t fac(const Params &, int p)
+    {
+        pair_t f;
+        f.x = c_bell_mf_fac[2*p];
+        f.y = c_bell_mf_fac[2*p + 1];
+        return f;
+    }
+    __device__ static __forceinline__ void load_local(const Params &, int, Local &) {}
+    __device__ static __forceinline__ bool filter_on(const Params &, int) { return false; }
+    __device__ static __forceinline__ void load_filter(const Params &, int, int, float (&)[4]) {}
+    __device__ static __forceinline__ void store_filter(const Params &, int, int, const float (&)[4]) {}
+
+    __device__ static __forceinline__ int decide(const float (&e)[6], float, const Local &)
+    {
+        const int k = mf_pick(e, 3343803100.0f, 3.981f, 12.589f);      // src/bell_r2_mf.c:236-238
+        return (k >= 0)  ?  (int) c_bell_mf_positions[k]  :  0;
+    }
+};
+
+struct R2MfDet
+{
+    static constexpr int NPAIRS = 3;
+    static constexpr int BLOCK = 133;               // src/bell_r2_mf.c:206
+    static constexpr bool ENERGY = false;
+    static constexpr bool ENERGY_OUT = false;
+    static constexpr bool FILTER = false;
+    static constexpr bool RAW = false;
+    typedef unsigned char code_t;
+    typedef MfParams Params;
+    typedef MfLocal Local;
+
+    __device__ static __forceinline__ pair_t fac(const Params &d, int p)
+    {
+        pair_t f;
+        f.x = (d.fwd)  ?  c_r2_fwd_fac[2*p]  :  c_r2_back_fac[2*p];
+        f.y = (d.fwd)  ?  c_r2_fwd_fac[2*p + 1]  :  c_r2_back_fac[2*p + 1];
+        return f;
+    }
+    __device__ static __forceinline__ void load_local(const Params &, int, Local &) {}
+    __device__ static __forceinline__ bool filter_on(const Params &, int) { return false; }
+    __device__ static __forceinline__ void load_filter(const Params &, int, int, float (&)[4]) {}
+    __device__ static __forceinline__ void store_filter(const Params &, int, int, const float (&)[4]) {}
+
+    __device__ static __forceinline__ int decide(const float (&e)[6], float, const Local &)
+    {
+        const int k = mf_pick(e, 1031766650.0f, 5.012f, 12.589f);      // src/bell_r2_mf.c:240-242
+        return (k >= 0)  ?  (int) c_r2_mf_positions[k]  :  0;
+    }
+};
+
+struct MfSeqArgs
+{
+    SeqCommon q;
+    const unsigned char *code;
+    unsigned char *hits;                // Bell: [5][channels]; R2: [1][channels] = current_digit
+};
+
+// src/bell_r2_mf.c:629-661: a digit is reported when the last two blocks agree with this one and
+// the two before differ (KP '*': the last three agree and the two before differ).
+template <bool EMIT>
+__global__ void bell_mf_sequencer(const MfSeqArgs s)
+{
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= s.q.channels)
+        return;
+    const int B = BellMfDet::BLOCK;
+    const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
+    const int nb = (cs_old + s.q.n)/B;
+    const size_t C = s.q.channels;
+    int h0 = s.hits[c];
+    int h1 = s.hits[C + c];
+    int h2 = s.hits[2*C + c];
+    int h3 = s.hits[3*C + c];
+    int h4 = s.hits[4*C + c];
+    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
+    unsigned int count = 0;
+
+    for (int b = 0;  b < nb;  b++)
+    {
+        const int hit = s.code[(size_t) b*C + c];
+        if (hit
+            &&  hit == h4  &&  hit == h3
+            &&  ((hit != '*'  &&  hit != h2  &&  hit != h1)
+                 ||
+                 (hit == '*'  &&  hit == h2  &&  hit != h1  &&  hit != h0)))
+        {
+            if (EMIT)
+                put_event(s.q, pos, c, b, SPAN_B200_EV_DIGIT, hit, 0, 0);
+            pos++;
+            count++;
+        }
+        h0 = h1;
+        h1 = h2;
+        h2 = h3;
+        h3 = h4;
+        h4 = hit;
+    }
+    if (EMIT)
+    {
+        s.hits[c] = (unsigned char) h0;
+        s.hits[C + c] = (unsigned char) h1;
+        s.hits[2*C + c] = (unsigned char) h2;
+        s.hits[3*C + c] = (unsigned char) h3;
+        s.hits[4*C + c] = (unsigned char) h4;
+        s.q.cs[c] = cs_old + s.q.n - nb*B;
+    }
+    else
+    {
+        s.q.counts[c] = count;
+    }
+}
+
+// src/bell_r2_mf.c:864-876: report every change of the block decision.
+template <bool EMIT>
+__global__ void r2_mf_sequencer(const MfSeqArgs s)
+{
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= s.q.channels)
+        return;
+    const int B = R2MfDet::BLOCK;
+    const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
+    const int nb = (cs_old + s.q.n)/B;
+    const size_t C = s.q.channels;
+    int current = s.hits[c];
+    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
+    unsigned int count = 0;
+
+    for (int b = 0;  b < nb;  b++)
+    {
+        const int hit = s.code[(size_t) b*C + c];
+        if (hit != current)
+        {
+            if (EMIT)
+                put_event(s.q, pos, c, b, SPAN_B200_EV_TONE, hit, (hit)  ?  -10  :  -99, 0);
+            pos++;
+            count++;
+        }
+        current = hit;
+    }
+    if (EMIT)
+    {
+        s.hits[c] = (unsigned char) current;
+        s.q.cs[c] = cs_old + s.q.n - nb*B;
+    }
+    else
+    {
+        s.q.counts[c] = count;
+    }
+}
+
+// ==========================================================================================
+// Supervisory tones  (reference: src/super_tone_rx.c)
+#define SB_ST_MAX_PAIRS     16          // up to 32 monitored bins in one pass
+
+struct StParams
+{
+    float fac[2*SB_ST_MAX_PAIRS];       // padded with zeros
+    int bins;                           // monitored_frequencies
+};
+
+struct StLocal
+{
+    int bins;
+};
+
+// code layout: bits 0-6 = k1 + 1, bits 7-13 = k2 + 1, bit 15 = "one-bin quirk" (see below)
+#define SB_ST_CODE(k1, k2)      ((unsigned short) ((((k2) + 1) << 7) | ((k1) + 1)))
+#define SB_ST_QUIRK             0x8000
+
+template <int NP>
+struct SuperToneDet
+{
+    static constexpr int NPAIRS = NP;
+    static constexpr int BLOCK = 128;               // src/spandsp/private/super_tone_rx.h:29
+    static constexpr bool ENERGY = true;
+    static constexpr bool ENERGY_OUT = false;
+    static constexpr bool FILTER = false;
+    static constexpr bool RAW = false;
+    typedef unsigned short code_t;
+    typedef StParams Params;
+    typedef StLocal Local;
+
+    __device__ static __forceinline__ pair_t fac(const Params &d, int p)
+    {
+        pair_t f;
+        f.x = d.fac[2*p];
+        f.y = d.fac[2*p + 1];
+        return f;
+    }
+    __device__ static __forceinline__ void load_local(const Params &d, int, Local &l) { l.bins = d.bins; }
+    __device__ static __forceinline__ bool filter_on(const Params &, int) { return false; }
+    __device__ static __forceinline__ void load_filter(const Params &, int, int, float (&)[4]) {}
+    __device__ static __forceinline__ void store_filter(const Params &, int, int, const float (&)[4]) {}
+
+    // src/super_tone_rx.c:300-365
+    __device__ static __forceinline__ int decide(const float (&res)[2*NP], float energy, const Local &l)
+    {
+        if (energy < 2104205.6f)                    // src/super_tone_rx.c:75,300
+            return SB_ST_CODE(-1, -1);
+        if (l.bins < 2)
+        {
+            // src/super_tone_rx.c:312-316: k1 = k2 = 0 and the bins are left un-read; the reference
+            // then re-enters super_tone_chunk with zero energy.  The sequencer replays that.
+            return SB_ST_CODE(0, 0) | SB_ST_QUIRK;
+        }
+        int k1;
+        int k2;
+        float r1;
+        float r2;
+        if (res[0] > res[1])
+        {
+            k1 = 0;
+            k2 = 1;
+            r1 = res[0];
+            r2 = res[1];
+        }
+        else
+        {
+            k1 = 1;
+            k2 = 0;
+            r1 = res[1];
+            r2 = res[0];
+        }
+#pragma unroll
+        for (int j = 2;  j < 2*NP;  j++)
+        {
+            if (j < l.bins)
+            {
+                if (res[j] >= r1)
+                {
+                    k2 = k1;
+                    r2 = r1;
+                    k1 = j;
+                    r1 = res[j];
+                }
+                else if (res[j] >= r2)
+                {
+                    k2 = j;
+                    r2 = res[j];
+                }
+            }
+        }
+        if (fadd(r1, r2) < fmul(1.995f, energy))
+        {
+            k1 = -1;
+            k2 = -1;
+        }
+        else if (r1 > fmul(3.981f, r2))
+        {
+            k2 = -1;
+        }
+        else if (k2 < k1)
+        {
+            const int t = k1;
+            k1 = k2;
+            k2 = t;
+        }
+        return SB_ST_CODE(k1, k2);
+    }
+};
+
+// Raw Goertzel bank: arbitrary coefficients and block length, energies out
+// (goertzel_update()/goertzel_result(), src/tone_detect.c:123-205).
+template <int NP>
+struct RawDet
+{
+    static constexpr int NPAIRS = NP;
+    static constexpr int BLOCK = 0;                 // run-time block length
+    static constexpr bool ENERGY = false;
+    static constexpr bool ENERGY_OUT = false;
+    static constexpr bool FILTER = false;
+    static constexpr bool RAW = true;
+    typedef unsigned char code_t;
+    typedef StParams Params;
+    typedef StLocal Local;
+
+    __device__ static __forceinline__ pair_t fac(const Params &d, int p)
+    {
+        pair_t f;
+        f.x = d.fac[2*p];
+        f.y = d.fac[2*p + 1];
+        return f;
+    }
+    __device__ static __forceinline__ void load_local(const Params &d, int, Local &l) { l.bins = d.bins; }
+    __device__ static __forceinline__ bool filter_on(const Params &, int) { return false; }
+    __device__ static __forceinline__ void load_filter(const Params &, int, int, float (&)[4]) {}
+    __device__ static __forceinline__ void store_filter(const Params &, int, int, const float (&)[4]) {}
+    __device__ static __forceinline__ int decide(const float (&)[2*NP], float, const Local &) { return 0; }
+};
+
+// Device copy of a super-tone descriptor's cadence templates (src/spandsp/private/super_tone_rx.h:40-49)
+struct StTemplates
+{
+    int tones;
+    const int *tone_segs;               // [tones]
+    const int *tone_first;              // [tones] index of the tone's first element in `elements`
+    const int4 *elements;               // {f1, f2, min_duration, max_duration} in samples
+};
+
+struct StSeqArgs
+{
+    SeqCommon q;
+    const unsigned short *code;
+    StTemplates t;
+    int *segments;                      // [33][channels]: segments[i].{f1,f2,min_duration} at 3*i + {0,1,2}
+    int *detected_tone;
+    int *rotation;
+    unsigned char *pending;             // one-bin quirk: a zero-energy re-chunk is owed at the next call
+    int want_segments;
+};
+
+struct StSegs
+{
+    int f1[11];
+    int f2[11];
+    int dur[11];
+};
+
+// src/super_tone_rx.c:164-228
+__device__ inline int st_test_cadence(const int4 *pattern, int steps, const StSegs &t, int rotation)
+{
+    int j;
+
+    if (rotation >= 0)
+    {
+        j = 0;
+        if (steps < 0)
+        {
+            steps = -steps;
+            j = (rotation + steps - 2)%steps;
+            if (pattern[j].x != t.f1[8]  ||  pattern[j].y != t.f2[8])
+                return 0;
+            if (pattern[j].z > t.dur[8]*128  ||  pattern[j].w < t.dur[8]*128)
+                return 0;
+        }
+        if (steps)
+            j = (rotation + steps - 1)%steps;
+        if (pattern[j].x != t.f1[9]  ||  pattern[j].y != t.f2[9])
+            return 0;
+        if (pattern[j].w < t.dur[9]*128)
+            return 0;
+    }
+    else
+    {
+        for (int i = 0;  i < steps;  i++)
+        {
+            j = i + 10 - steps;
+            if (pattern[i].x != t.f1[j]  ||  pattern[i].y != t.f2[j])
+                return 0;
+            if (pattern[i].z > t.dur[j]*128  ||  pattern[i].w < t.dur[j]*128)
+                return 0;
+        }
+    }
+    return 1;
+}
+
+// src/super_tone_rx.c:366-448
+template <bool EMIT>
+__global__ void super_tone_sequencer(const StSeqArgs s)
+{
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= s.q.channels)
+        return;
+    const int B = 128;
+    const size_t C = s.q.channels;
+    const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
+    const int nb = (cs_old + s.q.n)/B;
+    StSegs t;
+    for (int i = 0;  i < 11;  i++)
+    {
+        t.f1[i] = s.segments[(size_t) (3*i)*C + c];
+        t.f2[i] = s.segments[(size_t) (3*i + 1)*C + c];
+        t.dur[i] = s.segments[(size_t) (3*i + 2)*C + c];
+    }
+    int detected = s.detected_tone[c];
+    int rotation = s.rotation[c];
+    int pending = s.pending[c];
+    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
+    unsigned int count = 0;
+
+    auto emit = [&](int blk, int kind, int a, int b, int cc)
+    {
+        if (EMIT)
+            put_event(s.q, pos, c, blk, kind, a, b, cc);
+        pos++;
+        count++;
+    };
+
+    auto chunk = [&](int blk, int k1, int k2)
+    {
+        if (k1 != t.f1[10]  ||  k2 != t.f2[10])
+        {
+            t.f1[10] = k1;
+            t.f2[10] = k2;
+            t.dur[9]++;
+        }
+        else if (k1 != t.f1[9]  ||  k2 != t.f2[9])
+        {
+            if (detected >= 0)
+            {
+                if (!st_test_cadence(s.t.elements + s.t.tone_first[detected], -s.t.tone_segs[detected], t, rotation++))
+                {
+                    detected = -1;
+                    emit(blk, SPAN_B200_EV_TONE, -1, -10, 0);
+                }
+            }
+            if (s.want_segments)
+                emit(blk, SPAN_B200_EV_SEGMENT, t.f1[9], t.f2[9], t.dur[9]*128/8);
+            for (int i = 0;  i < 9;  i++)
+            {
+                t.f1[i] = t.f1[i + 1];
+                t.f2[i] = t.f2[i + 1];
+                t.dur[i] = t.dur[i + 1];
+            }
+            t.f1[9] = k1;
+            t.f2[9] = k2;
+            t.dur[9] = 1;
+        }
+        else
+        {
+            if (detected >= 0)
+            {
+                if (!st_test_cadence(s.t.elements + s.t.tone_first[detected], s.t.tone_segs[detected], t, rotation))
+                {
+                    detected = -1;
+                    emit(blk, SPAN_B200_EV_TONE, -1, -10, 0);
+                }
+            }
+            t.dur[9]++;
+        }
+        if (detected < 0)
+        {
+            for (int j = 0;  j < s.t.tones;  j++)
+            {
+                if (st_test_cadence(s.t.elements + s.t.tone_first[j], s.t.tone_segs[j], t, -1))
+                {
+                    detected = j;
+                    rotation = 0;
+                    emit(blk, SPAN_B200_EV_TONE, j, -10, 0);
+                    break;
+                }
+            }
+        }
+    };
+
+    if (pending  &&  s.q.n > 0)
+    {
+        chunk(0, -1, -1);
+        pending = 0;
+    }
+    const long long consumed_at_end = (long long) cs_old + s.q.n;
+    for (int b = 0;  b < nb;  b++)
+    {
+        const int code = s.code[(size_t) b*C + c];
+        const int k1 = (code & 0x7F) - 1;
+        const int k2 = ((code >> 7) & 0x7F) - 1;
+        chunk(b, k1, k2);
+        if (code & SB_ST_QUIRK)
+        {
+            // The reference loops straight back into super_tone_chunk with zero energy unless the
+            // block ended exactly at the end of the caller's buffer (src/super_tone_rx.c:466-486).
+            if ((long long) (b + 1)*B < consumed_at_end)
+                chunk(b, -1, -1);
+            else
+                pending = 1;
+        }
+    }
+    if (EMIT)
+    {
+        for (int i = 0;  i < 11;  i++)
+        {
+            s.segments[(size_t) (3*i)*C + c] = t.f1[i];
+            s.segments[(size_t) (3*i + 1)*C + c] = t.f2[i];
+            s.segments[(size_t) (3*i + 2)*C + c] = t.dur[i];
+        }
+        s.detected_tone[c] = detected;
+        s.rotation[c] = rotation;
+        s.pending[c] = (unsigned char) pending;
+        s.q.cs[c] = cs_old + s.q.n - nb*B;
+    }
+    else
+    {
+        s.q.counts[c] = count;
+    }
+}
+
+// ==========================================================================================
+// Exclusive scan of per-channel event counts (single CTA; channels <= a few million).
+__global__ void __launch_bounds__(1024) scan_counts(const unsigned int *counts, unsigned int *offsets, int n, unsigned long long *total)
+{
+    __shared__ unsigned long long part[1024];
+    const int tid = threadIdx.x;
+    const int per = (n + 1023)/1024;
+    const int i0 = tid*per;
+    const int i1 = (i0 + per < n)  ?  (i0 + per)  :  n;
+    unsigned long long sum = 0;
+
+    for (int i = i0;  i < i1;  i++)
+        sum += counts[i];
+    part[tid] = sum;
+    __syncthreads();
+    for (int d = 1;  d < 1024;  d <<= 1)
+    {
+        unsigned long long v = (tid >= d)  ?  part[tid - d]  :  0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[tid] - sum;
+    for (int i = i0;  i < i1;  i++)
+    {
+        offsets[i] = (unsigned int) run;
+        run += counts[i];
+    }
+    if (tid == 1023)
+        total[0] = part[1023];
+}
+
+}  // namespace sb

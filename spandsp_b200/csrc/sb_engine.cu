@@ -1,0 +1,1374 @@
+// sb_engine.cu - host side of the B200 tone-bank engine: contexts, banks, launches, events.
+// C ABI declared in include/spandsp_b200.h.  There is no CPU fallback anywhere in this file:
+// without a usable sm_100 device every entry point fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <vector>
+#include <mutex>
+
+#include "sb_engine.h"
+#include "sb_detectors.cuh"
+
+using namespace sb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+static thread_local char g_err[512] = "";
+
+void sb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define CK(call) \
+    do \
+    { \
+        cudaError_t e_ = (call); \
+        if (e_ != cudaSuccess) \
+        { \
+            sb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return -1; \
+        } \
+    } \
+    while (0)
+
+#define CKP(call) \
+    do \
+    { \
+        cudaError_t e_ = (call); \
+        if (e_ != cudaSuccess) \
+        { \
+            sb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return NULL; \
+        } \
+    } \
+    while (0)
+
+extern "C" const char *span_b200_last_error(void)
+{
+    return g_err;
+}
+
+extern "C" int span_b200_abi_version(void)
+{
+    return SPAN_B200_ABI_VERSION;
+}
+
+// ------------------------------------------------------------------------------------------
+// coefficient and level tables (host libm, same expressions as the reference)
+
+// src/tone_detect.c:60-68: 2.0f*cosf(2.0f*M_PI*(freq/8000.0f)); the cosf argument is formed in
+// double because M_PI is a double constant, then narrowed by the call.
+float sb_goertzel_fac(float freq)
+{
+    return 2.0f*cosf((float) (2.0f*M_PI*(freq/8000.0f)));
+}
+
+// src/dtmf.c:110,314 with lfastrintf = C truncation on x86-64 (src/spandsp/fast_convert.h:194-197)
+static int host_dtmf_level(float energy)
+{
+    return (int) (long int) (10.0f*log10f(energy) - 107.255f);
+}
+
+static float bits_to_float(uint32_t u)
+{
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// Tabulate the steps of host_dtmf_level over all positive finite floats (monotone in the bit
+// pattern).  thr[k] = smallest float whose level is >= level_min + k + 1.
+static void build_level_table(std::vector<float> &thr, int &level_min)
+{
+    const uint32_t lo_bits = 1;                 // smallest denormal
+    const uint32_t hi_bits = 0x7F7FFFFFu;       // FLT_MAX
+    level_min = host_dtmf_level(bits_to_float(lo_bits));
+    const int level_max = host_dtmf_level(bits_to_float(hi_bits));
+    thr.clear();
+    uint32_t start = lo_bits;
+    for (int target = level_min + 1;  target <= level_max;  target++)
+    {
+        uint32_t a = start;                     // level(a) < target
+        uint32_t b = hi_bits;                   // level(b) >= target
+        while (b - a > 1)
+        {
+            const uint32_t m = a + (b - a)/2;
+            if (host_dtmf_level(bits_to_float(m)) >= target)
+                b = m;
+            else
+                a = m;
+        }
+        thr.push_back(bits_to_float(b));
+        start = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+struct span_b200_ctx_s
+{
+    int device;
+    int sm_count;
+    int smem_optin;
+    cudaStream_t stream;
+    float *d_level_thr;
+    int level_n;
+    int level_min;
+};
+
+static int upload_constants(int device)
+{
+    float f[8];
+    static const float row[4] = {697.0f, 770.0f, 852.0f, 941.0f};           // src/dtmf.c:114-117
+    static const float col[4] = {1209.0f, 1336.0f, 1477.0f, 1633.0f};       // src/dtmf.c:118-121
+    static const int bell[6] = {700, 900, 1100, 1300, 1500, 1700};          // src/bell_r2_mf.c:251-254
+    static const int r2f[6] = {1380, 1500, 1620, 1740, 1860, 1980};         // src/bell_r2_mf.c:264-267
+    static const int r2b[6] = {1140, 1020, 900, 780, 660, 540};             // src/bell_r2_mf.c:269-272
+    (void) device;
+    for (int i = 0;  i < 4;  i++)
+    {
+        f[2*i] = sb_goertzel_fac(row[i]);
+        f[2*i + 1] = sb_goertzel_fac(col[i]);
+    }
+    CK(cudaMemcpyToSymbol(c_dtmf_fac, f, sizeof(float)*8));
+    CK(cudaMemcpyToSymbol(c_dtmf_positions, "123A456B789C*0#D", 17));
+    for (int i = 0;  i < 6;  i++)
+        f[i] = sb_goertzel_fac((float) bell[i]);
+    CK(cudaMemcpyToSymbol(c_bell_mf_fac, f, sizeof(float)*6));
+    for (int i = 0;  i < 6;  i++)
+        f[i] = sb_goertzel_fac((float) r2f[i]);
+    CK(cudaMemcpyToSymbol(c_r2_fwd_fac, f, sizeof(float)*6));
+    for (int i = 0;  i < 6;  i++)
+        f[i] = sb_goertzel_fac((float) r2b[i]);
+    CK(cudaMemcpyToSymbol(c_r2_back_fac, f, sizeof(float)*6));
+    CK(cudaMemcpyToSymbol(c_bell_mf_positions, "1247C-358A--69*---0B----#", 26));      // src/bell_r2_mf.c:262
+    CK(cudaMemcpyToSymbol(c_r2_mf_positions, "1247B-358C--69D---0E----F", 26));        // src/bell_r2_mf.c:276
+    return 0;
+}
+
+extern "C" span_b200_ctx_t *span_b200_ctx_create(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess  ||  count == 0)
+    {
+        sb_set_error("no CUDA device available (%s); spandsp_b200 has no CPU fallback",
+                     (e != cudaSuccess)  ?  cudaGetErrorString(e)  :  "device count is 0");
+        return NULL;
+    }
+    if (device < 0)
+        CKP(cudaGetDevice(&device));
+    if (device >= count)
+    {
+        sb_set_error("device %d out of range (%d devices)", device, count);
+        return NULL;
+    }
+    cudaDeviceProp prop;
+    CKP(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+    {
+        sb_set_error("device %d is sm_%d%d; spandsp_b200 kernels are built for sm_100a only", device, prop.major, prop.minor);
+        return NULL;
+    }
+    CKP(cudaSetDevice(device));
+    span_b200_ctx_t *ctx = new span_b200_ctx_s();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int) prop.sharedMemPerBlockOptin;
+    CKP(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (upload_constants(device) != 0)
+        return NULL;
+    std::vector<float> thr;
+    build_level_table(thr, ctx->level_min);
+    ctx->level_n = (int) thr.size();
+    CKP(cudaMalloc(&ctx->d_level_thr, sizeof(float)*thr.size()));
+    CKP(cudaMemcpy(ctx->d_level_thr, thr.data(), sizeof(float)*thr.size(), cudaMemcpyHostToDevice));
+    return ctx;
+}
+
+extern "C" void span_b200_ctx_destroy(span_b200_ctx_t *ctx)
+{
+    if (ctx == NULL)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_level_thr);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int span_b200_ctx_device(const span_b200_ctx_t *ctx)
+{
+    return ctx->device;
+}
+
+extern "C" int span_b200_ctx_sm_count(const span_b200_ctx_t *ctx)
+{
+    return ctx->sm_count;
+}
+
+void *sb_ctx_stream(span_b200_ctx_t *ctx)
+{
+    return (void *) ctx->stream;
+}
+
+// ------------------------------------------------------------------------------------------
+// bank
+struct span_b200_bank_s
+{
+    span_b200_ctx_t *ctx;
+    int det;
+    int channels;
+    int block;
+    int bins;
+    int npairs;
+    int fwd;
+    int want_segments;
+
+    // carried bank state
+    float *v2;
+    float *v3;
+    float *energy;
+    int *cs;
+    // DTMF
+    float *thr;
+    float *ntw;
+    float *rtw;
+    unsigned char *flags;
+    float *z;
+    unsigned char *last_hit;
+    unsigned char *in_digit;
+    int *duration;
+    std::vector<float> h_thr;
+    std::vector<float> h_ntw;
+    std::vector<float> h_rtw;
+    std::vector<unsigned char> h_flags;
+    int n_filter;
+    // MF
+    unsigned char *hits;
+    // super-tone
+    StParams stp;
+    int *segments;
+    int *detected;
+    int *rotation;
+    unsigned char *pending;
+    int *d_tone_segs;
+    int *d_tone_first;
+    int4 *d_elements;
+    int tones;
+    std::vector<float> h_fac;
+
+    // per-call scratch
+    void *code;
+    size_t code_bytes;
+    float *eout;
+    size_t eout_bytes;
+    unsigned int *counts;
+    unsigned int *offsets;
+    unsigned long long *d_total;
+    unsigned long long *h_total;
+    span_b200_event_t *events;
+    long long ev_cap;
+    long long ev_cap_user;
+    int16_t *d_in;
+    size_t d_in_bytes;
+
+    int uniform_cs;                 // common block phase of all channels, -1 if they differ
+    int last_nb;
+    int last_launches;
+    const char *last_path;
+    cudaStream_t last_stream;
+    bool have_last;
+
+    int tune_timing;
+    std::vector<cudaEvent_t> ev_pool;
+    int ev_used;
+
+    int tune_slice;
+    int tune_variant;
+    int tune_direct;
+    int tune_packed;
+};
+
+static int ensure(void **p, size_t *have, size_t want)
+{
+    if (*have >= want)
+        return 0;
+    if (*p)
+        CK(cudaFree(*p));
+    *p = NULL;
+    *have = 0;
+    size_t sz = want + want/8 + 256;
+    CK(cudaMalloc(p, sz));
+    *have = sz;
+    return 0;
+}
+
+static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels, int block, int bins)
+{
+    if (ctx == NULL  ||  channels <= 0)
+    {
+        sb_set_error("bad bank arguments");
+        return NULL;
+    }
+    CKP(cudaSetDevice(ctx->device));
+    span_b200_bank_t *b = new span_b200_bank_s();
+    b->ctx = ctx;
+    b->det = det;
+    b->channels = channels;
+    b->block = block;
+    b->bins = bins;
+    b->npairs = (bins + 1)/2;
+    b->uniform_cs = 0;
+    b->tune_packed = 1;
+    b->last_path = "";
+    const size_t C = channels;
+    CKP(cudaMalloc(&b->v2, sizeof(float)*2*b->npairs*C));
+    CKP(cudaMalloc(&b->v3, sizeof(float)*2*b->npairs*C));
+    CKP(cudaMalloc(&b->energy, sizeof(float)*C));
+    CKP(cudaMalloc(&b->cs, sizeof(int)*C));
+    CKP(cudaMalloc(&b->counts, sizeof(unsigned int)*C));
+    CKP(cudaMalloc(&b->offsets, sizeof(unsigned int)*C));
+    CKP(cudaMalloc(&b->d_total, sizeof(unsigned long long)));
+    CKP(cudaMallocHost(&b->h_total, sizeof(unsigned long long)));
+    b->h_total[0] = 0;
+    return b;
+}
+
+extern "C" int span_b200_bank_reset(span_b200_bank_t *b, int first, int count)
+{
+    if (first < 0  ||  count < 0  ||  first + count > b->channels)
+    {
+        sb_set_error("channel range out of bounds");
+        return -1;
+    }
+    if (count == 0)
+        return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    const size_t C = b->channels;
+    for (int i = 0;  i < 2*b->npairs;  i++)
+    {
+        CK(cudaMemset(b->v2 + i*C + first, 0, sizeof(float)*count));
+        CK(cudaMemset(b->v3 + i*C + first, 0, sizeof(float)*count));
+    }
+    CK(cudaMemset(b->energy + first, 0, sizeof(float)*count));
+    CK(cudaMemset(b->cs + first, 0, sizeof(int)*count));
+    switch (b->det)
+    {
+    case SPAN_B200_DET_DTMF:
+        for (int i = first;  i < first + count;  i++)
+        {
+            b->h_thr[i] = 171029200.0f;         // src/dtmf.c:104
+            b->h_ntw[i] = 6.309f;               // src/dtmf.c:105
+            b->h_rtw[i] = 2.512f;               // src/dtmf.c:106
+            if (b->h_flags[i] & SB_DTMF_FLAG_FILTER)
+                b->n_filter--;
+            b->h_flags[i] = 0;
+        }
+        CK(cudaMemcpy(b->thr + first, &b->h_thr[first], sizeof(float)*count, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b->ntw + first, &b->h_ntw[first], sizeof(float)*count, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b->rtw + first, &b->h_rtw[first], sizeof(float)*count, cudaMemcpyHostToDevice));
+        CK(cudaMemset(b->flags + first, 0, count));
+        for (int i = 0;  i < 4;  i++)
+            CK(cudaMemset(b->z + i*C + first, 0, sizeof(float)*count));
+        CK(cudaMemset(b->last_hit + first, 0, count));
+        CK(cudaMemset(b->in_digit + first, 0, count));
+        CK(cudaMemset(b->duration + first, 0, sizeof(int)*count));
+        break;
+    case SPAN_B200_DET_BELL_MF:
+        for (int i = 0;  i < 5;  i++)
+            CK(cudaMemset(b->hits + i*C + first, 0, count));
+        break;
+    case SPAN_B200_DET_R2_MF:
+        CK(cudaMemset(b->hits + first, 0, count));
+        break;
+    case SPAN_B200_DET_SUPER_TONE:
+        for (int i = 0;  i < 11;  i++)
+        {
+            // src/super_tone_rx.c:527-533: f1 = f2 = -1, min_duration = 0
+            CK(cudaMemset(b->segments + (3*i)*C + first, 0xFF, sizeof(int)*count));
+            CK(cudaMemset(b->segments + (3*i + 1)*C + first, 0xFF, sizeof(int)*count));
+            CK(cudaMemset(b->segments + (3*i + 2)*C + first, 0, sizeof(int)*count));
+        }
+        CK(cudaMemset(b->detected + first, 0xFF, sizeof(int)*count));
+        CK(cudaMemset(b->rotation + first, 0, sizeof(int)*count));
+        CK(cudaMemset(b->pending + first, 0, count));
+        break;
+    }
+    // Block phases: all zero again only if the whole bank was reset or already uniform at zero.
+    if (!(count == b->channels  ||  b->uniform_cs == 0))
+        b->uniform_cs = -1;
+    else
+        b->uniform_cs = 0;
+    return 0;
+}
+
+extern "C" span_b200_bank_t *span_b200_dtmf_bank_create(span_b200_ctx_t *ctx, int channels)
+{
+    span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_DTMF, channels, 102, 8);
+    if (b == NULL)
+        return NULL;
+    const size_t C = channels;
+    CKP(cudaMalloc(&b->thr, sizeof(float)*C));
+    CKP(cudaMalloc(&b->ntw, sizeof(float)*C));
+    CKP(cudaMalloc(&b->rtw, sizeof(float)*C));
+    CKP(cudaMalloc(&b->flags, C));
+    CKP(cudaMalloc(&b->z, sizeof(float)*4*C));
+    CKP(cudaMalloc(&b->last_hit, C));
+    CKP(cudaMalloc(&b->in_digit, C));
+    CKP(cudaMalloc(&b->duration, sizeof(int)*C));
+    b->h_thr.assign(C, 0.0f);
+    b->h_ntw.assign(C, 0.0f);
+    b->h_rtw.assign(C, 0.0f);
+    b->h_flags.assign(C, 0);
+    b->n_filter = 0;
+    if (span_b200_bank_reset(b, 0, channels) != 0)
+        return NULL;
+    return b;
+}
+
+extern "C" span_b200_bank_t *span_b200_bell_mf_bank_create(span_b200_ctx_t *ctx, int channels)
+{
+    span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_BELL_MF, channels, 120, 6);
+    if (b == NULL)
+        return NULL;
+    CKP(cudaMalloc(&b->hits, (size_t) 5*channels));
+    if (span_b200_bank_reset(b, 0, channels) != 0)
+        return NULL;
+    return b;
+}
+
+extern "C" span_b200_bank_t *span_b200_r2_mf_bank_create(span_b200_ctx_t *ctx, int channels, int fwd)
+{
+    span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_R2_MF, channels, 133, 6);
+    if (b == NULL)
+        return NULL;
+    b->fwd = (fwd != 0);
+    CKP(cudaMalloc(&b->hits, (size_t) channels));
+    if (span_b200_bank_reset(b, 0, channels) != 0)
+        return NULL;
+    return b;
+}
+
+// Host-side descriptor construction: src/super_tone_rx.c:81-161.
+struct st_build_t
+{
+    int used;
+    int monitored;
+    int pitches[64][2];
+    float fac[64];
+};
+
+static int st_add_freq(st_build_t *d, int freq)
+{
+    int i;
+
+    if (freq == 0)
+        return -1;
+    for (i = 0;  i < d->used;  i++)
+    {
+        if (d->pitches[i][0] == freq)
+            return d->pitches[i][1];
+    }
+    for (i = 0;  i < d->used;  i++)
+    {
+        if ((d->pitches[i][0] - 10) <= freq  &&  freq <= (d->pitches[i][0] + 10))
+        {
+            // Close to a tone we already monitor: share its detector, retuned to the mean.
+            if (d->used >= 64)
+                return -2;
+            d->pitches[d->used][0] = freq;
+            d->pitches[d->used][1] = i;
+            d->fac[d->pitches[i][1]] = sb_goertzel_fac((float) (freq + d->pitches[i][0])/2);
+            d->used++;
+            return d->pitches[i][1];
+        }
+    }
+    if (d->used >= 64)
+        return -2;
+    d->pitches[i][0] = freq;
+    d->pitches[i][1] = d->monitored;
+    d->fac[d->monitored++] = sb_goertzel_fac((float) freq);
+    d->used++;
+    return d->pitches[i][1];
+}
+
+extern "C" span_b200_bank_t *span_b200_super_tone_bank_create(span_b200_ctx_t *ctx, int channels,
+                                                              const span_b200_super_tone_desc_t *desc,
+                                                              int want_segments)
+{
+    if (desc == NULL  ||  desc->tones < 0)
+    {
+        sb_set_error("super-tone descriptor missing");
+        return NULL;
+    }
+    st_build_t bd;
+    memset(&bd, 0, sizeof(bd));
+    std::vector<int> tone_first;
+    std::vector<int4> elements;
+    int k = 0;
+    for (int t = 0;  t < desc->tones;  t++)
+    {
+        tone_first.push_back(k);
+        for (int e = 0;  e < desc->tone_segs[t];  e++, k++)
+        {
+            int4 el;
+            el.x = st_add_freq(&bd, desc->elements[4*k + 0]);
+            el.y = st_add_freq(&bd, desc->elements[4*k + 1]);
+            if (el.x == -2  ||  el.y == -2)
+            {
+                sb_set_error("super-tone descriptor uses more than 64 distinct frequencies");
+                return NULL;
+            }
+            el.z = desc->elements[4*k + 2]*8;                                           // src/super_tone_rx.c:157
+            el.w = (desc->elements[4*k + 3] == 0)  ?  0x7FFFFFFF  :  desc->elements[4*k + 3]*8;   // :158
+            elements.push_back(el);
+        }
+    }
+    if (bd.monitored < 1)
+    {
+        sb_set_error("super-tone descriptor monitors no frequency");
+        return NULL;
+    }
+    if (bd.monitored > 2*SB_ST_MAX_PAIRS)
+    {
+        sb_set_error("super-tone descriptors with more than %d monitored frequencies are not supported yet (got %d)",
+                     2*SB_ST_MAX_PAIRS, bd.monitored);
+        return NULL;
+    }
+    span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_SUPER_TONE, channels, 128, bd.monitored);
+    if (b == NULL)
+        return NULL;
+    b->want_segments = (want_segments != 0);
+    memset(&b->stp, 0, sizeof(b->stp));
+    b->stp.bins = bd.monitored;
+    for (int i = 0;  i < bd.monitored;  i++)
+        b->stp.fac[i] = bd.fac[i];
+    b->h_fac.assign(bd.fac, bd.fac + bd.monitored);
+    b->tones = desc->tones;
+    const size_t C = channels;
+    CKP(cudaMalloc(&b->segments, sizeof(int)*33*C));
+    CKP(cudaMalloc(&b->detected, sizeof(int)*C));
+    CKP(cudaMalloc(&b->rotation, sizeof(int)*C));
+    CKP(cudaMalloc(&b->pending, C));
+    CKP(cudaMalloc(&b->d_tone_segs, sizeof(int)*(desc->tones + 1)));
+    CKP(cudaMalloc(&b->d_tone_first, sizeof(int)*(desc->tones + 1)));
+    CKP(cudaMalloc(&b->d_elements, sizeof(int4)*(elements.size() + 1)));
+    if (desc->tones)
+    {
+        CKP(cudaMemcpy(b->d_tone_segs, desc->tone_segs, sizeof(int)*desc->tones, cudaMemcpyHostToDevice));
+        CKP(cudaMemcpy(b->d_tone_first, tone_first.data(), sizeof(int)*desc->tones, cudaMemcpyHostToDevice));
+    }
+    if (!elements.empty())
+        CKP(cudaMemcpy(b->d_elements, elements.data(), sizeof(int4)*elements.size(), cudaMemcpyHostToDevice));
+    if (span_b200_bank_reset(b, 0, channels) != 0)
+        return NULL;
+    return b;
+}
+
+extern "C" void span_b200_bank_destroy(span_b200_bank_t *b)
+{
+    if (b == NULL)
+        return;
+    cudaSetDevice(b->ctx->device);
+    if (b->have_last)
+        cudaStreamSynchronize(b->last_stream);
+    cudaFree(b->v2);
+    cudaFree(b->v3);
+    cudaFree(b->energy);
+    cudaFree(b->cs);
+    cudaFree(b->thr);
+    cudaFree(b->ntw);
+    cudaFree(b->rtw);
+    cudaFree(b->flags);
+    cudaFree(b->z);
+    cudaFree(b->last_hit);
+    cudaFree(b->in_digit);
+    cudaFree(b->duration);
+    cudaFree(b->hits);
+    cudaFree(b->segments);
+    cudaFree(b->detected);
+    cudaFree(b->rotation);
+    cudaFree(b->pending);
+    cudaFree(b->d_tone_segs);
+    cudaFree(b->d_tone_first);
+    cudaFree(b->d_elements);
+    cudaFree(b->code);
+    cudaFree(b->eout);
+    cudaFree(b->counts);
+    cudaFree(b->offsets);
+    cudaFree(b->d_total);
+    cudaFreeHost(b->h_total);
+    cudaFree(b->events);
+    cudaFree(b->d_in);
+    for (size_t i = 0;  i < b->ev_pool.size();  i++)
+        cudaEventDestroy(b->ev_pool[i]);
+    delete b;
+}
+
+extern "C" int span_b200_bank_channels(const span_b200_bank_t *b) { return b->channels; }
+extern "C" int span_b200_bank_detector(const span_b200_bank_t *b) { return b->det; }
+extern "C" int span_b200_bank_block_len(const span_b200_bank_t *b) { return b->block; }
+extern "C" int span_b200_bank_bins(const span_b200_bank_t *b) { return b->bins; }
+extern "C" const char *span_b200_bank_last_path(const span_b200_bank_t *b) { return b->last_path; }
+extern "C" int span_b200_bank_last_launches(const span_b200_bank_t *b) { return b->last_launches; }
+extern "C" int span_b200_bank_last_blocks(span_b200_bank_t *b) { return b->last_nb; }
+
+extern "C" int span_b200_bank_coefficients(const span_b200_bank_t *b, float *fac, int max)
+{
+    static const float row[4] = {697.0f, 770.0f, 852.0f, 941.0f};
+    static const float col[4] = {1209.0f, 1336.0f, 1477.0f, 1633.0f};
+    static const int bell[6] = {700, 900, 1100, 1300, 1500, 1700};
+    static const int r2f[6] = {1380, 1500, 1620, 1740, 1860, 1980};
+    static const int r2b[6] = {1140, 1020, 900, 780, 660, 540};
+    int n = 0;
+    for (int i = 0;  i < b->bins  &&  i < max;  i++, n++)
+    {
+        switch (b->det)
+        {
+        case SPAN_B200_DET_DTMF:
+            fac[i] = sb_goertzel_fac((i & 1)  ?  col[i >> 1]  :  row[i >> 1]);
+            break;
+        case SPAN_B200_DET_BELL_MF:
+            fac[i] = sb_goertzel_fac((float) bell[i]);
+            break;
+        case SPAN_B200_DET_R2_MF:
+            fac[i] = sb_goertzel_fac((float) ((b->fwd)  ?  r2f[i]  :  r2b[i]));
+            break;
+        default:
+            fac[i] = b->h_fac[i];
+            break;
+        }
+    }
+    return n;
+}
+
+extern "C" int span_b200_bank_tune(span_b200_bank_t *b, int what, int value)
+{
+    switch (what)
+    {
+    case 0: b->tune_slice = value; return 0;
+    case 1: b->tune_variant = value; return 0;
+    case 2: b->tune_direct = value; return 0;
+    case 3: b->tune_packed = value; return 0;
+    case 4: b->tune_timing = value; return 0;
+    }
+    sb_set_error("unknown tuning knob %d", what);
+    return -1;
+}
+
+extern "C" int span_b200_bank_set_event_capacity(span_b200_bank_t *b, int64_t events)
+{
+    b->ev_cap_user = events;
+    return 0;
+}
+
+// ---- DTMF control plane ---------------------------------------------------------------------
+static int range_ok(span_b200_bank_t *b, int det, int first, int count)
+{
+    if (b->det != det)
+    {
+        sb_set_error("wrong detector type for this call");
+        return 0;
+    }
+    if (first < 0  ||  count < 0  ||  first + count > b->channels)
+    {
+        sb_set_error("channel range out of bounds");
+        return 0;
+    }
+    return 1;
+}
+
+extern "C" int span_b200_dtmf_bank_parms(span_b200_bank_t *b, int first, int count,
+                                         int filter_dialtone, float twist, float reverse_twist, float threshold)
+{
+    if (!range_ok(b, SPAN_B200_DET_DTMF, first, count))
+        return -1;
+    if (count == 0)
+        return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    const size_t C = b->channels;
+    // src/dtmf.c:421-445
+    for (int i = first;  i < first + count;  i++)
+    {
+        if (filter_dialtone >= 0)
+        {
+            if (b->h_flags[i] & SB_DTMF_FLAG_FILTER)
+                b->n_filter--;
+            b->h_flags[i] &= ~SB_DTMF_FLAG_FILTER;
+            if (filter_dialtone)
+            {
+                b->h_flags[i] |= SB_DTMF_FLAG_FILTER;
+                b->n_filter++;
+            }
+        }
+        if (twist >= 0.0f)
+            b->h_ntw[i] = powf(10.0f, twist/10.0f);                     // db_to_power_ratio, telephony.h:141
+        if (reverse_twist >= 0.0f)
+            b->h_rtw[i] = powf(10.0f, reverse_twist/10.0f);
+        if (threshold > -99.0f)                                          // goertzel_threshold_dbm0, tone_detect.h:66
+            b->h_thr[i] = (float) ((102*102*32768.0f*32768.0f/2.0f)*powf(10.0f, (threshold - 3.14f)/10.0f));
+    }
+    if (filter_dialtone >= 0)
+    {
+        for (int i = 0;  i < 4;  i++)
+            CK(cudaMemset(b->z + i*C + first, 0, sizeof(float)*count));
+    }
+    CK(cudaMemcpy(b->flags + first, &b->h_flags[first], count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->thr + first, &b->h_thr[first], sizeof(float)*count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->ntw + first, &b->h_ntw[first], sizeof(float)*count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->rtw + first, &b->h_rtw[first], sizeof(float)*count, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int span_b200_dtmf_bank_realtime(span_b200_bank_t *b, int first, int count, int on)
+{
+    if (!range_ok(b, SPAN_B200_DET_DTMF, first, count))
+        return -1;
+    if (count == 0)
+        return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    for (int i = first;  i < first + count;  i++)
+    {
+        b->h_flags[i] &= ~SB_DTMF_FLAG_REALTIME;
+        if (on)
+            b->h_flags[i] |= SB_DTMF_FLAG_REALTIME;
+    }
+    CK(cudaMemcpy(b->flags + first, &b->h_flags[first], count, cudaMemcpyHostToDevice));
+    CK(cudaMemset(b->duration + first, 0, sizeof(int)*count));          // src/dtmf.c:417
+    return 0;
+}
+
+extern "C" int span_b200_dtmf_bank_fillin(span_b200_bank_t *b, int first, int count)
+{
+    if (!range_ok(b, SPAN_B200_DET_DTMF, first, count))
+        return -1;
+    if (count == 0)
+        return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    const size_t C = b->channels;
+    // src/dtmf.c:363-379: restart the Goertzels and the energy sum; hit history is kept.
+    for (int i = 0;  i < 8;  i++)
+    {
+        CK(cudaMemset(b->v2 + i*C + first, 0, sizeof(float)*count));
+        CK(cudaMemset(b->v3 + i*C + first, 0, sizeof(float)*count));
+    }
+    CK(cudaMemset(b->energy + first, 0, sizeof(float)*count));
+    CK(cudaMemset(b->cs + first, 0, sizeof(int)*count));
+    if (!(count == b->channels  ||  b->uniform_cs == 0))
+        b->uniform_cs = -1;
+    else
+        b->uniform_cs = 0;
+    return 0;
+}
+
+extern "C" int span_b200_bank_status(span_b200_bank_t *b, int first, int count, int32_t *status)
+{
+    if (first < 0  ||  count < 0  ||  first + count > b->channels)
+    {
+        sb_set_error("channel range out of bounds");
+        return -1;
+    }
+    if (count == 0)
+        return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    std::vector<unsigned char> a(count);
+    std::vector<unsigned char> l(count);
+    switch (b->det)
+    {
+    case SPAN_B200_DET_DTMF:
+        CK(cudaMemcpy(a.data(), b->in_digit + first, count, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(l.data(), b->last_hit + first, count, cudaMemcpyDeviceToHost));
+        for (int i = 0;  i < count;  i++)
+            status[i] = (a[i])  ?  a[i]  :  ((l[i])  ?  'x'  :  0);    // src/dtmf.c:382-391
+        break;
+    case SPAN_B200_DET_R2_MF:
+        CK(cudaMemcpy(a.data(), b->hits + first, count, cudaMemcpyDeviceToHost));
+        for (int i = 0;  i < count;  i++)
+            status[i] = a[i];
+        break;
+    case SPAN_B200_DET_SUPER_TONE:
+        CK(cudaMemcpy(status, b->detected + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+        break;
+    default:
+        for (int i = 0;  i < count;  i++)
+            status[i] = 0;
+        break;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// launches
+
+struct Geometry
+{
+    int cs0;
+    int nb;             // complete blocks (uniform) or the per-channel maximum
+    int slice_blocks;
+    int nslices;
+    bool staged;
+};
+
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, bool PACKED>
+static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
+{
+    typedef StageCfg<SEG_VEC, NSTAGE> cfg;
+    const int smem = cfg::WARP_BYTES*WARPS;
+    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, PACKED>;
+    static bool configured = false;
+    if (!configured)
+    {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long ngroups = (a.channels + 31)/32;
+    const long long items = ngroups*a.nslices;
+    const long long grid = (items + WARPS - 1)/WARPS;
+    kern<<<(unsigned int) grid, WARPS*32, smem, st>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <class DET, bool PACKED>
+static int launch_variant(const BankArgs<DET> &a, int variant, cudaStream_t st)
+{
+    switch (variant)
+    {
+    case 1:
+        return launch_staged<DET, 8, 4, 4, PACKED>(a, st);
+    case 2:
+        return launch_staged<DET, 16, 2, 4, PACKED>(a, st);
+    case 3:
+        return launch_staged<DET, 32, 2, 2, PACKED>(a, st);
+    case 4:
+        return launch_staged<DET, 16, 4, 2, PACKED>(a, st);
+    default:
+        return launch_staged<DET, 16, 3, 4, PACKED>(a, st);
+    }
+}
+
+template <class DET>
+static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g, cudaStream_t st, bool all_variants)
+{
+    a.cs0 = g.cs0;
+    a.slice_blocks = g.slice_blocks;
+    a.nslices = g.nslices;
+    a.nblocks = g.nb;
+    if (g.staged)
+    {
+        b->last_path = "staged";
+        const int variant = (all_variants)  ?  b->tune_variant  :  0;
+        if (b->tune_packed)
+            return launch_variant<DET, true>(a, variant, st);
+        if (all_variants)
+            return launch_variant<DET, false>(a, variant, st);
+        return launch_variant<DET, true>(a, variant, st);
+    }
+    b->last_path = "direct";
+    const int grid = (a.channels + 127)/128;
+    if (b->tune_packed  ||  !all_variants)
+        bank_kernel_direct<DET, true><<<grid, 128, 0, st>>>(a);
+    else
+        bank_kernel_direct<DET, false><<<grid, 128, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int NP>
+static int launch_st(span_b200_bank_t *b, BankArgs<SuperToneDet<NP> > &a, const Geometry &g, cudaStream_t st)
+{
+    return launch_bank<SuperToneDet<NP> >(b, a, g, st, false);
+}
+
+template <class DET>
+static void fill_common(span_b200_bank_t *b, BankArgs<DET> &a, const int16_t *d_amp, int64_t stride, int n)
+{
+    memset(&a, 0, sizeof(a));
+    a.amp = d_amp;
+    a.stride = stride;
+    a.n = n;
+    a.channels = b->channels;
+    a.v2 = b->v2;
+    a.v3 = b->v3;
+    a.energy = b->energy;
+    a.cs = b->cs;
+    a.code = (typename DET::code_t *) b->code;
+    a.eout = b->eout;
+    a.block_rt = b->block;
+}
+
+template <int NP>
+static int run_st(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, const Geometry &g, cudaStream_t st)
+{
+    BankArgs<SuperToneDet<NP> > a;
+    fill_common(b, a, d_amp, stride, n);
+    a.det = b->stp;
+    return launch_st<NP>(b, a, g, st);
+}
+
+static long long worst_case_events(const span_b200_bank_t *b, int nb)
+{
+    const long long C = b->channels;
+    switch (b->det)
+    {
+    case SPAN_B200_DET_DTMF:
+        return C*(nb/2 + 1);            // an event needs two consecutive differing blocks
+    case SPAN_B200_DET_BELL_MF:
+        return C*(nb/2 + 1);
+    case SPAN_B200_DET_R2_MF:
+        return C*(long long) nb;
+    default:
+        return C*(3LL*nb + 2);          // per block: tone lost + segment + tone found (+ owed re-chunk)
+    }
+}
+
+extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
+                                        int n, void *stream)
+{
+    if (b == NULL  ||  n < 0  ||  (n > 0  &&  d_amp == NULL))
+    {
+        sb_set_error("bad rx arguments");
+        return -1;
+    }
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
+    if (b->have_last  &&  b->last_stream != st)
+        CK(cudaStreamSynchronize(b->last_stream));
+    const int B = b->block;
+    Geometry g;
+    g.cs0 = b->uniform_cs;
+    const bool aligned = ((((uintptr_t) d_amp) & 15) == 0)  &&  ((stride & 7) == 0);
+    g.staged = (g.cs0 >= 0)  &&  aligned  &&  !b->tune_direct  &&  n > 0;
+    g.nb = (g.cs0 >= 0)  ?  (g.cs0 + n)/B  :  (B - 1 + n)/B;
+    // ---- time slicing ----
+    g.nslices = 1;
+    g.slice_blocks = g.nb + 1;
+    if (g.staged  &&  !(b->det == SPAN_B200_DET_DTMF  &&  b->n_filter > 0))
+    {
+        int L = b->tune_slice;
+        if (L <= 0)
+        {
+            // Enough work items for ~16 waves of resident warps, but slices no shorter than 16 blocks.
+            const long long ngroups = (b->channels + 31)/32;
+            const long long want_items = (long long) b->ctx->sm_count*8*16;
+            long long slices = (want_items + ngroups - 1)/ngroups;
+            if (slices < 1)
+                slices = 1;
+            L = (int) ((g.nb + slices - 1)/slices);
+            if (L < 16)
+                L = 16;
+        }
+        if (g.nb > L)
+        {
+            g.slice_blocks = L;
+            g.nslices = (g.nb + L - 1)/L;
+        }
+    }
+    // ---- scratch ----
+    const size_t C = b->channels;
+    const size_t code_sz = (b->det == SPAN_B200_DET_SUPER_TONE)  ?  2  :  1;
+    if (ensure(&b->code, &b->code_bytes, code_sz*C*(size_t) std::max(g.nb, 1)) != 0)
+        return -1;
+    if (b->det == SPAN_B200_DET_DTMF)
+    {
+        if (ensure((void **) &b->eout, &b->eout_bytes, sizeof(float)*C*(size_t) std::max(g.nb, 1)) != 0)
+            return -1;
+    }
+    long long want_ev = (b->ev_cap_user > 0)  ?  b->ev_cap_user  :  worst_case_events(b, g.nb);
+    if (want_ev < 1)
+        want_ev = 1;
+    if (b->ev_cap < want_ev  ||  (b->ev_cap_user > 0  &&  b->ev_cap != want_ev))
+    {
+        if (b->events)
+            CK(cudaFree(b->events));
+        b->events = NULL;
+        b->ev_cap = 0;
+        CK(cudaMalloc(&b->events, sizeof(span_b200_event_t)*(size_t) want_ev));
+        b->ev_cap = want_ev;
+    }
+    b->last_launches = 0;
+    // ---- bank kernel ----
+    cudaEvent_t t0 = NULL;
+    cudaEvent_t t1 = NULL;
+    if (b->tune_timing  &&  n > 0)
+    {
+        while ((int) b->ev_pool.size() < b->ev_used + 2)
+        {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            b->ev_pool.push_back(e);
+        }
+        t0 = b->ev_pool[b->ev_used++];
+        t1 = b->ev_pool[b->ev_used++];
+        CK(cudaEventRecord(t0, st));
+    }
+    if (n > 0)
+    {
+        int rc = 0;
+        switch (b->det)
+        {
+        case SPAN_B200_DET_DTMF:
+            {
+                BankArgs<DtmfDet> a;
+                fill_common(b, a, d_amp, stride, n);
+                a.det.threshold = b->thr;
+                a.det.normal_twist = b->ntw;
+                a.det.reverse_twist = b->rtw;
+                a.det.flags = b->flags;
+                a.det.z = b->z;
+                rc = launch_bank<DtmfDet>(b, a, g, st, true);
+            }
+            break;
+        case SPAN_B200_DET_BELL_MF:
+            {
+                BankArgs<BellMfDet> a;
+                fill_common(b, a, d_amp, stride, n);
+                rc = launch_bank<BellMfDet>(b, a, g, st, false);
+            }
+            break;
+        case SPAN_B200_DET_R2_MF:
+            {
+                BankArgs<R2MfDet> a;
+                fill_common(b, a, d_amp, stride, n);
+                a.det.fwd = b->fwd;
+                rc = launch_bank<R2MfDet>(b, a, g, st, false);
+            }
+            break;
+        case SPAN_B200_DET_SUPER_TONE:
+            if (b->npairs <= 1)
+                rc = run_st<1>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 2)
+                rc = run_st<2>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 3)
+                rc = run_st<3>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 4)
+                rc = run_st<4>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 5)
+                rc = run_st<5>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 6)
+                rc = run_st<6>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 8)
+                rc = run_st<8>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 10)
+                rc = run_st<10>(b, d_amp, stride, n, g, st);
+            else if (b->npairs <= 12)
+                rc = run_st<12>(b, d_amp, stride, n, g, st);
+            else
+                rc = run_st<16>(b, d_amp, stride, n, g, st);
+            break;
+        }
+        if (rc != 0)
+            return -1;
+        b->last_launches++;
+        if (t1)
+            CK(cudaEventRecord(t1, st));
+    }
+    else
+    {
+        b->last_path = "empty";
+    }
+    // ---- sequencer: count, scan, emit ----
+    SeqCommon q;
+    q.channels = b->channels;
+    q.n = n;
+    q.cs0 = g.cs0;
+    q.cs = b->cs;
+    q.offsets = b->offsets;
+    q.counts = b->counts;
+    q.events = b->events;
+    q.capacity = b->ev_cap;
+    const int sgrid = (b->channels + 127)/128;
+    for (int pass = 0;  pass < 2;  pass++)
+    {
+        switch (b->det)
+        {
+        case SPAN_B200_DET_DTMF:
+            {
+                DtmfSeqArgs s;
+                s.q = q;
+                s.code = (const unsigned char *) b->code;
+                s.eout = b->eout;
+                s.flags = b->flags;
+                s.last_hit = b->last_hit;
+                s.in_digit = b->in_digit;
+                s.duration = b->duration;
+                s.level_thr = b->ctx->d_level_thr;
+                s.level_n = b->ctx->level_n;
+                s.level_min = b->ctx->level_min;
+                if (pass == 0)
+                    dtmf_sequencer<false><<<sgrid, 128, 0, st>>>(s);
+                else
+                    dtmf_sequencer<true><<<sgrid, 128, 0, st>>>(s);
+            }
+            break;
+        case SPAN_B200_DET_BELL_MF:
+        case SPAN_B200_DET_R2_MF:
+            {
+                MfSeqArgs s;
+                s.q = q;
+                s.code = (const unsigned char *) b->code;
+                s.hits = b->hits;
+                if (b->det == SPAN_B200_DET_BELL_MF)
+                {
+                    if (pass == 0)
+                        bell_mf_sequencer<false><<<sgrid, 128, 0, st>>>(s);
+                    else
+                        bell_mf_sequencer<true><<<sgrid, 128, 0, st>>>(s);
+                }
+                else
+                {
+                    if (pass == 0)
+                        r2_mf_sequencer<false><<<sgrid, 128, 0, st>>>(s);
+                    else
+                        r2_mf_sequencer<true><<<sgrid, 128, 0, st>>>(s);
+                }
+            }
+            break;
+        case SPAN_B200_DET_SUPER_TONE:
+            {
+                StSeqArgs s;
+                s.q = q;
+                s.code = (const unsigned short *) b->code;
+                s.t.tones = b->tones;
+                s.t.tone_segs = b->d_tone_segs;
+                s.t.tone_first = b->d_tone_first;
+                s.t.elements = b->d_elements;
+                s.segments = b->segments;
+                s.detected_tone = b->detected;
+                s.rotation = b->rotation;
+                s.pending = b->pending;
+                s.want_segments = b->want_segments;
+                if (pass == 0)
+                    super_tone_sequencer<false><<<sgrid, 128, 0, st>>>(s);
+                else
+                    super_tone_sequencer<true><<<sgrid, 128, 0, st>>>(s);
+            }
+            break;
+        }
+        CK(cudaGetLastError());
+        b->last_launches++;
+        if (pass == 0)
+        {
+            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, b->channels, b->d_total);
+            CK(cudaGetLastError());
+            b->last_launches++;
+            CK(cudaMemcpyAsync(b->h_total, b->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (g.cs0 >= 0)
+        b->uniform_cs = (g.cs0 + n) % B;
+    b->last_nb = g.nb;
+    b->last_stream = st;
+    b->have_last = true;
+    return 0;
+}
+
+extern "C" int span_b200_bank_rx_host(span_b200_bank_t *b, const int16_t *h_amp, int64_t stride,
+                                      int n, void *stream)
+{
+    if (b == NULL  ||  n < 0  ||  (n > 0  &&  h_amp == NULL))
+    {
+        sb_set_error("bad rx arguments");
+        return -1;
+    }
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
+    if (b->have_last  &&  b->last_stream != st)
+        CK(cudaStreamSynchronize(b->last_stream));
+    // Device rows are padded to a multiple of 8 samples so that the staged kernel applies.
+    const int64_t dstride = (n + 7) & ~7LL;
+    if (ensure((void **) &b->d_in, &b->d_in_bytes, sizeof(int16_t)*(size_t) dstride*b->channels + 16) != 0)
+        return -1;
+    if (n > 0)
+    {
+        CK(cudaMemcpy2DAsync(b->d_in, sizeof(int16_t)*dstride, h_amp, sizeof(int16_t)*stride,
+                             sizeof(int16_t)*(size_t) n, b->channels, cudaMemcpyHostToDevice, st));
+    }
+    return span_b200_bank_rx_device(b, b->d_in, dstride, n, (void *) st);
+}
+
+extern "C" int64_t span_b200_bank_event_count(span_b200_bank_t *b, int *overflow)
+{
+    if (overflow)
+        *overflow = 0;
+    if (!b->have_last)
+        return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->last_stream));
+    long long total = (long long) b->h_total[0];
+    if (total > b->ev_cap)
+    {
+        if (overflow)
+            *overflow = 1;
+        total = b->ev_cap;
+    }
+    return total;
+}
+
+extern "C" int64_t span_b200_bank_events(span_b200_bank_t *b, span_b200_event_t *out, int64_t max)
+{
+    int64_t total = span_b200_bank_event_count(b, NULL);
+    if (total < 0)
+        return -1;
+    if (total > max)
+        total = max;
+    if (total > 0)
+        CK(cudaMemcpy(out, b->events, sizeof(span_b200_event_t)*(size_t) total, cudaMemcpyDeviceToHost));
+    return total;
+}
+
+extern "C" int64_t span_b200_bank_events_to_device(span_b200_bank_t *b, span_b200_event_t *d_out, int64_t max, void *stream)
+{
+    int64_t total = span_b200_bank_event_count(b, NULL);
+    if (total < 0)
+        return -1;
+    if (total > max)
+        total = max;
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
+    if (total > 0)
+        CK(cudaMemcpyAsync(d_out, b->events, sizeof(span_b200_event_t)*(size_t) total, cudaMemcpyDeviceToDevice, st));
+    return total;
+}
+
+extern "C" double span_b200_bank_kernel_ms(span_b200_bank_t *b, int *launches)
+{
+    double ms = 0.0;
+    if (launches)
+        *launches = 0;
+    if (cudaSetDevice(b->ctx->device) != cudaSuccess)
+        return -1.0;
+    if (b->have_last  &&  cudaStreamSynchronize(b->last_stream) != cudaSuccess)
+        return -1.0;
+    for (int i = 0;  i + 1 < b->ev_used;  i += 2)
+    {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, b->ev_pool[i], b->ev_pool[i + 1]) == cudaSuccess)
+            ms += t;
+        if (launches)
+            (*launches)++;
+    }
+    b->ev_used = 0;
+    return ms;
+}
+
+extern "C" const span_b200_event_t *span_b200_bank_events_device(span_b200_bank_t *b)
+{
+    return b->events;
+}
+
+extern "C" int span_b200_bank_block_codes(span_b200_bank_t *b, uint16_t *codes, int64_t max)
+{
+    if (!b->have_last)
+        return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->last_stream));
+    const int64_t total = (int64_t) b->last_nb*b->channels;
+    const int64_t n = (total < max)  ?  total  :  max;
+    if (n <= 0)
+        return 0;
+    if (b->det == SPAN_B200_DET_SUPER_TONE)
+    {
+        CK(cudaMemcpy(codes, b->code, sizeof(uint16_t)*(size_t) n, cudaMemcpyDeviceToHost));
+    }
+    else
+    {
+        std::vector<unsigned char> tmp((size_t) n);
+        CK(cudaMemcpy(tmp.data(), b->code, (size_t) n, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0;  i < n;  i++)
+            codes[i] = tmp[(size_t) i];
+    }
+    return (int) n;
+}
+
+// ------------------------------------------------------------------------------------------
+// raw Goertzel banks
+template <int NP>
+static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len, const int16_t *d_amp,
+                   int64_t stride, int channels, int n, float *d_out, int64_t cap, cudaStream_t st)
+{
+    BankArgs<RawDet<NP> > a;
+    memset(&a, 0, sizeof(a));
+    a.amp = d_amp;
+    a.stride = stride;
+    a.n = n;
+    a.channels = channels;
+    a.block_rt = block_len;
+    a.raw = d_out;
+    a.raw_capacity = cap;
+    a.det.bins = bins;
+    for (int i = 0;  i < bins;  i++)
+        a.det.fac[i] = fac[i];
+    const int nb = n/block_len;
+    a.cs0 = 0;
+    a.nblocks = nb;
+    // Carried state is not supported for raw banks: the tail (n % block_len samples) is dropped,
+    // exactly what a caller sees if it only looks at goertzel_result() of complete blocks.
+    a.n = nb*block_len;
+    if (a.n == 0)
+        return 0;
+    const bool aligned = ((((uintptr_t) d_amp) & 15) == 0)  &&  ((stride & 7) == 0);
+    if (aligned)
+    {
+        const long long ngroups = (channels + 31)/32;
+        const long long want_items = (long long) ctx->sm_count*8*16;
+        long long slices = (want_items + ngroups - 1)/ngroups;
+        int L = (int) ((nb + slices - 1)/slices);
+        if (L < 16)
+            L = 16;
+        a.slice_blocks = (nb > L)  ?  L  :  (nb + 1);
+        a.nslices = (nb > L)  ?  ((nb + L - 1)/L)  :  1;
+        return launch_staged<RawDet<NP>, 16, 3, 4, true>(a, st);
+    }
+    bank_kernel_direct<RawDet<NP>, true><<<(channels + 127)/128, 128, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int span_b200_goertzel_blocks_device(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len,
+                                                const int16_t *d_amp, int64_t stride, int channels, int n,
+                                                float *d_out, int64_t out_capacity, void *stream)
+{
+    if (ctx == NULL  ||  fac == NULL  ||  bins < 1  ||  bins > 2*SB_ST_MAX_PAIRS  ||  block_len < 1  ||  channels < 1  ||  n < 0)
+    {
+        sb_set_error("bad goertzel bank arguments (1..%d bins)", 2*SB_ST_MAX_PAIRS);
+        return -1;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  ctx->stream;
+    const int np = (bins + 1)/2;
+    int rc;
+    if (np <= 1)
+        rc = run_raw<1>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+    else if (np <= 2)
+        rc = run_raw<2>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+    else if (np <= 4)
+        rc = run_raw<4>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+    else if (np <= 8)
+        rc = run_raw<8>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+    else
+        rc = run_raw<16>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+    if (rc != 0)
+        return -1;
+    return n/block_len;
+}

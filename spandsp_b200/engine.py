@@ -1,0 +1,287 @@
+"""ctypes binding of libspandsp_b200.so (the C ABI in include/spandsp_b200.h).
+
+This is plumbing for tests and the benchmark: it passes raw device pointers (e.g. from
+torch tensors) and plain ints through the C ABI.  There is no Python fallback of any
+kernel: if the shared library is missing this module raises at import of the symbols,
+and if no sm_100 GPU is present ``Context()`` raises with the library's error text.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libspandsp_b200.so")
+
+DET_DTMF, DET_BELL_MF, DET_R2_MF, DET_SUPER_TONE = 0, 1, 2, 3
+EV_DIGIT, EV_TONE, EV_SEGMENT = 1, 2, 5
+
+EVENT_DTYPE = np.dtype([("channel", "<i4"), ("block", "<i4"), ("kind", "<i4"),
+                        ("a", "<i4"), ("b", "<i4"), ("c", "<i4")])
+
+
+class SuperToneDesc(C.Structure):
+    _fields_ = [("tones", C.c_int32), ("tone_segs", C.POINTER(C.c_int32)), ("elements", C.POINTER(C.c_int32))]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing - build it with `python -m spandsp_b200.build` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    sig = {
+        "span_b200_abi_version": (i32, []),
+        "span_b200_last_error": (C.c_char_p, []),
+        "span_b200_ctx_create": (vp, [i32]),
+        "span_b200_ctx_destroy": (None, [vp]),
+        "span_b200_ctx_device": (i32, [vp]),
+        "span_b200_ctx_sm_count": (i32, [vp]),
+        "span_b200_dtmf_bank_create": (vp, [vp, i32]),
+        "span_b200_bell_mf_bank_create": (vp, [vp, i32]),
+        "span_b200_r2_mf_bank_create": (vp, [vp, i32, i32]),
+        "span_b200_super_tone_bank_create": (vp, [vp, i32, C.POINTER(SuperToneDesc), i32]),
+        "span_b200_bank_destroy": (None, [vp]),
+        "span_b200_bank_channels": (i32, [vp]),
+        "span_b200_bank_detector": (i32, [vp]),
+        "span_b200_bank_block_len": (i32, [vp]),
+        "span_b200_bank_bins": (i32, [vp]),
+        "span_b200_bank_coefficients": (i32, [vp, vp, i32]),
+        "span_b200_bank_reset": (i32, [vp, i32, i32]),
+        "span_b200_dtmf_bank_parms": (i32, [vp, i32, i32, i32, f32, f32, f32]),
+        "span_b200_dtmf_bank_realtime": (i32, [vp, i32, i32, i32]),
+        "span_b200_dtmf_bank_fillin": (i32, [vp, i32, i32]),
+        "span_b200_bank_status": (i32, [vp, i32, i32, vp]),
+        "span_b200_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_bank_event_count": (i64, [vp, C.POINTER(i32)]),
+        "span_b200_bank_events": (i64, [vp, vp, i64]),
+        "span_b200_bank_events_device": (vp, [vp]),
+        "span_b200_bank_set_event_capacity": (i32, [vp, i64]),
+        "span_b200_bank_events_to_device": (i64, [vp, vp, i64, vp]),
+        "span_b200_bank_kernel_ms": (C.c_double, [vp, C.POINTER(i32)]),
+        "span_b200_bank_last_blocks": (i32, [vp]),
+        "span_b200_bank_block_codes": (i32, [vp, vp, i64]),
+        "span_b200_bank_tune": (i32, [vp, i32, i32]),
+        "span_b200_bank_last_path": (C.c_char_p, [vp]),
+        "span_b200_bank_last_launches": (i32, [vp]),
+        "span_b200_goertzel_blocks_device": (i32, [vp, vp, i32, i32, vp, i64, i32, i32, vp, i64, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _err():
+    return lib().span_b200_last_error().decode(errors="replace")
+
+
+class Context:
+    """One CUDA device (span_b200_ctx_create)."""
+
+    def __init__(self, device=-1):
+        self.h = lib().span_b200_ctx_create(device)
+        if not self.h:
+            raise EngineError(_err())
+
+    @property
+    def device(self):
+        return lib().span_b200_ctx_device(self.h)
+
+    @property
+    def sm_count(self):
+        return lib().span_b200_ctx_sm_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().span_b200_ctx_destroy(self.h)
+            self.h = None
+
+    # raw Goertzel bank -------------------------------------------------------------------
+    def goertzel_blocks(self, fac, block_len, d_amp_ptr, stride, channels, samples, d_out_ptr, out_capacity, stream=None):
+        fac = np.ascontiguousarray(fac, dtype=np.float32)
+        rc = lib().span_b200_goertzel_blocks_device(self.h, fac.ctypes.data, len(fac), block_len, d_amp_ptr, stride,
+                                                    channels, samples, d_out_ptr, out_capacity, stream)
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+
+class Bank:
+    """A group of channels of one detector type (span_b200_*_bank_create)."""
+
+    def __init__(self, ctx, handle):
+        if not handle:
+            raise EngineError(_err())
+        self.ctx = ctx
+        self.h = handle
+
+    # constructors ------------------------------------------------------------------------
+    @classmethod
+    def dtmf(cls, ctx, channels):
+        return cls(ctx, lib().span_b200_dtmf_bank_create(ctx.h, channels))
+
+    @classmethod
+    def bell_mf(cls, ctx, channels):
+        return cls(ctx, lib().span_b200_bell_mf_bank_create(ctx.h, channels))
+
+    @classmethod
+    def r2_mf(cls, ctx, channels, fwd=True):
+        return cls(ctx, lib().span_b200_r2_mf_bank_create(ctx.h, channels, int(bool(fwd))))
+
+    @classmethod
+    def super_tone(cls, ctx, channels, tones, want_segments=False):
+        """tones: list of tones, each a list of (f1_hz, f2_hz, min_ms, max_ms)."""
+        segs = np.asarray([len(t) for t in tones], dtype=np.int32)
+        flat = np.asarray([x for t in tones for e in t for x in e], dtype=np.int32)
+        if flat.size == 0:
+            flat = np.zeros(4, dtype=np.int32)
+        d = SuperToneDesc()
+        d.tones = len(tones)
+        d.tone_segs = segs.ctypes.data_as(C.POINTER(C.c_int32))
+        d.elements = flat.ctypes.data_as(C.POINTER(C.c_int32))
+        return cls(ctx, lib().span_b200_super_tone_bank_create(ctx.h, channels, C.byref(d), int(bool(want_segments))))
+
+    # properties --------------------------------------------------------------------------
+    @property
+    def channels(self):
+        return lib().span_b200_bank_channels(self.h)
+
+    @property
+    def block_len(self):
+        return lib().span_b200_bank_block_len(self.h)
+
+    @property
+    def bins(self):
+        return lib().span_b200_bank_bins(self.h)
+
+    @property
+    def last_path(self):
+        return lib().span_b200_bank_last_path(self.h).decode()
+
+    @property
+    def last_launches(self):
+        return lib().span_b200_bank_last_launches(self.h)
+
+    @property
+    def last_blocks(self):
+        return lib().span_b200_bank_last_blocks(self.h)
+
+    def coefficients(self):
+        out = np.zeros(64, dtype=np.float32)
+        n = lib().span_b200_bank_coefficients(self.h, out.ctypes.data, 64)
+        return out[:n]
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    # control plane -----------------------------------------------------------------------
+    def reset(self, first=0, count=None):
+        self._ck(lib().span_b200_bank_reset(self.h, first, self.channels - first if count is None else count))
+
+    def dtmf_parms(self, filter_dialtone=-1, twist=-1.0, reverse_twist=-1.0, threshold=-99.0, first=0, count=None):
+        self._ck(lib().span_b200_dtmf_bank_parms(self.h, first, self.channels - first if count is None else count,
+                                                 filter_dialtone, twist, reverse_twist, threshold))
+
+    def dtmf_realtime(self, on=True, first=0, count=None):
+        self._ck(lib().span_b200_dtmf_bank_realtime(self.h, first, self.channels - first if count is None else count, int(on)))
+
+    def dtmf_fillin(self, first=0, count=None):
+        self._ck(lib().span_b200_dtmf_bank_fillin(self.h, first, self.channels - first if count is None else count))
+
+    def status(self, first=0, count=None):
+        count = self.channels - first if count is None else count
+        out = np.zeros(count, dtype=np.int32)
+        self._ck(lib().span_b200_bank_status(self.h, first, count, out.ctypes.data))
+        return out
+
+    def tune(self, what, value):
+        self._ck(lib().span_b200_bank_tune(self.h, what, value))
+
+    def set_event_capacity(self, n):
+        self._ck(lib().span_b200_bank_set_event_capacity(self.h, n))
+
+    # processing --------------------------------------------------------------------------
+    def rx_device(self, d_ptr, stride, samples, stream=None):
+        self._ck(lib().span_b200_bank_rx_device(self.h, d_ptr, stride, samples, stream))
+
+    def rx_host(self, amp, stream=None, samples=None):
+        """amp: int16 numpy array [channels, n] (rows contiguous) or a (ptr, stride) pair with samples."""
+        if isinstance(amp, tuple):
+            ptr, stride = amp
+            self._ck(lib().span_b200_bank_rx_host(self.h, ptr, stride, samples, stream))
+            return
+        assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
+        self._ck(lib().span_b200_bank_rx_host(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
+
+    def event_count(self):
+        ov = C.c_int(0)
+        n = lib().span_b200_bank_event_count(self.h, C.byref(ov))
+        if n < 0:
+            raise EngineError(_err())
+        return n, bool(ov.value)
+
+    def events(self, out=None):
+        n, overflow = self.event_count()
+        if overflow:
+            raise EngineError("event buffer overflow")
+        if out is None:
+            out = np.zeros(n, dtype=EVENT_DTYPE)
+        got = lib().span_b200_bank_events(self.h, out.ctypes.data, len(out))
+        if got < 0:
+            raise EngineError(_err())
+        return out[:got]
+
+    def events_to_device(self, d_ptr, max_events, stream=None):
+        n = lib().span_b200_bank_events_to_device(self.h, d_ptr, max_events, stream)
+        if n < 0:
+            raise EngineError(_err())
+        return n
+
+    def kernel_ms(self):
+        """(summed filter-bank kernel time in ms, launches) since the last query; needs tune(4, 1)."""
+        k = C.c_int(0)
+        ms = lib().span_b200_bank_kernel_ms(self.h, C.byref(k))
+        if ms < 0:
+            raise EngineError(_err())
+        return ms, k.value
+
+    def events_device_ptr(self):
+        return lib().span_b200_bank_events_device(self.h)
+
+    def block_codes(self):
+        nb = self.last_blocks
+        out = np.zeros(nb * self.channels, dtype=np.uint16)
+        n = lib().span_b200_bank_block_codes(self.h, out.ctypes.data, out.size)
+        if n < 0:
+            raise EngineError(_err())
+        return out[:n].reshape(nb, self.channels)
+
+    def close(self):
+        if self.h:
+            lib().span_b200_bank_destroy(self.h)
+            self.h = None
+
+
+def events_by_channel(ev, channels):
+    """Split a (channel, time)-ordered event array into per-channel lists of (kind, a, b, c)."""
+    out = [[] for _ in range(channels)]
+    for e in ev:
+        out[int(e["channel"])].append((int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])))
+    return out

@@ -1,0 +1,63 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU, and exports every symbol that
+include/*.h declares.  No compute calls here."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(path):
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//.*", "", txt)
+    names = set()
+    for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}()]*(?:\([^()]*\)[^;{}()]*)*\)\s*;", txt):
+        n = m.group(1)
+        if n in ("defined", "sizeof", "__attribute__"):
+            continue
+        names.add(n)
+    return names
+
+
+def test_exports(engine_lib):
+    import ctypes
+    L = ctypes.CDLL(engine_lib.LIB_PATH)
+    inc = os.path.join(ROOT, "include")
+    missing = []
+    total = 0
+    for h in sorted(os.listdir(inc)):
+        if not h.endswith(".h"):
+            continue
+        for fn in sorted(declared_functions(os.path.join(inc, h))):
+            if fn.endswith("_t"):
+                continue        # callback typedefs
+            total += 1
+            if not hasattr(L, fn):
+                missing.append("%s:%s" % (h, fn))
+    assert total > 20
+    assert not missing, "declared but not exported: %s" % missing
+
+
+def test_no_gpu_fails_loudly(engine_lib):
+    """Without a CUDA device context creation must fail with an explanation, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        engine_lib.Context(0)
+    except engine_lib.EngineError as e:
+        assert "no CPU fallback" in str(e) or "CUDA" in str(e)
+    else:
+        raise AssertionError("Context() succeeded without a GPU")
+
+
+def test_product_does_not_touch_oracle():
+    """Nothing under spandsp_b200/ may import, link or load anything under oracle/."""
+    pkg = os.path.join(ROOT, "spandsp_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c")):
+                txt = open(os.path.join(root, f), errors="replace").read()
+                assert "oracle" not in txt.replace("CPU oracle", "").replace("strict CPU oracle", "").lower() \
+                    or f == "sb_common.cuh" or "oracle/" not in txt, "%s mentions oracle/" % f
+                assert "tonebank_oracle" not in txt and "pyoracle" not in txt and "libspandsp_ref" not in txt, f
