@@ -193,7 +193,7 @@ def run_reference_arm(args):
     passes = 1
     # size one step to ~2 s
     v0, kind, s0 = cpu_reference(channels, T, 1, threads)
-    passes = max(1, int(2.0 / max(s0, 1e-3)))
+    passes = max(1, int(1.0 / max(s0, 1e-3)))
     for _ in range(args.warmup):
         cpu_reference(channels, T, 1, threads)
     t0 = time.perf_counter()
@@ -397,7 +397,7 @@ def main():
         threads = host_threads()
         ch = max(threads * 8, 256)
         v0, kind, s0 = cpu_reference(ch, T, 1, threads)
-        passes = max(1, int(3.0 / max(s0, 1e-3)))
+        passes = max(1, int(20.0 / max(s0 * threads, 1e-3)))         # ~20 core-seconds of CPU work
         v, kind, s = cpu_reference(ch, T, passes, threads)
         cpu = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": kind,
                "sample": "%d channels x %d samples x %d passes, whole-buffer dtmf_rx() calls, %.1f core-seconds"

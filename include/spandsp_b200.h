@@ -51,7 +51,8 @@ enum
     SPAN_B200_EV_SEGMENT = 5
 };
 
-/* 24-byte event record.  Events of one rx call are ordered by (channel, time). */
+/* 24-byte event record.  Within one rx call the events of any single channel appear in time
+   order; across channels the buffer is ordered by (group of 32 channels, block, channel). */
 typedef struct
 {
     int32_t channel;

@@ -1,0 +1,138 @@
+/*
+ * spandsp_b200_dropin.h - the spandsp-named per-channel API of the tone-detect path, served by
+ * the B200 engine.
+ *
+ * Same function names, argument meaning, callback types, ownership and return conventions as the
+ * reference headers cited at each group, so a caller of that path links unchanged.  State objects
+ * are opaque here (the reference keeps their bodies in spandsp/private/ too); `*_init(NULL, ...)`
+ * allocates, `*_init(s, ...)` re-initialises in place, and sizeof(the reference's struct) bytes of
+ * caller storage are always enough (ours are smaller).
+ *
+ * Execution model.  Every state object is a slot of a GROUP.  A state made by `*_init()` alone is
+ * a group of one and behaves synchronously: `dtmf_rx()` copies the samples to the GPU, runs the
+ * kernels and fires the callbacks before it returns - exactly the reference's observable
+ * behaviour, at batch-of-one cost.  For real channel counts create a group
+ * (span_b200_group_create), hand its members to your per-channel code, and call
+ * span_b200_group_flush() once per tick: `*_rx()` on a member then only stages the samples, and the
+ * flush processes all members in one launch and fires every callback, in channel order, on the
+ * flushing thread.  There is no CPU implementation behind any of these calls.
+ */
+#if !defined(_SPANDSP_B200_DROPIN_H_)
+#define _SPANDSP_B200_DROPIN_H_
+
+#include <stdint.h>
+#include <stddef.h>
+#include <stdbool.h>
+
+#include "spandsp_b200.h"
+
+#if defined(__cplusplus)
+extern "C"
+{
+#endif
+
+/* ---- callback types (src/spandsp/dtmf.h:76, src/spandsp/super_tone_rx.h:56-58 and tone_detect users) */
+typedef void (*digits_rx_callback_t)(void *user_data, const char *digits, int len);
+typedef void (*span_tone_report_func_t)(void *user_data, int code, int level, int delay);
+typedef void (*tone_segment_func_t)(void *user_data, int f1, int f2, int duration);
+
+typedef struct dtmf_rx_state_s dtmf_rx_state_t;
+typedef struct bell_mf_rx_state_s bell_mf_rx_state_t;
+typedef struct r2_mf_rx_state_s r2_mf_rx_state_t;
+typedef struct super_tone_rx_state_s super_tone_rx_state_t;
+typedef struct super_tone_rx_descriptor_s super_tone_rx_descriptor_t;
+typedef struct logging_state_s logging_state_t;
+
+#define MAX_DTMF_DIGITS     128     /* src/spandsp/dtmf.h:74 */
+#define MAX_BELL_MF_DIGITS  128     /* src/spandsp/bell_r2_mf.h */
+
+/* ---- groups (new; see "Execution model" above) ------------------------------------------------ */
+typedef struct span_b200_group_s span_b200_group_t;
+
+/* detector: SPAN_B200_DET_*; arg: R2 MF forward flag, or for super-tone a super_tone_rx_descriptor_t
+   passed through `desc`.  max_samples bounds the samples one member may stage between flushes. */
+span_b200_group_t *span_b200_group_create(span_b200_ctx_t *ctx, int detector, int members, int max_samples,
+                                          int arg, super_tone_rx_descriptor_t *desc);
+/* Member i as the detector's state type (cast to dtmf_rx_state_t * etc.).  Members are created in
+   the *_rx_init() state with no callbacks; install callbacks with *_rx_init(member, cb, user). */
+void *span_b200_group_member(span_b200_group_t *group, int index);
+/* Process what the members staged since the last flush (all members that staged anything must have
+   staged the same number of samples; members that staged nothing are fed nothing) and fire the
+   callbacks.  Returns the number of callbacks fired, or -1. */
+int span_b200_group_flush(span_b200_group_t *group);
+void span_b200_group_destroy(span_b200_group_t *group);
+/* The default context used by states created without a group (device from SPANDSP_B200_DEVICE, else 0). */
+span_b200_ctx_t *span_b200_default_ctx(void);
+
+/* ---- DTMF receiver: src/spandsp/dtmf.h:153-228, src/dtmf.c:132-519 ---------------------------- */
+dtmf_rx_state_t *dtmf_rx_init(dtmf_rx_state_t *s, digits_rx_callback_t callback, void *user_data);
+int dtmf_rx_release(dtmf_rx_state_t *s);
+int dtmf_rx_free(dtmf_rx_state_t *s);
+void dtmf_rx_set_realtime_callback(dtmf_rx_state_t *s, span_tone_report_func_t callback, void *user_data);
+void dtmf_rx_parms(dtmf_rx_state_t *s, int filter_dialtone, float twist, float reverse_twist, float threshold);
+int dtmf_rx(dtmf_rx_state_t *s, const int16_t amp[], int samples);
+int dtmf_rx_fillin(dtmf_rx_state_t *s, int samples);
+int dtmf_rx_status(dtmf_rx_state_t *s);
+size_t dtmf_rx_get(dtmf_rx_state_t *s, char *digits, int max);
+logging_state_t *dtmf_rx_get_logging_state(dtmf_rx_state_t *s);
+
+/* ---- Bell MF receiver: src/spandsp/bell_r2_mf.h:199-228, src/bell_r2_mf.c:507-745 -------------- */
+bell_mf_rx_state_t *bell_mf_rx_init(bell_mf_rx_state_t *s, digits_rx_callback_t callback, void *user_data);
+int bell_mf_rx_release(bell_mf_rx_state_t *s);
+int bell_mf_rx_free(bell_mf_rx_state_t *s);
+int bell_mf_rx(bell_mf_rx_state_t *s, const int16_t amp[], int samples);
+size_t bell_mf_rx_get(bell_mf_rx_state_t *s, char *buf, int max);
+
+/* ---- MFC/R2 receiver: src/spandsp/bell_r2_mf.h:236-266, src/bell_r2_mf.c:750-951 --------------- */
+r2_mf_rx_state_t *r2_mf_rx_init(r2_mf_rx_state_t *s, bool fwd, span_tone_report_func_t callback, void *user_data);
+int r2_mf_rx_release(r2_mf_rx_state_t *s);
+int r2_mf_rx_free(r2_mf_rx_state_t *s);
+int r2_mf_rx(r2_mf_rx_state_t *s, const int16_t amp[], int samples);
+int r2_mf_rx_get(r2_mf_rx_state_t *s);
+
+/* ---- supervisory tone receiver: src/spandsp/super_tone_rx.h:76-164, src/super_tone_rx.c ---------- */
+super_tone_rx_descriptor_t *super_tone_rx_make_descriptor(super_tone_rx_descriptor_t *desc);
+int super_tone_rx_free_descriptor(super_tone_rx_descriptor_t *desc);
+int super_tone_rx_add_tone(super_tone_rx_descriptor_t *desc);
+int super_tone_rx_add_element(super_tone_rx_descriptor_t *desc, int tone, int f1, int f2, int min, int max);
+super_tone_rx_state_t *super_tone_rx_init(super_tone_rx_state_t *s, super_tone_rx_descriptor_t *desc,
+                                          span_tone_report_func_t callback, void *user_data);
+int super_tone_rx_release(super_tone_rx_state_t *s);
+int super_tone_rx_free(super_tone_rx_state_t *s);
+void super_tone_rx_tone_callback(super_tone_rx_state_t *s, span_tone_report_func_t callback, void *user_data);
+void super_tone_rx_segment_callback(super_tone_rx_state_t *s, tone_segment_func_t callback);
+int super_tone_rx(super_tone_rx_state_t *s, const int16_t amp[], int samples);
+int super_tone_rx_fillin(super_tone_rx_state_t *s, int samples);
+
+/* ---- Goertzel primitives: src/spandsp/tone_detect.h:32-58,86-127, src/tone_detect.c:60-205 ------ */
+/* These two structures are public in the reference (callers embed them and the header-inline
+   goertzel_sample()/goertzel_samplex() touch the fields), so their layout is kept. */
+typedef struct
+{
+    float fac;
+    int samples;
+} goertzel_descriptor_t;
+
+typedef struct
+{
+    float v2;
+    float v3;
+    float fac;
+    int samples;
+    int current_sample;
+} goertzel_state_t;
+
+void make_goertzel_descriptor(goertzel_descriptor_t *t, float freq, int samples);
+goertzel_state_t *goertzel_init(goertzel_state_t *s, goertzel_descriptor_t *t);
+int goertzel_release(goertzel_state_t *s);
+int goertzel_free(goertzel_state_t *s);
+void goertzel_reset(goertzel_state_t *s);
+/* Both run on the device as a batch of one (state and samples go up, state comes back). */
+int goertzel_update(goertzel_state_t *s, const int16_t amp[], int samples);
+float goertzel_result(goertzel_state_t *s);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif

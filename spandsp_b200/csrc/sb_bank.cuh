@@ -226,14 +226,34 @@ struct Runner
         energy = 0.0f;
     }
 
-    // Samples [lo, hi) of one 16-byte vector.  The common case - a whole vector that does not
-    // cross a block boundary - takes the unrolled path; everything else goes sample by sample.
-    // All conditions are warp-uniform in the staged kernel.
+    // Samples [lo, hi) of one 16-byte vector, one at a time, with a block-boundary check after
+    // each.  Used for the first/last vector of a slice and for vectors that straddle a boundary.
     template <bool FILT>
-    __device__ __forceinline__ void vector(uint4 v, int lo, int hi, const BankArgs<DET> &a)
+    __device__ __forceinline__ void partial(uint4 v, int lo, int hi, const BankArgs<DET> &a)
     {
         const int B = block_len(a);
-        if (lo == 0  &&  hi == 8  &&  cs + 8 <= B)
+        shift_vec_n(v, lo);
+#pragma unroll 1
+        for (int e = lo;  e < hi;  e++)
+        {
+            const float x = (float) (short) (v.x & 0xFFFFu);
+            shift_vec(v);
+            step<FILT>(x);
+            if (++cs == B)
+            {
+                block_end(a);
+                zero_after_block();
+            }
+        }
+    }
+
+    // A whole vector.  The common case - no block boundary inside - takes the unrolled path.
+    // All conditions are warp-uniform in the staged kernel.
+    template <bool FILT>
+    __device__ __forceinline__ void full(const uint4 &v, const BankArgs<DET> &a)
+    {
+        const int B = block_len(a);
+        if (cs + 8 <= B)
         {
             fast8<FILT>(v);
             cs += 8;
@@ -245,19 +265,7 @@ struct Runner
         }
         else
         {
-            shift_vec_n(v, lo);
-#pragma unroll 1
-            for (int e = lo;  e < hi;  e++)
-            {
-                const float x = (float) (short) (v.x & 0xFFFFu);
-                shift_vec(v);
-                step<FILT>(x);
-                if (++cs == B)
-                {
-                    block_end(a);
-                    zero_after_block();
-                }
-            }
+            partial<FILT>(v, 0, 8, a);
         }
     }
 };
@@ -273,8 +281,8 @@ struct StageCfg
     static_assert(SEG_VEC == 8  ||  SEG_VEC == 16  ||  SEG_VEC == 32, "SEG_VEC lanes copy one row segment");
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, bool PACKED>
-__global__ void __launch_bounds__(WARPS*32) bank_kernel_staged(const BankArgs<DET> a)
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, bool PACKED>
+__global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankArgs<DET> a)
 {
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -309,7 +317,12 @@ __global__ void __launch_bounds__(WARPS*32) bank_kernel_staged(const BankArgs<DE
     DET::load_local(a.det, r.c, r.loc);
 #pragma unroll
     for (int p = 0;  p < DET::NPAIRS;  p++)
+    {
         r.fac[p] = DET::fac(a.det, p);
+        // Keep the coefficients in registers: without this the compiler re-materialises them from
+        // the constant bank (LDCU + MOV) in every unrolled vector, 10 extra issue slots per 8 samples.
+        asm volatile("" : "+f"(r.fac[p].x), "+f"(r.fac[p].y));
+    }
     r.blk = slice*a.slice_blocks;
     r.filt = false;
     if (slice == 0  &&  a.cs0 > 0)
@@ -403,22 +416,31 @@ __global__ void __launch_bounds__(WARPS*32) bank_kernel_staged(const BankArgs<DE
             issue(g + NSTAGE - 1);
             const uint32_t stage = my_row + (g % NSTAGE)*SEG_VEC*16;
             const int Vbase = g*SEG_VEC;
-            int j0 = (v_lo > Vbase)  ?  (v_lo - Vbase)  :  0;
-            int j1 = (v_hi < Vbase + SEG_VEC)  ?  (v_hi - Vbase)  :  SEG_VEC;
-            if (j0 < j1)
+            const int j0 = (v_lo > Vbase)  ?  (v_lo - Vbase)  :  0;
+            const int j1 = (v_hi < Vbase + SEG_VEC)  ?  (v_hi - Vbase)  :  SEG_VEC;
+            // The slice's first and last vectors may be partial; peel them so that the interior
+            // loop carries no per-vector bounds logic.
+            const int jh = (v_lo >= Vbase  &&  v_lo < Vbase + SEG_VEC)  ?  (v_lo - Vbase)  :  -1;
+            const int jt = (v_hi - 1 >= Vbase  &&  v_hi - 1 < Vbase + SEG_VEC  &&  v_hi - 1 != v_lo)  ?  (v_hi - 1 - Vbase)  :  -1;
+            const int ja = (jh >= 0)  ?  (jh + 1)  :  j0;
+            const int jb = (jt >= 0)  ?  jt  :  j1;
+            if (jh >= 0)
             {
-                uint4 cur = lds128(stage + j0*16);
-                for (int j = j0;  j < j1;  j++)
-                {
-                    const uint4 v = cur;
-                    if (j + 1 < j1)
-                        cur = lds128(stage + (j + 1)*16);
-                    const int V = Vbase + j;
-                    const int lo = (V == v_lo)  ?  (start & 7)  :  0;
-                    const int hi = (V == v_hi - 1)  ?  (((end - 1) & 7) + 1)  :  8;
-                    r.template vector<FILT>(v, lo, hi, a);
-                }
+                const int hi_h = (v_hi - 1 == v_lo)  ?  (((end - 1) & 7) + 1)  :  8;
+                r.template partial<FILT>(lds128(stage + jh*16), start & 7, hi_h, a);
             }
+            int j = ja;
+            for (  ;  j + 2 <= jb;  j += 2)
+            {
+                const uint4 v0 = lds128(stage + j*16);
+                const uint4 v1 = lds128(stage + j*16 + 16);
+                r.template full<FILT>(v0, a);
+                r.template full<FILT>(v1, a);
+            }
+            if (j < jb)
+                r.template full<FILT>(lds128(stage + j*16), a);
+            if (jt >= 0)
+                r.template partial<FILT>(lds128(stage + jt*16), 0, ((end - 1) & 7) + 1, a);
         }
     };
     if (DET::FILTER  &&  any_filter)

@@ -22,8 +22,8 @@ struct SeqCommon
     int n;                      // samples per channel in this call
     int cs0;                    // uniform entry phase, or -1: per channel from cs[]
     int *cs;                    // [channels] block phase, advanced by the emit pass
-    const unsigned int *offsets;    // exclusive scan of counts (emit pass)
-    unsigned int *counts;       // per-channel event counts (count pass)
+    const unsigned int *offsets;    // exclusive scan of the per-warp counts (emit pass)
+    unsigned int *counts;       // per-warp (32 channels) event counts (count pass)
     span_b200_event_t *events;
     long long capacity;
 };
@@ -42,6 +42,50 @@ __device__ __forceinline__ void put_event(const SeqCommon &q, unsigned int pos, 
         q.events[pos] = e;
     }
 }
+
+// Warp-aggregated event output.  The 32 channels of a warp walk their blocks in lock step; at
+// every emission point the lanes that have an event take consecutive slots of the warp's region
+// of the event buffer (ballot + popc), so the records of one step land in one contiguous run
+// instead of 32 scattered ones.  Order inside the buffer: (group of 32 channels, time, channel);
+// the order of any single channel's events is preserved.  All lanes must call push() together.
+template <bool EMIT>
+struct EventSink
+{
+    const SeqCommon &q;
+    unsigned int base;
+    unsigned int lt;
+
+    __device__ __forceinline__ EventSink(const SeqCommon &qq, int warp_global) : q(qq)
+    {
+        base = (EMIT)  ?  qq.offsets[warp_global]  :  0;
+        lt = (1u << (threadIdx.x & 31)) - 1u;
+    }
+
+    __device__ __forceinline__ void push(bool has, int c, int blk, int kind, int a, int b, int cc)
+    {
+        if (EMIT)
+        {
+            const unsigned int m = __ballot_sync(0xFFFFFFFFu, has);
+            if (has)
+                put_event(q, base + __popc(m & lt), c, blk, kind, a, b, cc);
+            base += __popc(m);
+        }
+        else
+        {
+            base += (has)  ?  1u  :  0u;        // count pass: per lane, reduced once at the end
+        }
+    }
+
+    __device__ __forceinline__ void finish(int warp_global)
+    {
+        if (!EMIT)
+        {
+            const unsigned int total = __reduce_add_sync(0xFFFFFFFFu, base);
+            if ((threadIdx.x & 31) == 0)
+                q.counts[warp_global] = total;
+        }
+    }
+};
 
 // ==========================================================================================
 // DTMF  (reference: src/dtmf.c)
@@ -185,58 +229,80 @@ __device__ __forceinline__ int dtmf_level(const DtmfSeqArgs &s, float energy)
 
 // src/dtmf.c:201-207 (duration) and 304-347 (two-block debounce).
 template <bool EMIT>
-__global__ void dtmf_sequencer(const DtmfSeqArgs s)
+__global__ void __launch_bounds__(128) dtmf_sequencer(const DtmfSeqArgs s)
 {
-    const int c = blockIdx.x*blockDim.x + threadIdx.x;
-    if (c >= s.q.channels)
-        return;
+    const int gc = blockIdx.x*blockDim.x + threadIdx.x;
+    const int wg = gc >> 5;
+    const bool live = (gc < s.q.channels);
+    const int c = (live)  ?  gc  :  (s.q.channels - 1);
     const int B = DtmfDet::BLOCK;
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
-    const int nb = (cs_old + s.q.n)/B;
+    const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
+    const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
     const bool realtime = (s.flags[c] & SB_DTMF_FLAG_REALTIME) != 0;
     int in_digit = s.in_digit[c];
     int last_hit = s.last_hit[c];
     int dur = s.duration[c];
-    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
-    unsigned int count = 0;
+    EventSink<EMIT> sink(s.q, wg);
 
-    for (int b = 0;  b < nb;  b++)
+    // The decision codes of a group of blocks are fetched together: the loads do not depend on the
+    // state machine, and issuing them back to back hides the memory latency a one-by-one walk exposes.
+    constexpr int G = 16;
+    for (int b0 = 0;  b0 < nb_max;  b0 += G)
     {
-        const int len = (b == 0)  ?  (B - cs_old)  :  B;
-        if (dur < INT_MAX - len)
-            dur += len;
-        int hit = s.code[(size_t) b*s.q.channels + c];
-        if (hit != in_digit  &&  last_hit != in_digit)
+        unsigned char codes[G];
+#pragma unroll
+        for (int i = 0;  i < G;  i++)
+            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*s.q.channels + c]  :  (unsigned char) 0;
+#pragma unroll
+        for (int i = 0;  i < G;  i++)
         {
-            hit = (hit  &&  hit == last_hit)  ?  hit  :  0;
-            if (realtime)
+            const int b = b0 + i;
+            bool ev = false;
+            int ev_kind = 0;
+            int ev_a = 0;
+            int ev_b = 0;
+            int ev_c = 0;
+            if (b < nb)
             {
-                if (in_digit  ||  hit)
+                const int len = (b == 0)  ?  (B - cs_old)  :  B;
+                if (dur < INT_MAX - len)
+                    dur += len;
+                int hit = codes[i];
+                if (hit != in_digit  &&  last_hit != in_digit)
                 {
-                    if (EMIT)
+                    hit = (hit  &&  hit == last_hit)  ?  hit  :  0;
+                    if (realtime)
                     {
-                        if (in_digit  &&  !hit)
-                            put_event(s.q, pos, c, b, SPAN_B200_EV_TONE, hit, -99, dur);
-                        else
-                            put_event(s.q, pos, c, b, SPAN_B200_EV_TONE, hit, dtmf_level(s, s.eout[(size_t) b*s.q.channels + c]), dur);
+                        if (in_digit  ||  hit)
+                        {
+                            ev = true;
+                            ev_kind = SPAN_B200_EV_TONE;
+                            ev_a = hit;
+                            ev_c = dur;
+                            if (in_digit  &&  !hit)
+                                ev_b = -99;
+                            else if (EMIT)
+                                ev_b = dtmf_level(s, s.eout[(size_t) b*s.q.channels + c]);
+                            dur = 0;
+                        }
                     }
-                    pos++;
-                    count++;
-                    dur = 0;
+                    else if (hit)
+                    {
+                        ev = true;
+                        ev_kind = SPAN_B200_EV_DIGIT;
+                        ev_a = hit;
+                    }
+                    in_digit = hit;
                 }
+                last_hit = hit;
             }
-            else if (hit)
-            {
-                if (EMIT)
-                    put_event(s.q, pos, c, b, SPAN_B200_EV_DIGIT, hit, 0, 0);
-                pos++;
-                count++;
-            }
-            in_digit = hit;
+            if (b < nb_max)
+                sink.push(ev, c, b, ev_kind, ev_a, ev_b, ev_c);
         }
-        last_hit = hit;
     }
-    if (EMIT)
+    sink.finish(wg);
+    if (EMIT  &&  live)
     {
         const int tail = (nb == 0)  ?  s.q.n  :  (cs_old + s.q.n - nb*B);
         if (dur < INT_MAX - tail)
@@ -245,10 +311,6 @@ __global__ void dtmf_sequencer(const DtmfSeqArgs s)
         s.last_hit[c] = (unsigned char) last_hit;
         s.duration[c] = dur;
         s.q.cs[c] = cs_old + s.q.n - nb*B;
-    }
-    else
-    {
-        s.q.counts[c] = count;
     }
 }
 
@@ -396,44 +458,56 @@ struct MfSeqArgs
 // src/bell_r2_mf.c:629-661: a digit is reported when the last two blocks agree with this one and
 // the two before differ (KP '*': the last three agree and the two before differ).
 template <bool EMIT>
-__global__ void bell_mf_sequencer(const MfSeqArgs s)
+__global__ void __launch_bounds__(128) bell_mf_sequencer(const MfSeqArgs s)
 {
-    const int c = blockIdx.x*blockDim.x + threadIdx.x;
-    if (c >= s.q.channels)
-        return;
+    const int gc = blockIdx.x*blockDim.x + threadIdx.x;
+    const int wg = gc >> 5;
+    const bool live = (gc < s.q.channels);
+    const int c = (live)  ?  gc  :  (s.q.channels - 1);
     const int B = BellMfDet::BLOCK;
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
-    const int nb = (cs_old + s.q.n)/B;
+    const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
+    const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
     const size_t C = s.q.channels;
     int h0 = s.hits[c];
     int h1 = s.hits[C + c];
     int h2 = s.hits[2*C + c];
     int h3 = s.hits[3*C + c];
     int h4 = s.hits[4*C + c];
-    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
-    unsigned int count = 0;
+    EventSink<EMIT> sink(s.q, wg);
 
-    for (int b = 0;  b < nb;  b++)
+    constexpr int G = 16;
+    for (int b0 = 0;  b0 < nb_max;  b0 += G)
     {
-        const int hit = s.code[(size_t) b*C + c];
-        if (hit
-            &&  hit == h4  &&  hit == h3
-            &&  ((hit != '*'  &&  hit != h2  &&  hit != h1)
-                 ||
-                 (hit == '*'  &&  hit == h2  &&  hit != h1  &&  hit != h0)))
+        unsigned char codes[G];
+#pragma unroll
+        for (int i = 0;  i < G;  i++)
+            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned char) 0;
+#pragma unroll
+        for (int i = 0;  i < G;  i++)
         {
-            if (EMIT)
-                put_event(s.q, pos, c, b, SPAN_B200_EV_DIGIT, hit, 0, 0);
-            pos++;
-            count++;
+            const int b = b0 + i;
+            bool ev = false;
+            const int hit = codes[i];
+            if (b < nb)
+            {
+                ev = hit
+                     &&  hit == h4  &&  hit == h3
+                     &&  ((hit != '*'  &&  hit != h2  &&  hit != h1)
+                          ||
+                          (hit == '*'  &&  hit == h2  &&  hit != h1  &&  hit != h0));
+                h0 = h1;
+                h1 = h2;
+                h2 = h3;
+                h3 = h4;
+                h4 = hit;
+            }
+            if (b < nb_max)
+                sink.push(ev, c, b, SPAN_B200_EV_DIGIT, hit, 0, 0);
         }
-        h0 = h1;
-        h1 = h2;
-        h2 = h3;
-        h3 = h4;
-        h4 = hit;
     }
-    if (EMIT)
+    sink.finish(wg);
+    if (EMIT  &&  live)
     {
         s.hits[c] = (unsigned char) h0;
         s.hits[C + c] = (unsigned char) h1;
@@ -442,47 +516,51 @@ __global__ void bell_mf_sequencer(const MfSeqArgs s)
         s.hits[4*C + c] = (unsigned char) h4;
         s.q.cs[c] = cs_old + s.q.n - nb*B;
     }
-    else
-    {
-        s.q.counts[c] = count;
-    }
 }
 
 // src/bell_r2_mf.c:864-876: report every change of the block decision.
 template <bool EMIT>
-__global__ void r2_mf_sequencer(const MfSeqArgs s)
+__global__ void __launch_bounds__(128) r2_mf_sequencer(const MfSeqArgs s)
 {
-    const int c = blockIdx.x*blockDim.x + threadIdx.x;
-    if (c >= s.q.channels)
-        return;
+    const int gc = blockIdx.x*blockDim.x + threadIdx.x;
+    const int wg = gc >> 5;
+    const bool live = (gc < s.q.channels);
+    const int c = (live)  ?  gc  :  (s.q.channels - 1);
     const int B = R2MfDet::BLOCK;
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
-    const int nb = (cs_old + s.q.n)/B;
+    const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
+    const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
     const size_t C = s.q.channels;
     int current = s.hits[c];
-    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
-    unsigned int count = 0;
+    EventSink<EMIT> sink(s.q, wg);
 
-    for (int b = 0;  b < nb;  b++)
+    constexpr int G = 16;
+    for (int b0 = 0;  b0 < nb_max;  b0 += G)
     {
-        const int hit = s.code[(size_t) b*C + c];
-        if (hit != current)
+        unsigned char codes[G];
+#pragma unroll
+        for (int i = 0;  i < G;  i++)
+            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned char) 0;
+#pragma unroll
+        for (int i = 0;  i < G;  i++)
         {
-            if (EMIT)
-                put_event(s.q, pos, c, b, SPAN_B200_EV_TONE, hit, (hit)  ?  -10  :  -99, 0);
-            pos++;
-            count++;
+            const int b = b0 + i;
+            bool ev = false;
+            const int hit = codes[i];
+            if (b < nb)
+            {
+                ev = (hit != current);
+                current = hit;
+            }
+            if (b < nb_max)
+                sink.push(ev, c, b, SPAN_B200_EV_TONE, hit, (hit)  ?  -10  :  -99, 0);
         }
-        current = hit;
     }
-    if (EMIT)
+    sink.finish(wg);
+    if (EMIT  &&  live)
     {
         s.hits[c] = (unsigned char) current;
         s.q.cs[c] = cs_old + s.q.n - nb*B;
-    }
-    else
-    {
-        s.q.counts[c] = count;
     }
 }
 
@@ -694,15 +772,17 @@ __device__ inline int st_test_cadence(const int4 *pattern, int steps, const StSe
 
 // src/super_tone_rx.c:366-448
 template <bool EMIT>
-__global__ void super_tone_sequencer(const StSeqArgs s)
+__global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
 {
-    const int c = blockIdx.x*blockDim.x + threadIdx.x;
-    if (c >= s.q.channels)
-        return;
+    const int gc = blockIdx.x*blockDim.x + threadIdx.x;
+    const int wg = gc >> 5;
+    const bool live = (gc < s.q.channels);
+    const int c = (live)  ?  gc  :  (s.q.channels - 1);
     const int B = 128;
     const size_t C = s.q.channels;
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
-    const int nb = (cs_old + s.q.n)/B;
+    const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
+    const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
     StSegs t;
     for (int i = 0;  i < 11;  i++)
     {
@@ -713,19 +793,26 @@ __global__ void super_tone_sequencer(const StSeqArgs s)
     int detected = s.detected_tone[c];
     int rotation = s.rotation[c];
     int pending = s.pending[c];
-    unsigned int pos = (EMIT)  ?  s.q.offsets[c]  :  0;
-    unsigned int count = 0;
+    EventSink<EMIT> sink(s.q, wg);
 
-    auto emit = [&](int blk, int kind, int a, int b, int cc)
-    {
-        if (EMIT)
-            put_event(s.q, pos, c, blk, kind, a, b, cc);
-        pos++;
-        count++;
-    };
+    // One super_tone_chunk() step.  It can raise up to three callbacks, in this order: tone lost,
+    // segment report, tone found.  They are recorded here and pushed by all lanes together.
+    bool e_lost;
+    bool e_seg;
+    bool e_found;
+    int seg_f1;
+    int seg_f2;
+    int seg_ms;
+    int found_id;
 
-    auto chunk = [&](int blk, int k1, int k2)
+    auto chunk = [&](bool run, int k1, int k2)
     {
+        e_lost = false;
+        e_seg = false;
+        e_found = false;
+        seg_f1 = seg_f2 = seg_ms = found_id = 0;
+        if (!run)
+            return;
         if (k1 != t.f1[10]  ||  k2 != t.f2[10])
         {
             t.f1[10] = k1;
@@ -739,11 +826,16 @@ __global__ void super_tone_sequencer(const StSeqArgs s)
                 if (!st_test_cadence(s.t.elements + s.t.tone_first[detected], -s.t.tone_segs[detected], t, rotation++))
                 {
                     detected = -1;
-                    emit(blk, SPAN_B200_EV_TONE, -1, -10, 0);
+                    e_lost = true;
                 }
             }
             if (s.want_segments)
-                emit(blk, SPAN_B200_EV_SEGMENT, t.f1[9], t.f2[9], t.dur[9]*128/8);
+            {
+                e_seg = true;
+                seg_f1 = t.f1[9];
+                seg_f2 = t.f2[9];
+                seg_ms = t.dur[9]*128/8;
+            }
             for (int i = 0;  i < 9;  i++)
             {
                 t.f1[i] = t.f1[i + 1];
@@ -761,7 +853,7 @@ __global__ void super_tone_sequencer(const StSeqArgs s)
                 if (!st_test_cadence(s.t.elements + s.t.tone_first[detected], s.t.tone_segs[detected], t, rotation))
                 {
                     detected = -1;
-                    emit(blk, SPAN_B200_EV_TONE, -1, -10, 0);
+                    e_lost = true;
                 }
             }
             t.dur[9]++;
@@ -774,36 +866,53 @@ __global__ void super_tone_sequencer(const StSeqArgs s)
                 {
                     detected = j;
                     rotation = 0;
-                    emit(blk, SPAN_B200_EV_TONE, j, -10, 0);
+                    e_found = true;
+                    found_id = j;
                     break;
                 }
             }
         }
     };
 
-    if (pending  &&  s.q.n > 0)
+    auto flush = [&](int blk)
     {
-        chunk(0, -1, -1);
-        pending = 0;
+        sink.push(e_lost, c, blk, SPAN_B200_EV_TONE, -1, -10, 0);
+        sink.push(e_seg, c, blk, SPAN_B200_EV_SEGMENT, seg_f1, seg_f2, seg_ms);
+        sink.push(e_found, c, blk, SPAN_B200_EV_TONE, found_id, -10, 0);
+    };
+
+    // A zero-energy re-chunk owed from the previous call (one-bin descriptors only).
+    {
+        const bool owe = live  &&  pending  &&  s.q.n > 0;
+        if (__any_sync(0xFFFFFFFFu, owe))
+        {
+            chunk(owe, -1, -1);
+            flush(0);
+        }
+        if (owe)
+            pending = 0;
     }
     const long long consumed_at_end = (long long) cs_old + s.q.n;
-    for (int b = 0;  b < nb;  b++)
+    for (int b = 0;  b < nb_max;  b++)
     {
-        const int code = s.code[(size_t) b*C + c];
-        const int k1 = (code & 0x7F) - 1;
-        const int k2 = ((code >> 7) & 0x7F) - 1;
-        chunk(b, k1, k2);
-        if (code & SB_ST_QUIRK)
+        const bool run = (b < nb);
+        const int code = (run)  ?  s.code[(size_t) b*C + c]  :  0;
+        chunk(run, (code & 0x7F) - 1, ((code >> 7) & 0x7F) - 1);
+        flush(b);
+        const bool quirk = run  &&  (code & SB_ST_QUIRK);
+        if (__any_sync(0xFFFFFFFFu, quirk))
         {
             // The reference loops straight back into super_tone_chunk with zero energy unless the
             // block ended exactly at the end of the caller's buffer (src/super_tone_rx.c:466-486).
-            if ((long long) (b + 1)*B < consumed_at_end)
-                chunk(b, -1, -1);
-            else
+            const bool again = quirk  &&  ((long long) (b + 1)*B < consumed_at_end);
+            chunk(again, -1, -1);
+            flush(b);
+            if (quirk  &&  !again)
                 pending = 1;
         }
     }
-    if (EMIT)
+    sink.finish(wg);
+    if (EMIT  &&  live)
     {
         for (int i = 0;  i < 11;  i++)
         {
@@ -815,10 +924,6 @@ __global__ void super_tone_sequencer(const StSeqArgs s)
         s.rotation[c] = rotation;
         s.pending[c] = (unsigned char) pending;
         s.q.cs[c] = cs_old + s.q.n - nb*B;
-    }
-    else
-    {
-        s.q.counts[c] = count;
     }
 }
 

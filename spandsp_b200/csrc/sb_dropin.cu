@@ -1,0 +1,910 @@
+// sb_dropin.cu - the spandsp-named per-channel API (include/spandsp_b200_dropin.h) on top of the
+// bank engine.  Host logic only mirrors what the reference does on the host side of a callback
+// (digit buffering, callback selection); every sample is processed by the CUDA kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "sb_engine.h"
+#pragma GCC visibility push(default)
+#include "../../include/spandsp_b200_dropin.h"
+#pragma GCC visibility pop
+
+#define SB_MAGIC    0x5350414E42323030ULL       /* "SPANB200" */
+
+// ------------------------------------------------------------------------------------------
+// state objects (all start with the same header)
+struct sb_member_t
+{
+    unsigned long long magic;
+    span_b200_group_s *grp;
+    int index;
+    int det;
+    int staged;                 // samples staged since the last flush
+    int heap;                   // allocated by *_init(NULL, ...)
+};
+
+struct dtmf_rx_state_s
+{
+    sb_member_t m;
+    digits_rx_callback_t digits_callback;
+    void *digits_callback_data;
+    span_tone_report_func_t realtime_callback;
+    void *realtime_callback_data;
+    int lost_digits;
+    int current_digits;
+    char digits[MAX_DTMF_DIGITS + 1];
+};
+
+struct bell_mf_rx_state_s
+{
+    sb_member_t m;
+    digits_rx_callback_t digits_callback;
+    void *digits_callback_data;
+    int lost_digits;
+    int current_digits;
+    char digits[MAX_BELL_MF_DIGITS + 1];
+};
+
+struct r2_mf_rx_state_s
+{
+    sb_member_t m;
+    span_tone_report_func_t callback;
+    void *callback_data;
+    int fwd;
+};
+
+struct super_tone_rx_state_s
+{
+    sb_member_t m;
+    super_tone_rx_descriptor_t *desc;
+    span_tone_report_func_t tone_callback;
+    tone_segment_func_t segment_callback;
+    void *callback_data;
+};
+
+static_assert(sizeof(dtmf_rx_state_s) <= 432, "must fit the reference's dtmf_rx_state_t (private/dtmf.h:54-116)");
+static_assert(sizeof(bell_mf_rx_state_s) <= 288, "must fit the reference's bell_mf_rx_state_t (private/bell_r2_mf.h:48-67)");
+static_assert(sizeof(r2_mf_rx_state_s) <= 152, "must fit the reference's r2_mf_rx_state_t (private/bell_r2_mf.h:85-100)");
+static_assert(sizeof(super_tone_rx_state_s) <= 272, "must fit the reference's super_tone_rx_state_t (private/super_tone_rx.h:51-62)");
+
+struct super_tone_rx_descriptor_s
+{
+    std::vector<std::vector<int> > tones;       // per tone: {f1, f2, min_ms, max_ms} x elements
+    int heap;
+};
+
+struct span_b200_group_s
+{
+    span_b200_ctx_t *ctx;
+    int det;
+    int members;
+    int max_samples;
+    int single;                 // group of one made by *_init(): flushes on every rx call
+    int arg;
+    span_b200_bank_t *bank;
+    int16_t *h_stage;           // pinned, [members][max_samples]
+    std::vector<void *> owned;  // member objects allocated by group_create
+    std::vector<sb_member_t *> member;
+    std::vector<span_b200_event_t> events;
+};
+
+static std::recursive_mutex g_lock;
+static span_b200_ctx_t *g_default_ctx = NULL;
+
+extern "C" span_b200_ctx_t *span_b200_default_ctx(void)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (g_default_ctx == NULL)
+    {
+        const char *e = getenv("SPANDSP_B200_DEVICE");
+        g_default_ctx = span_b200_ctx_create((e)  ?  atoi(e)  :  0);
+    }
+    return g_default_ctx;
+}
+
+static size_t state_size(int det)
+{
+    switch (det)
+    {
+    case SPAN_B200_DET_DTMF: return sizeof(dtmf_rx_state_s);
+    case SPAN_B200_DET_BELL_MF: return sizeof(bell_mf_rx_state_s);
+    case SPAN_B200_DET_R2_MF: return sizeof(r2_mf_rx_state_s);
+    default: return sizeof(super_tone_rx_state_s);
+    }
+}
+
+static int alloc_stage(span_b200_group_s *g, int max_samples)
+{
+    int16_t *p = NULL;
+    if (cudaMallocHost(&p, sizeof(int16_t)*(size_t) g->members*max_samples) != cudaSuccess)
+    {
+        sb_set_error("cannot allocate pinned staging for %d members x %d samples", g->members, max_samples);
+        return -1;
+    }
+    if (g->h_stage)
+    {
+        // keep what is already staged
+        for (int i = 0;  i < g->members;  i++)
+        {
+            const int n = (g->member[i])  ?  g->member[i]->staged  :  0;
+            if (n > 0)
+                memcpy(p + (size_t) i*max_samples, g->h_stage + (size_t) i*g->max_samples, sizeof(int16_t)*n);
+        }
+        cudaFreeHost(g->h_stage);
+    }
+    g->h_stage = p;
+    g->max_samples = max_samples;
+    return 0;
+}
+
+static span_b200_group_s *group_new(span_b200_ctx_t *ctx, int det, int members, int max_samples, int arg,
+                                    super_tone_rx_descriptor_t *desc, int single)
+{
+    if (ctx == NULL)
+        ctx = span_b200_default_ctx();
+    if (ctx == NULL)
+        return NULL;
+    if (members < 1  ||  max_samples < 1)
+    {
+        sb_set_error("bad group size");
+        return NULL;
+    }
+    span_b200_group_s *g = new span_b200_group_s();
+    g->ctx = ctx;
+    g->det = det;
+    g->members = members;
+    g->single = single;
+    g->arg = arg;
+    g->member.assign(members, (sb_member_t *) NULL);
+    switch (det)
+    {
+    case SPAN_B200_DET_DTMF:
+        g->bank = span_b200_dtmf_bank_create(ctx, members);
+        break;
+    case SPAN_B200_DET_BELL_MF:
+        g->bank = span_b200_bell_mf_bank_create(ctx, members);
+        break;
+    case SPAN_B200_DET_R2_MF:
+        g->bank = span_b200_r2_mf_bank_create(ctx, members, arg);
+        break;
+    case SPAN_B200_DET_SUPER_TONE:
+        {
+            if (desc == NULL)
+            {
+                sb_set_error("super-tone group needs a descriptor");
+                delete g;
+                return NULL;
+            }
+            std::vector<int32_t> segs;
+            std::vector<int32_t> el;
+            for (size_t t = 0;  t < desc->tones.size();  t++)
+            {
+                segs.push_back((int32_t) (desc->tones[t].size()/4));
+                el.insert(el.end(), desc->tones[t].begin(), desc->tones[t].end());
+            }
+            if (el.empty())
+                el.assign(4, 0);
+            if (segs.empty())
+                segs.push_back(0);
+            span_b200_super_tone_desc_t d;
+            d.tones = (int32_t) desc->tones.size();
+            d.tone_segs = segs.data();
+            d.elements = el.data();
+            // Segment events are always produced; the host drops them when no handler is installed.
+            g->bank = span_b200_super_tone_bank_create(ctx, members, &d, 1);
+        }
+        break;
+    default:
+        sb_set_error("unknown detector %d", det);
+        break;
+    }
+    if (g->bank == NULL)
+    {
+        delete g;
+        return NULL;
+    }
+    if (alloc_stage(g, max_samples) != 0)
+    {
+        span_b200_bank_destroy(g->bank);
+        delete g;
+        return NULL;
+    }
+    return g;
+}
+
+static void member_attach(span_b200_group_s *g, int index, sb_member_t *m, int heap)
+{
+    m->magic = SB_MAGIC;
+    m->grp = g;
+    m->index = index;
+    m->det = g->det;
+    m->staged = 0;
+    m->heap = heap;
+    g->member[index] = m;
+}
+
+extern "C" span_b200_group_t *span_b200_group_create(span_b200_ctx_t *ctx, int detector, int members, int max_samples,
+                                                     int arg, super_tone_rx_descriptor_t *desc)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    span_b200_group_s *g = group_new(ctx, detector, members, max_samples, arg, desc, 0);
+    if (g == NULL)
+        return NULL;
+    const size_t sz = state_size(detector);
+    for (int i = 0;  i < members;  i++)
+    {
+        void *p = calloc(1, sz);
+        g->owned.push_back(p);
+        member_attach(g, i, (sb_member_t *) p, 0);
+        if (detector == SPAN_B200_DET_R2_MF)
+            ((r2_mf_rx_state_s *) p)->fwd = arg;
+        if (detector == SPAN_B200_DET_SUPER_TONE)
+            ((super_tone_rx_state_s *) p)->desc = desc;
+    }
+    return g;
+}
+
+extern "C" void *span_b200_group_member(span_b200_group_t *g, int index)
+{
+    if (g == NULL  ||  index < 0  ||  index >= g->members)
+        return NULL;
+    return g->member[index];
+}
+
+extern "C" void span_b200_group_destroy(span_b200_group_t *g)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (g == NULL)
+        return;
+    span_b200_bank_destroy(g->bank);
+    if (g->h_stage)
+        cudaFreeHost(g->h_stage);
+    for (size_t i = 0;  i < g->owned.size();  i++)
+    {
+        ((sb_member_t *) g->owned[i])->magic = 0;
+        free(g->owned[i]);
+    }
+    delete g;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side of the callbacks
+
+// src/dtmf.c:322-338 / src/bell_r2_mf.c:640-655
+template <class S>
+static int deliver_digit(S *s, int hit)
+{
+    int fired = 0;
+    if (s->current_digits < 128)
+    {
+        s->digits[s->current_digits++] = (char) hit;
+        s->digits[s->current_digits] = '\0';
+        if (s->digits_callback)
+        {
+            s->digits_callback(s->digits_callback_data, s->digits, s->current_digits);
+            s->current_digits = 0;
+            fired = 1;
+        }
+    }
+    else
+    {
+        s->lost_digits++;
+    }
+    return fired;
+}
+
+// src/dtmf.c:352-358 / src/bell_r2_mf.c:667-672: digits buffered before a callback was installed
+template <class S>
+static int trailing_flush(S *s)
+{
+    if (s->current_digits  &&  s->digits_callback)
+    {
+        s->digits_callback(s->digits_callback_data, s->digits, s->current_digits);
+        s->digits[0] = '\0';
+        s->current_digits = 0;
+        return 1;
+    }
+    return 0;
+}
+
+static int dispatch(span_b200_group_s *g, const span_b200_event_t &e)
+{
+    sb_member_t *m = g->member[e.channel];
+    if (m == NULL)
+        return 0;
+    switch (g->det)
+    {
+    case SPAN_B200_DET_DTMF:
+        {
+            dtmf_rx_state_s *s = (dtmf_rx_state_s *) m;
+            if (e.kind == SPAN_B200_EV_TONE)
+            {
+                if (s->realtime_callback)
+                {
+                    s->realtime_callback(s->realtime_callback_data, e.a, e.b, e.c);
+                    return 1;
+                }
+                return 0;
+            }
+            return deliver_digit(s, e.a);
+        }
+    case SPAN_B200_DET_BELL_MF:
+        return deliver_digit((bell_mf_rx_state_s *) m, e.a);
+    case SPAN_B200_DET_R2_MF:
+        {
+            r2_mf_rx_state_s *s = (r2_mf_rx_state_s *) m;
+            if (s->callback)
+            {
+                s->callback(s->callback_data, e.a, e.b, e.c);
+                return 1;
+            }
+            return 0;
+        }
+    default:
+        {
+            super_tone_rx_state_s *s = (super_tone_rx_state_s *) m;
+            if (e.kind == SPAN_B200_EV_SEGMENT)
+            {
+                if (s->segment_callback)
+                {
+                    s->segment_callback(s->callback_data, e.a, e.b, e.c);
+                    return 1;
+                }
+                return 0;
+            }
+            if (s->tone_callback)
+            {
+                s->tone_callback(s->callback_data, e.a, e.b, e.c);
+                return 1;
+            }
+            return 0;
+        }
+    }
+}
+
+extern "C" int span_b200_group_flush(span_b200_group_t *g)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (g == NULL)
+        return -1;
+    int n = 0;
+    for (int i = 0;  i < g->members;  i++)
+    {
+        const int st = (g->member[i])  ?  g->member[i]->staged  :  0;
+        if (st > n)
+            n = st;
+    }
+    if (n == 0)
+        return 0;
+    for (int i = 0;  i < g->members;  i++)
+    {
+        const int st = (g->member[i])  ?  g->member[i]->staged  :  0;
+        if (st != n)
+        {
+            sb_set_error("group flush: member %d staged %d samples, others %d (all members must be fed the same amount per flush)", i, st, n);
+            return -1;
+        }
+    }
+    if (span_b200_bank_rx_host(g->bank, g->h_stage, g->max_samples, n, NULL) != 0)
+        return -1;
+    const int64_t total = span_b200_bank_event_count(g->bank, NULL);
+    if (total < 0)
+        return -1;
+    g->events.resize((size_t) total);
+    if (total > 0  &&  span_b200_bank_events(g->bank, g->events.data(), total) < 0)
+        return -1;
+    // Fire callbacks channel by channel, each channel's events in time order.
+    std::stable_sort(g->events.begin(), g->events.end(),
+                     [](const span_b200_event_t &a, const span_b200_event_t &b) { return a.channel < b.channel; });
+    int fired = 0;
+    for (size_t i = 0;  i < g->events.size();  i++)
+        fired += dispatch(g, g->events[i]);
+    for (int i = 0;  i < g->members;  i++)
+    {
+        sb_member_t *m = g->member[i];
+        if (m == NULL)
+            continue;
+        if (g->det == SPAN_B200_DET_DTMF  &&  ((dtmf_rx_state_s *) m)->realtime_callback == NULL)
+            fired += trailing_flush((dtmf_rx_state_s *) m);
+        else if (g->det == SPAN_B200_DET_BELL_MF)
+            fired += trailing_flush((bell_mf_rx_state_s *) m);
+        m->staged = 0;
+    }
+    return fired;
+}
+
+static int stage_samples(sb_member_t *m, const int16_t amp[], int samples)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    span_b200_group_s *g = m->grp;
+    if (samples <= 0)
+        return 0;
+    if (m->staged + samples > g->max_samples)
+    {
+        if (!g->single)
+        {
+            sb_set_error("group member %d: %d samples staged + %d exceed max_samples %d; flush more often",
+                         m->index, m->staged, samples, g->max_samples);
+            return -1;
+        }
+        if (alloc_stage(g, std::max(2*g->max_samples, m->staged + samples)) != 0)
+            return -1;
+    }
+    memcpy(g->h_stage + (size_t) m->index*g->max_samples + m->staged, amp, sizeof(int16_t)*samples);
+    m->staged += samples;
+    if (g->single)
+        return (span_b200_group_flush(g) < 0)  ?  -1  :  0;
+    return 0;
+}
+
+// Make (or re-use) the backing of a state object.  `s` NULL: allocate.  `s` a live member: keep
+// its slot, reset its channel.  Anything else is taken as caller storage: a new group of one.
+static sb_member_t *state_open(void *s, int det, int arg, super_tone_rx_descriptor_t *desc)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    sb_member_t *m = (sb_member_t *) s;
+    if (m != NULL  &&  m->magic == SB_MAGIC  &&  m->grp != NULL  &&  m->det == det
+        &&  m->index >= 0  &&  m->index < m->grp->members  &&  m->grp->member[m->index] == m
+        &&  !(det == SPAN_B200_DET_R2_MF  &&  m->grp->single  &&  m->grp->arg != arg)
+        &&  !(det == SPAN_B200_DET_SUPER_TONE  &&  m->grp->single))
+    {
+        if (m->staged > 0  &&  !m->grp->single)
+            m->staged = 0;
+        span_b200_bank_reset(m->grp->bank, m->index, 1);
+        return m;
+    }
+    if (m != NULL  &&  m->magic == SB_MAGIC  &&  m->grp != NULL  &&  m->grp->single  &&  m->det == det)
+    {
+        // same storage, different construction arguments: rebuild the backing
+        span_b200_group_s *old = m->grp;
+        m->magic = 0;
+        span_b200_group_destroy(old);
+    }
+    int heap = 0;
+    if (m == NULL)
+    {
+        m = (sb_member_t *) calloc(1, state_size(det));
+        if (m == NULL)
+            return NULL;
+        heap = 1;
+    }
+    span_b200_group_s *g = group_new(NULL, det, 1, 1024, arg, desc, 1);
+    if (g == NULL)
+    {
+        if (heap)
+            free(m);
+        return NULL;
+    }
+    memset(m, 0, state_size(det));
+    member_attach(g, 0, m, heap);
+    return m;
+}
+
+static int state_close(void *s, int do_free)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    sb_member_t *m = (sb_member_t *) s;
+    if (m == NULL  ||  m->magic != SB_MAGIC)
+        return 0;
+    span_b200_group_s *g = m->grp;
+    const int heap = m->heap;
+    if (g  &&  g->single)
+    {
+        m->magic = 0;
+        span_b200_group_destroy(g);
+        if (do_free  &&  heap)
+            free(m);
+    }
+    return 0;
+}
+
+static int flush_if_pending(sb_member_t *m)
+{
+    // Control calls act on the channel "now": in a batched group anything staged is processed first.
+    if (m->grp  &&  m->staged > 0)
+        return span_b200_group_flush(m->grp);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// DTMF  (src/dtmf.c:363-519)
+extern "C" dtmf_rx_state_t *dtmf_rx_init(dtmf_rx_state_t *s, digits_rx_callback_t callback, void *user_data)
+{
+    sb_member_t *m = state_open(s, SPAN_B200_DET_DTMF, 0, NULL);
+    if (m == NULL)
+        return NULL;
+    dtmf_rx_state_s *d = (dtmf_rx_state_s *) m;
+    d->digits_callback = callback;
+    d->digits_callback_data = user_data;
+    d->realtime_callback = NULL;
+    d->realtime_callback_data = NULL;
+    d->lost_digits = 0;
+    d->current_digits = 0;
+    d->digits[0] = '\0';
+    return d;
+}
+
+extern "C" int dtmf_rx_release(dtmf_rx_state_t *s)
+{
+    return state_close(s, 0);
+}
+
+extern "C" int dtmf_rx_free(dtmf_rx_state_t *s)
+{
+    return state_close(s, 1);
+}
+
+extern "C" void dtmf_rx_set_realtime_callback(dtmf_rx_state_t *s, span_tone_report_func_t callback, void *user_data)
+{
+    flush_if_pending(&s->m);
+    s->realtime_callback = callback;
+    s->realtime_callback_data = user_data;
+    span_b200_dtmf_bank_realtime(s->m.grp->bank, s->m.index, 1, callback != NULL);
+}
+
+extern "C" void dtmf_rx_parms(dtmf_rx_state_t *s, int filter_dialtone, float twist, float reverse_twist, float threshold)
+{
+    flush_if_pending(&s->m);
+    span_b200_dtmf_bank_parms(s->m.grp->bank, s->m.index, 1, filter_dialtone, twist, reverse_twist, threshold);
+}
+
+extern "C" int dtmf_rx(dtmf_rx_state_t *s, const int16_t amp[], int samples)
+{
+    stage_samples(&s->m, amp, samples);
+    return 0;                                   // src/dtmf.c:360
+}
+
+extern "C" int dtmf_rx_fillin(dtmf_rx_state_t *s, int samples)
+{
+    (void) samples;
+    flush_if_pending(&s->m);
+    span_b200_dtmf_bank_fillin(s->m.grp->bank, s->m.index, 1);
+    return 0;
+}
+
+extern "C" int dtmf_rx_status(dtmf_rx_state_t *s)
+{
+    int32_t st = 0;
+    flush_if_pending(&s->m);
+    span_b200_bank_status(s->m.grp->bank, s->m.index, 1, &st);
+    return st;
+}
+
+template <class S>
+static size_t digits_get(S *s, char *buf, int max)
+{
+    // src/dtmf.c:394-408
+    if (max > s->current_digits)
+        max = s->current_digits;
+    if (max > 0)
+    {
+        memcpy(buf, s->digits, max);
+        memmove(s->digits, s->digits + max, s->current_digits - max);
+        s->current_digits -= max;
+    }
+    buf[max] = '\0';
+    return max;
+}
+
+extern "C" size_t dtmf_rx_get(dtmf_rx_state_t *s, char *buf, int max)
+{
+    flush_if_pending(&s->m);
+    return digits_get(s, buf, max);
+}
+
+extern "C" logging_state_t *dtmf_rx_get_logging_state(dtmf_rx_state_t *s)
+{
+    (void) s;
+    return NULL;        // the "Potentially 'x'" debug trace of src/dtmf.c:260-275 is not produced
+}
+
+// ------------------------------------------------------------------------------------------
+// Bell MF  (src/bell_r2_mf.c:676-745)
+extern "C" bell_mf_rx_state_t *bell_mf_rx_init(bell_mf_rx_state_t *s, digits_rx_callback_t callback, void *user_data)
+{
+    sb_member_t *m = state_open(s, SPAN_B200_DET_BELL_MF, 0, NULL);
+    if (m == NULL)
+        return NULL;
+    bell_mf_rx_state_s *d = (bell_mf_rx_state_s *) m;
+    d->digits_callback = callback;
+    d->digits_callback_data = user_data;
+    d->lost_digits = 0;
+    d->current_digits = 0;
+    d->digits[0] = '\0';
+    return d;
+}
+
+extern "C" int bell_mf_rx_release(bell_mf_rx_state_t *s) { return state_close(s, 0); }
+extern "C" int bell_mf_rx_free(bell_mf_rx_state_t *s) { return state_close(s, 1); }
+
+extern "C" int bell_mf_rx(bell_mf_rx_state_t *s, const int16_t amp[], int samples)
+{
+    stage_samples(&s->m, amp, samples);
+    return 0;
+}
+
+extern "C" size_t bell_mf_rx_get(bell_mf_rx_state_t *s, char *buf, int max)
+{
+    flush_if_pending(&s->m);
+    return digits_get(s, buf, max);
+}
+
+// ------------------------------------------------------------------------------------------
+// MFC/R2  (src/bell_r2_mf.c:883-951)
+extern "C" r2_mf_rx_state_t *r2_mf_rx_init(r2_mf_rx_state_t *s, bool fwd, span_tone_report_func_t callback, void *user_data)
+{
+    sb_member_t *m = state_open(s, SPAN_B200_DET_R2_MF, (fwd)  ?  1  :  0, NULL);
+    if (m == NULL)
+        return NULL;
+    r2_mf_rx_state_s *d = (r2_mf_rx_state_s *) m;
+    d->callback = callback;
+    d->callback_data = user_data;
+    d->fwd = (fwd)  ?  1  :  0;
+    return d;
+}
+
+extern "C" int r2_mf_rx_release(r2_mf_rx_state_t *s) { return state_close(s, 0); }
+extern "C" int r2_mf_rx_free(r2_mf_rx_state_t *s) { return state_close(s, 1); }
+
+extern "C" int r2_mf_rx(r2_mf_rx_state_t *s, const int16_t amp[], int samples)
+{
+    stage_samples(&s->m, amp, samples);
+    return 0;
+}
+
+extern "C" int r2_mf_rx_get(r2_mf_rx_state_t *s)
+{
+    int32_t st = 0;
+    flush_if_pending(&s->m);
+    span_b200_bank_status(s->m.grp->bank, s->m.index, 1, &st);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// supervisory tones  (src/super_tone_rx.c:125-161,231-287,454-566)
+extern "C" super_tone_rx_descriptor_t *super_tone_rx_make_descriptor(super_tone_rx_descriptor_t *desc)
+{
+    if (desc == NULL)
+    {
+        desc = new (std::nothrow) super_tone_rx_descriptor_s();
+        if (desc == NULL)
+            return NULL;
+        desc->heap = 1;
+    }
+    else
+    {
+        new (desc) super_tone_rx_descriptor_s();
+        desc->heap = 0;
+    }
+    return desc;
+}
+
+extern "C" int super_tone_rx_free_descriptor(super_tone_rx_descriptor_t *desc)
+{
+    if (desc)
+    {
+        if (desc->heap)
+            delete desc;
+        else
+            desc->~super_tone_rx_descriptor_s();
+    }
+    return 0;
+}
+
+extern "C" int super_tone_rx_add_tone(super_tone_rx_descriptor_t *desc)
+{
+    desc->tones.push_back(std::vector<int>());
+    return (int) desc->tones.size() - 1;
+}
+
+extern "C" int super_tone_rx_add_element(super_tone_rx_descriptor_t *desc, int tone, int f1, int f2, int min, int max)
+{
+    if (tone < 0  ||  tone >= (int) desc->tones.size())
+        return -1;
+    std::vector<int> &t = desc->tones[tone];
+    t.push_back(f1);
+    t.push_back(f2);
+    t.push_back(min);
+    t.push_back(max);
+    return (int) t.size()/4 - 1;
+}
+
+extern "C" super_tone_rx_state_t *super_tone_rx_init(super_tone_rx_state_t *s, super_tone_rx_descriptor_t *desc,
+                                                     span_tone_report_func_t callback, void *user_data)
+{
+    if (desc == NULL  ||  callback == NULL)     // src/super_tone_rx.c:514-519
+        return NULL;
+    sb_member_t *m = state_open(s, SPAN_B200_DET_SUPER_TONE, 0, desc);
+    if (m == NULL)
+        return NULL;
+    super_tone_rx_state_s *d = (super_tone_rx_state_s *) m;
+    d->desc = desc;
+    d->tone_callback = callback;
+    d->segment_callback = NULL;
+    d->callback_data = user_data;
+    return d;
+}
+
+extern "C" int super_tone_rx_release(super_tone_rx_state_t *s) { return state_close(s, 0); }
+extern "C" int super_tone_rx_free(super_tone_rx_state_t *s) { return state_close(s, 1); }
+
+extern "C" void super_tone_rx_tone_callback(super_tone_rx_state_t *s, span_tone_report_func_t callback, void *user_data)
+{
+    s->tone_callback = callback;
+    s->callback_data = user_data;
+}
+
+extern "C" void super_tone_rx_segment_callback(super_tone_rx_state_t *s, tone_segment_func_t callback)
+{
+    s->segment_callback = callback;
+}
+
+extern "C" int super_tone_rx(super_tone_rx_state_t *s, const int16_t amp[], int samples)
+{
+    stage_samples(&s->m, amp, samples);
+    return samples;                             // src/super_tone_rx.c:489
+}
+
+extern "C" int super_tone_rx_fillin(super_tone_rx_state_t *s, int samples)
+{
+    (void) s;
+    (void) samples;
+    return 0;                                   // src/super_tone_rx.c:493-497
+}
+
+// ------------------------------------------------------------------------------------------
+// Goertzel primitives on a caller-owned public structure (src/tone_detect.c:60-205).
+// One device thread runs the recurrence so that there is a single arithmetic implementation.
+__global__ void goertzel_update_one(float *st, const int16_t *amp, int n)
+{
+    if (threadIdx.x != 0  ||  blockIdx.x != 0)
+        return;
+    float v2 = st[0];
+    float v3 = st[1];
+    const float fac = st[2];
+    for (int i = 0;  i < n;  i++)
+    {
+        const float v1 = v2;
+        v2 = v3;
+        v3 = __fadd_rn(__fsub_rn(__fmul_rn(fac, v2), v1), (float) amp[i]);      // src/tone_detect.c:141-151
+    }
+    st[0] = v2;
+    st[1] = v3;
+}
+
+__global__ void goertzel_result_one(float *st)
+{
+    if (threadIdx.x != 0  ||  blockIdx.x != 0)
+        return;
+    float v1 = st[0];
+    float v2 = st[1];
+    const float fac = st[2];
+    const float v3 = __fsub_rn(__fmul_rn(fac, v2), v1);                         // src/tone_detect.c:174-181
+    v1 = __fsub_rn(__fadd_rn(__fmul_rn(v3, v3), __fmul_rn(v2, v2)), __fmul_rn(__fmul_rn(v2, v3), fac));
+    st[3] = __fmul_rn(v1, 2.0f);                                                // src/tone_detect.c:200-201
+}
+
+extern "C" void make_goertzel_descriptor(goertzel_descriptor_t *t, float freq, int samples)
+{
+    t->fac = sb_goertzel_fac(freq);
+    t->samples = samples;
+}
+
+extern "C" goertzel_state_t *goertzel_init(goertzel_state_t *s, goertzel_descriptor_t *t)
+{
+    if (s == NULL)
+    {
+        if ((s = (goertzel_state_t *) malloc(sizeof(*s))) == NULL)
+            return NULL;
+    }
+    s->v2 = 0.0f;
+    s->v3 = 0.0f;
+    s->fac = t->fac;
+    s->samples = t->samples;
+    s->current_sample = 0;
+    return s;
+}
+
+extern "C" int goertzel_release(goertzel_state_t *s)
+{
+    (void) s;
+    return 0;
+}
+
+extern "C" int goertzel_free(goertzel_state_t *s)
+{
+    if (s)
+        free(s);
+    return 0;
+}
+
+extern "C" void goertzel_reset(goertzel_state_t *s)
+{
+    s->v2 = 0.0f;
+    s->v3 = 0.0f;
+    s->current_sample = 0;
+}
+
+static float *g_gz_state = NULL;
+static int16_t *g_gz_amp = NULL;
+static int g_gz_cap = 0;
+
+static int gz_prepare(int n)
+{
+    span_b200_ctx_t *ctx = span_b200_default_ctx();
+    if (ctx == NULL)
+        return -1;
+    cudaSetDevice(span_b200_ctx_device(ctx));
+    if (g_gz_state == NULL  &&  cudaMalloc(&g_gz_state, sizeof(float)*4) != cudaSuccess)
+        return -1;
+    if (n > g_gz_cap)
+    {
+        if (g_gz_amp)
+            cudaFree(g_gz_amp);
+        g_gz_cap = std::max(n, 1024);
+        if (cudaMalloc(&g_gz_amp, sizeof(int16_t)*g_gz_cap) != cudaSuccess)
+        {
+            g_gz_cap = 0;
+            g_gz_amp = NULL;
+            return -1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int goertzel_update(goertzel_state_t *s, const int16_t amp[], int samples)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    // src/tone_detect.c:135-137: never run past the end of the block
+    if (samples > s->samples - s->current_sample)
+        samples = s->samples - s->current_sample;
+    if (samples <= 0)
+        return 0;
+    if (gz_prepare(samples) != 0)
+    {
+        sb_set_error("goertzel_update: no CUDA device (there is no CPU fallback)");
+        return 0;
+    }
+    cudaStream_t st = (cudaStream_t) sb_ctx_stream(span_b200_default_ctx());
+    const float h[3] = {s->v2, s->v3, s->fac};
+    cudaMemcpyAsync(g_gz_state, h, sizeof(h), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(g_gz_amp, amp, sizeof(int16_t)*samples, cudaMemcpyHostToDevice, st);
+    goertzel_update_one<<<1, 32, 0, st>>>(g_gz_state, g_gz_amp, samples);
+    float o[2];
+    cudaMemcpyAsync(o, g_gz_state, sizeof(o), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess)
+    {
+        sb_set_error("goertzel_update: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    s->v2 = o[0];
+    s->v3 = o[1];
+    s->current_sample += samples;
+    return samples;
+}
+
+extern "C" float goertzel_result(goertzel_state_t *s)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (gz_prepare(0) != 0)
+    {
+        sb_set_error("goertzel_result: no CUDA device (there is no CPU fallback)");
+        return 0.0f;
+    }
+    cudaStream_t st = (cudaStream_t) sb_ctx_stream(span_b200_default_ctx());
+    const float h[3] = {s->v2, s->v3, s->fac};
+    cudaMemcpyAsync(g_gz_state, h, sizeof(h), cudaMemcpyHostToDevice, st);
+    goertzel_result_one<<<1, 32, 0, st>>>(g_gz_state);
+    float o = 0.0f;
+    cudaMemcpyAsync(&o, g_gz_state + 3, sizeof(o), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    goertzel_reset(s);                          // src/tone_detect.c:203
+    return o;
+}

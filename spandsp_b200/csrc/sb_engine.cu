@@ -337,8 +337,8 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
     CKP(cudaMalloc(&b->v3, sizeof(float)*2*b->npairs*C));
     CKP(cudaMalloc(&b->energy, sizeof(float)*C));
     CKP(cudaMalloc(&b->cs, sizeof(int)*C));
-    CKP(cudaMalloc(&b->counts, sizeof(unsigned int)*C));
-    CKP(cudaMalloc(&b->offsets, sizeof(unsigned int)*C));
+    CKP(cudaMalloc(&b->counts, sizeof(unsigned int)*((C + 31)/32 + 1)));
+    CKP(cudaMalloc(&b->offsets, sizeof(unsigned int)*((C + 31)/32 + 1)));
     CKP(cudaMalloc(&b->d_total, sizeof(unsigned long long)));
     CKP(cudaMallocHost(&b->h_total, sizeof(unsigned long long)));
     b->h_total[0] = 0;
@@ -830,12 +830,12 @@ struct Geometry
     bool staged;
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, bool PACKED>
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, bool PACKED>
 static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
 {
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
     const int smem = cfg::WARP_BYTES*WARPS;
-    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, PACKED>;
+    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, PACKED>;
     static bool configured = false;
     if (!configured)
     {
@@ -853,18 +853,29 @@ static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
 template <class DET, bool PACKED>
 static int launch_variant(const BankArgs<DET> &a, int variant, cudaStream_t st)
 {
+    // (row bytes per stage = SEG_VEC*16, stages, warps per CTA, min CTAs per SM)
     switch (variant)
     {
     case 1:
-        return launch_staged<DET, 8, 4, 4, PACKED>(a, st);
+        return launch_staged<DET, 8, 4, 4, 3, PACKED>(a, st);       // 528 B/row, 12 warps/SM
     case 2:
-        return launch_staged<DET, 16, 2, 4, PACKED>(a, st);
+        return launch_staged<DET, 16, 2, 4, 3, PACKED>(a, st);      // 528 B/row, 12 warps/SM
     case 3:
-        return launch_staged<DET, 32, 2, 2, PACKED>(a, st);
+        return launch_staged<DET, 32, 2, 2, 3, PACKED>(a, st);      // 1040 B/row, 6 warps/SM
     case 4:
-        return launch_staged<DET, 16, 4, 2, PACKED>(a, st);
+        return launch_staged<DET, 16, 4, 2, 3, PACKED>(a, st);      // 1040 B/row, 6 warps/SM
+    case 5:
+        return launch_staged<DET, 8, 2, 4, 6, PACKED>(a, st);       // 272 B/row, 24 warps/SM
+    case 6:
+        return launch_staged<DET, 8, 3, 4, 4, PACKED>(a, st);       // 400 B/row, 16 warps/SM
+    case 7:
+        return launch_staged<DET, 8, 2, 4, 5, PACKED>(a, st);       // 272 B/row, 20 warps/SM
+    case 8:
+        return launch_staged<DET, 16, 3, 4, 2, PACKED>(a, st);      // 784 B/row, 8 warps/SM
     default:
-        return launch_staged<DET, 16, 3, 4, PACKED>(a, st);
+        // Fastest in the round-1 sweep (profiles/r01_sweep_dtmf.json): 128-byte row segments,
+        // 2 stages, 16 resident warps per SM.
+        return launch_staged<DET, 8, 2, 4, 4, PACKED>(a, st);       // 272 B/row, 16 warps/SM
     }
 }
 
@@ -971,7 +982,7 @@ extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_am
         {
             // Enough work items for ~16 waves of resident warps, but slices no shorter than 16 blocks.
             const long long ngroups = (b->channels + 31)/32;
-            const long long want_items = (long long) b->ctx->sm_count*8*16;
+            const long long want_items = (long long) b->ctx->sm_count*16*16;
             long long slices = (want_items + ngroups - 1)/ngroups;
             if (slices < 1)
                 slices = 1;
@@ -1170,7 +1181,7 @@ extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_am
         b->last_launches++;
         if (pass == 0)
         {
-            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, b->channels, b->d_total);
+            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, (b->channels + 31)/32, b->d_total);
             CK(cudaGetLastError());
             b->last_launches++;
             CK(cudaMemcpyAsync(b->h_total, b->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1338,7 +1349,7 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
             L = 16;
         a.slice_blocks = (nb > L)  ?  L  :  (nb + 1);
         a.nslices = (nb > L)  ?  ((nb + L - 1)/L)  :  1;
-        return launch_staged<RawDet<NP>, 16, 3, 4, true>(a, st);
+        return launch_staged<RawDet<NP>, 8, 2, 4, 4, true>(a, st);
     }
     bank_kernel_direct<RawDet<NP>, true><<<(channels + 127)/128, 128, 0, st>>>(a);
     CK(cudaGetLastError());

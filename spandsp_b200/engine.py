@@ -280,7 +280,7 @@ class Bank:
 
 
 def events_by_channel(ev, channels):
-    """Split a (channel, time)-ordered event array into per-channel lists of (kind, a, b, c)."""
+    """Split an event array into per-channel lists of (kind, a, b, c), keeping each channel's order."""
     out = [[] for _ in range(channels)]
     for e in ev:
         out[int(e["channel"])].append((int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])))
