@@ -187,7 +187,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    channels = max(threads * 8, 256)
+    channels = max(threads * 16, 256)
     channels_total = 65536 if args.gpus == 1 else 131072 * args.gpus
     T = T_SAMPLES
     passes = 1
@@ -395,7 +395,7 @@ def main():
     cpu = None
     if not args.no_cpu:
         threads = host_threads()
-        ch = max(threads * 8, 256)
+        ch = max(threads * 16, 256)
         v0, kind, s0 = cpu_reference(ch, T, 1, threads)
         passes = max(1, int(20.0 / max(s0 * threads, 1e-3)))         # ~20 core-seconds of CPU work
         v, kind, s = cpu_reference(ch, T, passes, threads)
