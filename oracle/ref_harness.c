@@ -55,7 +55,13 @@
 #include "spandsp/private/tone_generate.h"
 #include "spandsp/private/super_tone_tx.h"
 
+#include "spandsp/math_fixed.h"
 #include "ref_harness.h"
+
+/* The generated tables the V.29 receiver is built on (static const in the generated headers). */
+#include "v29rx_rrc.h"
+#include "v29rx_godard.h"
+#include "math_fixed_tables.h"
 
 #define EXPORT __attribute__((visibility("default")))
 
@@ -557,4 +563,252 @@ EXPORT int ref_goertzel_blocks(float freq, int samples, const int16_t *amp, int 
             out[nb++] = goertzel_result(&s);
     }
     return nb;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* V.29 (v29_tx -> awgn -> v29_rx)                                                        */
+
+typedef struct
+{
+    uint32_t lfsr;
+} prbs_t;
+
+static int prbs_get_bit(void *user)
+{
+    prbs_t *p = (prbs_t *) user;
+    /* x^23 + x^18 + 1 */
+    const int bit = ((p->lfsr >> 22) ^ (p->lfsr >> 17)) & 1;
+    p->lfsr = ((p->lfsr << 1) | bit) & 0x7FFFFF;
+    return bit;
+}
+
+/* `lead` samples of silence, then a V.29 transmission of PRBS data for the rest of the buffer. */
+EXPORT int ref_v29_generate(int16_t *amp, int n, int bit_rate, int tep, float power_dbm0, uint32_t lfsr_seed,
+                            int lead, int noise_seed, float noise_dbm0)
+{
+    v29_tx_state_t *tx;
+    prbs_t prbs;
+    int len;
+
+    prbs.lfsr = (lfsr_seed & 0x7FFFFF)  ?  (lfsr_seed & 0x7FFFFF)  :  1;
+    memset(amp, 0, sizeof(int16_t)*n);
+    if (lead > n)
+        lead = n;
+    tx = v29_tx_init(NULL, bit_rate, tep != 0, prbs_get_bit, &prbs);
+    v29_tx_power(tx, power_dbm0);
+    len = v29_tx(tx, amp + lead, n - lead);
+    v29_tx_free(tx);
+    add_awgn(amp, n, noise_seed, noise_dbm0);
+    return len;
+}
+
+typedef struct
+{
+    int8_t *bits;
+    int cap;
+    int n;
+    ref_v29_sym_t *syms;
+    int sym_cap;
+    int nsyms;
+} v29_rec_t;
+
+static void v29_put_bit(void *user, int bit)
+{
+    v29_rec_t *r = (v29_rec_t *) user;
+    if (r->n < r->cap)
+        r->bits[r->n] = (int8_t) bit;
+    r->n++;
+}
+
+static void v29_qam(void *user, const complexf_t *z, const complexf_t *target, int symbol)
+{
+    v29_rec_t *r = (v29_rec_t *) user;
+    if (r->nsyms < r->sym_cap)
+    {
+        r->syms[r->nsyms].re = z->re;
+        r->syms[r->nsyms].im = z->im;
+        r->syms[r->nsyms].tre = target->re;
+        r->syms[r->nsyms].tim = target->im;
+        r->syms[r->nsyms].state = symbol;
+    }
+    r->nsyms++;
+}
+
+/* One channel.  bits[] receives what put_bit delivered, in order: 0/1 data bits and the negative
+   SIG_STATUS_* codes (no separate status handler is installed, src/v29rx.c:171-178).
+   final[]: {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling bits,
+             total_baud_timing_correction, constellation_state, carrier_phase} */
+EXPORT int ref_v29_run(const int16_t *amp, int n, int chunk, int bit_rate, float cutoff, int want_qam,
+                       int8_t *bits, int bits_cap, int32_t *nbits,
+                       ref_v29_sym_t *syms, int sym_cap, int32_t *nsyms,
+                       float *eq_coeff, int32_t *final)
+{
+    v29_rx_state_t *rx;
+    v29_rec_t rec;
+    int pos;
+    int len;
+    int i;
+
+    rec.bits = bits;
+    rec.cap = bits_cap;
+    rec.n = 0;
+    rec.syms = syms;
+    rec.sym_cap = sym_cap;
+    rec.nsyms = 0;
+    rx = v29_rx_init(NULL, bit_rate, v29_put_bit, &rec);
+    if (rx == NULL)
+        return -1;
+    if (cutoff > -99.0f)
+        v29_rx_set_signal_cutoff(rx, cutoff);
+    if (want_qam)
+        v29_rx_set_qam_report_handler(rx, v29_qam, &rec);
+    for (pos = 0;  pos < n;  pos += len)
+    {
+        len = (n - pos < chunk)  ?  (n - pos)  :  chunk;
+        v29_rx(rx, amp + pos, len);
+    }
+    *nbits = rec.n;
+    *nsyms = rec.nsyms;
+    if (eq_coeff)
+    {
+        for (i = 0;  i < V29_EQUALIZER_LEN;  i++)
+        {
+            eq_coeff[2*i] = rx->eq_coeff[i].re;
+            eq_coeff[2*i + 1] = rx->eq_coeff[i].im;
+        }
+    }
+    if (final)
+    {
+        final[0] = rx->training_stage;
+        final[1] = rx->carrier_phase_rate;
+        final[2] = rx->eq_put_step;
+        final[3] = rx->signal_present;
+        memcpy(&final[4], &rx->agc_scaling, 4);
+        final[5] = rx->godard.total_baud_timing_correction;
+        final[6] = rx->constellation_state;
+        final[7] = (int32_t) rx->carrier_phase;
+    }
+    v29_rx_free(rx);
+    return 0;
+}
+
+typedef struct
+{
+    const int16_t *amp;
+    int64_t stride;
+    int c0;
+    int c1;
+    int n;
+    int chunk;
+    int bit_rate;
+    float cutoff;
+    int8_t *bits;
+    int64_t bits_cap;
+    int32_t *nbits;
+} v29_job_t;
+
+static void *v29_worker(void *arg)
+{
+    v29_job_t *j = (v29_job_t *) arg;
+    int32_t nsyms;
+    int32_t nb;
+    int c;
+    int8_t *scratch = NULL;
+
+    if (j->bits == NULL)
+        scratch = (int8_t *) malloc(16);
+    for (c = j->c0;  c < j->c1;  c++)
+    {
+        ref_v29_run(j->amp + (int64_t) c*j->stride, j->n, j->chunk, j->bit_rate, j->cutoff, 0,
+                    (j->bits)  ?  (j->bits + (int64_t) c*j->bits_cap)  :  scratch, (j->bits)  ?  (int) j->bits_cap  :  0, &nb,
+                    NULL, 0, &nsyms, NULL, NULL);
+        if (j->nbits)
+            j->nbits[c] = nb;
+    }
+    free(scratch);
+    return NULL;
+}
+
+/* Many channels on nthreads host threads; returns elapsed seconds (CPU baseline for cfg4). */
+EXPORT double ref_v29_run_batch(const int16_t *amp, int64_t stride, int channels, int n, int chunk, int bit_rate, float cutoff,
+                                int nthreads, int8_t *bits, int64_t bits_cap, int32_t *nbits)
+{
+    pthread_t *th;
+    v29_job_t *jobs;
+    struct timespec t0;
+    struct timespec t1;
+    int i;
+
+    if (nthreads < 1)
+        nthreads = 1;
+    if (nthreads > channels)
+        nthreads = channels;
+    th = (pthread_t *) malloc(sizeof(pthread_t)*nthreads);
+    jobs = (v29_job_t *) malloc(sizeof(v29_job_t)*nthreads);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (i = 0;  i < nthreads;  i++)
+    {
+        jobs[i].amp = amp;
+        jobs[i].stride = stride;
+        jobs[i].c0 = (int) ((int64_t) channels*i/nthreads);
+        jobs[i].c1 = (int) ((int64_t) channels*(i + 1)/nthreads);
+        jobs[i].n = n;
+        jobs[i].chunk = chunk;
+        jobs[i].bit_rate = bit_rate;
+        jobs[i].cutoff = cutoff;
+        jobs[i].bits = bits;
+        jobs[i].bits_cap = bits_cap;
+        jobs[i].nbits = nbits;
+        if (nthreads == 1)
+            v29_worker(&jobs[i]);
+        else
+            pthread_create(&th[i], NULL, v29_worker, &jobs[i]);
+    }
+    if (nthreads > 1)
+    {
+        for (i = 0;  i < nthreads;  i++)
+            pthread_join(th[i], NULL);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(th);
+    free(jobs);
+    return (double) (t1.tv_sec - t0.tv_sec) + 1.0e-9*(double) (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* The constant tables the receiver uses, as the reference build sees them. */
+EXPORT void ref_v29_tables(float *rrc_re, float *rrc_im, float *sine, uint16_t *sqrt_tab, float *godard, int32_t *ints)
+{
+    int i;
+    int j;
+
+    for (i = 0;  i < RX_PULSESHAPER_COEFF_SETS;  i++)
+    {
+        for (j = 0;  j < 27;  j++)
+        {
+            rrc_re[i*27 + j] = rx_pulseshaper_re[i][j];
+            rrc_im[i*27 + j] = rx_pulseshaper_im[i][j];
+        }
+    }
+    for (i = 0;  i < 2048;  i++)
+        sine[i] = dds_lookupf((uint32_t) i << 21);
+    for (i = 0;  i < 193;  i++)
+        sqrt_tab[i] = fixed_sqrt_table[i];
+    godard[0] = godard_desc.low_band_edge_coeff[0];
+    godard[1] = godard_desc.low_band_edge_coeff[1];
+    godard[2] = godard_desc.low_band_edge_coeff[2];
+    godard[3] = godard_desc.high_band_edge_coeff[0];
+    godard[4] = godard_desc.high_band_edge_coeff[1];
+    godard[5] = godard_desc.high_band_edge_coeff[2];
+    godard[6] = godard_desc.mixed_band_edges_coeff_3;
+    godard[7] = godard_desc.coarse_trigger;
+    godard[8] = godard_desc.fine_trigger;
+    ints[0] = godard_desc.coarse_step;
+    ints[1] = godard_desc.fine_step;
+    ints[2] = DDS_PHASE_RATE(1700.0f);
+    ints[3] = DDS_PHASE_RATE(1700.0f - 20.0f);
+    ints[4] = DDS_PHASE_RATE(1700.0f + 20.0f);
+    ints[5] = DDS_PHASE(45.0f);
+    ints[6] = DDS_PHASE(-45.0f);
+    ints[7] = power_meter_level_dbm0(-28.5f + 2.5f);
+    ints[8] = power_meter_level_dbm0(-28.5f - 2.5f);
 }

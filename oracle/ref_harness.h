@@ -7,7 +7,7 @@
 
 #include <stdint.h>
 
-#define REF_HARNESS_ABI         3
+#define REF_HARNESS_ABI         4
 
 enum
 {
@@ -70,5 +70,15 @@ typedef struct
     int32_t ndigits;            /* POLL mode: digits drained at the end (super-tone: monitored bins) */
     char digits[256];
 } ref_final_t;
+
+/* One equalized symbol as delivered to qam_report_handler_t (src/spandsp/v29rx.h:130) */
+typedef struct
+{
+    float re;
+    float im;
+    float tre;
+    float tim;
+    int32_t state;
+} ref_v29_sym_t;
 
 #endif

@@ -1,0 +1,112 @@
+"""GPU parity of the V.29 receiver banks against the reference (golden vectors from the strict
+build; the compiled reference itself where it is present).
+
+Bar (BASELINE.json north_star): bit stream and status reports identical; equalizer soft symbols
+within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "v29_golden.npz")
+RTOL = 1e-5
+
+
+def close(a, b):
+    # relative to the constellation scale (|z| is O(1..5)); absolute floor for values near zero
+    return np.allclose(a, b, rtol=RTOL, atol=RTOL)
+
+
+def check_channel(bank, ch, exp_bits, exp_syms, exp_eq, exp_final):
+    bits = bank.bits(ch)
+    assert len(bits) == len(exp_bits), "bit count %d != %d" % (len(bits), len(exp_bits))
+    assert (bits == exp_bits).all(), "first difference at %d" % int(np.argmax(bits != exp_bits))
+    syms = bank.symbols(ch)
+    assert len(syms) == len(exp_syms)
+    assert (syms["state"] == exp_syms["state"]).all()
+    assert (syms["tre"] == exp_syms["tre"]).all() and (syms["tim"] == exp_syms["tim"]).all()
+    assert close(syms["re"], exp_syms["re"]) and close(syms["im"], exp_syms["im"])
+    eq, info = bank.channel_state(ch)
+    assert close(eq, exp_eq)
+    for i in (0, 2, 3, 5, 6):       # stage, eq_put_step, signal_present, total timing correction, constellation state
+        assert info[i] == exp_final[i], "final[%d]: %d != %d" % (i, info[i], exp_final[i])
+    assert abs(int(info[1]) - int(exp_final[1])) <= 64      # carrier_phase_rate (integrates float->int steps)
+
+
+@pytest.mark.parametrize("chunk", [0, 160, 333])
+def test_v29_golden(gpu_ctx, engine_lib, chunk):
+    import torch
+    g = np.load(GOLD)
+    for k in range(5):
+        rate, n, lead, cutoff = g["cfg%d" % k]
+        amp = g["amp%d" % k]
+        bank = engine_lib.V29Bank(gpu_ctx, 1, int(rate), want_symbols=True)
+        if cutoff > -99:
+            bank.set_signal_cutoff(float(cutoff))
+        if chunk == 0:
+            bank.rx_host(amp[None, :])
+            bits = [bank.bits(0)]
+            syms = [bank.symbols(0)]
+        else:
+            bits, syms = [], []
+            d = torch.from_numpy(amp).cuda()
+            for pos in range(0, len(amp), chunk):
+                ln = min(chunk, len(amp) - pos)
+                bank.rx_device(d.data_ptr() + 2 * pos, len(amp), ln)
+                bits.append(bank.bits(0).copy())
+                syms.append(bank.symbols(0).copy())
+        b = np.concatenate(bits)
+        s = np.concatenate(syms)
+        eb, es = g["bits%d" % k], g["syms%d" % k]
+        assert len(b) == len(eb) and (b == eb).all(), "case %d" % k
+        assert len(s) == len(es) and (s["state"] == es["state"]).all()
+        assert close(s["re"], es["re"]) and close(s["im"], es["im"])
+        eq, info = bank.channel_state(0)
+        assert close(eq, g["eq%d" % k])
+        assert info[0] == g["final%d" % k][0]
+        bank.close()
+
+
+def test_v29_many_channels_vs_reference(gpu_ctx, engine_lib, oracles):
+    """70 channels with different data, levels, noise and start offsets, all three bit rates."""
+    if "strict" not in oracles:
+        pytest.skip("compiled reference not available here")
+    S = oracles["strict"]
+    rng = np.random.default_rng(5)
+    for rate in (9600, 7200, 4800):
+        n = 16000
+        chans = []
+        for c in range(70):
+            chans.append(po.v29_generate(S, n, rate, bool(c & 1), float(rng.uniform(-25, -8)), c + 1, int(rng.integers(0, 900)),
+                                         1000 + c, float(rng.uniform(-60, -48))))
+        amp = np.stack(chans)
+        bank = engine_lib.V29Bank(gpu_ctx, 70, rate, want_symbols=True)
+        bank.rx_host(amp)
+        for c in range(70):
+            r = po.v29_run(S, amp[c], rate, n, -100.0, True)
+            check_channel(bank, c, r["bits"], r["syms"], r["eq_coeff"], r["final"])
+        bank.close()
+
+
+def test_v29_noise_only_and_restart(gpu_ctx, engine_lib, oracles):
+    """Noise above the carrier-detect threshold: training fails and the modem parks (src/v29rx.c:599-606)."""
+    if "strict" not in oracles:
+        pytest.skip("compiled reference not available here")
+    S = oracles["strict"]
+    amp = np.zeros(12000, dtype=np.int16)
+    S.awgn_add(amp, 42, -20.0)
+    r = po.v29_run(S, amp, 9600, 12000, -100.0, True)
+    bank = engine_lib.V29Bank(gpu_ctx, 1, 9600, want_symbols=True)
+    bank.rx_host(amp[None, :])
+    check_channel(bank, 0, r["bits"], r["syms"], r["eq_coeff"], r["final"])
+    assert r["final"][0] == 7       # parked
+    bank.restart(9600)
+    sig = po.v29_generate(S, 12000, 9600, False, -13.0, 9, 100, 77, -55.0)
+    r = po.v29_run(S, sig, 9600, 12000, -100.0, True)
+    bank.rx_host(sig[None, :])
+    check_channel(bank, 0, r["bits"], r["syms"], r["eq_coeff"], r["final"])
+    bank.close()
