@@ -296,6 +296,66 @@ __device__ __forceinline__ int f2i(float f)
     return __float2int_rz(f);
 }
 
+// cosf()/sinf() as the host C library computes them.  The reference calls libm's cosf/sinf once per
+// training (src/v29rx.c:618-623); the values feed the adaptive loops, whose discrete timing decisions
+// amplify a 1-ulp difference into visible (1e-3) excursions of the soft symbols, so they have to be
+// reproduced exactly.  Third-party arithmetic: GNU libc 2.39 (the image's libm.so.6), sysdeps/ieee754/
+// flt-32/s_cosf.c, s_sinf.c, s_sincosf.h - the "sincosf" of ARM's optimized routines: reduce by pi/2 in
+// double with a 2^24-prescaled 2/pi, then an odd/even minimax polynomial in double, rounded once to
+// float.  Constants are the published ones (they can be read back from __sincosf_table in libm.so.6).
+// Arguments here are phases in [0, 2*pi), so only the two fast paths (|x| < pi/4, |x| < 120) are needed.
+// tools/check_host_sincosf.py checks this restatement against the live libm on 1e6 arguments.
+__device__ __forceinline__ double sincosf_poly(double x, double x2, bool cos_table_negated, int n)
+{
+    const double c0 = (cos_table_negated)  ?  -0x1p0  :  0x1p0;
+    const double c1 = (cos_table_negated)  ?  0x1.ffffffd0c621cp-2  :  -0x1.ffffffd0c621cp-2;
+    const double c2 = (cos_table_negated)  ?  -0x1.55553e1068f19p-5  :  0x1.55553e1068f19p-5;
+    const double c3 = (cos_table_negated)  ?  0x1.6c087e89a359dp-10  :  -0x1.6c087e89a359dp-10;
+    const double c4 = (cos_table_negated)  ?  -0x1.99343027bf8c3p-16  :  0x1.99343027bf8c3p-16;
+    const double s1 = -0x1.555545995a603p-3;
+    const double s2 = 0x1.1107605230bc4p-7;
+    const double s3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0)
+    {
+        const double x3 = __dmul_rn(x, x2);
+        const double t1 = __dadd_rn(s2, __dmul_rn(x2, s3));
+        const double x7 = __dmul_rn(x3, x2);
+        const double sv = __dadd_rn(x, __dmul_rn(x3, s1));
+        return __dadd_rn(sv, __dmul_rn(x7, t1));
+    }
+    const double x4 = __dmul_rn(x2, x2);
+    const double t2 = __dadd_rn(c3, __dmul_rn(x2, c4));
+    const double t1 = __dadd_rn(c0, __dmul_rn(x2, c1));
+    const double x6 = __dmul_rn(x4, x2);
+    const double cv = __dadd_rn(t1, __dmul_rn(x4, c2));
+    return __dadd_rn(cv, __dmul_rn(x6, t2));
+}
+
+__device__ __forceinline__ unsigned int abstop12(float f)
+{
+    return (__float_as_uint(f) >> 20) & 0x7FFu;
+}
+
+// is_cos: 1 for cosf, 0 for sinf
+__device__ float host_sincosf(float y, int is_cos)
+{
+    double x = (double) y;
+    if (abstop12(y) < abstop12(0x1.921FB6p-1f))
+    {
+        if (abstop12(y) < abstop12(0x1p-12f))
+            return (is_cos)  ?  1.0f  :  y;
+        return (float) sincosf_poly(x, __dmul_rn(x, x), false, is_cos);
+    }
+    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __dsub_rn(x, __dmul_rn((double) n, 0x1.921FB54442D18p0));
+    const double sgn = ((n & 3) == 1  ||  (n & 3) == 2)  ?  -1.0  :  1.0;
+    return (float) sincosf_poly(__dmul_rn(x, sgn), __dmul_rn(x, x), (n & 2) != 0, (is_cos)  ?  (n ^ 1)  :  n);
+}
+
+__device__ __forceinline__ float host_cosf(float y) { return host_sincosf(y, 1); }
+__device__ __forceinline__ float host_sinf(float y) { return host_sincosf(y, 0); }
+
 struct Consts
 {
     const float *rrc_re;                // [48][27]
@@ -750,8 +810,8 @@ struct Rx
                     }
                     // dds_phase_to_radians (src/dds_float.c:2103-2106) of the angle as uint32
                     const float p = fdiv(fmul(fmul((float) (unsigned int) angle, 2.0f), 3.1415926f), fmul(65536.0f, 65536.0f));
-                    const float cr = cosf(p);
-                    const float ci = -sinf(p);
+                    const float cr = host_cosf(p);
+                    const float ci = -host_sinf(p);
                     for (int q = 0;  q < V29_EQ_LEN;  q++)
                     {
                         const float xr = eq_buf[(2*q)*32];

@@ -18,7 +18,13 @@ RTOL = 1e-5
 
 def close(a, b):
     # relative to the constellation scale (|z| is O(1..5)); absolute floor for values near zero
-    return np.allclose(a, b, rtol=RTOL, atol=RTOL)
+    ok = np.allclose(a, b, rtol=RTOL, atol=RTOL)
+    if not ok:
+        d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))
+        i = int(np.argmax(d))
+        print("max abs diff %.3e at %d (%.7g vs %.7g), count over tol %d of %d"
+              % (d[i], i, a[i], b[i], int((d > RTOL + RTOL * np.abs(b)).sum()), len(d)))
+    return ok
 
 
 def check_channel(bank, ch, exp_bits, exp_syms, exp_eq, exp_final):
