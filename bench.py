@@ -99,55 +99,66 @@ def synth_dtmf_numpy(channels, T, seed):
 # clocks
 
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed region (NVML, 2 ms
+    period in a thread; the timed region is only tens of milliseconds long)."""
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except Exception:
+                return self.idx
+        return self.idx
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, pw, rs))
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: %s" % (self.err or "nvml")]}
+        sm = [x[0] for x in self.samples]
+        reasons = set()
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        for x in self.samples:
+            for bit, name in bits.items():
+                if x[3] & bit:
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power)) if power else None}
+        pw = [x[2] for x in self.samples if x[2] is not None]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(pw)) if pw else None}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -279,27 +290,41 @@ def main():
     ev_cap = C * (T // 102 // 2 + 1)
     d_events = None
     if world > 1:
-        d_events = torch.empty((ev_cap, 6), dtype=torch.int32, device=dev)
+        # two buffers: the NCCL gather of step k-1 runs while the kernels of step k execute
+        d_events = [torch.empty((ev_cap, 6), dtype=torch.int32, device=dev) for _ in range(2)]
+    pending = {"n": None, "buf": None, "total": 0}
 
-    def gather_events(n_local):
+    def gather_events(buf, n_local):
         """NCCL: event counts all-gathered, records gathered to rank 0 (padded to the max count)."""
         cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
         allc = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(allc, cnt)
-        mx = int(max(int(c.item()) for c in allc))
-        send = d_events[:mx]
+        counts = [int(c.item()) for c in allc]
+        mx = max(max(counts), 1)
+        send = buf[:mx]
         if rank == 0:
             bufs = [torch.empty_like(send) for _ in range(world)]
             dist.gather(send, bufs, dst=0)
         else:
             dist.gather(send, None, dst=0)
-        return sum(int(c.item()) for c in allc)
+        return sum(counts)
+
+    def flush_gather():
+        if pending["n"] is not None:
+            pending["total"] = gather_events(pending["buf"], pending["n"])
+            pending["n"] = None
+
+    step_no = [0]
 
     def step_device():
         bank.rx_device(d_amp.data_ptr(), T, T, stream)
         if world > 1:
-            n = bank.events_to_device(d_events.data_ptr(), ev_cap, stream)
-            return gather_events(n)
+            flush_gather()                                  # step k-1's records travel while step k computes
+            buf = d_events[step_no[0] & 1]
+            step_no[0] += 1
+            pending["n"] = bank.events_to_device(buf.data_ptr(), ev_cap, stream)
+            pending["buf"] = buf
+            return pending["total"]
         n, ov = bank.event_count()
         return n
 
@@ -311,6 +336,8 @@ def main():
     # ---- device-resident arm ------------------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
+    if world > 1:
+        flush_gather()
     bank.kernel_ms()
     barrier()
     sampler = ClockSampler(local)
@@ -322,6 +349,9 @@ def main():
     total_events = 0
     for _ in range(args.steps):
         total_events = step_device()
+    if world > 1:
+        flush_gather()
+        total_events = pending["total"]
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

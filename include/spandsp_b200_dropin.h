@@ -131,6 +131,34 @@ void goertzel_reset(goertzel_state_t *s);
 int goertzel_update(goertzel_state_t *s, const int16_t amp[], int samples);
 float goertzel_result(goertzel_state_t *s);
 
+/* ---- V.29 receiver: src/spandsp/v29rx.h:130-244, src/v29rx.c:145-195,867-1153 -------------------- */
+typedef struct
+{
+    float re;
+    float im;
+} complexf_t;                                                           /* src/spandsp/complex.h:42-48 */
+typedef void (*span_put_bit_func_t)(void *user_data, int bit);          /* src/spandsp/async.h:123 */
+typedef void (*span_modem_status_func_t)(void *user_data, int status);  /* src/spandsp/async.h:131 */
+typedef void (*qam_report_handler_t)(void *user_data, const complexf_t *constel, const complexf_t *target, int symbol);
+typedef struct v29_rx_state_s v29_rx_state_t;
+
+/* Synchronous, one receiver per state (a bank of one).  Banks of many receivers: spandsp_b200_v29.h. */
+v29_rx_state_t *v29_rx_init(v29_rx_state_t *s, int bit_rate, span_put_bit_func_t put_bit, void *user_data);
+int v29_rx_restart(v29_rx_state_t *s, int bit_rate, bool old_train);
+int v29_rx_release(v29_rx_state_t *s);
+int v29_rx_free(v29_rx_state_t *s);
+logging_state_t *v29_rx_get_logging_state(v29_rx_state_t *s);
+void v29_rx_set_put_bit(v29_rx_state_t *s, span_put_bit_func_t put_bit, void *user_data);
+void v29_rx_set_modem_status_handler(v29_rx_state_t *s, span_modem_status_func_t handler, void *user_data);
+int v29_rx(v29_rx_state_t *s, const int16_t amp[], int len);
+int v29_rx_fillin(v29_rx_state_t *s, int len);
+int v29_rx_equalizer_state(v29_rx_state_t *s, complexf_t **coeffs);
+float v29_rx_carrier_frequency(v29_rx_state_t *s);
+float v29_rx_symbol_timing_correction(v29_rx_state_t *s);
+float v29_rx_signal_power(v29_rx_state_t *s);
+void v29_rx_set_signal_cutoff(v29_rx_state_t *s, float cutoff);
+void v29_rx_set_qam_report_handler(v29_rx_state_t *s, qam_report_handler_t handler, void *user_data);
+
 #if defined(__cplusplus)
 }
 #endif

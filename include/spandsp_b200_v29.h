@@ -31,6 +31,7 @@ typedef struct
     float target_re;
     float target_im;
     int32_t state;
+    int32_t bit_pos;        /* number of put_bit calls of this rx call that preceded the report */
 } span_b200_v29_symbol_t;
 
 /* v29_rx_init(NULL, bit_rate, ...) x channels (src/v29rx.c:1100-1134).  bit_rate: 9600, 7200 or 4800;
@@ -42,6 +43,8 @@ int span_b200_v29_bank_channels(const span_b200_v29_bank_t *bank);
 int span_b200_v29_bank_restart(span_b200_v29_bank_t *bank, int first, int count, int bit_rate);
 /* v29_rx_set_signal_cutoff() (src/v29rx.c:163-168) */
 int span_b200_v29_bank_set_signal_cutoff(span_b200_v29_bank_t *bank, int first, int count, float cutoff);
+/* v29_rx_fillin() (src/v29rx.c:967-996): sustain carrier phase and symbol timing over `samples` lost samples. */
+int span_b200_v29_bank_fillin(span_b200_v29_bank_t *bank, int first, int count, int samples);
 
 /* v29_rx() (src/v29rx.c:867) for every channel; device / host sample memory as in spandsp_b200.h. */
 int span_b200_v29_bank_rx_device(span_b200_v29_bank_t *bank, const int16_t *d_amp, int64_t stride, int samples, void *stream);
@@ -55,9 +58,9 @@ int64_t span_b200_v29_bank_symbols(span_b200_v29_bank_t *bank, int channel, span
 int span_b200_v29_bank_output_layout(span_b200_v29_bank_t *bank, const int8_t **d_bits, int64_t *bits_cap,
                                      const int32_t **d_nbits, const span_b200_v29_symbol_t **d_syms,
                                      int64_t *sym_cap, const int32_t **d_nsyms);
-/* eq_coeff: 33 complex taps (v29_rx_equalizer_state, src/v29rx.c:180-195); info[8] =
+/* eq_coeff: 33 complex taps (v29_rx_equalizer_state, src/v29rx.c:180-195); info[10] =
    {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling (float bits),
-    total_baud_timing_correction, constellation_state, carrier_phase}. */
+    total_baud_timing_correction, constellation_state, carrier_phase, power meter reading, bit_rate}. */
 int span_b200_v29_bank_channel_state(span_b200_v29_bank_t *bank, int channel, float *eq_coeff, int32_t *info);
 
 /* The constant tables the receiver is built on, as computed by this library's own generators

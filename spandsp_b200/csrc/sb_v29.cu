@@ -916,6 +916,7 @@ struct Rx
                 s.target_re = tre;
                 s.target_im = tim;
                 s.state = constellation_state;
+                s.bit_pos = nbits;
                 syms[nsyms] = s;
             }
             nsyms++;
@@ -1421,6 +1422,43 @@ extern "C" int span_b200_v29_bank_set_signal_cutoff(span_b200_v29_bank_t *b, int
     return 0;
 }
 
+// v29_rx_fillin(): integer bookkeeping only (src/v29rx.c:967-996); done on the host copy of four fields.
+extern "C" int span_b200_v29_bank_fillin(span_b200_v29_bank_t *b, int first, int count, int samples)
+{
+    if (first < 0  ||  count < 0  ||  first + count > b->channels  ||  samples < 0)
+    {
+        sb_set_error("bad fillin arguments");
+        return -1;
+    }
+    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    const size_t C = b->channels;
+    std::vector<int> present(count), stage(count), phase(count), rate(count), put(count);
+    CK(cudaMemcpy(present.data(), b->istate + v29::I_SIGNAL_PRESENT*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(stage.data(), b->istate + v29::I_STAGE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(phase.data(), b->istate + v29::I_CARRIER_PHASE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rate.data(), b->istate + v29::I_PHASE_RATE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(put.data(), b->istate + v29::I_EQ_PUT_STEP*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    for (int c = 0;  c < count;  c++)
+    {
+        if (present[c] <= 0  ||  stage[c] == v29::STAGE_PARKED)
+            continue;
+        unsigned int ph = (unsigned int) phase[c];
+        for (int i = 0;  i < samples;  i++)
+        {
+            ph += (unsigned int) rate[c];
+            put[c] -= V29_COEFF_SETS;
+            if (put[c] <= 0)
+                put[c] += V29_COEFF_SETS*10/(3*2);
+        }
+        phase[c] = (int) ph;
+    }
+    CK(cudaMemcpy(b->istate + v29::I_CARRIER_PHASE*C + first, phase.data(), sizeof(int)*count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->istate + v29::I_EQ_PUT_STEP*C + first, put.data(), sizeof(int)*count, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 static int v29_ensure(void **p, size_t have_elems, size_t want_elems, size_t elem)
 {
     (void) have_elems;
@@ -1603,9 +1641,9 @@ extern "C" int span_b200_v29_bank_channel_state(span_b200_v29_bank_t *b, int cha
     }
     if (info)
     {
-        static const int fields[8] = {v29::I_STAGE, v29::I_PHASE_RATE, v29::I_EQ_PUT_STEP, v29::I_SIGNAL_PRESENT, -1,
-                                      v29::I_TOTAL_TIMING, v29::I_CONSTELLATION, v29::I_CARRIER_PHASE};
-        for (int i = 0;  i < 8;  i++)
+        static const int fields[10] = {v29::I_STAGE, v29::I_PHASE_RATE, v29::I_EQ_PUT_STEP, v29::I_SIGNAL_PRESENT, -1,
+                                       v29::I_TOTAL_TIMING, v29::I_CONSTELLATION, v29::I_CARRIER_PHASE, v29::I_POWER, v29::I_BIT_RATE};
+        for (int i = 0;  i < 10;  i++)
         {
             if (fields[i] >= 0)
                 CK(cudaMemcpy(&info[i], b->istate + (size_t) fields[i]*C + channel, sizeof(int), cudaMemcpyDeviceToHost));

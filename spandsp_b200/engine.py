@@ -78,6 +78,7 @@ def lib():
         "span_b200_v29_bank_channels": (i32, [vp]),
         "span_b200_v29_bank_restart": (i32, [vp, i32, i32, i32]),
         "span_b200_v29_bank_set_signal_cutoff": (i32, [vp, i32, i32, f32]),
+        "span_b200_v29_bank_fillin": (i32, [vp, i32, i32, i32]),
         "span_b200_v29_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
         "span_b200_v29_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
         "span_b200_v29_bank_counts": (i32, [vp, vp, vp]),
@@ -291,7 +292,7 @@ class Bank:
             self.h = None
 
 
-V29_SYMBOL_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4"), ("state", "<i4")])
+V29_SYMBOL_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4"), ("state", "<i4"), ("bit_pos", "<i4")])
 
 
 class V29Bank:
@@ -344,7 +345,7 @@ class V29Bank:
 
     def channel_state(self, channel):
         eq = np.zeros(66, dtype=np.float32)
-        info = np.zeros(8, dtype=np.int32)
+        info = np.zeros(10, dtype=np.int32)
         self._ck(lib().span_b200_v29_bank_channel_state(self.h, channel, eq.ctypes.data, info.ctypes.data))
         return eq, info
 

@@ -209,3 +209,77 @@ def test_goertzel_public_struct(L):
             out.append(L.goertzel_result(C.addressof(st)))
             assert st.current_sample == 0 and st.v2 == 0.0
     assert (np.asarray(out, dtype=np.float32) == g["goertzel_energy"][:20, 2]).all()
+
+
+def test_v29_dropin(engine_lib, gpu_ctx):
+    """v29_rx_init / v29_rx / qam handler / status handler / getters, one channel, 160-sample calls."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "v29_golden.npz"))
+    lib = C.CDLL(engine_lib.LIB_PATH)
+    vp = C.c_void_p
+    PUT = C.CFUNCTYPE(None, vp, C.c_int)
+    STATUS = C.CFUNCTYPE(None, vp, C.c_int)
+
+    class Cf(C.Structure):
+        _fields_ = [("re", C.c_float), ("im", C.c_float)]
+
+    QAM = C.CFUNCTYPE(None, vp, C.POINTER(Cf), C.POINTER(Cf), C.c_int)
+    lib.v29_rx_init.restype = vp
+    lib.v29_rx_init.argtypes = [vp, C.c_int, PUT, vp]
+    lib.v29_rx.argtypes = [vp, vp, C.c_int]
+    lib.v29_rx_set_qam_report_handler.argtypes = [vp, QAM, vp]
+    lib.v29_rx_set_modem_status_handler.argtypes = [vp, STATUS, vp]
+    lib.v29_rx_set_signal_cutoff.argtypes = [vp, C.c_float]
+    lib.v29_rx_free.argtypes = [vp]
+    lib.v29_rx_carrier_frequency.restype = C.c_float
+    lib.v29_rx_carrier_frequency.argtypes = [vp]
+    lib.v29_rx_signal_power.restype = C.c_float
+    lib.v29_rx_signal_power.argtypes = [vp]
+    lib.v29_rx_symbol_timing_correction.restype = C.c_float
+    lib.v29_rx_symbol_timing_correction.argtypes = [vp]
+    lib.v29_rx_equalizer_state.argtypes = [vp, C.POINTER(C.POINTER(Cf))]
+    assert not lib.v29_rx_init(None, 1234, PUT(0), None)            # bad rate -> NULL (src/v29rx.c:1102-1111)
+    for k in (0, 2, 3):
+        rate, n, lead, cutoff = g["cfg%d" % k]
+        log = []
+        put = PUT(lambda ud, bit: log.append(("b", bit)))
+        qam = QAM(lambda ud, z, t, sym: log.append(("q", z.contents.re, z.contents.im, t.contents.re, t.contents.im, sym)))
+        s = lib.v29_rx_init(None, int(rate), put, None)
+        assert s
+        lib.v29_rx_set_qam_report_handler(s, qam, None)
+        if cutoff > -99:
+            lib.v29_rx_set_signal_cutoff(s, float(cutoff))
+        amp = np.ascontiguousarray(g["amp%d" % k])
+        for pos in range(0, len(amp), 160):
+            assert lib.v29_rx(s, amp[pos:pos + 160].ctypes.data, min(160, len(amp) - pos)) == 0
+        bits = np.asarray([x[1] for x in log if x[0] == "b"], dtype=np.int8)
+        syms = [x for x in log if x[0] == "q"]
+        assert (bits == g["bits%d" % k]).all()
+        es = g["syms%d" % k]
+        assert len(syms) == len(es)
+        assert np.allclose([x[1] for x in syms], es["re"], rtol=1e-5, atol=1e-5)
+        assert [x[5] for x in syms] == list(es["state"])
+        # in normal operation every qam report follows the 2..4 bits of its baud
+        tail = log[-60:]
+        kinds = "".join(x[0] for x in tail)
+        assert "qq" not in kinds
+        f = lib.v29_rx_carrier_frequency(s)
+        assert 1690.0 < f < 1710.0
+        assert -30.0 < lib.v29_rx_signal_power(s) < 0.0
+        assert abs(lib.v29_rx_symbol_timing_correction(s)) < 50.0
+        pc = C.POINTER(Cf)()
+        assert lib.v29_rx_equalizer_state(s, C.byref(pc)) == 33
+        eq = np.asarray([(pc[i].re, pc[i].im) for i in range(33)], dtype=np.float32).reshape(-1)
+        assert np.allclose(eq, g["eq%d" % k], rtol=1e-5, atol=1e-5)
+        lib.v29_rx_free(s)
+    # a status handler takes the status reports out of the put_bit stream
+    log = []
+    put = PUT(lambda ud, bit: log.append(("b", bit)))
+    st = STATUS(lambda ud, status: log.append(("s", status)))
+    s = lib.v29_rx_init(None, 9600, put, None)
+    lib.v29_rx_set_modem_status_handler(s, st, None)
+    amp = np.ascontiguousarray(g["amp1"])
+    lib.v29_rx(s, amp.ctypes.data, len(amp))
+    assert [x[1] for x in log if x[0] == "s"] == [-2, -3, -4]
+    assert all(x[1] >= 0 for x in log if x[0] == "b")
+    lib.v29_rx_free(s)
