@@ -108,6 +108,14 @@ class ClockSampler:
         self.stop_flag = False
         self.thread = None
         self.err = None
+        self.t0 = None
+        self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -134,7 +142,7 @@ class ClockSampler:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, mx, pw, rs))
+                self.samples.append((sm, mx, pw, rs, time.perf_counter()))
                 time.sleep(0.002)
         except Exception as e:  # noqa: BLE001
             self.err = str(e)
@@ -147,6 +155,11 @@ class ClockSampler:
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=5)
+        allsamples = self.samples
+        if self.t0 is not None and self.t1 is not None:
+            inside = [x for x in allsamples if self.t0 <= x[4] <= self.t1]
+            if inside:
+                self.samples = inside
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: %s" % (self.err or "nvml")]}
         sm = [x[0] for x in self.samples]
@@ -283,9 +296,13 @@ def main():
         bank.tune(3, args.packed)
     bank.tune(4, 1)
 
-    stream = torch.cuda.current_stream().cuda_stream
     d_amp = synth_dtmf_torch(torch, C, T, 1234567 + rank, dev)
     torch.cuda.synchronize()
+    # One explicit stream for the library's launches AND the timing events (a NULL stream would make the
+    # library use its own context stream, which torch's events do not see).
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
 
     ev_cap = C * (T // 102 // 2 + 1)
     d_events = None
@@ -334,17 +351,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm ------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # NVML start-up takes longer than the timed region; start early
     for _ in range(args.warmup):
         step_device()
     if world > 1:
         flush_gather()
     bank.kernel_ms()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     total_events = 0
     for _ in range(args.steps):
@@ -354,6 +372,7 @@ def main():
         total_events = pending["total"]
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     kern_ms, kern_n = bank.kernel_ms()

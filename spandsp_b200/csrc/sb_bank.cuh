@@ -62,7 +62,7 @@ __device__ __forceinline__ int block_len(const BankArgs<DET> &a)
 
 // ------------------------------------------------------------------------------------------
 // Per-thread channel runner
-template <class DET, bool PACKED>
+template <class DET, int NPACK>
 struct Runner
 {
     static constexpr int NP = DET::NPAIRS;
@@ -148,12 +148,17 @@ struct Runner
         }
         if (DET::ENERGY)
             energy = fadd(energy, fmul(x, x));              // src/dtmf.c:189, super_tone_rx.c:477
+        // The first NPACK pairs use the 2-wide add/sub (FADD2), the rest scalar FADDs: the mix is a
+        // tuning knob (FADD2 saves issue slots but is not spread over the FP32 sub-pipes like FADD).
 #pragma unroll
         for (int p = 0;  p < NP;  p++)
         {
             const pair_t v1 = v2[p];
             v2[p] = v3[p];
-            v3[p] = padd_scalar<PACKED>(psub<PACKED>(pmul(fac[p], v2[p]), v1), x);
+            if (p < NPACK)
+                v3[p] = padd_scalar<true>(psub<true>(pmul(fac[p], v2[p]), v1), x);
+            else
+                v3[p] = padd_scalar<false>(psub<false>(pmul(fac[p], v2[p]), v1), x);
         }
     }
 
@@ -281,7 +286,7 @@ struct StageCfg
     static_assert(SEG_VEC == 8  ||  SEG_VEC == 16  ||  SEG_VEC == 32, "SEG_VEC lanes copy one row segment");
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, bool PACKED>
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK>
 __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankArgs<DET> a)
 {
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     const int start = (int) s0;
     const int end = (int) s1;
 
-    Runner<DET, PACKED> r;
+    Runner<DET, NPACK> r;
     r.channels = a.channels;
     r.c = group*32 + lane;
     r.active = (r.c < a.channels);
@@ -460,14 +465,14 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
 // ------------------------------------------------------------------------------------------
 // Direct kernel: any block phase per channel, any alignment.  One thread per channel over the
 // whole call; samples are read with 16-bit loads through L1.
-template <class DET, bool PACKED>
+template <class DET, int NPACK>
 __global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
 {
     const int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= a.channels)
         return;
 
-    Runner<DET, PACKED> r;
+    Runner<DET, NPACK> r;
     r.channels = a.channels;
     r.c = c;
     r.active = true;

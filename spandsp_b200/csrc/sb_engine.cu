@@ -330,7 +330,7 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
     b->bins = bins;
     b->npairs = (bins + 1)/2;
     b->uniform_cs = 0;
-    b->tune_packed = 1;
+    b->tune_packed = 4;
     b->last_path = "";
     const size_t C = channels;
     CKP(cudaMalloc(&b->v2, sizeof(float)*2*b->npairs*C));
@@ -830,12 +830,12 @@ struct Geometry
     bool staged;
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, bool PACKED>
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK>
 static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
 {
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
     const int smem = cfg::WARP_BYTES*WARPS;
-    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, PACKED>;
+    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK>;
     static bool configured = false;
     if (!configured)
     {
@@ -850,32 +850,18 @@ static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
     return 0;
 }
 
-template <class DET, bool PACKED>
+template <class DET, int NPACK>
 static int launch_variant(const BankArgs<DET> &a, int variant, cudaStream_t st)
 {
-    // (row bytes per stage = SEG_VEC*16, stages, warps per CTA, min CTAs per SM)
+    // (row bytes per stage = SEG_VEC*16, stages, warps per CTA, min CTAs per SM).  The round-1 sweep
+    // (profiles/r01_sweep_dtmf*.json) covered nine shapes; the two ends of it are kept.
     switch (variant)
     {
-    case 1:
-        return launch_staged<DET, 8, 4, 4, 3, PACKED>(a, st);       // 528 B/row, 12 warps/SM
-    case 2:
-        return launch_staged<DET, 16, 2, 4, 3, PACKED>(a, st);      // 528 B/row, 12 warps/SM
-    case 3:
-        return launch_staged<DET, 32, 2, 2, 3, PACKED>(a, st);      // 1040 B/row, 6 warps/SM
-    case 4:
-        return launch_staged<DET, 16, 4, 2, 3, PACKED>(a, st);      // 1040 B/row, 6 warps/SM
-    case 5:
-        return launch_staged<DET, 8, 2, 4, 6, PACKED>(a, st);       // 272 B/row, 24 warps/SM
-    case 6:
-        return launch_staged<DET, 8, 3, 4, 4, PACKED>(a, st);       // 400 B/row, 16 warps/SM
-    case 7:
-        return launch_staged<DET, 8, 2, 4, 5, PACKED>(a, st);       // 272 B/row, 20 warps/SM
     case 8:
-        return launch_staged<DET, 16, 3, 4, 2, PACKED>(a, st);      // 784 B/row, 8 warps/SM
+        return launch_staged<DET, 16, 3, 4, 2, NPACK>(a, st);       // 784 B/row, 8 warps/SM
     default:
-        // Fastest in the round-1 sweep (profiles/r01_sweep_dtmf.json): 128-byte row segments,
-        // 2 stages, 16 resident warps per SM.
-        return launch_staged<DET, 8, 2, 4, 4, PACKED>(a, st);       // 272 B/row, 16 warps/SM
+        // Fastest in the sweep: 128-byte row segments, 2 stages, 16-20 resident warps per SM.
+        return launch_staged<DET, 8, 2, 4, 4, NPACK>(a, st);        // 272 B/row
     }
 }
 
@@ -890,18 +876,18 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
     {
         b->last_path = "staged";
         const int variant = (all_variants)  ?  b->tune_variant  :  0;
-        if (b->tune_packed)
-            return launch_variant<DET, true>(a, variant, st);
-        if (all_variants)
-            return launch_variant<DET, false>(a, variant, st);
-        return launch_variant<DET, true>(a, variant, st);
+        // Knob 3 = 0 selects scalar FADDs instead of FADD2 (DTMF only; kept for the comparison in
+        // packed is 7-9 % faster, mixing packed and scalar pairs brings nothing).
+        if (all_variants  &&  b->tune_packed == 0)
+            return launch_variant<DET, 0>(a, variant, st);
+        return launch_variant<DET, DET::NPAIRS>(a, variant, st);
     }
     b->last_path = "direct";
     const int grid = (a.channels + 127)/128;
     if (b->tune_packed  ||  !all_variants)
-        bank_kernel_direct<DET, true><<<grid, 128, 0, st>>>(a);
+        bank_kernel_direct<DET, DET::NPAIRS><<<grid, 128, 0, st>>>(a);
     else
-        bank_kernel_direct<DET, false><<<grid, 128, 0, st>>>(a);
+        bank_kernel_direct<DET, 0><<<grid, 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1349,9 +1335,9 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
             L = 16;
         a.slice_blocks = (nb > L)  ?  L  :  (nb + 1);
         a.nslices = (nb > L)  ?  ((nb + L - 1)/L)  :  1;
-        return launch_staged<RawDet<NP>, 8, 2, 4, 4, true>(a, st);
+        return launch_staged<RawDet<NP>, 8, 2, 4, 4, NP>(a, st);
     }
-    bank_kernel_direct<RawDet<NP>, true><<<(channels + 127)/128, 128, 0, st>>>(a);
+    bank_kernel_direct<RawDet<NP>, NP><<<(channels + 127)/128, 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return 0;
 }

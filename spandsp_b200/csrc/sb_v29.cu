@@ -448,7 +448,8 @@ struct Rx
     int phase_rate, phase_rate_save, power, on_power, off_power;
     int eq_step, eq_put_step, eq_skip, baud_half, constellation_state, total_timing;
     int last_angle0, last_angle1;
-    int diff_angles[16];
+    int *diff_angles;       // [16], shared memory, lane-interleaved (dynamic indexing would force the
+                            // whole receiver out of registers if it were a member array)
     // shared-memory arrays of this lane
     float *eq_coeff;        // [66]
     float *eq_buf;          // [66]
@@ -479,7 +480,7 @@ struct Rx
     }
 
     // src/v29rx.c:214-258
-    __device__ void equalizer_reset(const Consts &k)
+    __device__ __forceinline__ void equalizer_reset(const Consts &k)
     {
         for (int i = 0;  i < 2*V29_EQ_LEN;  i++)
         {
@@ -491,7 +492,7 @@ struct Rx
         eq_step = 0;
     }
 
-    __device__ void equalizer_restore(const Consts &k)
+    __device__ __forceinline__ void equalizer_restore(const Consts &k)
     {
         for (int i = 0;  i < 2*V29_EQ_LEN;  i++)
         {
@@ -502,14 +503,14 @@ struct Rx
         eq_step = 0;
     }
 
-    __device__ void equalizer_save()
+    __device__ __forceinline__ void equalizer_save()
     {
         for (int i = 0;  i < 2*V29_EQ_LEN;  i++)
             fstate[(size_t) (F_EQ_COEFF_SAVE + i)*channels + c] = eq_coeff[i*32];
     }
 
     // src/v29rx.c:1019-1097
-    __device__ void restart(const Consts &k, int rate, bool old_train)
+    __device__ __forceinline__ void restart(const Consts &k, int rate, bool old_train)
     {
         training_cd = (rate == 9600)  ?  0  :  (rate == 7200)  ?  2  :  4;
         bit_rate = rate;
@@ -525,7 +526,7 @@ struct Rx
         low_samples = 0;
         drop_pending = 0;
         for (int i = 0;  i < 16;  i++)
-            diff_angles[i] = 0;
+            diff_angles[i*32] = 0;
         carrier_phase = 0;
         power = 0;                                  // power_meter_init(&s->power, 4)
         constellation_state = 0;
@@ -552,7 +553,7 @@ struct Rx
     }
 
     // src/spandsp/arctan2.h:47-80
-    __device__ int arctan2(float y, float x)
+    __device__ __forceinline__ int arctan2(float y, float x)
     {
         if (y == 0.0f)
             return (x < 0.0f)  ?  (int) 0x80000000  :  0;
@@ -673,7 +674,7 @@ struct Rx
     }
 
     // src/v29rx.c:402-480
-    __device__ void decode_baud(const Consts &k, float zre, float zim)
+    __device__ __forceinline__ void decode_baud(const Consts &k, float zre, float zim)
     {
         int nearest;
         int raw_bits;
@@ -746,7 +747,7 @@ struct Rx
     }
 
     // src/v29rx.c:486-785
-    __device__ void process_half_baud(const Consts &k, float sre, float sim)
+    __device__ __forceinline__ void process_half_baud(const Consts &k, float sre, float sim)
     {
         eq_buf[(2*eq_step)*32] = sre;
         eq_buf[(2*eq_step + 1)*32] = sim;
@@ -773,7 +774,7 @@ struct Rx
             {
                 training_stage = STAGE_LOG_PHASE;
                 for (int i = 0;  i < 16;  i++)
-                    diff_angles[i] = 0;
+                    diff_angles[i*32] = 0;
                 last_angle0 = arctan2(zim, zre);
                 if (agc_scaling_save == 0.0f)
                     agc_scaling_save = agc_scaling;
@@ -793,14 +794,14 @@ struct Rx
                     last_angle1 = angle;
                 else
                     last_angle0 = angle;
-                diff_angles[i & 0xF] = diff_angles[(i - 2) & 0xF] + (ang >> 4);
+                diff_angles[(i & 0xF)*32] = diff_angles[((i - 2) & 0xF)*32] + (ang >> 4);
                 if ((ang > k.phase_p45  ||  ang < k.phase_m45)  &&  training_count >= 13)
                 {
                     i = (training_count - 8) & ~1;
                     if (i > 1)
                     {
                         const int j = i & 0xF;
-                        ang = (diff_angles[j] + diff_angles[j | 0x1])/(i - 1);
+                        ang = (diff_angles[j*32] + diff_angles[(j | 0x1)*32])/(i - 1);
                         phase_rate += 3*16*(ang/20);
                     }
                     if (phase_rate < k.rate_low  ||  phase_rate > k.rate_high)
@@ -982,7 +983,7 @@ struct Rx
     }
 
     // One input sample: src/v29rx.c:885-960
-    __device__ void sample(const Consts &k, const float *s_rrc_re, const float *s_rrc_im, short amp)
+    __device__ __forceinline__ void sample(const Consts &k, const float *s_rrc_re, const float *s_rrc_im, short amp)
     {
         rrc[rrc_step*32] = (float) amp;
         if (++rrc_step >= V29_FILTER_STEPS)
@@ -1033,7 +1034,7 @@ struct Rx
     }
 };
 
-#define V29_SMEM_FLOATS_PER_WARP    ((2*V29_EQ_LEN + 2*V29_EQ_LEN + V29_FILTER_STEPS)*32)
+#define V29_SMEM_FLOATS_PER_WARP    ((2*V29_EQ_LEN + 2*V29_EQ_LEN + V29_FILTER_STEPS + 16)*32)
 
 // 32 channels per CTA (one warp): few channels exist (thousands), so spread them over all SMs.
 __global__ void __launch_bounds__(32) v29_rx_kernel(const Args a)
@@ -1061,6 +1062,7 @@ __global__ void __launch_bounds__(32) v29_rx_kernel(const Args a)
     r.eq_coeff = lane_base + lane;
     r.eq_buf = lane_base + (2*V29_EQ_LEN)*32 + lane;
     r.rrc = lane_base + (4*V29_EQ_LEN)*32 + lane;
+    r.diff_angles = (int *) (lane_base + (4*V29_EQ_LEN + V29_FILTER_STEPS)*32 + lane);
     const float *F = a.fstate;
     const int *I = a.istate;
 #define LF(f) F[(size_t) (f)*C + c]
@@ -1109,7 +1111,7 @@ __global__ void __launch_bounds__(32) v29_rx_kernel(const Args a)
     r.last_angle0 = LI(I_LAST_ANGLE0);
     r.last_angle1 = LI(I_LAST_ANGLE1);
     for (int i = 0;  i < 16;  i++)
-        r.diff_angles[i] = LI(I_DIFF_ANGLES + i);
+        r.diff_angles[i*32] = LI(I_DIFF_ANGLES + i);
     r.constellation_state = LI(I_CONSTELLATION);
     r.total_timing = LI(I_TOTAL_TIMING);
     r.bits = a.bits + (size_t) c*a.bits_cap;
@@ -1170,7 +1172,7 @@ __global__ void __launch_bounds__(32) v29_rx_kernel(const Args a)
     SI(I_LAST_ANGLE0, r.last_angle0);
     SI(I_LAST_ANGLE1, r.last_angle1);
     for (int i = 0;  i < 16;  i++)
-        SI(I_DIFF_ANGLES + i, r.diff_angles[i]);
+        SI(I_DIFF_ANGLES + i, r.diff_angles[i*32]);
     SI(I_CONSTELLATION, r.constellation_state);
     SI(I_TOTAL_TIMING, r.total_timing);
     a.nbits[c] = r.nbits;

@@ -25,7 +25,9 @@ print("generated", amp.shape, "in %.1fs" % (time.time() - t0), flush=True)
 dev = torch.device("cuda", 0)
 ctx = engine.Context(0)
 d = torch.from_numpy(amp).to(dev)
-stream = torch.cuda.current_stream().cuda_stream
+ws = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(ws)
+stream = ws.cuda_stream
 out = {}
 for want in (0, 1):
     bank = engine.V29Bank(ctx, C, 9600, want_symbols=bool(want))
@@ -47,7 +49,7 @@ for want in (0, 1):
     print(json.dumps(out["symbols_%d" % want]), flush=True)
     bank.close()
 threads = len(os.sched_getaffinity(0))
-chans = min(C, threads * 4)
+chans = min(C, threads * 32)
 secs = po.v29_run_batch(F or S, amp[:chans], 9600, T, -100.0, threads)
 out["cpu_reference"] = {"msamples_s": chans * T / secs / 1e6, "threads": threads, "channels": chans, "kind": "fast" if F else "strict"}
 print(json.dumps(out["cpu_reference"]), flush=True)

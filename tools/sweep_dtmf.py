@@ -12,7 +12,7 @@ from spandsp_b200 import engine  # noqa: E402
 C = int(os.environ.get("SWEEP_C", "65536"))
 T = 79968
 variants = [int(x) for x in os.environ.get("SWEEP_VARIANTS", "0,1,2,5,6,7,8").split(",")]
-packs = [int(x) for x in os.environ.get("SWEEP_PACKED", "0,1").split(",")]
+packs = [int(x) for x in os.environ.get("SWEEP_PACKED", "0,2,3,4").split(",")]
 slices = [int(x) for x in os.environ.get("SWEEP_SLICES", "0,16,64").split(",")]
 
 dev = torch.device("cuda", 0)
