@@ -746,15 +746,9 @@ struct Rx
         report_status(SIG_STATUS_TRAINING_FAILED);
     }
 
-    // src/v29rx.c:486-785
-    __device__ __forceinline__ void process_half_baud(const Consts &k, float sre, float sim)
+    // src/v29rx.c:526-785: the once-per-baud part of process_half_baud()
+    __device__ __forceinline__ void process_baud(const Consts &k)
     {
-        eq_buf[(2*eq_step)*32] = sre;
-        eq_buf[(2*eq_step + 1)*32] = sim;
-        if (++eq_step >= V29_EQ_LEN)
-            eq_step = 0;
-        if ((baud_half ^= 1))
-            return;
         eq_put_step += godard_per_baud(k);
         float zre;
         float zim;
@@ -982,17 +976,28 @@ struct Rx
         return (int) k.sqrt_tab[((x >> 24) & 0xFF) - 64] >> (shift >> 1);
     }
 
-    // One input sample: src/v29rx.c:885-960
-    __device__ __forceinline__ void sample(const Consts &k, const float *s_rrc_re, const float *s_rrc_im, short amp)
+    // v29_rx()'s per-sample body (src/v29rx.c:885-960) is split in three so that the 32 channels of a
+    // warp can be kept in step on *symbol* time rather than sample time (see v29_rx_kernel):
+    //   front(): everything up to and including the real FIR and the Godard filters; tells whether this
+    //            sample is a T/2 instant (eq_put_step <= 0);
+    //   half():  the T/2 work: AGC, imaginary FIR, down-mix, equalizer buffer insert; tells whether a
+    //            whole baud is now complete;
+    //   baud():  timing correction, equalizer, training state machine / slicer, qam report.
+    // The carrier NCO advance that ends the reference's loop body is done by whichever part ends the sample.
+    int h_step;
+    int h_pw;
+    float h_sre;
+
+    __device__ __forceinline__ bool front(const Consts &k, const float *s_rrc_re, short amp)
     {
         rrc[rrc_step*32] = (float) amp;
         if (++rrc_step >= V29_FILTER_STEPS)
             rrc_step = 0;
         const int pw = signal_detect(k, amp);
         if (pw == 0)
-            return;
+            return false;
         if (training_stage == STAGE_PARKED)
-            return;
+            return false;
         eq_put_step -= V29_COEFF_SETS;
         int step = -eq_put_step;
         if (step < 0)
@@ -1001,7 +1006,7 @@ struct Rx
             step = 0;
         else if (step > V29_COEFF_SETS - 1)
             step = V29_COEFF_SETS - 1;
-        float v = rrc_dot(s_rrc_re + step*V29_FILTER_STEPS);
+        const float v = rrc_dot(s_rrc_re + step*V29_FILTER_STEPS);
         const float sre = fmul(v, agc_scaling);
         // godard_ted_rx, src/godard.c:144-161
         {
@@ -1014,22 +1019,47 @@ struct Rx
         }
         if (eq_put_step <= 0)
         {
-            if (agc_scaling_save == 0.0f)
-            {
-                int root_power = fixed_sqrt32(k, (unsigned int) pw);
-                if (root_power == 0)
-                    root_power = 1;
-                agc_scaling = fdiv(fdiv(1.25f, 1.0f), (float) root_power);
-            }
-            v = rrc_dot(s_rrc_im + step*V29_FILTER_STEPS);
-            const float sim = fmul(v, agc_scaling);
-            const float zr = k.sine[(carrier_phase + (1u << 30)) >> 21];     // dds_lookup_complexf, src/dds_float.c:2177
-            const float zi = k.sine[carrier_phase >> 21];
-            const float zzre = fsub(fmul(sre, zr), fmul(sim, zi));
-            const float zzim = fsub(fmul(-sre, zi), fmul(sim, zr));
-            eq_put_step += V29_COEFF_SETS*10/(3*2);
-            process_half_baud(k, zzre, zzim);
+            h_step = step;
+            h_pw = pw;
+            h_sre = sre;
+            return true;
         }
+        carrier_phase += (unsigned int) phase_rate;
+        return false;
+    }
+
+    __device__ __forceinline__ bool half(const Consts &k, const float *s_rrc_im)
+    {
+        if (agc_scaling_save == 0.0f)
+        {
+            int root_power = fixed_sqrt32(k, (unsigned int) h_pw);
+            if (root_power == 0)
+                root_power = 1;
+            agc_scaling = fdiv(fdiv(1.25f, 1.0f), (float) root_power);
+        }
+        const float v = rrc_dot(s_rrc_im + h_step*V29_FILTER_STEPS);
+        const float sim = fmul(v, agc_scaling);
+        const float zr = k.sine[(carrier_phase + (1u << 30)) >> 21];     // dds_lookup_complexf, src/dds_float.c:2177
+        const float zi = k.sine[carrier_phase >> 21];
+        const float zzre = fsub(fmul(h_sre, zr), fmul(sim, zi));
+        const float zzim = fsub(fmul(-h_sre, zi), fmul(sim, zr));
+        eq_put_step += V29_COEFF_SETS*10/(3*2);
+        // process_half_baud, first part (src/v29rx.c:516-525)
+        eq_buf[(2*eq_step)*32] = zzre;
+        eq_buf[(2*eq_step + 1)*32] = zzim;
+        if (++eq_step >= V29_EQ_LEN)
+            eq_step = 0;
+        if ((baud_half ^= 1))
+        {
+            carrier_phase += (unsigned int) phase_rate;
+            return false;
+        }
+        return true;
+    }
+
+    __device__ __forceinline__ void baud(const Consts &k)
+    {
+        process_baud(k);
         carrier_phase += (unsigned int) phase_rate;
     }
 };
@@ -1121,10 +1151,37 @@ __global__ void __launch_bounds__(32) v29_rx_kernel(const Args a)
     r.sym_cap = (int) a.sym_cap;
     r.nsyms = 0;
 
+    // Lanes are kept in step on symbol time: one trip of this loop takes every receiving channel
+    // through one whole baud - two T/2 instants, each reached after one or two input samples - so the
+    // expensive parts (imaginary FIR, equalizer, training/slicer) run with all lanes converged even
+    // though the channels' symbol clocks sit at different sample phases.  Channels without carrier (or
+    // parked) simply consume up to four samples per trip.  Each channel still sees its own samples in
+    // order, which is all the reference's per-channel semantics require.
     const int16_t *row = a.amp + (long long) c*a.stride;
+    int pos = 0;
 #pragma unroll 1
-    for (int i = 0;  i < a.n;  i++)
-        r.sample(a.k, s_rrc_re, s_rrc_im, __ldg(row + i));
+    while (pos < a.n)
+    {
+#pragma unroll 1
+        for (int h = 0;  h < 2;  h++)
+        {
+            bool due = false;
+#pragma unroll 1
+            for (int q = 0;  q < 2;  q++)
+            {
+                if (pos < a.n  &&  !due)
+                {
+                    due = r.front(a.k, s_rrc_re, __ldg(row + pos));
+                    pos++;
+                }
+            }
+            if (due)
+            {
+                if (r.half(a.k, s_rrc_im))
+                    r.baud(a.k);
+            }
+        }
+    }
 
     float *FW = a.fstate;
     int *IW = a.istate;

@@ -19,7 +19,7 @@ F = po.load("fast") if po.available("fast") else None
 assert S is not None, "needs oracle/_ref for v29_tx signal generation"
 base = 64
 t0 = time.time()
-sig = np.stack([po.v29_generate(S, T, 9600, False, -13.0, c + 1, 0, 1234567 + c, -50.0) for c in range(base)])
+sig = np.stack([po.v29_generate(S, T, 9600, False, -13.0, c + 1, (c * 37) % 400, 1234567 + c, -50.0) for c in range(base)])
 amp = np.tile(sig, (C // base, 1))
 print("generated", amp.shape, "in %.1fs" % (time.time() - t0), flush=True)
 dev = torch.device("cuda", 0)
