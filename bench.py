@@ -389,7 +389,8 @@ def main():
         h_amp = torch.empty((C, T), dtype=torch.int16, pin_memory=True)
         h_amp.copy_(d_amp)
         torch.cuda.synchronize()
-        h_events = np.zeros(ev_cap, dtype=engine.EVENT_DTYPE)
+        h_events_t = torch.empty((ev_cap, 6), dtype=torch.int32, pin_memory=True)      # pinned: D2H at link speed
+        h_events = h_events_t.numpy().view(engine.EVENT_DTYPE).reshape(-1)
         bank.reset()
         if args.realtime:
             bank.dtmf_realtime(True)

@@ -136,6 +136,16 @@ int span_b200_bank_rx_device(span_b200_bank_t *bank, const int16_t *d_amp, int64
 int span_b200_bank_rx_host(span_b200_bank_t *bank, const int16_t *h_amp, int64_t stride,
                            int samples, void *stream);
 
+/* Same two calls for 8-bit companded samples (G.711), one byte per sample, channel-major
+   [channel][sample] with the row stride in samples (= bytes): the expansion of
+   ulaw_to_linear()/alaw_to_linear() (src/spandsp/g711.h:165-172,239-252) is fused into the kernel's load,
+   so the detectors see exactly the int16 stream the reference would after expanding, at half the
+   bytes per sample.  alaw: 0 = u-law, 1 = A-law. */
+int span_b200_bank_rx_device_g711(span_b200_bank_t *bank, const uint8_t *d_data, int64_t stride,
+                                  int samples, int alaw, void *stream);
+int span_b200_bank_rx_host_g711(span_b200_bank_t *bank, const uint8_t *h_data, int64_t stride,
+                                int samples, int alaw, void *stream);
+
 /* Wait for the last rx call of this bank and return how many events it produced
    (-1 on error).  *overflow is set when the event buffer capacity was exceeded (the surplus
    is dropped). */

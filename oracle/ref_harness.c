@@ -56,6 +56,8 @@
 #include "spandsp/private/super_tone_tx.h"
 
 #include "spandsp/math_fixed.h"
+#include "spandsp/bit_operations.h"
+#include "spandsp/g711.h"
 #include "ref_harness.h"
 
 /* The generated tables the V.29 receiver is built on (static const in the generated headers). */
@@ -811,4 +813,24 @@ EXPORT void ref_v29_tables(float *rrc_re, float *rrc_im, float *sine, uint16_t *
     ints[6] = DDS_PHASE(-45.0f);
     ints[7] = power_meter_level_dbm0(-28.5f + 2.5f);
     ints[8] = power_meter_level_dbm0(-28.5f - 2.5f);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* G.711 (src/spandsp/g711.h inline functions)                                            */
+
+/* law: 0 = u-law, 1 = A-law */
+EXPORT void ref_g711_encode(int law, const int16_t *in, uint8_t *out, int n)
+{
+    int i;
+
+    for (i = 0;  i < n;  i++)
+        out[i] = (law)  ?  linear_to_alaw(in[i])  :  linear_to_ulaw(in[i]);
+}
+
+EXPORT void ref_g711_expand(int law, const uint8_t *in, int16_t *out, int n)
+{
+    int i;
+
+    for (i = 0;  i < n;  i++)
+        out[i] = (law)  ?  alaw_to_linear(in[i])  :  ulaw_to_linear(in[i]);
 }

@@ -51,6 +51,7 @@ struct BankArgs
     float *raw;                     // [block][bin][channel] bin energies (only where DET::RAW)
     long long raw_capacity;         // floats
     int block_rt;                   // block length where DET::BLOCK == 0 (raw Goertzel banks)
+    const float *lut;               // 8-bit (G.711) input: 256-entry expansion table, as float
     typename DET::Params det;
 };
 
@@ -204,18 +205,42 @@ struct Runner
         cs = 0;
     }
 
-    // Eight samples of one 16-byte vector, no block boundary inside.
+    // Eight consecutive samples, no block boundary inside.
+    template <bool FILT>
+    __device__ __forceinline__ void fast8f(const float (&x)[8])
+    {
+#pragma unroll
+        for (int i = 0;  i < 8;  i++)
+            step<FILT>(x[i]);
+    }
+
     template <bool FILT>
     __device__ __forceinline__ void fast8(const uint4 &v)
     {
-        step<FILT>(sample_of<0>(v));
-        step<FILT>(sample_of<1>(v));
-        step<FILT>(sample_of<2>(v));
-        step<FILT>(sample_of<3>(v));
-        step<FILT>(sample_of<4>(v));
-        step<FILT>(sample_of<5>(v));
-        step<FILT>(sample_of<6>(v));
-        step<FILT>(sample_of<7>(v));
+        float x[8];
+        x[0] = sample_of<0>(v);
+        x[1] = sample_of<1>(v);
+        x[2] = sample_of<2>(v);
+        x[3] = sample_of<3>(v);
+        x[4] = sample_of<4>(v);
+        x[5] = sample_of<5>(v);
+        x[6] = sample_of<6>(v);
+        x[7] = sample_of<7>(v);
+        fast8f<FILT>(x);
+    }
+
+    // Eight companded samples (two 32-bit words) through the expansion table in shared memory.
+    template <bool FILT>
+    __device__ __forceinline__ void fast8_g711(unsigned int w0, unsigned int w1, const float *lut)
+    {
+        float x[8];
+#pragma unroll
+        for (int i = 0;  i < 4;  i++)
+        {
+            x[i] = lut[(w0 >> (8*i)) & 0xFFu];
+            x[4 + i] = lut[(w1 >> (8*i)) & 0xFFu];
+        }
+        fast8f<FILT>(x);
     }
 
     // What "reset" means at a block end: goertzel_result()/goertzel_reset() clear the bins
@@ -231,18 +256,36 @@ struct Runner
         energy = 0.0f;
     }
 
-    // Samples [lo, hi) of one 16-byte vector, one at a time, with a block-boundary check after
-    // each.  Used for the first/last vector of a slice and for vectors that straddle a boundary.
-    template <bool FILT>
-    __device__ __forceinline__ void partial(uint4 v, int lo, int hi, const BankArgs<DET> &a)
+    // Samples [lo, hi) of a vector, one at a time, with a block-boundary check after each.  Used
+    // for the first/last vector of a slice and for the samples around a block boundary.
+    // IN8: the vector holds 16 companded bytes instead of 8 int16.
+    template <bool FILT, bool IN8>
+    __device__ __forceinline__ void partial(uint4 v, int lo, int hi, const BankArgs<DET> &a, const float *lut)
     {
         const int B = block_len(a);
-        shift_vec_n(v, lo);
+        if (IN8)
+        {
+            for (int i = 0;  i < lo;  i++)
+                shift_vec8(v);
+        }
+        else
+        {
+            shift_vec_n(v, lo);
+        }
 #pragma unroll 1
         for (int e = lo;  e < hi;  e++)
         {
-            const float x = (float) (short) (v.x & 0xFFFFu);
-            shift_vec(v);
+            float x;
+            if (IN8)
+            {
+                x = lut[v.x & 0xFFu];
+                shift_vec8(v);
+            }
+            else
+            {
+                x = (float) (short) (v.x & 0xFFFFu);
+                shift_vec(v);
+            }
             step<FILT>(x);
             if (++cs == B)
             {
@@ -252,25 +295,60 @@ struct Runner
         }
     }
 
-    // A whole vector.  The common case - no block boundary inside - takes the unrolled path.
-    // All conditions are warp-uniform in the staged kernel.
-    template <bool FILT>
-    __device__ __forceinline__ void full(const uint4 &v, const BankArgs<DET> &a)
+    // A whole vector.  The common case - no block boundary inside a group of eight samples - takes the
+    // unrolled path.  All conditions are warp-uniform in the staged kernel.
+    template <bool FILT, bool IN8>
+    __device__ __forceinline__ void full(const uint4 &v, const BankArgs<DET> &a, const float *lut)
     {
         const int B = block_len(a);
-        if (cs + 8 <= B)
+        if (!IN8)
         {
-            fast8<FILT>(v);
-            cs += 8;
-            if (cs == B)
+            if (cs + 8 <= B)
             {
-                block_end(a);
-                zero_after_block();
+                fast8<FILT>(v);
+                cs += 8;
+                if (cs == B)
+                {
+                    block_end(a);
+                    zero_after_block();
+                }
+            }
+            else
+            {
+                partial<FILT, false>(v, 0, 8, a, lut);
             }
         }
         else
         {
-            partial<FILT>(v, 0, 8, a);
+            // two groups of eight companded samples
+            if (cs + 8 <= B)
+            {
+                fast8_g711<FILT>(v.x, v.y, lut);
+                cs += 8;
+                if (cs == B)
+                {
+                    block_end(a);
+                    zero_after_block();
+                }
+            }
+            else
+            {
+                partial<FILT, true>(v, 0, 8, a, lut);
+            }
+            if (cs + 8 <= B)
+            {
+                fast8_g711<FILT>(v.z, v.w, lut);
+                cs += 8;
+                if (cs == B)
+                {
+                    block_end(a);
+                    zero_after_block();
+                }
+            }
+            else
+            {
+                partial<FILT, true>(v, 8, 16, a, lut);
+            }
         }
     }
 };
@@ -286,14 +364,26 @@ struct StageCfg
     static_assert(SEG_VEC == 8  ||  SEG_VEC == 16  ||  SEG_VEC == 32, "SEG_VEC lanes copy one row segment");
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK>
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK, bool IN8>
 __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankArgs<DET> a)
 {
+    constexpr int VSH = (IN8)  ?  4  :  3;          // log2(samples per 16-byte vector)
+    constexpr int VMASK = (1 << VSH) - 1;
+    constexpr int BPS = (IN8)  ?  1  :  2;          // bytes per sample
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // 8-bit input: the 256-entry expansion table sits in front of the rings (1 KB per CTA)
+    const float *lut = (const float *) smem_raw;
+    if (IN8)
+    {
+        float *w = (float *) smem_raw;
+        for (int i = threadIdx.x;  i < 256;  i += WARPS*32)
+            w[i] = a.lut[i];
+        __syncthreads();
+    }
     const int ngroups = (a.channels + 31) >> 5;
     const long long item = (long long) blockIdx.x*WARPS + warp;
     const int group = (int) (item % ngroups);
@@ -350,13 +440,13 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     }
 
     // ---- staging geometry ----
-    const uint32_t warp_smem = (uint32_t) __cvta_generic_to_shared(smem_raw) + warp*cfg::WARP_BYTES;
+    const uint32_t warp_smem = (uint32_t) __cvta_generic_to_shared(smem_raw) + ((IN8)  ?  1024  :  0) + warp*cfg::WARP_BYTES;
     const uint32_t my_row = warp_smem + lane*cfg::ROW_BYTES;
-    const int v_lo = start >> 3;
-    const int v_hi = (end + 7) >> 3;
+    const int v_lo = start >> VSH;
+    const int v_hi = (end + VMASK) >> VSH;
     const int g_lo = v_lo/SEG_VEC;
     const int g_hi = (v_hi + SEG_VEC - 1)/SEG_VEC;
-    const long long row_bytes = (long long) a.n*2;
+    const long long row_bytes = (long long) a.n*BPS;
 
     // copy role of this lane: SEG_VEC lanes cover one row segment; 32/SEG_VEC rows per instruction
     constexpr int RPI = 32/SEG_VEC;
@@ -365,8 +455,8 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
 
     // Row pointer of this lane's first copy and the byte step between its successive copies.
     const bool full_group = (group*32 + 32 <= a.channels);
-    const char *cp_src0 = (const char *) (a.amp + (long long) (group*32 + cp_row0)*a.stride) + (long long) cp_vec*16;
-    const long long cp_step = (long long) RPI*a.stride*2;
+    const char *cp_src0 = (const char *) a.amp + (long long) (group*32 + cp_row0)*a.stride*BPS + (long long) cp_vec*16;
+    const long long cp_step = (long long) RPI*a.stride*BPS;
     const uint32_t cp_dst0 = warp_smem + cp_row0*cfg::ROW_BYTES + cp_vec*16;
 
     auto issue = [&](int g)
@@ -399,7 +489,7 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
                     int ch = group*32 + i*RPI + cp_row0;
                     if (ch >= a.channels)
                         ch = a.channels - 1;
-                    const char *src = (const char *) (a.amp + (long long) ch*a.stride) + off + cp_vec*16;
+                    const char *src = (const char *) a.amp + (long long) ch*a.stride*BPS + off + cp_vec*16;
                     cp_async_16(dst, src, sb);
                     dst += RPI*cfg::ROW_BYTES;
                 }
@@ -431,21 +521,21 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
             const int jb = (jt >= 0)  ?  jt  :  j1;
             if (jh >= 0)
             {
-                const int hi_h = (v_hi - 1 == v_lo)  ?  (((end - 1) & 7) + 1)  :  8;
-                r.template partial<FILT>(lds128(stage + jh*16), start & 7, hi_h, a);
+                const int hi_h = (v_hi - 1 == v_lo)  ?  (((end - 1) & VMASK) + 1)  :  (VMASK + 1);
+                r.template partial<FILT, IN8>(lds128(stage + jh*16), start & VMASK, hi_h, a, lut);
             }
             int j = ja;
             for (  ;  j + 2 <= jb;  j += 2)
             {
                 const uint4 v0 = lds128(stage + j*16);
                 const uint4 v1 = lds128(stage + j*16 + 16);
-                r.template full<FILT>(v0, a);
-                r.template full<FILT>(v1, a);
+                r.template full<FILT, IN8>(v0, a, lut);
+                r.template full<FILT, IN8>(v1, a, lut);
             }
             if (j < jb)
-                r.template full<FILT>(lds128(stage + j*16), a);
+                r.template full<FILT, IN8>(lds128(stage + j*16), a, lut);
             if (jt >= 0)
-                r.template partial<FILT>(lds128(stage + jt*16), 0, ((end - 1) & 7) + 1, a);
+                r.template partial<FILT, IN8>(lds128(stage + jt*16), 0, ((end - 1) & VMASK) + 1, a, lut);
         }
     };
     if (DET::FILTER  &&  any_filter)
@@ -465,7 +555,7 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
 // ------------------------------------------------------------------------------------------
 // Direct kernel: any block phase per channel, any alignment.  One thread per channel over the
 // whole call; samples are read with 16-bit loads through L1.
-template <class DET, int NPACK>
+template <class DET, int NPACK, bool IN8>
 __global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
 {
     const int c = blockIdx.x*blockDim.x + threadIdx.x;
@@ -493,12 +583,13 @@ __global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
         DET::load_filter(a.det, c, a.channels, r.z);
     }
     const int16_t *row = a.amp + (long long) c*a.stride;
+    const unsigned char *row8 = (const unsigned char *) a.amp + (long long) c*a.stride;
     if (DET::FILTER  &&  r.filt)
     {
 #pragma unroll 1
         for (int i = 0;  i < a.n;  i++)
         {
-            r.template step<true>((float) __ldg(row + i));
+            r.template step<true>((IN8)  ?  __ldg(a.lut + __ldg(row8 + i))  :  (float) __ldg(row + i));
             if (++r.cs == block_len(a))
             {
                 r.block_end(a);
@@ -512,7 +603,7 @@ __global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
 #pragma unroll 1
         for (int i = 0;  i < a.n;  i++)
         {
-            r.template step<false>((float) __ldg(row + i));
+            r.template step<false>((IN8)  ?  __ldg(a.lut + __ldg(row8 + i))  :  (float) __ldg(row + i));
             if (++r.cs == block_len(a))
             {
                 r.block_end(a);

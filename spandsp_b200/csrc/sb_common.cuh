@@ -130,6 +130,15 @@ __device__ __forceinline__ void shift_vec(uint4 &v)
     v.w = v.w >> 16;
 }
 
+// Shift a 16-byte vector right by one byte (companded input).
+__device__ __forceinline__ void shift_vec8(uint4 &v)
+{
+    v.x = __funnelshift_r(v.x, v.y, 8);
+    v.y = __funnelshift_r(v.y, v.z, 8);
+    v.z = __funnelshift_r(v.z, v.w, 8);
+    v.w = v.w >> 8;
+}
+
 __device__ __forceinline__ void shift_vec_n(uint4 &v, int lanes)
 {
     for (int i = 0;  i < lanes;  i++)

@@ -893,22 +893,37 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             pending = 0;
     }
     const long long consumed_at_end = (long long) cs_old + s.q.n;
-    for (int b = 0;  b < nb_max;  b++)
+    constexpr int G = 16;
+    for (int b0 = 0;  b0 < nb_max;  b0 += G)
     {
-        const bool run = (b < nb);
-        const int code = (run)  ?  s.code[(size_t) b*C + c]  :  0;
-        chunk(run, (code & 0x7F) - 1, ((code >> 7) & 0x7F) - 1);
-        flush(b);
-        const bool quirk = run  &&  (code & SB_ST_QUIRK);
-        if (__any_sync(0xFFFFFFFFu, quirk))
+        unsigned short codes[G];
+#pragma unroll
+        for (int i = 0;  i < G;  i++)
+            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned short) 0;
+#pragma unroll 1
+        for (int i = 0;  i < G;  i++)
         {
-            // The reference loops straight back into super_tone_chunk with zero energy unless the
-            // block ended exactly at the end of the caller's buffer (src/super_tone_rx.c:466-486).
-            const bool again = quirk  &&  ((long long) (b + 1)*B < consumed_at_end);
-            chunk(again, -1, -1);
+            const int b = b0 + i;
+            if (b >= nb_max)
+                break;
+            const bool run = (b < nb);
+            int code = 0;
+#pragma unroll
+            for (int q = 0;  q < G;  q++)
+                code = (q == i)  ?  (int) codes[q]  :  code;
+            chunk(run, (code & 0x7F) - 1, ((code >> 7) & 0x7F) - 1);
             flush(b);
-            if (quirk  &&  !again)
-                pending = 1;
+            const bool quirk = run  &&  (code & SB_ST_QUIRK);
+            if (__any_sync(0xFFFFFFFFu, quirk))
+            {
+                // The reference loops straight back into super_tone_chunk with zero energy unless the
+                // block ended exactly at the end of the caller's buffer (src/super_tone_rx.c:466-486).
+                const bool again = quirk  &&  ((long long) (b + 1)*B < consumed_at_end);
+                chunk(again, -1, -1);
+                flush(b);
+                if (quirk  &&  !again)
+                    pending = 1;
+            }
         }
     }
     sink.finish(wg);

@@ -73,6 +73,26 @@ float sb_goertzel_fac(float freq)
     return 2.0f*cosf((float) (2.0f*M_PI*(freq/8000.0f)));
 }
 
+// G.711 expansion (src/spandsp/g711.h:165-172 u-law with bias 0x84, :239-252 A-law with AMI mask 0x55)
+int sb_ulaw_to_linear(unsigned char ulaw)
+{
+    ulaw = (unsigned char) ~ulaw;
+    const int t = (((ulaw & 0x0F) << 3) + 0x84) << (((int) ulaw & 0x70) >> 4);
+    return (short) ((ulaw & 0x80)  ?  (0x84 - t)  :  (t - 0x84));
+}
+
+int sb_alaw_to_linear(unsigned char alaw)
+{
+    alaw ^= 0x55;
+    int i = ((alaw & 0x0F) << 4);
+    const int seg = (((int) alaw & 0x70) >> 4);
+    if (seg)
+        i = (i + 0x108) << (seg - 1);
+    else
+        i += 8;
+    return (short) ((alaw & 0x80)  ?  i  :  -i);
+}
+
 // src/dtmf.c:110,314 with lfastrintf = C truncation on x86-64 (src/spandsp/fast_convert.h:194-197)
 static int host_dtmf_level(float energy)
 {
@@ -124,6 +144,7 @@ struct span_b200_ctx_s
     float *d_level_thr;
     int level_n;
     int level_min;
+    float *d_g711_lut;              // [2][256]: u-law, A-law expansion as float
 };
 
 static int upload_constants(int device)
@@ -193,6 +214,14 @@ extern "C" span_b200_ctx_t *span_b200_ctx_create(int device)
     ctx->level_n = (int) thr.size();
     CKP(cudaMalloc(&ctx->d_level_thr, sizeof(float)*thr.size()));
     CKP(cudaMemcpy(ctx->d_level_thr, thr.data(), sizeof(float)*thr.size(), cudaMemcpyHostToDevice));
+    float lut[512];
+    for (int i = 0;  i < 256;  i++)
+    {
+        lut[i] = (float) sb_ulaw_to_linear((unsigned char) i);
+        lut[256 + i] = (float) sb_alaw_to_linear((unsigned char) i);
+    }
+    CKP(cudaMalloc(&ctx->d_g711_lut, sizeof(lut)));
+    CKP(cudaMemcpy(ctx->d_g711_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     return ctx;
 }
 
@@ -203,6 +232,7 @@ extern "C" void span_b200_ctx_destroy(span_b200_ctx_t *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_level_thr);
+    cudaFree(ctx->d_g711_lut);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -830,12 +860,12 @@ struct Geometry
     bool staged;
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK>
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK, bool IN8 = false>
 static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
 {
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
-    const int smem = cfg::WARP_BYTES*WARPS;
-    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK>;
+    const int smem = cfg::WARP_BYTES*WARPS + ((IN8)  ?  1024  :  0);
+    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK, IN8>;
     static bool configured = false;
     if (!configured)
     {
@@ -868,6 +898,23 @@ static int launch_variant(const BankArgs<DET> &a, int variant, cudaStream_t st)
 template <class DET>
 static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g, cudaStream_t st, bool all_variants)
 {
+    if (a.lut)
+    {
+        // 8-bit companded input: one staged shape, or the direct kernel
+        a.cs0 = g.cs0;
+        a.slice_blocks = g.slice_blocks;
+        a.nslices = g.nslices;
+        a.nblocks = g.nb;
+        if (g.staged)
+        {
+            b->last_path = "staged";
+            return launch_staged<DET, 8, 2, 4, 4, DET::NPAIRS, true>(a, st);
+        }
+        b->last_path = "direct";
+        bank_kernel_direct<DET, DET::NPAIRS, true><<<(a.channels + 127)/128, 128, 0, st>>>(a);
+        CK(cudaGetLastError());
+        return 0;
+    }
     a.cs0 = g.cs0;
     a.slice_blocks = g.slice_blocks;
     a.nslices = g.nslices;
@@ -885,9 +932,9 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
     b->last_path = "direct";
     const int grid = (a.channels + 127)/128;
     if (b->tune_packed  ||  !all_variants)
-        bank_kernel_direct<DET, DET::NPAIRS><<<grid, 128, 0, st>>>(a);
+        bank_kernel_direct<DET, DET::NPAIRS, false><<<grid, 128, 0, st>>>(a);
     else
-        bank_kernel_direct<DET, 0><<<grid, 128, 0, st>>>(a);
+        bank_kernel_direct<DET, 0, false><<<grid, 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return 0;
 }
@@ -916,10 +963,11 @@ static void fill_common(span_b200_bank_t *b, BankArgs<DET> &a, const int16_t *d_
 }
 
 template <int NP>
-static int run_st(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, const Geometry &g, cudaStream_t st)
+static int run_st(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, const Geometry &g, cudaStream_t st, const float *lut)
 {
     BankArgs<SuperToneDet<NP> > a;
     fill_common(b, a, d_amp, stride, n);
+    a.lut = lut;
     a.det = b->stp;
     return launch_st<NP>(b, a, g, st);
 }
@@ -940,8 +988,8 @@ static long long worst_case_events(const span_b200_bank_t *b, int nb)
     }
 }
 
-extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
-                                        int n, void *stream)
+// law: -1 = int16 linear samples; 0 = u-law bytes; 1 = A-law bytes (stride in samples either way)
+static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, void *stream, int law)
 {
     if (b == NULL  ||  n < 0  ||  (n > 0  &&  d_amp == NULL))
     {
@@ -955,8 +1003,9 @@ extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_am
     const int B = b->block;
     Geometry g;
     g.cs0 = b->uniform_cs;
-    const bool aligned = ((((uintptr_t) d_amp) & 15) == 0)  &&  ((stride & 7) == 0);
+    const bool aligned = ((((uintptr_t) d_amp) & 15) == 0)  &&  ((stride & ((law >= 0)  ?  15  :  7)) == 0);
     g.staged = (g.cs0 >= 0)  &&  aligned  &&  !b->tune_direct  &&  n > 0;
+    const float *lut = (law >= 0)  ?  (b->ctx->d_g711_lut + 256*law)  :  NULL;
     g.nb = (g.cs0 >= 0)  ?  (g.cs0 + n)/B  :  (B - 1 + n)/B;
     // ---- time slicing ----
     g.nslices = 1;
@@ -1029,6 +1078,7 @@ extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_am
             {
                 BankArgs<DtmfDet> a;
                 fill_common(b, a, d_amp, stride, n);
+                a.lut = lut;
                 a.det.threshold = b->thr;
                 a.det.normal_twist = b->ntw;
                 a.det.reverse_twist = b->rtw;
@@ -1041,6 +1091,7 @@ extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_am
             {
                 BankArgs<BellMfDet> a;
                 fill_common(b, a, d_amp, stride, n);
+                a.lut = lut;
                 rc = launch_bank<BellMfDet>(b, a, g, st, false);
             }
             break;
@@ -1048,31 +1099,32 @@ extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_am
             {
                 BankArgs<R2MfDet> a;
                 fill_common(b, a, d_amp, stride, n);
+                a.lut = lut;
                 a.det.fwd = b->fwd;
                 rc = launch_bank<R2MfDet>(b, a, g, st, false);
             }
             break;
         case SPAN_B200_DET_SUPER_TONE:
             if (b->npairs <= 1)
-                rc = run_st<1>(b, d_amp, stride, n, g, st);
+                rc = run_st<1>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 2)
-                rc = run_st<2>(b, d_amp, stride, n, g, st);
+                rc = run_st<2>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 3)
-                rc = run_st<3>(b, d_amp, stride, n, g, st);
+                rc = run_st<3>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 4)
-                rc = run_st<4>(b, d_amp, stride, n, g, st);
+                rc = run_st<4>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 5)
-                rc = run_st<5>(b, d_amp, stride, n, g, st);
+                rc = run_st<5>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 6)
-                rc = run_st<6>(b, d_amp, stride, n, g, st);
+                rc = run_st<6>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 8)
-                rc = run_st<8>(b, d_amp, stride, n, g, st);
+                rc = run_st<8>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 10)
-                rc = run_st<10>(b, d_amp, stride, n, g, st);
+                rc = run_st<10>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 12)
-                rc = run_st<12>(b, d_amp, stride, n, g, st);
+                rc = run_st<12>(b, d_amp, stride, n, g, st, lut);
             else
-                rc = run_st<16>(b, d_amp, stride, n, g, st);
+                rc = run_st<16>(b, d_amp, stride, n, g, st, lut);
             break;
         }
         if (rc != 0)
@@ -1181,6 +1233,43 @@ extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_am
     return 0;
 }
 
+extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
+                                        int n, void *stream)
+{
+    return rx_core(b, d_amp, stride, n, stream, -1);
+}
+
+extern "C" int span_b200_bank_rx_device_g711(span_b200_bank_t *b, const uint8_t *d_data, int64_t stride,
+                                             int n, int alaw, void *stream)
+{
+    return rx_core(b, (const int16_t *) d_data, stride, n, stream, (alaw)  ?  1  :  0);
+}
+
+extern "C" int span_b200_bank_rx_host_g711(span_b200_bank_t *b, const uint8_t *h_data, int64_t stride,
+                                           int n, int alaw, void *stream)
+{
+    if (b == NULL  ||  n < 0  ||  (n > 0  &&  h_data == NULL))
+    {
+        sb_set_error("bad rx arguments");
+        return -1;
+    }
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
+    if (b->have_last  &&  b->last_stream != st)
+        CK(cudaStreamSynchronize(b->last_stream));
+    const int64_t dstride = (n + 15) & ~15LL;
+    if (ensure((void **) &b->d_in, &b->d_in_bytes, (size_t) dstride*b->channels + 16) != 0)
+        return -1;
+    if (n > 0)
+    {
+        if (stride == n  &&  dstride == n)
+            CK(cudaMemcpyAsync(b->d_in, h_data, (size_t) n*b->channels, cudaMemcpyHostToDevice, st));
+        else
+            CK(cudaMemcpy2DAsync(b->d_in, (size_t) dstride, h_data, (size_t) stride, (size_t) n, b->channels, cudaMemcpyHostToDevice, st));
+    }
+    return rx_core(b, b->d_in, dstride, n, (void *) st, (alaw)  ?  1  :  0);
+}
+
 extern "C" int span_b200_bank_rx_host(span_b200_bank_t *b, const int16_t *h_amp, int64_t stride,
                                       int n, void *stream)
 {
@@ -1199,8 +1288,16 @@ extern "C" int span_b200_bank_rx_host(span_b200_bank_t *b, const int16_t *h_amp,
         return -1;
     if (n > 0)
     {
-        CK(cudaMemcpy2DAsync(b->d_in, sizeof(int16_t)*dstride, h_amp, sizeof(int16_t)*stride,
-                             sizeof(int16_t)*(size_t) n, b->channels, cudaMemcpyHostToDevice, st));
+        if (stride == n  &&  dstride == n)
+        {
+            // contiguous on both sides: one flat copy (measured 55 GB/s vs ~50 GB/s for the pitched form)
+            CK(cudaMemcpyAsync(b->d_in, h_amp, sizeof(int16_t)*(size_t) n*b->channels, cudaMemcpyHostToDevice, st));
+        }
+        else
+        {
+            CK(cudaMemcpy2DAsync(b->d_in, sizeof(int16_t)*dstride, h_amp, sizeof(int16_t)*stride,
+                                 sizeof(int16_t)*(size_t) n, b->channels, cudaMemcpyHostToDevice, st));
+        }
     }
     return span_b200_bank_rx_device(b, b->d_in, dstride, n, (void *) st);
 }
@@ -1337,7 +1434,7 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
         a.nslices = (nb > L)  ?  ((nb + L - 1)/L)  :  1;
         return launch_staged<RawDet<NP>, 8, 2, 4, 4, NP>(a, st);
     }
-    bank_kernel_direct<RawDet<NP>, NP><<<(channels + 127)/128, 128, 0, st>>>(a);
+    bank_kernel_direct<RawDet<NP>, NP, false><<<(channels + 127)/128, 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return 0;
 }

@@ -9,3 +9,5 @@
 void sb_set_error(const char *fmt, ...);
 float sb_goertzel_fac(float freq);
 void *sb_ctx_stream(span_b200_ctx_t *ctx);
+int sb_ulaw_to_linear(unsigned char ulaw);
+int sb_alaw_to_linear(unsigned char alaw);

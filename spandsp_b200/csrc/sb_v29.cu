@@ -1165,6 +1165,10 @@ __global__ void __launch_bounds__(32) v29_rx_kernel(const Args a)
 #pragma unroll 1
         for (int h = 0;  h < 2;  h++)
         {
+            // A channel that enters the trip half-way through a baud sits out the first slot, so that
+            // every channel completes its baud in the second slot (and is baud-aligned from then on).
+            if (h == 0  &&  r.baud_half)
+                continue;
             bool due = false;
 #pragma unroll 1
             for (int q = 0;  q < 2;  q++)

@@ -61,6 +61,8 @@ def lib():
         "span_b200_bank_status": (i32, [vp, i32, i32, vp]),
         "span_b200_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
         "span_b200_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_bank_rx_device_g711": (i32, [vp, vp, i64, i32, i32, vp]),
+        "span_b200_bank_rx_host_g711": (i32, [vp, vp, i64, i32, i32, vp]),
         "span_b200_bank_event_count": (i64, [vp, C.POINTER(i32)]),
         "span_b200_bank_events": (i64, [vp, vp, i64]),
         "span_b200_bank_events_device": (vp, [vp]),
@@ -242,6 +244,18 @@ class Bank:
             return
         assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
         self._ck(lib().span_b200_bank_rx_host(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
+
+    def rx_device_g711(self, d_ptr, stride, samples, alaw=False, stream=None):
+        self._ck(lib().span_b200_bank_rx_device_g711(self.h, d_ptr, stride, samples, int(alaw), stream))
+
+    def rx_host_g711(self, data, alaw=False, stream=None, samples=None):
+        """data: uint8 numpy array [channels, n] or a (ptr, stride) pair with samples."""
+        if isinstance(data, tuple):
+            ptr, stride = data
+            self._ck(lib().span_b200_bank_rx_host_g711(self.h, ptr, stride, samples, int(alaw), stream))
+            return
+        assert data.dtype == np.uint8 and data.ndim == 2 and data.shape[0] == self.channels and data.strides[1] == 1
+        self._ck(lib().span_b200_bank_rx_host_g711(self.h, data.ctypes.data, data.strides[0], data.shape[1], int(alaw), stream))
 
     def event_count(self):
         ov = C.c_int(0)
