@@ -257,6 +257,7 @@ def main():
     ap.add_argument("--packed", type=int, default=-1, help="f32x2 adds on/off (tuning)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-g711", action="store_true")
     ap.add_argument("--realtime", type=int, default=1, help="1: realtime (on/off + level) events, 0: digit events")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -421,6 +422,44 @@ def main():
                "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
                "path": "span_b200_bank_rx_host (pinned int16 [channel][sample]) + span_b200_bank_events"}
         del h_amp
+        # ---- same, with 8-bit u-law input (G.711 expand fused into the kernel load).
+        # Reported beside e2e, not instead of it: the reference API takes int16.
+        gpath = os.path.join(ROOT, "tests", "golden", "g711_golden.npz")
+        if os.path.exists(gpath) and not args.no_g711:
+            enc = torch.from_numpy(np.load(gpath)["encode_ulaw"]).to(dev)
+            h_u8 = torch.empty((C, T), dtype=torch.uint8, pin_memory=True)
+            for c0 in range(0, C, 2048):
+                c1 = min(C, c0 + 2048)
+                h_u8[c0:c1].copy_(enc[(d_amp[c0:c1].to(torch.int32) + 32768).long()])
+            torch.cuda.synchronize()
+            del enc
+            bank.reset()
+            if args.realtime:
+                bank.dtmf_realtime(True)
+
+            def step_host_g711():
+                bank.rx_host_g711((h_u8.data_ptr(), T), False, stream, samples=T)
+                return len(bank.events(out=h_events))
+
+            for _ in range(2):
+                nev8 = step_host_g711()
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(e2e_steps):
+                nev8 = step_host_g711()
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            gms = max(e0.elapsed_time(e1), wall * 1e3)
+            t = torch.tensor([gms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gms = float(t.item())
+            e2e["g711_ulaw"] = {"value": C * world * T * e2e_steps / (gms / 1e3) / 1e6, "unit": "Msamples/s",
+                                "h2d_bytes_per_step": int(C * T), "d2h_bytes_per_step": int(nev8 * 24 + 8),
+                                "ms_per_step": gms / e2e_steps, "path": "span_b200_bank_rx_host_g711 (pinned u-law bytes)"}
+            del h_u8
 
     if rank != 0:
         if world > 1:
