@@ -159,6 +159,26 @@ float v29_rx_signal_power(v29_rx_state_t *s);
 void v29_rx_set_signal_cutoff(v29_rx_state_t *s, float cutoff);
 void v29_rx_set_qam_report_handler(v29_rx_state_t *s, qam_report_handler_t handler, void *user_data);
 
+/* ---- V.17 receiver: src/spandsp/v17rx.h:236-333, src/v17rx.c:157-204,1214-1541 -------------------- */
+typedef struct v17_rx_state_s v17_rx_state_t;
+
+/* Synchronous, one receiver per state (a bank of one).  Banks of many receivers: spandsp_b200_v17.h. */
+v17_rx_state_t *v17_rx_init(v17_rx_state_t *s, int bit_rate, span_put_bit_func_t put_bit, void *user_data);
+int v17_rx_restart(v17_rx_state_t *s, int bit_rate, int short_train);
+int v17_rx_release(v17_rx_state_t *s);
+int v17_rx_free(v17_rx_state_t *s);
+logging_state_t *v17_rx_get_logging_state(v17_rx_state_t *s);
+void v17_rx_set_put_bit(v17_rx_state_t *s, span_put_bit_func_t put_bit, void *user_data);
+void v17_rx_set_modem_status_handler(v17_rx_state_t *s, span_modem_status_func_t handler, void *user_data);
+int v17_rx(v17_rx_state_t *s, const int16_t amp[], int len);
+int v17_rx_fillin(v17_rx_state_t *s, int len);
+int v17_rx_equalizer_state(v17_rx_state_t *s, complexf_t **coeffs);
+float v17_rx_carrier_frequency(v17_rx_state_t *s);
+float v17_rx_symbol_timing_correction(v17_rx_state_t *s);
+float v17_rx_signal_power(v17_rx_state_t *s);
+void v17_rx_set_signal_cutoff(v17_rx_state_t *s, float cutoff);
+void v17_rx_set_qam_report_handler(v17_rx_state_t *s, qam_report_handler_t handler, void *user_data);
+
 #if defined(__cplusplus)
 }
 #endif

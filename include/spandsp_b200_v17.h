@@ -1,0 +1,74 @@
+/*
+ * spandsp_b200_v17.h - C ABI of the V.17 receiver banks (bulk interface).
+ *
+ * A bank = N independent V.17 receivers (src/v17rx.c) processed by one call; channel c reads
+ * d_amp[c*stride .. c*stride + samples).  What the reference delivers through callbacks is returned
+ * as per-channel streams, exactly as for V.29 (spandsp_b200_v29.h):
+ *   - the put_bit stream (span_put_bit_func_t, src/spandsp/async.h:123): one int8 per call, 0/1 for
+ *     data bits and the negative SIG_STATUS_* codes (async.h:66-103) exactly where the reference would
+ *     have delivered them (no separate status handler: src/v17rx.c:181-189);
+ *   - optionally the equalized symbols of qam_report_handler_t (src/spandsp/v29rx.h:130), reported
+ *     once per baud in every training stage (src/v17rx.c:1115-1131).
+ */
+#if !defined(_SPANDSP_B200_V17_H_)
+#define _SPANDSP_B200_V17_H_
+
+#include <stdint.h>
+
+#include "spandsp_b200.h"
+#include "spandsp_b200_v29.h"
+
+#if defined(__cplusplus)
+extern "C"
+{
+#endif
+
+typedef struct span_b200_v17_bank_s span_b200_v17_bank_t;
+
+/* One qam_report: equalizer output z, the target, and the constellation_state argument. */
+typedef span_b200_v29_symbol_t span_b200_v17_symbol_t;
+
+/* v17_rx_init(NULL, bit_rate, ...) x channels (src/v17rx.c:1496-1530).  bit_rate: 14400, 12000, 9600,
+   7200, or 4800 (the V.32bis mode without trellis the reference carries); anything else fails as in the
+   reference.  want_symbols != 0 records the qam_report stream. */
+span_b200_v17_bank_t *span_b200_v17_bank_create(span_b200_ctx_t *ctx, int channels, int bit_rate, int want_symbols);
+void span_b200_v17_bank_destroy(span_b200_v17_bank_t *bank);
+int span_b200_v17_bank_channels(const span_b200_v17_bank_t *bank);
+/* v17_rx_restart(s, bit_rate, short_train) (src/v17rx.c:1386) for channels [first, first+count).
+   short_train: 0 = long training, 1 = short training (reuse the saved equalizer, carrier and gain),
+   2 = keep whatever the receiver currently holds (the reference's internal "no change" value). */
+int span_b200_v17_bank_restart(span_b200_v17_bank_t *bank, int first, int count, int bit_rate, int short_train);
+/* v17_rx_set_signal_cutoff() (src/v17rx.c:173-178) */
+int span_b200_v17_bank_set_signal_cutoff(span_b200_v17_bank_t *bank, int first, int count, float cutoff);
+/* v17_rx_fillin() (src/v17rx.c:1313-1343) */
+int span_b200_v17_bank_fillin(span_b200_v17_bank_t *bank, int first, int count, int samples);
+
+/* v17_rx() (src/v17rx.c:1214) for every channel; device / host sample memory as in spandsp_b200.h. */
+int span_b200_v17_bank_rx_device(span_b200_v17_bank_t *bank, const int16_t *d_amp, int64_t stride, int samples, void *stream);
+int span_b200_v17_bank_rx_host(span_b200_v17_bank_t *bank, const int16_t *h_amp, int64_t stride, int samples, void *stream);
+
+/* Results of the last rx call.  counts: per channel number of put_bit calls / qam reports. */
+int span_b200_v17_bank_counts(span_b200_v17_bank_t *bank, int32_t *nbits, int32_t *nsyms);
+int64_t span_b200_v17_bank_bits(span_b200_v17_bank_t *bank, int channel, int8_t *out, int64_t max);
+int64_t span_b200_v17_bank_symbols(span_b200_v17_bank_t *bank, int channel, span_b200_v17_symbol_t *out, int64_t max);
+/* Device-side layout of the result buffers ([channel][capacity]) for callers that consume them on the GPU. */
+int span_b200_v17_bank_output_layout(span_b200_v17_bank_t *bank, const int8_t **d_bits, int64_t *bits_cap,
+                                     const int32_t **d_nbits, const span_b200_v17_symbol_t **d_syms,
+                                     int64_t *sym_cap, const int32_t **d_nsyms);
+/* eq_coeff: 33 complex taps (v17_rx_equalizer_state, src/v17rx.c:192-204); info[12] =
+   {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling (float bits),
+    total_baud_timing_correction, diff, carrier_phase, power meter reading, bit_rate, short_train, trellis_ptr}. */
+int span_b200_v17_bank_channel_state(span_b200_v17_bank_t *bank, int channel, float *eq_coeff, int32_t *info);
+
+/* The constant tables the receiver is built on, as computed by this library's own generators (for
+   verification against the reference's generated / checked-in headers).  rrc_*: [192][27]; godard: 9 floats;
+   ints: 12; constellations: 244 complex points (14400: 128, 12000: 64, 9600: 32, 7200: 16, 4800: 4);
+   maps: [4][36][36][8]; map4800: [36][36]. */
+int span_b200_v17_tables(float *rrc_re, float *rrc_im, float *godard, int32_t *ints, float *constellations,
+                         uint8_t *maps, uint8_t *map4800);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif

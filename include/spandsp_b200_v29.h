@@ -41,6 +41,9 @@ void span_b200_v29_bank_destroy(span_b200_v29_bank_t *bank);
 int span_b200_v29_bank_channels(const span_b200_v29_bank_t *bank);
 /* v29_rx_restart(s, bit_rate, false) (src/v29rx.c:1019) for channels [first, first+count). */
 int span_b200_v29_bank_restart(span_b200_v29_bank_t *bank, int first, int count, int bit_rate);
+/* v29_rx_restart(s, bit_rate, old_train): old_train != 0 reuses the saved equalizer, carrier and gain
+   (src/v29rx.c:1064-1069). */
+int span_b200_v29_bank_restart_ex(span_b200_v29_bank_t *bank, int first, int count, int bit_rate, int old_train);
 /* v29_rx_set_signal_cutoff() (src/v29rx.c:163-168) */
 int span_b200_v29_bank_set_signal_cutoff(span_b200_v29_bank_t *bank, int first, int count, float cutoff);
 /* v29_rx_fillin() (src/v29rx.c:967-996): sustain carrier phase and symbol timing over `samples` lost samples. */

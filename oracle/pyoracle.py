@@ -207,7 +207,7 @@ def v29_generate(o, n, bit_rate=9600, tep=False, power_dbm0=-13.0, lfsr_seed=1, 
     return amp
 
 
-def v29_run(o, amp, bit_rate=9600, chunk=160, cutoff=-100.0, want_qam=True):
+def v29_run(o, amp, bit_rate=9600, chunk=160, cutoff=-100.0, want_qam=True, restart_at=-1, restart_old_train=0):
     """One channel through the reference's v29_rx.  Returns dict(bits int8[], syms, eq_coeff[66], final[8])."""
     amp = np.ascontiguousarray(amp, dtype=np.int16)
     n = len(amp)
@@ -217,8 +217,9 @@ def v29_run(o, amp, bit_rate=9600, chunk=160, cutoff=-100.0, want_qam=True):
     ns = C.c_int32(0)
     eq = np.zeros(66, dtype=np.float32)
     fin = np.zeros(8, dtype=np.int32)
-    o.lib.ref_v29_run.restype = C.c_int
-    rc = o.lib.ref_v29_run(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(bit_rate), C.c_float(cutoff), C.c_int(int(want_qam)),
+    o.lib.ref_v29_run_ex.restype = C.c_int
+    rc = o.lib.ref_v29_run_ex(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(bit_rate), C.c_float(cutoff), C.c_int(int(want_qam)),
+                           C.c_int(restart_at), C.c_int(restart_old_train),
                            C.c_void_p(bits.ctypes.data), C.c_int(bits.size), C.byref(nb), C.c_void_p(syms.ctypes.data), C.c_int(syms.size),
                            C.byref(ns), C.c_void_p(eq.ctypes.data), C.c_void_p(fin.ctypes.data))
     if rc != 0:
@@ -245,6 +246,61 @@ def v29_tables(lib, fn_name):
     getattr(lib, fn_name)(C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data), C.c_void_p(si.ctypes.data), C.c_void_p(sq.ctypes.data),
                           C.c_void_p(g.ctypes.data), C.c_void_p(it.ctypes.data))
     return {"rrc_re": re, "rrc_im": im, "sine": si, "sqrt": sq, "godard": g, "ints": it}
+
+
+def v17_generate(o, n, bit_rate=14400, tep=False, power_dbm0=-13.0, lfsr_seed=1, lead=0, burst1=-1, gap=0, burst2=0,
+                 noise_seed=1234567, noise_dbm0=-50.0):
+    """v17_tx of PRBS data (+ awgn): silence, a long-trained burst, optionally a gap and a short-trained burst."""
+    amp = np.zeros(n, dtype=np.int16)
+    o.lib.ref_v17_generate.restype = C.c_int
+    rc = o.lib.ref_v17_generate(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(bit_rate), C.c_int(int(tep)), C.c_float(power_dbm0),
+                                C.c_uint32(lfsr_seed), C.c_int(lead), C.c_int(burst1), C.c_int(gap), C.c_int(burst2),
+                                C.c_int(noise_seed), C.c_float(noise_dbm0))
+    if rc < 0:
+        raise RuntimeError("ref_v17_generate failed")
+    return amp
+
+
+def v17_run(o, amp, bit_rate=14400, chunk=160, cutoff=-100.0, want_qam=True, restart_at=-1, restart_short=1):
+    """One channel through the reference's v17_rx.  Returns dict(bits int8[], syms, eq_coeff[66], final[10])."""
+    amp = np.ascontiguousarray(amp, dtype=np.int16)
+    n = len(amp)
+    bits = np.zeros(n * 2 + 64, dtype=np.int8)
+    syms = np.zeros(n * 2 // 5 + 16, dtype=V29_SYM_DTYPE)
+    nb = C.c_int32(0)
+    ns = C.c_int32(0)
+    eq = np.zeros(66, dtype=np.float32)
+    fin = np.zeros(10, dtype=np.int32)
+    o.lib.ref_v17_run.restype = C.c_int
+    rc = o.lib.ref_v17_run(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(bit_rate), C.c_float(cutoff), C.c_int(int(want_qam)),
+                           C.c_int(restart_at), C.c_int(restart_short),
+                           C.c_void_p(bits.ctypes.data), C.c_int(bits.size), C.byref(nb), C.c_void_p(syms.ctypes.data), C.c_int(syms.size),
+                           C.byref(ns), C.c_void_p(eq.ctypes.data), C.c_void_p(fin.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("ref_v17_run failed")
+    return {"bits": bits[:nb.value].copy(), "syms": syms[:ns.value].copy(), "eq_coeff": eq, "final": fin}
+
+
+def v17_run_batch(o, amp, bit_rate=14400, chunk=160, cutoff=-100.0, nthreads=1):
+    """Many channels, timing only (CPU baseline).  Returns seconds."""
+    amp = np.asarray(amp)
+    assert amp.dtype == np.int16 and amp.ndim == 2 and amp.strides[1] == 2
+    o.lib.ref_v17_run_batch.restype = C.c_double
+    return o.lib.ref_v17_run_batch(C.c_void_p(amp.ctypes.data), C.c_int64(amp.strides[0] // 2), C.c_int(amp.shape[0]), C.c_int(amp.shape[1]),
+                                   C.c_int(chunk), C.c_int(bit_rate), C.c_float(cutoff), C.c_int(nthreads))
+
+
+def v17_tables(lib, fn_name):
+    re = np.zeros(192 * 27, np.float32)
+    im = np.zeros(192 * 27, np.float32)
+    g = np.zeros(9, np.float32)
+    it = np.zeros(12, np.int32)
+    con = np.zeros(244 * 2, np.float32)
+    maps = np.zeros(4 * 36 * 36 * 8, np.uint8)
+    m48 = np.zeros(36 * 36, np.uint8)
+    getattr(lib, fn_name)(C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data), C.c_void_p(g.ctypes.data), C.c_void_p(it.ctypes.data),
+                          C.c_void_p(con.ctypes.data), C.c_void_p(maps.ctypes.data), C.c_void_p(m48.ctypes.data))
+    return {"rrc_re": re, "rrc_im": im, "godard": g, "ints": it, "constellations": con, "maps": maps, "map4800": m48}
 
 
 _cache = {}

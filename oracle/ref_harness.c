@@ -640,10 +640,27 @@ static void v29_qam(void *user, const complexf_t *z, const complexf_t *target, i
    SIG_STATUS_* codes (no separate status handler is installed, src/v29rx.c:171-178).
    final[]: {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling bits,
              total_baud_timing_correction, constellation_state, carrier_phase} */
+EXPORT int ref_v29_run_ex(const int16_t *amp, int n, int chunk, int bit_rate, float cutoff, int want_qam,
+                          int restart_at, int restart_old_train,
+                          int8_t *bits, int bits_cap, int32_t *nbits,
+                          ref_v29_sym_t *syms, int sym_cap, int32_t *nsyms,
+                          float *eq_coeff, int32_t *final);
+
 EXPORT int ref_v29_run(const int16_t *amp, int n, int chunk, int bit_rate, float cutoff, int want_qam,
                        int8_t *bits, int bits_cap, int32_t *nbits,
                        ref_v29_sym_t *syms, int sym_cap, int32_t *nsyms,
                        float *eq_coeff, int32_t *final)
+{
+    return ref_v29_run_ex(amp, n, chunk, bit_rate, cutoff, want_qam, -1, 0, bits, bits_cap, nbits, syms, sym_cap, nsyms, eq_coeff, final);
+}
+
+/* As ref_v29_run; if restart_at >= 0, v29_rx_restart(rx, bit_rate, restart_old_train) is called before the
+   rx call that starts at the first chunk boundary >= restart_at. */
+EXPORT int ref_v29_run_ex(const int16_t *amp, int n, int chunk, int bit_rate, float cutoff, int want_qam,
+                          int restart_at, int restart_old_train,
+                          int8_t *bits, int bits_cap, int32_t *nbits,
+                          ref_v29_sym_t *syms, int sym_cap, int32_t *nsyms,
+                          float *eq_coeff, int32_t *final)
 {
     v29_rx_state_t *rx;
     v29_rec_t rec;
@@ -666,6 +683,11 @@ EXPORT int ref_v29_run(const int16_t *amp, int n, int chunk, int bit_rate, float
         v29_rx_set_qam_report_handler(rx, v29_qam, &rec);
     for (pos = 0;  pos < n;  pos += len)
     {
+        if (restart_at >= 0  &&  pos >= restart_at)
+        {
+            v29_rx_restart(rx, bit_rate, restart_old_train != 0);
+            restart_at = -1;
+        }
         len = (n - pos < chunk)  ?  (n - pos)  :  chunk;
         v29_rx(rx, amp + pos, len);
     }

@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-shared",
 ]
 
-SOURCES = ["sb_engine.cu", "sb_v29.cu", "sb_dropin.cu"]
+SOURCES = ["sb_engine.cu", "sb_v29.cu", "sb_v17.cu", "sb_dropin.cu"]
 
 
 def sources():
@@ -38,10 +38,26 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile every .cu to an object in parallel, then link the shared library."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + cflags + ["-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)

@@ -1,0 +1,1027 @@
+// sb_modem.cuh - what the V.29 and V.17 receiver banks share: strict arithmetic wrappers, the host-side
+// generators of the constant tables, the receiver core (signal detect, RRC band-pass FIR, Godard timing,
+// AGC, T/2 equalizer buffer, complex equalizer / LMS, carrier loop), the kernels and the bank bookkeeping.
+//
+// Reference: src/v29rx.c, src/v17rx.c (the two receivers share this structure line for line),
+// src/godard.c:144-220, src/power_meter.c:65-69, src/math_fixed.c:158-169, src/dds_float.c:2135-2180,
+// src/spandsp/arctan2.h:47-80, src/vector_float.c:890-939 (scalar dot products),
+// src/complex_vector_float.c:137-219.
+//
+// Arithmetic contract: every float operation is an explicitly rounded single operation in the reference's
+// operand order (the pinned oracle is the strict build with sequential dot products); integers follow C
+// semantics of the reference on x86-64 (arithmetic right shifts, int16 wrap-around, cvttss2si for
+// float->int32).  The one libm call in the sample loop, cosf/sinf at the equalizer "spin", is reproduced
+// exactly (host_sincosf below).
+//
+// Everything a receiver does per sample is written as __host__ __device__ code.  The product only ever
+// runs it on the GPU (modem_rx_kernel); tests/hostsim compiles the same receiver for the host so that
+// the training state machines can be debugged against the oracle in a container without a GPU.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#pragma GCC visibility push(default)
+#include "../../include/spandsp_b200_v29.h"
+#pragma GCC visibility pop
+
+#define SB_HD __host__ __device__ __forceinline__
+
+#define SBM_FILTER_STEPS    27      // V29_RX_FILTER_STEPS / V17_RX_FILTER_STEPS
+#define SBM_EQ_LEN          33      // V29_EQUALIZER_LEN / V17_EQUALIZER_LEN
+#define SBM_EQ_PRE_LEN      16
+
+#define SIG_STATUS_CARRIER_DOWN             (-1)    // src/spandsp/async.h:66-103
+#define SIG_STATUS_CARRIER_UP               (-2)
+#define SIG_STATUS_TRAINING_IN_PROGRESS     (-3)
+#define SIG_STATUS_TRAINING_SUCCEEDED       (-4)
+#define SIG_STATUS_TRAINING_FAILED          (-5)
+
+namespace sbm {
+
+// ------------------------------------------------------------------------------------------
+// strict arithmetic
+
+#if defined(__CUDA_ARCH__)
+SB_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+SB_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+SB_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+SB_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+SB_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+SB_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+SB_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+SB_HD int clz32(unsigned int x) { return __clz((int) x); }
+SB_HD unsigned int float_bits(float f) { return __float_as_uint(f); }
+SB_HD int float_to_int_rz(float f) { return __float2int_rz(f); }
+SB_HD int double_to_int_rz(double f) { return __double2int_rz(f); }
+template <class T> SB_HD T ldg(const T *p) { return __ldg(p); }
+#else
+// Host build (tests/hostsim only): plain IEEE single operations; compiled without FMA contraction.
+SB_HD float fmul(float a, float b) { volatile float r = a*b; return r; }
+SB_HD float fadd(float a, float b) { volatile float r = a + b; return r; }
+SB_HD float fsub(float a, float b) { volatile float r = a - b; return r; }
+SB_HD float fdiv(float a, float b) { volatile float r = a/b; return r; }
+SB_HD double dmul(double a, double b) { volatile double r = a*b; return r; }
+SB_HD double dadd(double a, double b) { volatile double r = a + b; return r; }
+SB_HD double dsub(double a, double b) { volatile double r = a - b; return r; }
+SB_HD int clz32(unsigned int x) { return __builtin_clz(x); }
+SB_HD unsigned int float_bits(float f) { unsigned int u; memcpy(&u, &f, 4); return u; }
+SB_HD int float_to_int_rz(float f) { return (int) f; }
+SB_HD int double_to_int_rz(double f) { return (int) f; }
+template <class T> SB_HD T ldg(const T *p) { return *p; }
+#endif
+
+// (int32_t) of a float the way x86-64's cvttss2si does it: out-of-range and NaN give INT_MIN.
+SB_HD int f2i(float f)
+{
+    if (!(f > -2147483904.0f  &&  f < 2147483648.0f))
+        return (int) 0x80000000;
+    return float_to_int_rz(f);
+}
+
+// cosf()/sinf() as the host C library computes them.  The reference calls libm's cosf/sinf once per
+// training (src/v29rx.c:618-623, src/v17rx.c:707-711,784-788); the values feed the adaptive loops, whose
+// discrete timing decisions amplify a 1-ulp difference into visible (1e-3) excursions of the soft
+// symbols, so they have to be reproduced exactly.  Third-party arithmetic: GNU libc 2.39 (the image's
+// libm.so.6), sysdeps/ieee754/flt-32/s_cosf.c, s_sinf.c, s_sincosf.h - the "sincosf" of ARM's optimized
+// routines: reduce by pi/2 in double with a 2^24-prescaled 2/pi, then an odd/even minimax polynomial in
+// double, rounded once to float.  Constants are the published ones (they can be read back from
+// __sincosf_table in libm.so.6).  Arguments here are phases in [0, 2*pi), so only the two fast paths
+// (|x| < pi/4, |x| < 120) are needed.  tools/check_host_sincosf.py checks this restatement against the
+// live libm on 1e6 arguments.
+SB_HD double sincosf_poly(double x, double x2, bool cos_table_negated, int n)
+{
+    const double c0 = (cos_table_negated)  ?  -0x1p0  :  0x1p0;
+    const double c1 = (cos_table_negated)  ?  0x1.ffffffd0c621cp-2  :  -0x1.ffffffd0c621cp-2;
+    const double c2 = (cos_table_negated)  ?  -0x1.55553e1068f19p-5  :  0x1.55553e1068f19p-5;
+    const double c3 = (cos_table_negated)  ?  0x1.6c087e89a359dp-10  :  -0x1.6c087e89a359dp-10;
+    const double c4 = (cos_table_negated)  ?  -0x1.99343027bf8c3p-16  :  0x1.99343027bf8c3p-16;
+    const double s1 = -0x1.555545995a603p-3;
+    const double s2 = 0x1.1107605230bc4p-7;
+    const double s3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0)
+    {
+        const double x3 = dmul(x, x2);
+        const double t1 = dadd(s2, dmul(x2, s3));
+        const double x7 = dmul(x3, x2);
+        const double sv = dadd(x, dmul(x3, s1));
+        return dadd(sv, dmul(x7, t1));
+    }
+    const double x4 = dmul(x2, x2);
+    const double t2 = dadd(c3, dmul(x2, c4));
+    const double t1 = dadd(c0, dmul(x2, c1));
+    const double x6 = dmul(x4, x2);
+    const double cv = dadd(t1, dmul(x4, c2));
+    return dadd(cv, dmul(x6, t2));
+}
+
+SB_HD unsigned int abstop12(float f)
+{
+    return (float_bits(f) >> 20) & 0x7FFu;
+}
+
+// is_cos: 1 for cosf, 0 for sinf
+__host__ __device__ inline float host_sincosf(float y, int is_cos)
+{
+    double x = (double) y;
+    if (abstop12(y) < abstop12(0x1.921FB6p-1f))
+    {
+        if (abstop12(y) < abstop12(0x1p-12f))
+            return (is_cos)  ?  1.0f  :  y;
+        return (float) sincosf_poly(x, dmul(x, x), false, is_cos);
+    }
+    const double r = dmul(x, 0x1.45F306DC9C883p+23);
+    const int n = (double_to_int_rz(r) + 0x800000) >> 24;
+    x = dsub(x, dmul((double) n, 0x1.921FB54442D18p0));
+    const double sgn = ((n & 3) == 1  ||  (n & 3) == 2)  ?  -1.0  :  1.0;
+    return (float) sincosf_poly(dmul(x, sgn), dmul(x, x), (n & 2) != 0, (is_cos)  ?  (n ^ 1)  :  n);
+}
+
+SB_HD float host_cosf(float y) { return host_sincosf(y, 1); }
+SB_HD float host_sinf(float y) { return host_sincosf(y, 0); }
+
+// src/spandsp/arctan2.h:47-80
+SB_HD int arctan2(float y, float x)
+{
+    if (y == 0.0f)
+        return (x < 0.0f)  ?  (int) 0x80000000  :  0;
+    if (x == 0.0f)
+        return (y < 0.0f)  ?  (int) 0xC0000000  :  0x40000000;
+    const float abs_y = fabsf(y);
+    float angle;
+    if (x < 0.0f)
+        angle = fsub(3.0f, fdiv(fadd(x, abs_y), fsub(abs_y, x)));
+    else
+        angle = fsub(1.0f, fdiv(fsub(x, abs_y), fadd(abs_y, x)));
+    angle = fmul(angle, 536870912.0f);
+    if (y < 0.0f)
+        angle = -angle;
+    return f2i(angle);
+}
+
+// dds_phase_to_radians (src/dds_float.c:2103-2106)
+SB_HD float phase_to_radians(unsigned int phase)
+{
+    return fdiv(fmul(fmul((float) phase, 2.0f), 3.1415926f), fmul(65536.0f, 65536.0f));
+}
+
+// ------------------------------------------------------------------------------------------
+// constant tables: host generators.  The reference builds these with generator programs at build time;
+// the library redoes them (including the print-to-decimal / parse-as-float step) so that the float tables
+// are bit-identical (tests/test_v29_tables.py, tests/test_v17_tables.py).
+
+static inline float decimal_roundtrip(double v, int decimals)
+{
+    // The generators print "%.<d>f" into a C header and the compiler parses the literal as float.
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.*f", decimals, v);
+    return strtof(buf, NULL);
+}
+
+// Radix-2 decimation-in-time transform with e^{+j} twiddles from a table built with the
+// generator's own constant for pi (src/filter_tools.c:73-124).
+struct cplx
+{
+    double re;
+    double im;
+};
+
+static inline void dit_transform(cplx *data, cplx *temp, int n, const std::vector<cplx> &circle, int full)
+{
+    if (n <= 1)
+        return;
+    const int h = n/2;
+    for (int i = 0;  i < h;  i++)
+    {
+        temp[i] = data[2*i];
+        temp[h + i] = data[2*i + 1];
+    }
+    dit_transform(&temp[0], &data[0], h, circle, full);
+    dit_transform(&temp[h], &data[h], h, circle, full);
+    int p = 0;
+    const int t = full/n;
+    for (int i = 0;  i < h;  i++)
+    {
+        const cplx &w = circle[p];
+        const cplx &o = temp[h + i];
+        cplx wkt;
+        wkt.re = w.re*o.re - w.im*o.im;
+        wkt.im = w.re*o.im + w.im*o.re;
+        data[i].re = temp[i].re + wkt.re;
+        data[i].im = temp[i].im + wkt.im;
+        data[h + i].re = temp[i].re - wkt.re;
+        data[h + i].im = temp[i].im - wkt.im;
+        p += t;
+    }
+}
+
+// Root raised cosine prototype by frequency sampling (src/filter_tools.c:126-190), then the polyphase
+// band-pass sets (src/make_modem_filter.c:155-271).  V.29: 48 sets x 27 taps at 1700 Hz (:401-413);
+// V.17: 192 sets x 27 taps at 1800 Hz (:319-332); both 2400 baud, excess bandwidth 0.5.
+static inline void make_rx_rrc(std::vector<float> &re, std::vector<float> &im, int coeff_sets, double carrier_hz)
+{
+    const int SEQ_LEN = 8192;
+    const double GEN_PI = 3.1415926535;
+    const int per_filter = SBM_FILTER_STEPS;
+    const int total = coeff_sets*per_filter + 1;
+    const double alpha = 2400.0/(2.0*(double) (coeff_sets*8000));
+    const double beta = 0.5;
+    const double f1 = (1.0 - beta)*alpha;
+    const double f2 = (1.0 + beta)*alpha;
+    const double tau = 0.5/alpha;
+
+    std::vector<cplx> vec(SEQ_LEN);
+    std::vector<cplx> temp(SEQ_LEN);
+    for (int i = 0;  i < SEQ_LEN;  i++)
+        vec[i].re = vec[i].im = 0.0;
+    for (int i = 0;  i <= SEQ_LEN/2;  i++)
+    {
+        const double f = (double) i/(double) SEQ_LEN;
+        double v;
+        if (f <= f1)
+            v = 1.0;
+        else if (f <= f2)
+            v = 0.5*(1.0 + cos((GEN_PI*tau/beta)*(f - f1)));
+        else
+            v = 0.0;
+        vec[i].re = v;
+        vec[i].im = 0.0;
+    }
+    for (int i = 0;  i <= SEQ_LEN/2;  i++)
+        vec[i].re = sqrt(vec[i].re);
+    for (int i = 0;  i <= SEQ_LEN/2;  i++)
+        vec[i].re *= tau;
+    for (int i = 1;  i < SEQ_LEN/2;  i++)
+        vec[SEQ_LEN - i] = vec[i];
+    std::vector<cplx> circle(SEQ_LEN/2);
+    for (int i = 0;  i < SEQ_LEN/2;  i++)
+    {
+        const double x = (2.0*GEN_PI*i)/(double) SEQ_LEN;
+        circle[i].re = cos(x);
+        circle[i].im = sin(x);
+    }
+    dit_transform(vec.data(), temp.data(), SEQ_LEN, circle, SEQ_LEN);
+    std::vector<double> coeffs(total);
+    const int h = (total - 1)/2;
+    for (int i = 0;  i < total;  i++)
+        coeffs[i] = vec[(SEQ_LEN - h + i) % SEQ_LEN].re/(double) SEQ_LEN;
+    double gain = 0.0;
+    for (int i = coeff_sets/2;  i < total;  i += coeff_sets)
+        gain += coeffs[i];
+    for (int i = 0;  i < total;  i++)
+        coeffs[i] /= gain;
+    double carrier = carrier_hz;
+    carrier *= 2.0*GEN_PI/8000;
+    re.assign(coeff_sets*per_filter, 0.0f);
+    im.assign(coeff_sets*per_filter, 0.0f);
+    for (int j = 0;  j < coeff_sets;  j++)
+    {
+        for (int i = 0;  i < per_filter;  i++)
+        {
+            const int m = i - (per_filter >> 1);
+            const int x = i*coeff_sets + j;
+            re[j*per_filter + i] = decimal_roundtrip(coeffs[x]*cos(carrier*m), 10);
+            im[j*per_filter + i] = decimal_roundtrip(coeffs[x]*sin(carrier*m), 10);
+        }
+    }
+}
+
+// src/dds_float.c:51-2101: sin(2*pi*i/2048) as 8-decimal literals.
+static inline void make_sine_table(std::vector<float> &t)
+{
+    t.resize(2048);
+    for (int i = 0;  i < 2048;  i++)
+        t[i] = decimal_roundtrip(sin(2.0*M_PI*(double) i/2048.0), 8);
+}
+
+// src/make_math_fixed_tables.c:59-72
+static inline void make_sqrt_table(std::vector<unsigned short> &t)
+{
+    t.resize(193);
+    for (int i = 64;  i <= 256;  i++)
+    {
+        int v = (int) (sqrt(i/256.0)*65536.0 + 0.5);
+        if (v > 65535)
+            v = 65535;
+        t[i - 64] = (unsigned short) v;
+    }
+}
+
+// src/make_modem_godard_descriptor.c:60-80; arguments from src/Makefile.am (V.29: 1700.0 2400.0 0.99
+// 1000.0 30.0 5 1; V.17: 1800.0 2400.0 0.99 1000.0 100.0 15 1); floats are printed with 6 decimals.
+struct godard_desc_t
+{
+    float low[3];
+    float high[3];
+    float mixed3;
+    float coarse_trigger;
+    float fine_trigger;
+    int coarse_step;
+    int fine_step;
+};
+
+static inline void make_godard(godard_desc_t &g, double carrier, double fine_trigger, int coarse_step)
+{
+    const double alpha = 0.99;
+    const double low_edge = 2.0*M_PI*(carrier - 2400.0/2.0)/8000.0;
+    const double high_edge = 2.0*M_PI*(carrier + 2400.0/2.0)/8000.0;
+    g.low[0] = decimal_roundtrip(2.0*alpha*cos(low_edge), 6);
+    g.high[0] = decimal_roundtrip(2.0*alpha*cos(high_edge), 6);
+    g.low[1] = g.high[1] = decimal_roundtrip(-alpha*alpha, 6);
+    g.low[2] = decimal_roundtrip(-alpha*sin(low_edge), 6);
+    g.high[2] = decimal_roundtrip(-alpha*sin(high_edge), 6);
+    g.mixed3 = decimal_roundtrip(-alpha*alpha*(sin(high_edge)*cos(low_edge) - sin(low_edge)*cos(high_edge)), 6);
+    g.coarse_trigger = decimal_roundtrip(1000.0, 6);
+    g.fine_trigger = decimal_roundtrip(fine_trigger, 6);
+    g.coarse_step = coarse_step;
+    g.fine_step = 1;
+}
+
+// src/power_meter.c:86-96
+static inline int host_power_meter_level_dbm0(float level)
+{
+    float l;
+
+    level -= (3.14f + 3.02f);
+    if (level > 0.0)
+        level = 0.0;
+    l = powf(10.0f, level/10.0f)*(32767.0f*32767.0f);
+    return (int) l;
+}
+
+// DDS_PHASE_RATE / DDS_PHASE (src/spandsp/dds.h:31-32)
+static inline int32_t host_dds_phase_rate(float hz) { return (int32_t) (hz*65536.0f*65536.0f/8000); }
+static inline int32_t host_dds_phase(float angle)
+{
+    return (int32_t) ((uint32_t) (((angle < 0.0f)  ?  (360.0f + angle)  :  angle)*65536.0f*65536.0f/360.0f));
+}
+
+// ------------------------------------------------------------------------------------------
+// device side: what every receiver needs
+
+struct CoreConsts
+{
+    const float *rrc_re;                // [COEFF_SETS][27]
+    const float *rrc_im;
+    const float *sine;                  // [2048]
+    const unsigned short *sqrt_tab;     // [193]
+    float g_low[3];
+    float g_high[3];
+    float g_mixed3;
+    float g_coarse_trigger;
+    float g_fine_trigger;
+    int g_coarse_step;
+    int g_fine_step;
+    int rate_nominal;                   // DDS_PHASE_RATE(carrier)
+    int rate_low;                       // DDS_PHASE_RATE(carrier - 20)
+    int rate_high;                      // DDS_PHASE_RATE(carrier + 20)
+    float agc_initial;                  // (target/RX_PULSESHAPER_GAIN)/735.0f
+    float agc_target;                   // target/RX_PULSESHAPER_GAIN
+};
+
+// Per-channel state in global memory, structure of arrays: field f of channel c at [f*C + c].
+enum
+{
+    F_AGC = 0, F_AGC_SAVE, F_EQ_DELTA, F_TRAINING_ERROR, F_TRACK_P, F_TRACK_I,
+    F_LBE0, F_LBE1, F_HBE0, F_HBE1, F_DC0, F_DC1, F_BAUD_PHASE,
+    F_EQ_COEFF,                                     // 66
+    F_EQ_COEFF_SAVE = F_EQ_COEFF + 2*SBM_EQ_LEN,    // 66
+    F_EQ_BUF = F_EQ_COEFF_SAVE + 2*SBM_EQ_LEN,      // 66
+    F_RRC = F_EQ_BUF + 2*SBM_EQ_LEN,                // 27
+    F_CORE_COUNT = F_RRC + SBM_FILTER_STEPS
+};
+
+enum
+{
+    I_BIT_RATE = 0, I_RRC_STEP, I_SCRAMBLE, I_STAGE, I_TRAIN_COUNT,
+    I_LAST_SAMPLE, I_SIGNAL_PRESENT, I_DROP_PENDING, I_LOW_SAMPLES, I_HIGH_SAMPLE, I_CARRIER_PHASE, I_PHASE_RATE,
+    I_PHASE_RATE_SAVE, I_POWER, I_ON_POWER, I_OFF_POWER, I_EQ_STEP, I_EQ_PUT_STEP, I_EQ_SKIP, I_BAUD_HALF,
+    I_LAST_ANGLE0, I_LAST_ANGLE1, I_TOTAL_TIMING,
+    I_DIFF_ANGLES,                      // 16
+    I_CORE_COUNT = I_DIFF_ANGLES + 16
+};
+
+struct ModemArgs
+{
+    const int16_t *amp;
+    long long stride;
+    int n;
+    int channels;
+    float *fstate;
+    int *istate;
+    signed char *bits;                  // [channel][bits_cap]: 0/1 data bits and negative status codes
+    long long bits_cap;
+    int *nbits;                         // [channel]
+    span_b200_v29_symbol_t *syms;       // [channel][sym_cap], or NULL
+    long long sym_cap;
+    int *nsyms;
+};
+
+// State visitors: one list of fields (visit()) serves loading, storing and counting.
+struct StateLoader
+{
+    const float *F;
+    const int *I;
+    size_t C;
+    size_t c;
+    SB_HD void f(int slot, float &v) { v = F[(size_t) slot*C + c]; }
+    SB_HD void i(int slot, int &v) { v = I[(size_t) slot*C + c]; }
+    SB_HD void u(int slot, unsigned int &v) { v = (unsigned int) I[(size_t) slot*C + c]; }
+    SB_HD void fa(int slot, float *p, int n) { for (int k = 0;  k < n;  k++) p[k*32] = F[(size_t) (slot + k)*C + c]; }
+    SB_HD void ia(int slot, int *p, int n) { for (int k = 0;  k < n;  k++) p[k*32] = I[(size_t) (slot + k)*C + c]; }
+};
+
+struct StateStorer
+{
+    float *F;
+    int *I;
+    size_t C;
+    size_t c;
+    SB_HD void f(int slot, float &v) { F[(size_t) slot*C + c] = v; }
+    SB_HD void i(int slot, int &v) { I[(size_t) slot*C + c] = v; }
+    SB_HD void u(int slot, unsigned int &v) { I[(size_t) slot*C + c] = (int) v; }
+    SB_HD void fa(int slot, float *p, int n) { for (int k = 0;  k < n;  k++) F[(size_t) (slot + k)*C + c] = p[k*32]; }
+    SB_HD void ia(int slot, int *p, int n) { for (int k = 0;  k < n;  k++) I[(size_t) (slot + k)*C + c] = p[k*32]; }
+};
+
+// One receiver.  Scalars live in registers; the per-channel arrays live in shared memory,
+// lane-interleaved (element e of lane l at [e*32 + l]) so that any per-lane index is conflict-free.
+// D is the concrete receiver (CRTP): it supplies restart_after_carrier_down() and process_baud().
+template <class D, int COEFF_SETS>
+struct RxCore
+{
+    static const int SETS = COEFF_SETS;
+    // float state
+    float agc_scaling, agc_scaling_save, eq_delta, training_error, track_p, track_i;
+    float lbe0, lbe1, hbe0, hbe1, dc0, dc1, baud_phase;
+    // int state
+    int bit_rate, rrc_step, training_stage, training_count;
+    unsigned int scramble_reg, carrier_phase;
+    int last_sample, signal_present, drop_pending, low_samples, high_sample;
+    int phase_rate, phase_rate_save, power, on_power, off_power;
+    int eq_step, eq_put_step, eq_skip, baud_half, total_timing;
+    int last_angle0, last_angle1;
+    // shared-memory arrays of this lane (dynamic indexing would force the whole receiver out of registers
+    // if they were member arrays)
+    int *diff_angles;       // [16]
+    float *eq_coeff;        // [66]
+    float *eq_buf;          // [66]
+    float *rrc;             // [27]
+    // outputs
+    signed char *bits;
+    int nbits;
+    int bits_cap;
+    span_b200_v29_symbol_t *syms;
+    int nsyms;
+    int sym_cap;
+    // channel
+    int c;
+    int channels;
+    float *fstate;
+
+    SB_HD D &self() { return *static_cast<D *>(this); }
+
+    static const int CORE_LANE_WORDS = 4*SBM_EQ_LEN + SBM_FILTER_STEPS + 16;
+
+    // lane_base: this lane's column of the lane-interleaved block
+    SB_HD void bind_core(float *lane_base)
+    {
+        eq_coeff = lane_base;
+        eq_buf = lane_base + (2*SBM_EQ_LEN)*32;
+        rrc = lane_base + (4*SBM_EQ_LEN)*32;
+        diff_angles = (int *) (lane_base + (4*SBM_EQ_LEN + SBM_FILTER_STEPS)*32);
+    }
+
+    template <class V> SB_HD void visit_core(V &v)
+    {
+        v.f(F_AGC, agc_scaling);
+        v.f(F_AGC_SAVE, agc_scaling_save);
+        v.f(F_EQ_DELTA, eq_delta);
+        v.f(F_TRAINING_ERROR, training_error);
+        v.f(F_TRACK_P, track_p);
+        v.f(F_TRACK_I, track_i);
+        v.f(F_LBE0, lbe0);
+        v.f(F_LBE1, lbe1);
+        v.f(F_HBE0, hbe0);
+        v.f(F_HBE1, hbe1);
+        v.f(F_DC0, dc0);
+        v.f(F_DC1, dc1);
+        v.f(F_BAUD_PHASE, baud_phase);
+        v.fa(F_EQ_COEFF, eq_coeff, 2*SBM_EQ_LEN);
+        v.fa(F_EQ_BUF, eq_buf, 2*SBM_EQ_LEN);
+        v.fa(F_RRC, rrc, SBM_FILTER_STEPS);
+        v.i(I_BIT_RATE, bit_rate);
+        v.i(I_RRC_STEP, rrc_step);
+        v.u(I_SCRAMBLE, scramble_reg);
+        v.i(I_STAGE, training_stage);
+        v.i(I_TRAIN_COUNT, training_count);
+        v.i(I_LAST_SAMPLE, last_sample);
+        v.i(I_SIGNAL_PRESENT, signal_present);
+        v.i(I_DROP_PENDING, drop_pending);
+        v.i(I_LOW_SAMPLES, low_samples);
+        v.i(I_HIGH_SAMPLE, high_sample);
+        v.u(I_CARRIER_PHASE, carrier_phase);
+        v.i(I_PHASE_RATE, phase_rate);
+        v.i(I_PHASE_RATE_SAVE, phase_rate_save);
+        v.i(I_POWER, power);
+        v.i(I_ON_POWER, on_power);
+        v.i(I_OFF_POWER, off_power);
+        v.i(I_EQ_STEP, eq_step);
+        v.i(I_EQ_PUT_STEP, eq_put_step);
+        v.i(I_EQ_SKIP, eq_skip);
+        v.i(I_BAUD_HALF, baud_half);
+        v.i(I_LAST_ANGLE0, last_angle0);
+        v.i(I_LAST_ANGLE1, last_angle1);
+        v.i(I_TOTAL_TIMING, total_timing);
+        v.ia(I_DIFF_ANGLES, diff_angles, 16);
+    }
+
+    SB_HD void out_bit(int v)
+    {
+        if (nbits < bits_cap)
+            bits[nbits] = (signed char) v;
+        nbits++;
+    }
+
+    // src/v29rx.c:171-178, src/v17rx.c:181-189: without a status handler the status goes through put_bit
+    SB_HD void report_status(int status)
+    {
+        out_bit(status);
+    }
+
+    SB_HD void report_symbol(float zre, float zim, float tre, float tim, int state)
+    {
+        if (syms)
+        {
+            if (nsyms < sym_cap)
+            {
+                span_b200_v29_symbol_t s;
+                s.re = zre;
+                s.im = zim;
+                s.target_re = tre;
+                s.target_im = tim;
+                s.state = state;
+                s.bit_pos = nbits;
+                syms[nsyms] = s;
+            }
+            nsyms++;
+        }
+    }
+
+    // src/v29rx.c:214-258, src/v17rx.c:219-264
+    SB_HD void equalizer_reset()
+    {
+        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+        {
+            eq_coeff[i*32] = 0.0f;
+            eq_buf[i*32] = 0.0f;
+        }
+        eq_coeff[(2*SBM_EQ_PRE_LEN)*32] = 3.0f;
+        eq_put_step = COEFF_SETS*10/(3*2) - 1;
+        eq_step = 0;
+    }
+
+    SB_HD void equalizer_restore()
+    {
+        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+        {
+            eq_coeff[i*32] = fstate[(size_t) (F_EQ_COEFF_SAVE + i)*channels + c];
+            eq_buf[i*32] = 0.0f;
+        }
+        eq_put_step = COEFF_SETS*10/(3*2) - 1;
+        eq_step = 0;
+    }
+
+    SB_HD void equalizer_save()
+    {
+        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+            fstate[(size_t) (F_EQ_COEFF_SAVE + i)*channels + c] = eq_coeff[i*32];
+    }
+
+    // godard_ted_init (src/godard.c:222-240)
+    SB_HD void godard_init()
+    {
+        lbe0 = lbe1 = hbe0 = hbe1 = dc0 = dc1 = baud_phase = 0.0f;
+        total_timing = 0;
+    }
+
+    // src/vector_float.c:932-939 with the scalar vec_dot_prodf (:890-900): two segments, each summed
+    // in order from 0.0f, then added.
+    SB_HD float rrc_dot(const float *coef)
+    {
+        float za = 0.0f;
+        float zb = 0.0f;
+        const int first = SBM_FILTER_STEPS - rrc_step;      // taps in the first segment
+        int j = rrc_step;
+#pragma unroll 9
+        for (int i = 0;  i < SBM_FILTER_STEPS;  i++)
+        {
+            const float p = fmul(rrc[j*32], coef[i]);
+            if (i < first)
+                za = fadd(za, p);
+            else
+                zb = fadd(zb, p);
+            if (++j >= SBM_FILTER_STEPS)
+                j = 0;
+        }
+        return fadd(za, zb);
+    }
+
+    // src/complex_vector_float.c:137-150,187-196
+    SB_HD void equalizer_get(float &zre, float &zim)
+    {
+        float are = 0.0f, aim = 0.0f, bre = 0.0f, bim = 0.0f;
+        const int first = SBM_EQ_LEN - eq_step;
+        int j = eq_step;
+#pragma unroll 3
+        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        {
+            const float xr = eq_buf[(2*j)*32];
+            const float xi = eq_buf[(2*j + 1)*32];
+            const float yr = eq_coeff[(2*i)*32];
+            const float yi = eq_coeff[(2*i + 1)*32];
+            const float pr = fsub(fmul(xr, yr), fmul(xi, yi));
+            const float pi = fadd(fmul(xr, yi), fmul(xi, yr));
+            if (i < first)
+            {
+                are = fadd(are, pr);
+                aim = fadd(aim, pi);
+            }
+            else
+            {
+                bre = fadd(bre, pr);
+                bim = fadd(bim, pi);
+            }
+            if (++j >= SBM_EQ_LEN)
+                j = 0;
+        }
+        zre = fadd(are, bre);
+        zim = fadd(aim, bim);
+    }
+
+    // src/v29rx.c:281-290, src/v17rx.c:296-307 + src/complex_vector_float.c:199-219
+    SB_HD void tune_equalizer(float zre, float zim, float tre, float tim)
+    {
+        const float ere = fmul(fsub(tre, zre), eq_delta);
+        const float eim = fmul(fsub(tim, zim), eq_delta);
+        int j = eq_step;
+#pragma unroll 3
+        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        {
+            const float xr = eq_buf[(2*j)*32];
+            const float xi = eq_buf[(2*j + 1)*32];
+            const float yr = eq_coeff[(2*i)*32];
+            const float yi = eq_coeff[(2*i + 1)*32];
+            eq_coeff[(2*i)*32] = fadd(fmul(yr, 0.9999f), fadd(fmul(xi, eim), fmul(xr, ere)));
+            eq_coeff[(2*i + 1)*32] = fadd(fmul(yi, 0.9999f), fsub(fmul(xr, eim), fmul(xi, ere)));
+            if (++j >= SBM_EQ_LEN)
+                j = 0;
+        }
+    }
+
+    // The equalizer "spin" (src/v29rx.c:618-625, src/v17rx.c:707-713,784-790)
+    SB_HD void spin_equalizer_buffer(unsigned int phase_step)
+    {
+        const float p = phase_to_radians(phase_step);
+        const float cr = host_cosf(p);
+        const float ci = -host_sinf(p);
+        for (int q = 0;  q < SBM_EQ_LEN;  q++)
+        {
+            const float xr = eq_buf[(2*q)*32];
+            const float xi = eq_buf[(2*q + 1)*32];
+            eq_buf[(2*q)*32] = fsub(fmul(xr, cr), fmul(xi, ci));
+            eq_buf[(2*q + 1)*32] = fadd(fmul(xr, ci), fmul(xi, cr));
+        }
+    }
+
+    // src/v29rx.c:297-331, src/v17rx.c:313-338
+    SB_HD void track_carrier(float zre, float zim, float tre, float tim)
+    {
+        const float error = fsub(fmul(zim, tre), fmul(zre, tim));
+        phase_rate += f2i(fmul(track_i, error));
+        carrier_phase += (unsigned int) f2i(fmul(track_p, error));
+    }
+
+    // src/godard.c:165-220
+    SB_HD int godard_per_baud(const CoreConsts &k)
+    {
+        float v = fadd(fsub(fmul(fmul(lbe1, hbe0), k.g_low[2]), fmul(fmul(lbe0, hbe1), k.g_high[2])),
+                       fmul(fmul(lbe1, hbe1), k.g_mixed3));
+        const float p = fsub(v, dc1);
+        dc1 = dc0;
+        dc0 = v;
+        baud_phase = fsub(baud_phase, p);
+        v = fabsf(baud_phase);
+        int corr = 0;
+        if (v > k.g_fine_trigger)
+        {
+            int i = (v > k.g_coarse_trigger)  ?  k.g_coarse_step  :  k.g_fine_step;
+            if (baud_phase < 0.0f)
+                i = -i;
+            corr = i;
+            total_timing += i;
+        }
+        return corr;
+    }
+
+    // src/v29rx.c:788-864, src/v17rx.c:1136-1208 (IAXMODEM_STUFF is defined in both files)
+    template <class K> SB_HD int signal_detect(const K &k, short amp)
+    {
+        const short x = (short) (amp >> 1);
+        short diff = (short) (x - (short) last_sample);
+        last_sample = x;
+        power += (((int) diff*(int) diff - power) >> 4);                // power_meter_update, shift 4
+        const int pw = power;
+        diff = (short) abs((int) diff);
+        if (10*(int) diff < high_sample)
+        {
+            if (++low_samples > 120)
+            {
+                power = 0;
+                high_sample = 0;
+                low_samples = 0;
+            }
+        }
+        else
+        {
+            low_samples = 0;
+            if ((int) diff > high_sample)
+                high_sample = diff;
+        }
+        if (signal_present > 0)
+        {
+            if (drop_pending  ||  pw < off_power)
+            {
+                if (--signal_present <= 0)
+                {
+                    self().restart_after_carrier_down(k);
+                    report_status(SIG_STATUS_CARRIER_DOWN);
+                    return 0;
+                }
+                drop_pending = 1;
+            }
+        }
+        else
+        {
+            if (pw < on_power)
+                return 0;
+            signal_present = 1;
+            drop_pending = 0;
+            report_status(SIG_STATUS_CARRIER_UP);
+        }
+        return pw;
+    }
+
+    // src/math_fixed.c:158-169
+    SB_HD int fixed_sqrt32(const CoreConsts &k, unsigned int x)
+    {
+        if (x == 0)
+            return 0;
+        const int shift = 30 - ((31 - clz32(x)) & ~1);
+        x <<= shift;
+        return (int) k.sqrt_tab[((x >> 24) & 0xFF) - 64] >> (shift >> 1);
+    }
+
+    // xxx_rx()'s per-sample body (src/v29rx.c:885-960, src/v17rx.c:1231-1308) is split in three so that
+    // the 32 channels of a warp can be kept in step on *symbol* time rather than sample time (see
+    // modem_rx_kernel):
+    //   front(): everything up to and including the real FIR and the Godard filters; tells whether this
+    //            sample is a T/2 instant (eq_put_step <= 0);
+    //   half():  the T/2 work: AGC, imaginary FIR, down-mix, equalizer buffer insert; tells whether a
+    //            whole baud is now complete;
+    //   baud():  timing correction, equalizer, training state machine / slicer, qam report.
+    // The carrier NCO advance that ends the reference's loop body is done by whichever part ends the sample.
+    int h_step;
+    int h_pw;
+    float h_sre;
+
+    template <class K> SB_HD bool front(const K &k, const float *s_rrc_re, short amp)
+    {
+        rrc[rrc_step*32] = (float) amp;
+        if (++rrc_step >= SBM_FILTER_STEPS)
+            rrc_step = 0;
+        const int pw = signal_detect(k, amp);
+        if (pw == 0)
+            return false;
+        if (training_stage == D::STAGE_PARKED)
+            return false;
+        eq_put_step -= COEFF_SETS;
+        int step = -eq_put_step;
+        if (step < 0)
+            step += COEFF_SETS;
+        if (step < 0)
+            step = 0;
+        else if (step > COEFF_SETS - 1)
+            step = COEFF_SETS - 1;
+        const float v = rrc_dot(s_rrc_re + step*SBM_FILTER_STEPS);
+        const float sre = fmul(v, agc_scaling);
+        // godard_ted_rx, src/godard.c:144-161
+        {
+            float t = fadd(fadd(fmul(lbe0, k.g_low[0]), fmul(lbe1, k.g_low[1])), sre);
+            lbe1 = lbe0;
+            lbe0 = t;
+            t = fadd(fadd(fmul(hbe0, k.g_high[0]), fmul(hbe1, k.g_high[1])), sre);
+            hbe1 = hbe0;
+            hbe0 = t;
+        }
+        if (eq_put_step <= 0)
+        {
+            h_step = step;
+            h_pw = pw;
+            h_sre = sre;
+            return true;
+        }
+        carrier_phase += (unsigned int) phase_rate;
+        return false;
+    }
+
+    template <class K> SB_HD bool half(const K &k, const float *s_rrc_im)
+    {
+        if (agc_scaling_save == 0.0f)
+        {
+            int root_power = fixed_sqrt32(k, (unsigned int) h_pw);
+            if (root_power == 0)
+                root_power = 1;
+            agc_scaling = fdiv(k.agc_target, (float) root_power);
+        }
+        const float v = rrc_dot(s_rrc_im + h_step*SBM_FILTER_STEPS);
+        const float sim = fmul(v, agc_scaling);
+        const float zr = k.sine[(carrier_phase + (1u << 30)) >> 21];     // dds_lookup_complexf, src/dds_float.c:2177
+        const float zi = k.sine[carrier_phase >> 21];
+        const float zzre = fsub(fmul(h_sre, zr), fmul(sim, zi));
+        const float zzim = fsub(fmul(-h_sre, zi), fmul(sim, zr));
+        eq_put_step += COEFF_SETS*10/(3*2);
+        // process_half_baud, first part (src/v29rx.c:516-525, src/v17rx.c:638-647)
+        eq_buf[(2*eq_step)*32] = zzre;
+        eq_buf[(2*eq_step + 1)*32] = zzim;
+        if (++eq_step >= SBM_EQ_LEN)
+            eq_step = 0;
+        if ((baud_half ^= 1))
+        {
+            carrier_phase += (unsigned int) phase_rate;
+            return false;
+        }
+        return true;
+    }
+
+    template <class K> SB_HD void baud(const K &k)
+    {
+        self().process_baud(k);
+        carrier_phase += (unsigned int) phase_rate;
+    }
+
+    // All samples of one call, lanes kept in step on symbol time: one trip of the outer loop takes every
+    // receiving channel through one whole baud - two T/2 instants, each reached after one or two input
+    // samples - so the expensive parts (imaginary FIR, equalizer, training/slicer) run with all lanes
+    // converged even though the channels' symbol clocks sit at different sample phases.  Channels without
+    // carrier (or parked) simply consume up to four samples per trip.  Each channel still sees its own
+    // samples in order, which is all the reference's per-channel semantics require.
+    template <class K> SB_HD void run(const K &k, const float *s_rrc_re, const float *s_rrc_im, const int16_t *row, int n)
+    {
+        int pos = 0;
+#pragma unroll 1
+        while (pos < n)
+        {
+#pragma unroll 1
+            for (int h = 0;  h < 2;  h++)
+            {
+                // A channel that enters the trip half-way through a baud sits out the first slot, so that
+                // every channel completes its baud in the second slot (and is baud-aligned from then on).
+                if (h == 0  &&  baud_half)
+                    continue;
+                bool due = false;
+#pragma unroll 1
+                for (int q = 0;  q < 2;  q++)
+                {
+                    if (pos < n  &&  !due)
+                    {
+                        due = front(k, s_rrc_re, ldg(row + pos));
+                        pos++;
+                    }
+                }
+                if (due)
+                {
+                    if (half(k, s_rrc_im))
+                        baud(k);
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// kernels
+
+#if defined(__CUDACC__)
+
+template <class RX>
+struct KernelArgs
+{
+    ModemArgs a;
+    typename RX::Consts k;
+};
+
+// Shared memory: [rrc_re | rrc_im | RX tables | lane-interleaved per-channel arrays]
+template <class RX> constexpr int modem_smem_words()
+{
+    return 2*RX::SETS*SBM_FILTER_STEPS + RX::TABLE_WORDS + RX::LANE_WORDS*32;
+}
+
+template <class RX>
+__device__ __forceinline__ void modem_bind(RX &r, const KernelArgs<RX> &ka, float *smem, int lane, int c,
+                                           const float *&s_rrc_re, const float *&s_rrc_im)
+{
+    float *w_rrc_re = smem;
+    float *w_rrc_im = smem + RX::SETS*SBM_FILTER_STEPS;
+    float *tables = smem + 2*RX::SETS*SBM_FILTER_STEPS;
+    float *lane_base = tables + RX::TABLE_WORDS;
+    for (int i = lane;  i < RX::SETS*SBM_FILTER_STEPS;  i += 32)
+    {
+        w_rrc_re[i] = ka.k.rrc_re[i];
+        w_rrc_im[i] = ka.k.rrc_im[i];
+    }
+    RX::fill_tables(tables, ka.k, lane, 32);
+    __syncwarp();
+    s_rrc_re = w_rrc_re;
+    s_rrc_im = w_rrc_im;
+    r.c = c;
+    r.channels = ka.a.channels;
+    r.fstate = ka.a.fstate;
+    r.bind(tables, lane_base + lane);
+}
+
+// 32 channels per CTA (one warp): few channels exist (thousands), so spread them over all SMs.
+template <class RX>
+__global__ void __launch_bounds__(32) modem_rx_kernel(const KernelArgs<RX> ka)
+{
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x;
+    const int c = blockIdx.x*32 + lane;
+    RX r;
+    const float *s_rrc_re;
+    const float *s_rrc_im;
+    modem_bind(r, ka, smem, lane, (c < ka.a.channels)  ?  c  :  0, s_rrc_re, s_rrc_im);
+    if (c >= ka.a.channels)
+        return;
+    StateLoader ld = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
+    r.visit(ld);
+    r.bits = ka.a.bits + (size_t) c*ka.a.bits_cap;
+    r.bits_cap = (int) ka.a.bits_cap;
+    r.nbits = 0;
+    r.syms = (ka.a.syms)  ?  (ka.a.syms + (size_t) c*ka.a.sym_cap)  :  NULL;
+    r.sym_cap = (int) ka.a.sym_cap;
+    r.nsyms = 0;
+    r.run(ka.k, s_rrc_re, s_rrc_im, ka.a.amp + (long long) c*ka.a.stride, ka.a.n);
+    StateStorer st = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
+    r.visit(st);
+    ka.a.nbits[c] = r.nbits;
+    if (ka.a.nsyms)
+        ka.a.nsyms[c] = r.nsyms;
+}
+
+// xxx_rx_init() (mode < 0: all state zeroed first, then init with `mode` = -1 - restart argument) or
+// xxx_rx_restart() (mode >= 0) for channels [first, first + count).  `mode` is the receiver's own restart
+// argument (V.29: old_train; V.17: short_train).
+template <class RX>
+__global__ void __launch_bounds__(32) modem_init_kernel(const KernelArgs<RX> ka, int first, int count, int bit_rate, int mode,
+                                                        int on_power, int off_power)
+{
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x;
+    const int idx = blockIdx.x*32 + lane;
+    const int c = first + idx;
+    RX r;
+    const float *s_rrc_re;
+    const float *s_rrc_im;
+    modem_bind(r, ka, smem, lane, (idx < count)  ?  c  :  first, s_rrc_re, s_rrc_im);
+    if (idx >= count)
+        return;
+    r.bits = NULL;
+    r.bits_cap = 0;
+    r.nbits = 0;
+    r.syms = NULL;
+    r.sym_cap = 0;
+    r.nsyms = 0;
+    if (mode < 0)
+    {
+        r.init(ka.k, bit_rate, on_power, off_power);
+    }
+    else
+    {
+        StateLoader ld = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
+        r.visit(ld);
+        r.restart(ka.k, bit_rate, mode);
+    }
+    StateStorer st = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
+    r.visit(st);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sbm

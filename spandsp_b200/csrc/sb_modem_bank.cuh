@@ -1,0 +1,457 @@
+// sb_modem_bank.cuh - host side of the modem receiver banks (V.29, V.17): device tables, per-channel
+// state arrays, launches, result read-back.  The C ABI functions of include/spandsp_b200_v29.h and
+// include/spandsp_b200_v17.h are thin wrappers over these templates.
+#pragma once
+
+#include <vector>
+
+#include "sb_engine.h"
+#include "sb_modem.cuh"
+
+#define CK(call) \
+    do \
+    { \
+        cudaError_t e_ = (call); \
+        if (e_ != cudaSuccess) \
+        { \
+            sb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return -1; \
+        } \
+    } \
+    while (0)
+
+#define CKP(call) \
+    do \
+    { \
+        cudaError_t e_ = (call); \
+        if (e_ != cudaSuccess) \
+        { \
+            sb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return NULL; \
+        } \
+    } \
+    while (0)
+
+namespace sbm {
+
+template <class RX>
+struct ModemBank
+{
+    span_b200_ctx_t *ctx;
+    int channels;
+    int bit_rate;
+    float *fstate;
+    int *istate;
+    std::vector<void *> owned;          // device allocations holding the constant tables
+    typename RX::Consts k;
+    signed char *bits;
+    long long bits_cap;
+    int *nbits;
+    span_b200_v29_symbol_t *syms;
+    long long sym_cap;
+    int *nsyms;
+    int want_symbols;
+    int16_t *d_in;
+    size_t d_in_bytes;
+    cudaStream_t last_stream;
+    bool have_last;
+    int on_power;
+    int off_power;
+    int bits_per_sample_x2;             // output capacity: put_bit calls per input sample, times two
+};
+
+template <class T>
+static int modem_upload(std::vector<void *> &owned, const T **dst, const void *src, size_t bytes)
+{
+    void *p = NULL;
+    CK(cudaMalloc(&p, bytes));
+    owned.push_back(p);
+    CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+    *dst = (const T *) p;
+    return 0;
+}
+
+// Tables every receiver needs: RRC sets, sine table, sqrt table, Godard descriptor, carrier constants.
+template <class RX>
+static int modem_core_tables(ModemBank<RX> *b, double carrier_hz, double godard_fine_trigger, int godard_coarse_step, float agc_target)
+{
+    std::vector<float> re;
+    std::vector<float> im;
+    std::vector<float> st;
+    std::vector<unsigned short> sq;
+    godard_desc_t g;
+    make_rx_rrc(re, im, RX::SETS, carrier_hz);
+    make_sine_table(st);
+    make_sqrt_table(sq);
+    make_godard(g, carrier_hz, godard_fine_trigger, godard_coarse_step);
+    if (modem_upload(b->owned, &b->k.rrc_re, re.data(), sizeof(float)*re.size()) != 0
+        ||
+        modem_upload(b->owned, &b->k.rrc_im, im.data(), sizeof(float)*im.size()) != 0
+        ||
+        modem_upload(b->owned, &b->k.sine, st.data(), sizeof(float)*st.size()) != 0
+        ||
+        modem_upload(b->owned, &b->k.sqrt_tab, sq.data(), sizeof(unsigned short)*sq.size()) != 0)
+    {
+        return -1;
+    }
+    for (int i = 0;  i < 3;  i++)
+    {
+        b->k.g_low[i] = g.low[i];
+        b->k.g_high[i] = g.high[i];
+    }
+    b->k.g_mixed3 = g.mixed3;
+    b->k.g_coarse_trigger = g.coarse_trigger;
+    b->k.g_fine_trigger = g.fine_trigger;
+    b->k.g_coarse_step = g.coarse_step;
+    b->k.g_fine_step = g.fine_step;
+    const float carrier = (float) carrier_hz;
+    b->k.rate_nominal = host_dds_phase_rate(carrier);
+    b->k.rate_low = host_dds_phase_rate(carrier - 20.0f);
+    b->k.rate_high = host_dds_phase_rate(carrier + 20.0f);
+    b->k.agc_target = agc_target/1.000000f;                 // RX_PULSESHAPER_GAIN is 1.0 in the float build
+    b->k.agc_initial = (agc_target/1.000000f)/735.0f;       // src/v29rx.c:1078, src/v17rx.c:1474
+    return 0;
+}
+
+template <class RX>
+static KernelArgs<RX> modem_args(ModemBank<RX> *b, const int16_t *d_amp, int64_t stride, int n)
+{
+    KernelArgs<RX> ka;
+    ka.a.amp = d_amp;
+    ka.a.stride = stride;
+    ka.a.n = n;
+    ka.a.channels = b->channels;
+    ka.a.fstate = b->fstate;
+    ka.a.istate = b->istate;
+    ka.a.bits = b->bits;
+    ka.a.bits_cap = b->bits_cap;
+    ka.a.nbits = b->nbits;
+    ka.a.syms = (b->want_symbols)  ?  b->syms  :  NULL;
+    ka.a.sym_cap = b->sym_cap;
+    ka.a.nsyms = b->nsyms;
+    ka.k = b->k;
+    return ka;
+}
+
+template <class RX>
+static int modem_configure()
+{
+    static bool configured = false;
+    if (!configured)
+    {
+        const int smem = (int) sizeof(float)*modem_smem_words<RX>();
+        CK(cudaFuncSetAttribute(modem_rx_kernel<RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(modem_init_kernel<RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    return 0;
+}
+
+// mode < 0: xxx_rx_init(); mode >= 0: xxx_rx_restart(s, bit_rate, mode)
+template <class RX>
+static int modem_init_channels(ModemBank<RX> *b, int first, int count, int bit_rate, int mode)
+{
+    if (count <= 0)
+        return 0;
+    if (modem_configure<RX>() != 0)
+        return -1;
+    const int smem = (int) sizeof(float)*modem_smem_words<RX>();
+    cudaStream_t st = (cudaStream_t) sb_ctx_stream(b->ctx);
+    KernelArgs<RX> ka = modem_args(b, NULL, 0, 0);
+    modem_init_kernel<RX><<<(count + 31)/32, 32, smem, st>>>(ka, first, count, bit_rate, mode, b->on_power, b->off_power);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+template <class RX>
+static int modem_alloc_state(ModemBank<RX> *b)
+{
+    const size_t C = b->channels;
+    CK(cudaMalloc(&b->fstate, sizeof(float)*RX::F_COUNT*C));
+    CK(cudaMalloc(&b->istate, sizeof(int)*RX::I_COUNT*C));
+    CK(cudaMemset(b->fstate, 0, sizeof(float)*RX::F_COUNT*C));
+    CK(cudaMemset(b->istate, 0, sizeof(int)*RX::I_COUNT*C));
+    CK(cudaMalloc(&b->nbits, sizeof(int)*C));
+    CK(cudaMalloc(&b->nsyms, sizeof(int)*C));
+    CK(cudaMemset(b->nbits, 0, sizeof(int)*C));
+    CK(cudaMemset(b->nsyms, 0, sizeof(int)*C));
+    return 0;
+}
+
+template <class RX>
+static void modem_destroy(ModemBank<RX> *b)
+{
+    if (b == NULL)
+        return;
+    cudaSetDevice(span_b200_ctx_device(b->ctx));
+    if (b->have_last)
+        cudaStreamSynchronize(b->last_stream);
+    cudaFree(b->fstate);
+    cudaFree(b->istate);
+    for (size_t i = 0;  i < b->owned.size();  i++)
+        cudaFree(b->owned[i]);
+    cudaFree(b->bits);
+    cudaFree(b->nbits);
+    cudaFree(b->syms);
+    cudaFree(b->nsyms);
+    cudaFree(b->d_in);
+    delete b;
+}
+
+template <class RX>
+static int modem_quiesce(ModemBank<RX> *b)
+{
+    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    return 0;
+}
+
+template <class RX>
+static int modem_range_ok(ModemBank<RX> *b, int first, int count)
+{
+    if (b == NULL  ||  first < 0  ||  count < 0  ||  first + count > b->channels)
+    {
+        sb_set_error("channel range out of bounds");
+        return 0;
+    }
+    return 1;
+}
+
+// xxx_rx_set_signal_cutoff() (src/v29rx.c:163-168, src/v17rx.c:173-178)
+template <class RX>
+static int modem_set_signal_cutoff(ModemBank<RX> *b, int first, int count, float cutoff)
+{
+    if (!modem_range_ok(b, first, count))
+        return -1;
+    if (modem_quiesce(b) != 0)
+        return -1;
+    const int on = (int32_t) (host_power_meter_level_dbm0(cutoff + 2.5f)*0.4f);
+    const int off = (int32_t) (host_power_meter_level_dbm0(cutoff - 2.5f)*0.4f);
+    if (first == 0  &&  count == b->channels)
+    {
+        b->on_power = on;
+        b->off_power = off;
+    }
+    std::vector<int> v(count, on);
+    CK(cudaMemcpy(b->istate + (size_t) I_ON_POWER*b->channels + first, v.data(), sizeof(int)*count, cudaMemcpyHostToDevice));
+    v.assign(count, off);
+    CK(cudaMemcpy(b->istate + (size_t) I_OFF_POWER*b->channels + first, v.data(), sizeof(int)*count, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// xxx_rx_fillin(): integer bookkeeping only (src/v29rx.c:967-996, src/v17rx.c:1313-1343); done on the
+// host copy of four fields.
+template <class RX>
+static int modem_fillin(ModemBank<RX> *b, int first, int count, int samples)
+{
+    if (!modem_range_ok(b, first, count)  ||  samples < 0)
+    {
+        sb_set_error("bad fillin arguments");
+        return -1;
+    }
+    if (modem_quiesce(b) != 0)
+        return -1;
+    const size_t C = b->channels;
+    std::vector<int> present(count), stage(count), phase(count), rate(count), put(count);
+    CK(cudaMemcpy(present.data(), b->istate + I_SIGNAL_PRESENT*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(stage.data(), b->istate + I_STAGE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(phase.data(), b->istate + I_CARRIER_PHASE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rate.data(), b->istate + I_PHASE_RATE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(put.data(), b->istate + I_EQ_PUT_STEP*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
+    for (int c = 0;  c < count;  c++)
+    {
+        if (present[c] <= 0  ||  stage[c] == RX::STAGE_PARKED)
+            continue;
+        unsigned int ph = (unsigned int) phase[c];
+        for (int i = 0;  i < samples;  i++)
+        {
+            ph += (unsigned int) rate[c];
+            put[c] -= RX::SETS;
+            if (put[c] <= 0)
+                put[c] += RX::SETS*10/(3*2);
+        }
+        phase[c] = (int) ph;
+    }
+    CK(cudaMemcpy(b->istate + I_CARRIER_PHASE*C + first, phase.data(), sizeof(int)*count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->istate + I_EQ_PUT_STEP*C + first, put.data(), sizeof(int)*count, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static inline int modem_realloc(void **p, size_t bytes)
+{
+    if (*p)
+        CK(cudaFree(*p));
+    *p = NULL;
+    CK(cudaMalloc(p, bytes));
+    return 0;
+}
+
+template <class RX>
+static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t stride, int n, void *stream)
+{
+    if (b == NULL  ||  n < 0  ||  (n > 0  &&  d_amp == NULL))
+    {
+        sb_set_error("bad rx arguments");
+        return -1;
+    }
+    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
+    if (b->have_last  &&  b->last_stream != st)
+        CK(cudaStreamSynchronize(b->last_stream));
+    // Worst case: bits per baud at 2400 baud/8000 Hz plus timing drift, plus status reports.
+    const long long want_bits = (long long) n*b->bits_per_sample_x2/2 + 64;
+    if (b->bits_cap < want_bits)
+    {
+        if (b->have_last)
+            CK(cudaStreamSynchronize(b->last_stream));
+        if (modem_realloc((void **) &b->bits, (size_t) want_bits*b->channels) != 0)
+            return -1;
+        b->bits_cap = want_bits;
+    }
+    const long long want_syms = (long long) n*2/5 + 16;
+    if (b->want_symbols  &&  b->sym_cap < want_syms)
+    {
+        if (b->have_last)
+            CK(cudaStreamSynchronize(b->last_stream));
+        if (modem_realloc((void **) &b->syms, (size_t) want_syms*b->channels*sizeof(span_b200_v29_symbol_t)) != 0)
+            return -1;
+        b->sym_cap = want_syms;
+    }
+    if (modem_configure<RX>() != 0)
+        return -1;
+    KernelArgs<RX> ka = modem_args(b, d_amp, stride, n);
+    const int smem = (int) sizeof(float)*modem_smem_words<RX>();
+    modem_rx_kernel<RX><<<(b->channels + 31)/32, 32, smem, st>>>(ka);
+    CK(cudaGetLastError());
+    b->last_stream = st;
+    b->have_last = true;
+    return 0;
+}
+
+template <class RX>
+static int modem_rx_host(ModemBank<RX> *b, const int16_t *h_amp, int64_t stride, int n, void *stream)
+{
+    if (b == NULL  ||  n < 0  ||  (n > 0  &&  h_amp == NULL))
+    {
+        sb_set_error("bad rx arguments");
+        return -1;
+    }
+    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
+    if (b->have_last  &&  b->last_stream != st)
+        CK(cudaStreamSynchronize(b->last_stream));
+    const size_t want = sizeof(int16_t)*(size_t) n*b->channels + 16;
+    if (b->d_in_bytes < want)
+    {
+        if (b->have_last)
+            CK(cudaStreamSynchronize(b->last_stream));
+        if (modem_realloc((void **) &b->d_in, want) != 0)
+            return -1;
+        b->d_in_bytes = want;
+    }
+    if (n > 0)
+        CK(cudaMemcpy2DAsync(b->d_in, sizeof(int16_t)*(size_t) n, h_amp, sizeof(int16_t)*stride, sizeof(int16_t)*(size_t) n,
+                             b->channels, cudaMemcpyHostToDevice, st));
+    return modem_rx_device(b, b->d_in, n, n, (void *) st);
+}
+
+template <class RX>
+static int modem_counts(ModemBank<RX> *b, int32_t *nbits, int32_t *nsyms)
+{
+    if (modem_quiesce(b) != 0)
+        return -1;
+    if (nbits)
+        CK(cudaMemcpy(nbits, b->nbits, sizeof(int)*(size_t) b->channels, cudaMemcpyDeviceToHost));
+    if (nsyms)
+        CK(cudaMemcpy(nsyms, b->nsyms, sizeof(int)*(size_t) b->channels, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+template <class RX>
+static int64_t modem_bits(ModemBank<RX> *b, int channel, int8_t *out, int64_t max)
+{
+    if (channel < 0  ||  channel >= b->channels)
+        return -1;
+    if (modem_quiesce(b) != 0)
+        return -1;
+    int n = 0;
+    CK(cudaMemcpy(&n, b->nbits + channel, sizeof(int), cudaMemcpyDeviceToHost));
+    long long k = n;
+    if (k > b->bits_cap)
+        k = b->bits_cap;
+    if (k > max)
+        k = max;
+    if (k > 0)
+        CK(cudaMemcpy(out, b->bits + (size_t) channel*b->bits_cap, (size_t) k, cudaMemcpyDeviceToHost));
+    return k;
+}
+
+template <class RX>
+static int64_t modem_symbols(ModemBank<RX> *b, int channel, span_b200_v29_symbol_t *out, int64_t max)
+{
+    if (channel < 0  ||  channel >= b->channels  ||  !b->want_symbols)
+        return -1;
+    if (modem_quiesce(b) != 0)
+        return -1;
+    int n = 0;
+    CK(cudaMemcpy(&n, b->nsyms + channel, sizeof(int), cudaMemcpyDeviceToHost));
+    long long k = n;
+    if (k > b->sym_cap)
+        k = b->sym_cap;
+    if (k > max)
+        k = max;
+    if (k > 0)
+        CK(cudaMemcpy(out, b->syms + (size_t) channel*b->sym_cap, sizeof(span_b200_v29_symbol_t)*(size_t) k, cudaMemcpyDeviceToHost));
+    return k;
+}
+
+template <class RX>
+static int modem_output_layout(ModemBank<RX> *b, const int8_t **d_bits, int64_t *bits_cap, const int32_t **d_nbits,
+                               const span_b200_v29_symbol_t **d_syms, int64_t *sym_cap, const int32_t **d_nsyms)
+{
+    if (d_bits)
+        *d_bits = (const int8_t *) b->bits;
+    if (bits_cap)
+        *bits_cap = b->bits_cap;
+    if (d_nbits)
+        *d_nbits = b->nbits;
+    if (d_syms)
+        *d_syms = b->syms;
+    if (sym_cap)
+        *sym_cap = b->sym_cap;
+    if (d_nsyms)
+        *d_nsyms = b->nsyms;
+    return 0;
+}
+
+// eq_coeff: 33 complex taps; info[i] = istate field fields[i] (or, for fields[i] < 0, the float field
+// -1 - fields[i] as its bit pattern).
+template <class RX>
+static int modem_channel_state(ModemBank<RX> *b, int channel, float *eq_coeff, int32_t *info, const int *fields, int nfields)
+{
+    if (channel < 0  ||  channel >= b->channels)
+        return -1;
+    if (modem_quiesce(b) != 0)
+        return -1;
+    const size_t C = b->channels;
+    if (eq_coeff)
+    {
+        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+            CK(cudaMemcpy(&eq_coeff[i], b->fstate + (size_t) (F_EQ_COEFF + i)*C + channel, sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (info)
+    {
+        for (int i = 0;  i < nfields;  i++)
+        {
+            if (fields[i] >= 0)
+                CK(cudaMemcpy(&info[i], b->istate + (size_t) fields[i]*C + channel, sizeof(int), cudaMemcpyDeviceToHost));
+            else
+                CK(cudaMemcpy(&info[i], b->fstate + (size_t) (-1 - fields[i])*C + channel, sizeof(float), cudaMemcpyDeviceToHost));
+        }
+    }
+    return 0;
+}
+
+}  // namespace sbm

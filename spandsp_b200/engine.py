@@ -88,6 +88,20 @@ def lib():
         "span_b200_v29_bank_symbols": (i64, [vp, i32, vp, i64]),
         "span_b200_v29_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_v29_tables": (i32, [vp, vp, vp, vp, vp, vp]),
+        "span_b200_v29_bank_restart_ex": (i32, [vp, i32, i32, i32, i32]),
+        "span_b200_v17_bank_create": (vp, [vp, i32, i32, i32]),
+        "span_b200_v17_bank_destroy": (None, [vp]),
+        "span_b200_v17_bank_channels": (i32, [vp]),
+        "span_b200_v17_bank_restart": (i32, [vp, i32, i32, i32, i32]),
+        "span_b200_v17_bank_set_signal_cutoff": (i32, [vp, i32, i32, f32]),
+        "span_b200_v17_bank_fillin": (i32, [vp, i32, i32, i32]),
+        "span_b200_v17_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_v17_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_v17_bank_counts": (i32, [vp, vp, vp]),
+        "span_b200_v17_bank_bits": (i64, [vp, i32, vp, i64]),
+        "span_b200_v17_bank_symbols": (i64, [vp, i32, vp, i64]),
+        "span_b200_v17_bank_channel_state": (i32, [vp, i32, vp, vp]),
+        "span_b200_v17_tables": (i32, [vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -311,62 +325,84 @@ V29_SYMBOL_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim
 
 class V29Bank:
     """N V.29 receivers (span_b200_v29_bank_create)."""
+    PREFIX = "span_b200_v29_bank_"
+    INFO = 10
 
     def __init__(self, ctx, channels, bit_rate=9600, want_symbols=False):
         self.ctx = ctx
-        self.h = lib().span_b200_v29_bank_create(ctx.h, channels, bit_rate, int(want_symbols))
+        self.h = self._fn("create")(ctx.h, channels, bit_rate, int(want_symbols))
         if not self.h:
             raise EngineError(_err())
         self.channels = channels
+
+    def _fn(self, name):
+        return getattr(lib(), self.PREFIX + name)
 
     def _ck(self, rc):
         if rc < 0:
             raise EngineError(_err())
         return rc
 
-    def restart(self, bit_rate, first=0, count=None):
-        self._ck(lib().span_b200_v29_bank_restart(self.h, first, self.channels - first if count is None else count, bit_rate))
+    def restart(self, bit_rate, first=0, count=None, mode=0):
+        """mode: V.29 old_train (0/1); V.17 short_train (0/1/2)."""
+        n = self.channels - first if count is None else count
+        if self.PREFIX == "span_b200_v29_bank_":
+            self._ck(lib().span_b200_v29_bank_restart_ex(self.h, first, n, bit_rate, mode))
+        else:
+            self._ck(self._fn("restart")(self.h, first, n, bit_rate, mode))
+
+    def fillin(self, samples, first=0, count=None):
+        self._ck(self._fn("fillin")(self.h, first, self.channels - first if count is None else count, samples))
 
     def set_signal_cutoff(self, cutoff, first=0, count=None):
-        self._ck(lib().span_b200_v29_bank_set_signal_cutoff(self.h, first, self.channels - first if count is None else count, cutoff))
+        self._ck(self._fn("set_signal_cutoff")(self.h, first, self.channels - first if count is None else count, cutoff))
 
     def rx_device(self, d_ptr, stride, samples, stream=None):
-        self._ck(lib().span_b200_v29_bank_rx_device(self.h, d_ptr, stride, samples, stream))
+        self._ck(self._fn("rx_device")(self.h, d_ptr, stride, samples, stream))
 
     def rx_host(self, amp, stream=None):
         assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
-        self._ck(lib().span_b200_v29_bank_rx_host(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
+        self._ck(self._fn("rx_host")(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
 
     def counts(self):
         nb = np.zeros(self.channels, dtype=np.int32)
         ns = np.zeros(self.channels, dtype=np.int32)
-        self._ck(lib().span_b200_v29_bank_counts(self.h, nb.ctypes.data, ns.ctypes.data))
+        self._ck(self._fn("counts")(self.h, nb.ctypes.data, ns.ctypes.data))
         return nb, ns
 
     def bits(self, channel, cap=1 << 22):
         out = np.zeros(cap, dtype=np.int8)
-        n = lib().span_b200_v29_bank_bits(self.h, channel, out.ctypes.data, cap)
+        n = self._fn("bits")(self.h, channel, out.ctypes.data, cap)
         if n < 0:
             raise EngineError(_err())
         return out[:n]
 
     def symbols(self, channel, cap=1 << 20):
         out = np.zeros(cap, dtype=V29_SYMBOL_DTYPE)
-        n = lib().span_b200_v29_bank_symbols(self.h, channel, out.ctypes.data, cap)
+        n = self._fn("symbols")(self.h, channel, out.ctypes.data, cap)
         if n < 0:
             raise EngineError(_err())
         return out[:n]
 
     def channel_state(self, channel):
         eq = np.zeros(66, dtype=np.float32)
-        info = np.zeros(10, dtype=np.int32)
-        self._ck(lib().span_b200_v29_bank_channel_state(self.h, channel, eq.ctypes.data, info.ctypes.data))
+        info = np.zeros(self.INFO, dtype=np.int32)
+        self._ck(self._fn("channel_state")(self.h, channel, eq.ctypes.data, info.ctypes.data))
         return eq, info
 
     def close(self):
         if self.h:
-            lib().span_b200_v29_bank_destroy(self.h)
+            self._fn("destroy")(self.h)
             self.h = None
+
+
+class V17Bank(V29Bank):
+    """N V.17 receivers (span_b200_v17_bank_create)."""
+    PREFIX = "span_b200_v17_bank_"
+    INFO = 12
+
+    def __init__(self, ctx, channels, bit_rate=14400, want_symbols=False):
+        V29Bank.__init__(self, ctx, channels, bit_rate, want_symbols)
 
 
 def events_by_channel(ev, channels):

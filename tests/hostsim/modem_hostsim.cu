@@ -1,0 +1,251 @@
+// modem_hostsim.cu - TEST INFRASTRUCTURE ONLY.  Compiles the receivers of spandsp_b200/csrc/sb_v29_rx.cuh and
+// sb_v17_rx.cuh (the very code the CUDA kernels run, written __host__ __device__) for the HOST, one channel
+// at a time, so that the training state machines, the trellis decoder and the state save/restore can be
+// compared with the oracle in a container without a GPU (tests/test_hostsim_modem.py).  Nothing in the
+// product library links or loads this; the product path exists on the GPU only.
+#include "../../spandsp_b200/csrc/sb_modem.cuh"
+#include "../../spandsp_b200/csrc/sb_v29_rx.cuh"
+#include "../../spandsp_b200/csrc/sb_v17_rx.cuh"
+
+using namespace sbm;
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+struct HostTables
+{
+    std::vector<float> re, im, sine;
+    std::vector<unsigned short> sq;
+    V29Tables t29;
+    V17Tables t17;
+    std::vector<unsigned char> maps, map4800;
+};
+
+static void core_consts(CoreConsts &k, HostTables &h, int sets, double carrier, double fine, int coarse, float agc_target)
+{
+    godard_desc_t g;
+    make_rx_rrc(h.re, h.im, sets, carrier);
+    make_sine_table(h.sine);
+    make_sqrt_table(h.sq);
+    make_godard(g, carrier, fine, coarse);
+    k.rrc_re = h.re.data();
+    k.rrc_im = h.im.data();
+    k.sine = h.sine.data();
+    k.sqrt_tab = h.sq.data();
+    for (int i = 0;  i < 3;  i++)
+    {
+        k.g_low[i] = g.low[i];
+        k.g_high[i] = g.high[i];
+    }
+    k.g_mixed3 = g.mixed3;
+    k.g_coarse_trigger = g.coarse_trigger;
+    k.g_fine_trigger = g.fine_trigger;
+    k.g_coarse_step = g.coarse_step;
+    k.g_fine_step = g.fine_step;
+    k.rate_nominal = host_dds_phase_rate((float) carrier);
+    k.rate_low = host_dds_phase_rate((float) carrier - 20.0f);
+    k.rate_high = host_dds_phase_rate((float) carrier + 20.0f);
+    k.agc_target = agc_target/1.000000f;
+    k.agc_initial = (agc_target/1.000000f)/735.0f;
+}
+
+template <class RX>
+struct HostChannel
+{
+    typename RX::Consts k;
+    std::vector<float> smem;
+    std::vector<float> fstate;
+    std::vector<int> istate;
+    const float *s_re;
+    const float *s_im;
+    float *tables;
+    float *lane;
+
+    void setup()
+    {
+        smem.assign(2*RX::SETS*SBM_FILTER_STEPS + RX::TABLE_WORDS + RX::LANE_WORDS*32, 0.0f);
+        fstate.assign(RX::F_COUNT, 0.0f);
+        istate.assign(RX::I_COUNT, 0);
+        memcpy(smem.data(), k.rrc_re, sizeof(float)*RX::SETS*SBM_FILTER_STEPS);
+        memcpy(smem.data() + RX::SETS*SBM_FILTER_STEPS, k.rrc_im, sizeof(float)*RX::SETS*SBM_FILTER_STEPS);
+        s_re = smem.data();
+        s_im = smem.data() + RX::SETS*SBM_FILTER_STEPS;
+        tables = smem.data() + 2*RX::SETS*SBM_FILTER_STEPS;
+        lane = tables + RX::TABLE_WORDS;
+        RX::fill_tables(tables, k, 0, 1);
+    }
+
+    void attach(RX &r)
+    {
+        r.c = 0;
+        r.channels = 1;
+        r.fstate = fstate.data();
+        r.bind(tables, lane);
+        r.bits = NULL;
+        r.bits_cap = 0;
+        r.nbits = 0;
+        r.syms = NULL;
+        r.sym_cap = 0;
+        r.nsyms = 0;
+    }
+
+    void init(int bit_rate, int on_power, int off_power)
+    {
+        RX r;
+        memset(&r, 0, sizeof(r));
+        attach(r);
+        r.init(k, bit_rate, on_power, off_power);
+        StateStorer st = {fstate.data(), istate.data(), 1, 0};
+        r.visit(st);
+    }
+
+    int restart(int bit_rate, int mode)
+    {
+        RX r;
+        memset(&r, 0, sizeof(r));
+        attach(r);
+        StateLoader ld = {fstate.data(), istate.data(), 1, 0};
+        r.visit(ld);
+        const int rc = r.restart(k, bit_rate, mode);
+        StateStorer st = {fstate.data(), istate.data(), 1, 0};
+        r.visit(st);
+        return rc;
+    }
+
+    // one rx call: load state, run, store state - exactly what modem_rx_kernel does per launch
+    void rx(const int16_t *amp, int n, int8_t *bits, int bits_cap, int *nbits, span_b200_v29_symbol_t *syms, int sym_cap, int *nsyms)
+    {
+        RX r;
+        memset(&r, 0, sizeof(r));
+        attach(r);
+        StateLoader ld = {fstate.data(), istate.data(), 1, 0};
+        r.visit(ld);
+        r.bits = (signed char *) bits;
+        r.bits_cap = bits_cap;
+        r.syms = syms;
+        r.sym_cap = sym_cap;
+        r.run(k, s_re, s_im, amp, n);
+        StateStorer st = {fstate.data(), istate.data(), 1, 0};
+        r.visit(st);
+        *nbits = r.nbits;
+        *nsyms = r.nsyms;
+    }
+};
+
+template <class RX>
+static int run_channel(HostChannel<RX> &ch, const int16_t *amp, int n, int chunk, int bit_rate, int restart_at, int restart_mode,
+                       int8_t *bits, int bits_cap, int32_t *nbits, span_b200_v29_symbol_t *syms, int sym_cap, int32_t *nsyms,
+                       float *eq_coeff)
+{
+    int tb = 0;
+    int ts = 0;
+    int len;
+    if (chunk <= 0)
+        chunk = n;
+    for (int pos = 0;  pos < n;  pos += len)
+    {
+        if (restart_at >= 0  &&  pos >= restart_at)
+        {
+            ch.restart(bit_rate, restart_mode);
+            restart_at = -1;
+        }
+        len = (n - pos < chunk)  ?  (n - pos)  :  chunk;
+        int nb = 0;
+        int ns = 0;
+        // bit positions in the symbol records count from the start of each rx call; make them global
+        span_b200_v29_symbol_t *sp = (syms  &&  ts < sym_cap)  ?  (syms + ts)  :  NULL;
+        ch.rx(amp + pos, len, (tb < bits_cap)  ?  (bits + tb)  :  bits, (tb < bits_cap)  ?  (bits_cap - tb)  :  0, &nb,
+              sp, (sp)  ?  (sym_cap - ts)  :  0, &ns);
+        if (sp)
+        {
+            for (int i = 0;  i < ns  &&  ts + i < sym_cap;  i++)
+                sp[i].bit_pos += tb;
+        }
+        tb += nb;
+        ts += ns;
+    }
+    *nbits = tb;
+    *nsyms = ts;
+    if (eq_coeff)
+    {
+        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+            eq_coeff[i] = ch.fstate[F_EQ_COEFF + i];
+    }
+    return 0;
+}
+
+// final[]: as oracle ref_v17_run: {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling bits,
+//           total_baud_timing_correction, diff, carrier_phase, short_train, trellis_ptr}
+EXPORT int hostsim_v17_run(const int16_t *amp, int n, int chunk, int bit_rate, float cutoff, int restart_at, int restart_short,
+                           int8_t *bits, int bits_cap, int32_t *nbits, span_b200_v29_symbol_t *syms, int sym_cap, int32_t *nsyms,
+                           float *eq_coeff, int32_t *final)
+{
+    static HostTables h;
+    HostChannel<RxV17> ch;
+    core_consts(ch.k, h, V17_COEFF_SETS, 1800.0, 100.0, 15, 2.17f);
+    make_v17_tables(h.t17);
+    make_v17_maps(h.t17, h.maps, h.map4800);
+    ch.k.tables = &h.t17;
+    ch.k.maps = h.maps.data();
+    ch.k.map4800 = h.map4800.data();
+    ch.k.phase_p90 = host_dds_phase(90.0f);
+    ch.k.phase_m90 = host_dds_phase(-90.0f);
+    ch.k.phase_180 = host_dds_phase(180.0f);
+    ch.k.phase_a = host_dds_phase(270.0f + 18.433f);
+    ch.k.phase_b = host_dds_phase(180.0f + 18.433f);
+    ch.k.phase_c = host_dds_phase(18.433f);
+    const float fast = 0.21f/SBM_EQ_LEN;
+    ch.k.eq_delta_fast = fast;
+    ch.k.eq_delta_slow = 0.1f*fast;
+    ch.setup();
+    if (cutoff <= -99.0f)
+        cutoff = -45.5f;
+    ch.init(bit_rate, (int32_t) (host_power_meter_level_dbm0(cutoff + 2.5f)*0.4f), (int32_t) (host_power_meter_level_dbm0(cutoff - 2.5f)*0.4f));
+    run_channel(ch, amp, n, chunk, bit_rate, restart_at, restart_short, bits, bits_cap, nbits, syms, sym_cap, nsyms, eq_coeff);
+    if (final)
+    {
+        final[0] = ch.istate[I_STAGE];
+        final[1] = ch.istate[I_PHASE_RATE];
+        final[2] = ch.istate[I_EQ_PUT_STEP];
+        final[3] = ch.istate[I_SIGNAL_PRESENT];
+        memcpy(&final[4], &ch.fstate[F_AGC], 4);
+        final[5] = ch.istate[I_TOTAL_TIMING];
+        final[6] = ch.istate[RxV17::I_DIFF];
+        final[7] = ch.istate[I_CARRIER_PHASE];
+        final[8] = ch.istate[RxV17::I_SHORT_TRAIN];
+        final[9] = ch.istate[RxV17::I_TRELLIS_PTR];
+    }
+    return 0;
+}
+
+// final[]: as oracle ref_v29_run: {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling bits,
+//           total_baud_timing_correction, constellation_state, carrier_phase}
+EXPORT int hostsim_v29_run(const int16_t *amp, int n, int chunk, int bit_rate, float cutoff, int restart_at, int restart_old_train,
+                           int8_t *bits, int bits_cap, int32_t *nbits, span_b200_v29_symbol_t *syms, int sym_cap, int32_t *nsyms,
+                           float *eq_coeff, int32_t *final)
+{
+    static HostTables h;
+    HostChannel<RxV29> ch;
+    core_consts(ch.k, h, V29_COEFF_SETS, 1700.0, 30.0, 5, 1.25f);
+    make_v29_tables(h.t29);
+    ch.k.tables = &h.t29;
+    ch.k.phase_p45 = host_dds_phase(45.0f);
+    ch.k.phase_m45 = host_dds_phase(-45.0f);
+    ch.k.eq_delta = 0.21f/SBM_EQ_LEN;
+    ch.setup();
+    if (cutoff <= -99.0f)
+        cutoff = -28.5f;
+    ch.init(bit_rate, (int32_t) (host_power_meter_level_dbm0(cutoff + 2.5f)*0.4f), (int32_t) (host_power_meter_level_dbm0(cutoff - 2.5f)*0.4f));
+    run_channel(ch, amp, n, chunk, bit_rate, restart_at, restart_old_train, bits, bits_cap, nbits, syms, sym_cap, nsyms, eq_coeff);
+    if (final)
+    {
+        final[0] = ch.istate[I_STAGE];
+        final[1] = ch.istate[I_PHASE_RATE];
+        final[2] = ch.istate[I_EQ_PUT_STEP];
+        final[3] = ch.istate[I_SIGNAL_PRESENT];
+        memcpy(&final[4], &ch.fstate[F_AGC], 4);
+        final[5] = ch.istate[I_TOTAL_TIMING];
+        final[6] = ch.istate[RxV29::I_CONSTELLATION];
+        final[7] = ch.istate[I_CARRIER_PHASE];
+    }
+    return 0;
+}

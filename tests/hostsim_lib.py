@@ -1,0 +1,53 @@
+"""ctypes loader for tests/hostsim (the modem receivers compiled for the host).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostsim", "modem_hostsim.cu")
+LIB = os.path.join(HERE, "hostsim", "libmodem_hostsim.so")
+CSRC = os.path.join(os.path.dirname(HERE), "spandsp_b200", "csrc")
+
+SYM_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4"), ("state", "<i4"), ("bit_pos", "<i4")])
+
+
+def build(force=False):
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh")]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    subprocess.run([os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
+                    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-shared", "-o", LIB, SRC], check=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def run(modem, amp, bit_rate, chunk=160, cutoff=-100.0, restart_at=-1, restart_mode=1):
+    """modem: 'v17' or 'v29'.  Same result layout as pyoracle.v17_run / v29_run."""
+    amp = np.ascontiguousarray(amp, dtype=np.int16)
+    n = len(amp)
+    bits = np.zeros(n * 2 + 64, dtype=np.int8)
+    syms = np.zeros(n * 2 // 5 + 16, dtype=SYM_DTYPE)
+    nb = C.c_int32(0)
+    ns = C.c_int32(0)
+    eq = np.zeros(66, dtype=np.float32)
+    fin = np.zeros(10, dtype=np.int32)
+    fn = getattr(lib(), "hostsim_%s_run" % modem)
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(bit_rate), C.c_float(cutoff),
+            C.c_int(restart_at), C.c_int(restart_mode),
+            C.c_void_p(bits.ctypes.data), C.c_int(bits.size), C.byref(nb), C.c_void_p(syms.ctypes.data), C.c_int(syms.size),
+            C.byref(ns), C.c_void_p(eq.ctypes.data), C.c_void_p(fin.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("hostsim run failed")
+    return {"bits": bits[:nb.value].copy(), "syms": syms[:ns.value].copy(), "eq_coeff": eq, "final": fin}

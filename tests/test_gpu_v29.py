@@ -116,3 +116,25 @@ def test_v29_noise_only_and_restart(gpu_ctx, engine_lib, oracles):
     bank.rx_host(sig[None, :])
     check_channel(bank, 0, r["bits"], r["syms"], r["eq_coeff"], r["final"])
     bank.close()
+
+
+def test_v29_old_train_restart(gpu_ctx, engine_lib, oracles):
+    """v29_rx_restart(s, rate, old_train = true) (src/v29rx.c:1064-1069): saved equalizer, carrier and gain are reused."""
+    if "strict" not in oracles:
+        pytest.skip("compiled reference not available here")
+    S = oracles["strict"]
+    a = po.v29_generate(S, 14000, 9600, False, -13.0, 3, 100, 555, -55.0)
+    a[11000:] = 0
+    b = po.v29_generate(S, 12000, 9600, False, -13.0, 4, 300, 556, -55.0)
+    amp = np.concatenate([a, b])
+    r = po.v29_run(S, amp, 9600, 14080, -100.0, True, 14080, 1)
+    bank = engine_lib.V29Bank(gpu_ctx, 1, 9600, want_symbols=True)
+    bank.rx_host(np.ascontiguousarray(amp[None, :14080]))
+    b1, s1 = bank.bits(0).copy(), bank.symbols(0).copy()
+    bank.restart(9600, mode=1)
+    bank.rx_host(np.ascontiguousarray(amp[None, 14080:]))
+    bits = np.concatenate([b1, bank.bits(0)])
+    syms = np.concatenate([s1, bank.symbols(0)])
+    assert len(bits) == len(r["bits"]) and (bits == r["bits"]).all()
+    assert len(syms) == len(r["syms"]) and close(syms["re"], r["syms"]["re"]) and close(syms["im"], r["syms"]["im"])
+    bank.close()
