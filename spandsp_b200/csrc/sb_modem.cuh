@@ -36,6 +36,10 @@
 #define SBM_FILTER_STEPS    27      // V29_RX_FILTER_STEPS / V17_RX_FILTER_STEPS
 #define SBM_EQ_LEN          33      // V29_EQUALIZER_LEN / V17_EQUALIZER_LEN
 #define SBM_EQ_PRE_LEN      16
+#define SBM_SINE_WORDS      2048    // dds sine table
+#define SBM_SQRT_WORDS      100     // 193 uint16 of the fixed_sqrt table, padded to keep 16-byte alignment
+#define SBM_IN_RING         32      // samples per lane in the input staging ring (power of two)
+#define SBM_RRC_ROW         28      // coefficient rows in shared memory, padded from 27 so that they load as float4
 
 #define SIG_STATUS_CARRIER_DOWN             (-1)    // src/spandsp/async.h:66-103
 #define SIG_STATUS_CARRIER_UP               (-2)
@@ -423,7 +427,8 @@ struct ModemArgs
     int *nsyms;
 };
 
-// State visitors: one list of fields (visit()) serves loading, storing and counting.
+// State visitors: one list of fields (visit()) serves loading and storing.  Every field is visited by
+// reference, whether it lives in a register or in this lane's column of shared memory.
 struct StateLoader
 {
     const float *F;
@@ -433,8 +438,6 @@ struct StateLoader
     SB_HD void f(int slot, float &v) { v = F[(size_t) slot*C + c]; }
     SB_HD void i(int slot, int &v) { v = I[(size_t) slot*C + c]; }
     SB_HD void u(int slot, unsigned int &v) { v = (unsigned int) I[(size_t) slot*C + c]; }
-    SB_HD void fa(int slot, float *p, int n) { for (int k = 0;  k < n;  k++) p[k*32] = F[(size_t) (slot + k)*C + c]; }
-    SB_HD void ia(int slot, int *p, int n) { for (int k = 0;  k < n;  k++) p[k*32] = I[(size_t) (slot + k)*C + c]; }
 };
 
 struct StateStorer
@@ -446,8 +449,6 @@ struct StateStorer
     SB_HD void f(int slot, float &v) { F[(size_t) slot*C + c] = v; }
     SB_HD void i(int slot, int &v) { I[(size_t) slot*C + c] = v; }
     SB_HD void u(int slot, unsigned int &v) { I[(size_t) slot*C + c] = (int) v; }
-    SB_HD void fa(int slot, float *p, int n) { for (int k = 0;  k < n;  k++) F[(size_t) (slot + k)*C + c] = p[k*32]; }
-    SB_HD void ia(int slot, int *p, int n) { for (int k = 0;  k < n;  k++) I[(size_t) (slot + k)*C + c] = p[k*32]; }
 };
 
 // One receiver.  Scalars live in registers; the per-channel arrays live in shared memory,
@@ -468,11 +469,16 @@ struct RxCore
     int eq_step, eq_put_step, eq_skip, baud_half, total_timing;
     int last_angle0, last_angle1;
     // shared-memory arrays of this lane (dynamic indexing would force the whole receiver out of registers
-    // if they were member arrays)
+    // if they were member arrays).  Lane-interleaved: element e of lane l at [e*32 + l] (complex: float2
+    // elements), so any per-lane index is bank-conflict free.  The two rings (RRC history, equalizer
+    // buffer) are kept twice, the copy of slot k at k + N, so that the N taps that start at any ring
+    // position are contiguous and the inner loops need no wrap-around arithmetic.
+    const float *sine;              // [2048] dds sine table (shared memory copy)
+    const unsigned short *sqrt_tab; // [193] fixed_sqrt table (shared memory copy)
     int *diff_angles;       // [16]
-    float *eq_coeff;        // [66]
-    float *eq_buf;          // [66]
-    float *rrc;             // [27]
+    float2 *eq_coeff;       // [33]
+    float2 *eq_buf;         // [66]: ring of 33, doubled
+    float *rrc;             // [54]: ring of 27, doubled
     // outputs
     signed char *bits;
     int nbits;
@@ -487,15 +493,16 @@ struct RxCore
 
     SB_HD D &self() { return *static_cast<D *>(this); }
 
-    static const int CORE_LANE_WORDS = 4*SBM_EQ_LEN + SBM_FILTER_STEPS + 16;
+    static const int CORE_LANE_WORDS = 2*SBM_EQ_LEN + 4*SBM_EQ_LEN + 2*SBM_FILTER_STEPS + 16;
+    static const int IN_RING_WORDS = SBM_IN_RING/2;     // per lane, contiguous (not interleaved): cp.async needs 16 bytes in a row
 
-    // lane_base: this lane's column of the lane-interleaved block
-    SB_HD void bind_core(float *lane_base)
+    // lane_base: this lane's float2 column of the lane-interleaved block (block base + 2*lane words)
+    SB_HD void bind_core(float *block, int lane)
     {
-        eq_coeff = lane_base;
-        eq_buf = lane_base + (2*SBM_EQ_LEN)*32;
-        rrc = lane_base + (4*SBM_EQ_LEN)*32;
-        diff_angles = (int *) (lane_base + (4*SBM_EQ_LEN + SBM_FILTER_STEPS)*32);
+        eq_coeff = ((float2 *) block) + lane;
+        eq_buf = ((float2 *) (block + (2*SBM_EQ_LEN)*32)) + lane;
+        rrc = block + (6*SBM_EQ_LEN)*32 + lane;
+        diff_angles = (int *) (block + (6*SBM_EQ_LEN + 2*SBM_FILTER_STEPS)*32) + lane;
     }
 
     template <class V> SB_HD void visit_core(V &v)
@@ -513,9 +520,15 @@ struct RxCore
         v.f(F_DC0, dc0);
         v.f(F_DC1, dc1);
         v.f(F_BAUD_PHASE, baud_phase);
-        v.fa(F_EQ_COEFF, eq_coeff, 2*SBM_EQ_LEN);
-        v.fa(F_EQ_BUF, eq_buf, 2*SBM_EQ_LEN);
-        v.fa(F_RRC, rrc, SBM_FILTER_STEPS);
+        for (int k = 0;  k < SBM_EQ_LEN;  k++)
+        {
+            v.f(F_EQ_COEFF + 2*k, eq_coeff[k*32].x);
+            v.f(F_EQ_COEFF + 2*k + 1, eq_coeff[k*32].y);
+            v.f(F_EQ_BUF + 2*k, eq_buf[k*32].x);
+            v.f(F_EQ_BUF + 2*k + 1, eq_buf[k*32].y);
+        }
+        for (int k = 0;  k < SBM_FILTER_STEPS;  k++)
+            v.f(F_RRC + k, rrc[k*32]);
         v.i(I_BIT_RATE, bit_rate);
         v.i(I_RRC_STEP, rrc_step);
         v.u(I_SCRAMBLE, scramble_reg);
@@ -539,7 +552,24 @@ struct RxCore
         v.i(I_LAST_ANGLE0, last_angle0);
         v.i(I_LAST_ANGLE1, last_angle1);
         v.i(I_TOTAL_TIMING, total_timing);
-        v.ia(I_DIFF_ANGLES, diff_angles, 16);
+        for (int k = 0;  k < 16;  k++)
+            v.i(I_DIFF_ANGLES + k, diff_angles[k*32]);
+    }
+
+    // After loading: fill the second copy of the two rings
+    SB_HD void mirror_rings()
+    {
+        for (int k = 0;  k < SBM_EQ_LEN;  k++)
+            eq_buf[(k + SBM_EQ_LEN)*32] = eq_buf[k*32];
+        for (int k = 0;  k < SBM_FILTER_STEPS;  k++)
+            rrc[(k + SBM_FILTER_STEPS)*32] = rrc[k*32];
+    }
+
+    SB_HD void rrc_clear()
+    {
+        for (int i = 0;  i < 2*SBM_FILTER_STEPS;  i++)
+            rrc[i*32] = 0.0f;
+        rrc_step = 0;
     }
 
     SB_HD void out_bit(int v)
@@ -577,31 +607,36 @@ struct RxCore
     // src/v29rx.c:214-258, src/v17rx.c:219-264
     SB_HD void equalizer_reset()
     {
+        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+            eq_coeff[i*32] = make_float2(0.0f, 0.0f);
         for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
-        {
-            eq_coeff[i*32] = 0.0f;
-            eq_buf[i*32] = 0.0f;
-        }
-        eq_coeff[(2*SBM_EQ_PRE_LEN)*32] = 3.0f;
+            eq_buf[i*32] = make_float2(0.0f, 0.0f);
+        eq_coeff[SBM_EQ_PRE_LEN*32] = make_float2(3.0f, 0.0f);
         eq_put_step = COEFF_SETS*10/(3*2) - 1;
         eq_step = 0;
     }
 
     SB_HD void equalizer_restore()
     {
-        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < SBM_EQ_LEN;  i++)
         {
-            eq_coeff[i*32] = fstate[(size_t) (F_EQ_COEFF_SAVE + i)*channels + c];
-            eq_buf[i*32] = 0.0f;
+            eq_coeff[i*32] = make_float2(fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c],
+                                         fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i + 1)*channels + c]);
         }
+        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+            eq_buf[i*32] = make_float2(0.0f, 0.0f);
         eq_put_step = COEFF_SETS*10/(3*2) - 1;
         eq_step = 0;
     }
 
     SB_HD void equalizer_save()
     {
-        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
-            fstate[(size_t) (F_EQ_COEFF_SAVE + i)*channels + c] = eq_coeff[i*32];
+        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        {
+            const float2 y = eq_coeff[i*32];
+            fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c] = y.x;
+            fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i + 1)*channels + c] = y.y;
+        }
     }
 
     // godard_ted_init (src/godard.c:222-240)
@@ -611,26 +646,49 @@ struct RxCore
         total_timing = 0;
     }
 
-    // src/vector_float.c:932-939 with the scalar vec_dot_prodf (:890-900): two segments, each summed
-    // in order from 0.0f, then added.
-    SB_HD float rrc_dot(const float *coef)
+    // The real and the imaginary RRC band-pass FIR of one sample, together (src/v29rx.c:914,946,
+    // src/v17rx.c:1259,1290).  Each is vec_circular_dot_prodf (src/vector_float.c:932-939) with the scalar
+    // vec_dot_prodf (:890-900): two segments - the taps before and after the ring's physical wrap - each
+    // summed in order from 0.0f, then added.  rrc_step is the position after the insert, i.e. the oldest
+    // sample; coefficient rows are padded to 28 floats so that they load as float4.
+    SB_HD void rrc_dot2(const float *row_re, const float *row_im, float &v_re, float &v_im)
     {
-        float za = 0.0f;
-        float zb = 0.0f;
+        float zar = 0.0f, zbr = 0.0f, zai = 0.0f, zbi = 0.0f;
         const int first = SBM_FILTER_STEPS - rrc_step;      // taps in the first segment
-        int j = rrc_step;
-#pragma unroll 9
-        for (int i = 0;  i < SBM_FILTER_STEPS;  i++)
+        const float *x = rrc + rrc_step*32;
+        const float4 *cr4 = (const float4 *) row_re;
+        const float4 *ci4 = (const float4 *) row_im;
+#pragma unroll
+        for (int q = 0;  q < 7;  q++)
         {
-            const float p = fmul(rrc[j*32], coef[i]);
-            if (i < first)
-                za = fadd(za, p);
-            else
-                zb = fadd(zb, p);
-            if (++j >= SBM_FILTER_STEPS)
-                j = 0;
+            const float4 cr = cr4[q];
+            const float4 ci = ci4[q];
+            const float crs[4] = {cr.x, cr.y, cr.z, cr.w};
+            const float cis[4] = {ci.x, ci.y, ci.z, ci.w};
+#pragma unroll
+            for (int e = 0;  e < 4;  e++)
+            {
+                const int i = 4*q + e;
+                if (i < SBM_FILTER_STEPS)
+                {
+                    const float xv = x[i*32];
+                    const float pr = fmul(xv, crs[e]);
+                    const float pi = fmul(xv, cis[e]);
+                    if (i < first)
+                    {
+                        zar = fadd(zar, pr);
+                        zai = fadd(zai, pi);
+                    }
+                    else
+                    {
+                        zbr = fadd(zbr, pr);
+                        zbi = fadd(zbi, pi);
+                    }
+                }
+            }
         }
-        return fadd(za, zb);
+        v_re = fadd(zar, zbr);
+        v_im = fadd(zai, zbi);
     }
 
     // src/complex_vector_float.c:137-150,187-196
@@ -638,16 +696,14 @@ struct RxCore
     {
         float are = 0.0f, aim = 0.0f, bre = 0.0f, bim = 0.0f;
         const int first = SBM_EQ_LEN - eq_step;
-        int j = eq_step;
-#pragma unroll 3
+        const float2 *xb = eq_buf + eq_step*32;
+#pragma unroll
         for (int i = 0;  i < SBM_EQ_LEN;  i++)
         {
-            const float xr = eq_buf[(2*j)*32];
-            const float xi = eq_buf[(2*j + 1)*32];
-            const float yr = eq_coeff[(2*i)*32];
-            const float yi = eq_coeff[(2*i + 1)*32];
-            const float pr = fsub(fmul(xr, yr), fmul(xi, yi));
-            const float pi = fadd(fmul(xr, yi), fmul(xi, yr));
+            const float2 x = xb[i*32];
+            const float2 y = eq_coeff[i*32];
+            const float pr = fsub(fmul(x.x, y.x), fmul(x.y, y.y));
+            const float pi = fadd(fmul(x.x, y.y), fmul(x.y, y.x));
             if (i < first)
             {
                 are = fadd(are, pr);
@@ -658,8 +714,6 @@ struct RxCore
                 bre = fadd(bre, pr);
                 bim = fadd(bim, pi);
             }
-            if (++j >= SBM_EQ_LEN)
-                j = 0;
         }
         zre = fadd(are, bre);
         zim = fadd(aim, bim);
@@ -670,33 +724,28 @@ struct RxCore
     {
         const float ere = fmul(fsub(tre, zre), eq_delta);
         const float eim = fmul(fsub(tim, zim), eq_delta);
-        int j = eq_step;
-#pragma unroll 3
+        const float2 *xb = eq_buf + eq_step*32;
+#pragma unroll
         for (int i = 0;  i < SBM_EQ_LEN;  i++)
         {
-            const float xr = eq_buf[(2*j)*32];
-            const float xi = eq_buf[(2*j + 1)*32];
-            const float yr = eq_coeff[(2*i)*32];
-            const float yi = eq_coeff[(2*i + 1)*32];
-            eq_coeff[(2*i)*32] = fadd(fmul(yr, 0.9999f), fadd(fmul(xi, eim), fmul(xr, ere)));
-            eq_coeff[(2*i + 1)*32] = fadd(fmul(yi, 0.9999f), fsub(fmul(xr, eim), fmul(xi, ere)));
-            if (++j >= SBM_EQ_LEN)
-                j = 0;
+            const float2 x = xb[i*32];
+            float2 y = eq_coeff[i*32];
+            y.x = fadd(fmul(y.x, 0.9999f), fadd(fmul(x.y, eim), fmul(x.x, ere)));
+            y.y = fadd(fmul(y.y, 0.9999f), fsub(fmul(x.x, eim), fmul(x.y, ere)));
+            eq_coeff[i*32] = y;
         }
     }
 
-    // The equalizer "spin" (src/v29rx.c:618-625, src/v17rx.c:707-713,784-790)
+    // The equalizer "spin" (src/v29rx.c:618-625, src/v17rx.c:707-713,784-790); both ring copies
     SB_HD void spin_equalizer_buffer(unsigned int phase_step)
     {
         const float p = phase_to_radians(phase_step);
         const float cr = host_cosf(p);
         const float ci = -host_sinf(p);
-        for (int q = 0;  q < SBM_EQ_LEN;  q++)
+        for (int q = 0;  q < 2*SBM_EQ_LEN;  q++)
         {
-            const float xr = eq_buf[(2*q)*32];
-            const float xi = eq_buf[(2*q + 1)*32];
-            eq_buf[(2*q)*32] = fsub(fmul(xr, cr), fmul(xi, ci));
-            eq_buf[(2*q + 1)*32] = fadd(fmul(xr, ci), fmul(xi, cr));
+            const float2 x = eq_buf[q*32];
+            eq_buf[q*32] = make_float2(fsub(fmul(x.x, cr), fmul(x.y, ci)), fadd(fmul(x.x, ci), fmul(x.y, cr)));
         }
     }
 
@@ -785,7 +834,7 @@ struct RxCore
             return 0;
         const int shift = 30 - ((31 - clz32(x)) & ~1);
         x <<= shift;
-        return (int) k.sqrt_tab[((x >> 24) & 0xFF) - 64] >> (shift >> 1);
+        return (int) sqrt_tab[((x >> 24) & 0xFF) - 64] >> (shift >> 1);
     }
 
     // xxx_rx()'s per-sample body (src/v29rx.c:885-960, src/v17rx.c:1231-1308) is split in three so that
@@ -797,13 +846,15 @@ struct RxCore
     //            whole baud is now complete;
     //   baud():  timing correction, equalizer, training state machine / slicer, qam report.
     // The carrier NCO advance that ends the reference's loop body is done by whichever part ends the sample.
-    int h_step;
     int h_pw;
     float h_sre;
+    float h_vim;
 
-    template <class K> SB_HD bool front(const K &k, const float *s_rrc_re, short amp)
+    template <class K> SB_HD bool front(const K &k, const float *s_rrc_re, const float *s_rrc_im, short amp)
     {
-        rrc[rrc_step*32] = (float) amp;
+        const float xv = (float) amp;
+        rrc[rrc_step*32] = xv;
+        rrc[(rrc_step + SBM_FILTER_STEPS)*32] = xv;
         if (++rrc_step >= SBM_FILTER_STEPS)
             rrc_step = 0;
         const int pw = signal_detect(k, amp);
@@ -819,7 +870,10 @@ struct RxCore
             step = 0;
         else if (step > COEFF_SETS - 1)
             step = COEFF_SETS - 1;
-        const float v = rrc_dot(s_rrc_re + step*SBM_FILTER_STEPS);
+        // Both FIRs at once: the imaginary one is only needed at T/2 instants, but computed together the
+        // four accumulation chains overlap and the samples are fetched once.
+        float v;
+        rrc_dot2(s_rrc_re + step*SBM_RRC_ROW, s_rrc_im + step*SBM_RRC_ROW, v, h_vim);
         const float sre = fmul(v, agc_scaling);
         // godard_ted_rx, src/godard.c:144-161
         {
@@ -832,7 +886,6 @@ struct RxCore
         }
         if (eq_put_step <= 0)
         {
-            h_step = step;
             h_pw = pw;
             h_sre = sre;
             return true;
@@ -841,7 +894,7 @@ struct RxCore
         return false;
     }
 
-    template <class K> SB_HD bool half(const K &k, const float *s_rrc_im)
+    template <class K> SB_HD bool half(const K &k)
     {
         if (agc_scaling_save == 0.0f)
         {
@@ -850,16 +903,15 @@ struct RxCore
                 root_power = 1;
             agc_scaling = fdiv(k.agc_target, (float) root_power);
         }
-        const float v = rrc_dot(s_rrc_im + h_step*SBM_FILTER_STEPS);
-        const float sim = fmul(v, agc_scaling);
-        const float zr = k.sine[(carrier_phase + (1u << 30)) >> 21];     // dds_lookup_complexf, src/dds_float.c:2177
-        const float zi = k.sine[carrier_phase >> 21];
+        const float sim = fmul(h_vim, agc_scaling);
+        const float zr = sine[(carrier_phase + (1u << 30)) >> 21];       // dds_lookup_complexf, src/dds_float.c:2177
+        const float zi = sine[carrier_phase >> 21];
         const float zzre = fsub(fmul(h_sre, zr), fmul(sim, zi));
         const float zzim = fsub(fmul(-h_sre, zi), fmul(sim, zr));
         eq_put_step += COEFF_SETS*10/(3*2);
         // process_half_baud, first part (src/v29rx.c:516-525, src/v17rx.c:638-647)
-        eq_buf[(2*eq_step)*32] = zzre;
-        eq_buf[(2*eq_step + 1)*32] = zzim;
+        eq_buf[eq_step*32] = make_float2(zzre, zzim);
+        eq_buf[(eq_step + SBM_EQ_LEN)*32] = make_float2(zzre, zzim);
         if (++eq_step >= SBM_EQ_LEN)
             eq_step = 0;
         if ((baud_half ^= 1))
@@ -882,12 +934,74 @@ struct RxCore
     // converged even though the channels' symbol clocks sit at different sample phases.  Channels without
     // carrier (or parked) simply consume up to four samples per trip.  Each channel still sees its own
     // samples in order, which is all the reference's per-channel semantics require.
+    // Input staging.  Each lane consumes its own row at its own pace (3 or 4 samples per baud), and a
+    // warp has one scoreboard, so a per-lane register prefetch would make every lane wait for the most
+    // recent load of any lane.  Instead each lane owns a ring of SBM_IN_RING samples in shared memory that
+    // it tops up with 16-byte cp.async copies well ahead of use; the copies never pass through registers
+    // and the only wait is cp.async.wait_group for groups issued several bauds earlier.
+    short *in_ring;
+
+#if defined(__CUDA_ARCH__)
+    static __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes)
+    {
+        const unsigned int dst = (unsigned int) __cvta_generic_to_shared(smem_dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+    }
+    static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+    template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+#endif
+
     template <class K> SB_HD void run(const K &k, const float *s_rrc_re, const float *s_rrc_im, const int16_t *row, int n)
     {
         int pos = 0;
+#if defined(__CUDA_ARCH__)
+        const bool staged = (((size_t) row) & 15) == 0;
+        int fill = 0;
+        if (staged)
+        {
+            for (int g = 0;  g < (SBM_IN_RING - 8)/8;  g++)
+            {
+                if (fill < n)
+                {
+                    cp_async16(in_ring + (fill & (SBM_IN_RING - 1)), row + fill, (n - fill >= 8)  ?  16  :  2*(n - fill));
+                    fill += 8;
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+#endif
 #pragma unroll 1
         while (pos < n)
         {
+            // The (up to) four samples of this trip, packed
+            unsigned long long cur;
+#if defined(__CUDA_ARCH__)
+            if (staged)
+            {
+                if (fill < n  &&  fill - pos <= SBM_IN_RING - 8)
+                {
+                    cp_async16(in_ring + (fill & (SBM_IN_RING - 1)), row + fill, (n - fill >= 8)  ?  16  :  2*(n - fill));
+                    fill += 8;
+                }
+                cp_async_commit();
+                cp_async_wait<2>();
+                const unsigned int a0 = (unsigned short) in_ring[pos & (SBM_IN_RING - 1)];
+                const unsigned int a1 = (unsigned short) in_ring[(pos + 1) & (SBM_IN_RING - 1)];
+                const unsigned int a2 = (unsigned short) in_ring[(pos + 2) & (SBM_IN_RING - 1)];
+                const unsigned int a3 = (unsigned short) in_ring[(pos + 3) & (SBM_IN_RING - 1)];
+                cur = (unsigned long long) (a0 | (a1 << 16)) | ((unsigned long long) (a2 | (a3 << 16)) << 32);
+            }
+            else
+#endif
+            {
+                cur = 0;
+                for (int i = 0;  i < 4;  i++)
+                {
+                    if (pos + i < n)
+                        cur |= (unsigned long long) (unsigned short) ldg(row + pos + i) << (16*i);
+                }
+            }
 #pragma unroll 1
             for (int h = 0;  h < 2;  h++)
             {
@@ -901,13 +1015,15 @@ struct RxCore
                 {
                     if (pos < n  &&  !due)
                     {
-                        due = front(k, s_rrc_re, ldg(row + pos));
+                        const short amp = (short) (cur & 0xFFFFu);
+                        cur >>= 16;
+                        due = front(k, s_rrc_re, s_rrc_im, amp);
                         pos++;
                     }
                 }
                 if (due)
                 {
-                    if (half(k, s_rrc_im))
+                    if (half(k))
                         baud(k);
                 }
             }
@@ -930,7 +1046,7 @@ struct KernelArgs
 // Shared memory: [rrc_re | rrc_im | RX tables | lane-interleaved per-channel arrays]
 template <class RX> constexpr int modem_smem_words()
 {
-    return 2*RX::SETS*SBM_FILTER_STEPS + RX::TABLE_WORDS + RX::LANE_WORDS*32;
+    return 2*RX::SETS*SBM_RRC_ROW + SBM_SINE_WORDS + SBM_SQRT_WORDS + RX::TABLE_WORDS + (RX::LANE_WORDS + RX::IN_RING_WORDS)*32;
 }
 
 template <class RX>
@@ -938,13 +1054,21 @@ __device__ __forceinline__ void modem_bind(RX &r, const KernelArgs<RX> &ka, floa
                                            const float *&s_rrc_re, const float *&s_rrc_im)
 {
     float *w_rrc_re = smem;
-    float *w_rrc_im = smem + RX::SETS*SBM_FILTER_STEPS;
-    float *tables = smem + 2*RX::SETS*SBM_FILTER_STEPS;
-    float *lane_base = tables + RX::TABLE_WORDS;
-    for (int i = lane;  i < RX::SETS*SBM_FILTER_STEPS;  i += 32)
+    float *w_rrc_im = smem + RX::SETS*SBM_RRC_ROW;
+    float *w_sine = smem + 2*RX::SETS*SBM_RRC_ROW;
+    unsigned int *w_sqrt = (unsigned int *) (w_sine + SBM_SINE_WORDS);
+    float *tables = w_sine + SBM_SINE_WORDS + SBM_SQRT_WORDS;
+    float *lane_block = tables + RX::TABLE_WORDS;
+    for (int i = lane;  i < SBM_SINE_WORDS;  i += 32)
+        w_sine[i] = ka.k.sine[i];
+    for (int i = lane;  i < 97;  i += 32)
+        w_sqrt[i] = (unsigned int) ka.k.sqrt_tab[2*i] | ((2*i + 1 < 193)  ?  ((unsigned int) ka.k.sqrt_tab[2*i + 1] << 16)  :  0u);
+    for (int i = lane;  i < RX::SETS*SBM_RRC_ROW;  i += 32)
     {
-        w_rrc_re[i] = ka.k.rrc_re[i];
-        w_rrc_im[i] = ka.k.rrc_im[i];
+        const int row = i/SBM_RRC_ROW;
+        const int tap = i - row*SBM_RRC_ROW;
+        w_rrc_re[i] = (tap < SBM_FILTER_STEPS)  ?  ka.k.rrc_re[row*SBM_FILTER_STEPS + tap]  :  0.0f;
+        w_rrc_im[i] = (tap < SBM_FILTER_STEPS)  ?  ka.k.rrc_im[row*SBM_FILTER_STEPS + tap]  :  0.0f;
     }
     RX::fill_tables(tables, ka.k, lane, 32);
     __syncwarp();
@@ -953,7 +1077,10 @@ __device__ __forceinline__ void modem_bind(RX &r, const KernelArgs<RX> &ka, floa
     r.c = c;
     r.channels = ka.a.channels;
     r.fstate = ka.a.fstate;
-    r.bind(tables, lane_base + lane);
+    r.sine = w_sine;
+    r.sqrt_tab = (const unsigned short *) w_sqrt;
+    r.in_ring = (short *) (lane_block + RX::LANE_WORDS*32) + lane*SBM_IN_RING;
+    r.bind(tables, lane_block, lane);
 }
 
 // 32 channels per CTA (one warp): few channels exist (thousands), so spread them over all SMs.
@@ -971,6 +1098,7 @@ __global__ void __launch_bounds__(32) modem_rx_kernel(const KernelArgs<RX> ka)
         return;
     StateLoader ld = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
     r.visit(ld);
+    r.mirror_rings();
     r.bits = ka.a.bits + (size_t) c*ka.a.bits_cap;
     r.bits_cap = (int) ka.a.bits_cap;
     r.nbits = 0;
@@ -1016,6 +1144,7 @@ __global__ void __launch_bounds__(32) modem_init_kernel(const KernelArgs<RX> ka,
     {
         StateLoader ld = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
         r.visit(ld);
+        r.mirror_rings();
         r.restart(ka.k, bit_rate, mode);
     }
     StateStorer st = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};

@@ -218,7 +218,7 @@ struct RxV17 : RxCore<RxV17, V17_COEFF_SETS>
         F_DISTANCES = F_CORE_COUNT,                 // 8
         F_COUNT = F_DISTANCES + 8
     };
-    static const int TABLE_WORDS = (sizeof(V17Tables) + 3)/4;
+    static const int TABLE_WORDS = ((sizeof(V17Tables) + 15)/16)*4;     // keeps what follows 16-byte aligned
     static const int LANE_WORDS = Core::CORE_LANE_WORDS + TRELLIS_WORDS;
 
     int diff;
@@ -235,15 +235,15 @@ struct RxV17 : RxCore<RxV17, V17_COEFF_SETS>
     {
         const unsigned int *src = (const unsigned int *) k.tables;
         unsigned int *d = (unsigned int *) dst;
-        for (int i = lane;  i < TABLE_WORDS;  i += nlanes)
+        for (int i = lane;  i < (int) ((sizeof(*k.tables) + 3)/4);  i += nlanes)
             d[i] = src[i];
     }
 
-    SB_HD void bind(const float *tables, float *lane_base)
+    SB_HD void bind(const float *tables, float *lane_block, int lane)
     {
         t = (const V17Tables *) tables;
-        bind_core(lane_base);
-        trellis = (int *) (lane_base + Core::CORE_LANE_WORDS*32);
+        bind_core(lane_block, lane);
+        trellis = (int *) (lane_block + Core::CORE_LANE_WORDS*32) + lane;
     }
 
     template <class V> SB_HD void visit(V &v)
@@ -255,7 +255,8 @@ struct RxV17 : RxCore<RxV17, V17_COEFF_SETS>
         v.i(I_BITS_PER_SYMBOL, bits_per_symbol);
         v.i(I_TRELLIS_PTR, trellis_ptr);
         v.i(I_CON_OFFSET, con_offset);
-        v.ia(I_TRELLIS, trellis, TRELLIS_WORDS);
+        for (int w = 0;  w < TRELLIS_WORDS;  w++)
+            v.i(I_TRELLIS + w, trellis[w*32]);
         v.f(F_DISTANCES + 0, dist0);
         v.f(F_DISTANCES + 1, dist1);
         v.f(F_DISTANCES + 2, dist2);
@@ -314,10 +315,8 @@ struct RxV17 : RxCore<RxV17, V17_COEFF_SETS>
             return -1;
         }
         bit_rate = rate;
-        for (int i = 0;  i < SBM_FILTER_STEPS;  i++)
-            rrc[i*32] = 0.0f;
+        rrc_clear();
         training_error = 0.0f;
-        rrc_step = 0;
         diff = 1;
         scramble_reg = 0x2ECDD5;
         training_stage = STAGE_SYMBOL_ACQUISITION;

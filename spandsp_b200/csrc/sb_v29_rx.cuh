@@ -92,7 +92,7 @@ struct RxV29 : RxCore<RxV29, V29_COEFF_SETS>
     {
         F_COUNT = F_CORE_COUNT
     };
-    static const int TABLE_WORDS = (sizeof(V29Tables) + 3)/4;
+    static const int TABLE_WORDS = ((sizeof(V29Tables) + 15)/16)*4;     // keeps what follows 16-byte aligned
     static const int LANE_WORDS = Core::CORE_LANE_WORDS;
 
     int training_cd;
@@ -105,14 +105,14 @@ struct RxV29 : RxCore<RxV29, V29_COEFF_SETS>
     {
         const unsigned int *src = (const unsigned int *) k.tables;
         unsigned int *d = (unsigned int *) dst;
-        for (int i = lane;  i < TABLE_WORDS;  i += nlanes)
+        for (int i = lane;  i < (int) ((sizeof(*k.tables) + 3)/4);  i += nlanes)
             d[i] = src[i];
     }
 
-    SB_HD void bind(const float *tables, float *lane_base)
+    SB_HD void bind(const float *tables, float *lane_block, int lane)
     {
         t = (const V29Tables *) tables;
-        bind_core(lane_base);
+        bind_core(lane_block, lane);
     }
 
     template <class V> SB_HD void visit(V &v)
@@ -129,9 +129,7 @@ struct RxV29 : RxCore<RxV29, V29_COEFF_SETS>
     {
         training_cd = (rate == 9600)  ?  0  :  (rate == 7200)  ?  2  :  4;
         bit_rate = rate;
-        for (int i = 0;  i < SBM_FILTER_STEPS;  i++)
-            rrc[i*32] = 0.0f;
-        rrc_step = 0;
+        rrc_clear();
         scramble_reg = 0;
         training_scramble_reg = 0x2A;
         training_stage = STAGE_SYMBOL_ACQUISITION;

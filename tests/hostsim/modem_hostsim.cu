@@ -62,14 +62,20 @@ struct HostChannel
 
     void setup()
     {
-        smem.assign(2*RX::SETS*SBM_FILTER_STEPS + RX::TABLE_WORDS + RX::LANE_WORDS*32, 0.0f);
+        smem.assign(2*RX::SETS*SBM_RRC_ROW + RX::TABLE_WORDS + RX::LANE_WORDS*32, 0.0f);
         fstate.assign(RX::F_COUNT, 0.0f);
         istate.assign(RX::I_COUNT, 0);
-        memcpy(smem.data(), k.rrc_re, sizeof(float)*RX::SETS*SBM_FILTER_STEPS);
-        memcpy(smem.data() + RX::SETS*SBM_FILTER_STEPS, k.rrc_im, sizeof(float)*RX::SETS*SBM_FILTER_STEPS);
+        for (int row = 0;  row < RX::SETS;  row++)
+        {
+            for (int tap = 0;  tap < SBM_FILTER_STEPS;  tap++)
+            {
+                smem[row*SBM_RRC_ROW + tap] = k.rrc_re[row*SBM_FILTER_STEPS + tap];
+                smem[RX::SETS*SBM_RRC_ROW + row*SBM_RRC_ROW + tap] = k.rrc_im[row*SBM_FILTER_STEPS + tap];
+            }
+        }
         s_re = smem.data();
-        s_im = smem.data() + RX::SETS*SBM_FILTER_STEPS;
-        tables = smem.data() + 2*RX::SETS*SBM_FILTER_STEPS;
+        s_im = smem.data() + RX::SETS*SBM_RRC_ROW;
+        tables = smem.data() + 2*RX::SETS*SBM_RRC_ROW;
         lane = tables + RX::TABLE_WORDS;
         RX::fill_tables(tables, k, 0, 1);
     }
@@ -79,7 +85,10 @@ struct HostChannel
         r.c = 0;
         r.channels = 1;
         r.fstate = fstate.data();
-        r.bind(tables, lane);
+        r.in_ring = NULL;
+        r.sine = k.sine;
+        r.sqrt_tab = k.sqrt_tab;
+        r.bind(tables, lane, 0);
         r.bits = NULL;
         r.bits_cap = 0;
         r.nbits = 0;
@@ -105,6 +114,7 @@ struct HostChannel
         attach(r);
         StateLoader ld = {fstate.data(), istate.data(), 1, 0};
         r.visit(ld);
+        r.mirror_rings();
         const int rc = r.restart(k, bit_rate, mode);
         StateStorer st = {fstate.data(), istate.data(), 1, 0};
         r.visit(st);
@@ -119,6 +129,7 @@ struct HostChannel
         attach(r);
         StateLoader ld = {fstate.data(), istate.data(), 1, 0};
         r.visit(ld);
+        r.mirror_rings();
         r.bits = (signed char *) bits;
         r.bits_cap = bits_cap;
         r.syms = syms;
