@@ -179,6 +179,27 @@ float v17_rx_signal_power(v17_rx_state_t *s);
 void v17_rx_set_signal_cutoff(v17_rx_state_t *s, float cutoff);
 void v17_rx_set_qam_report_handler(v17_rx_state_t *s, qam_report_handler_t handler, void *user_data);
 
+/* ---- V.27ter receiver: src/spandsp/v27ter_rx.h:71-165, src/v27ter_rx.c:137-189,863-1210 ---------- */
+typedef struct v27ter_rx_state_s v27ter_rx_state_t;
+
+/* Synchronous, one receiver per state (a bank of one).  Banks of many receivers: spandsp_b200_v27ter.h.
+   The qam report handler also receives the Gardner timing hops (NULL, NULL, integrator value), as in the reference. */
+v27ter_rx_state_t *v27ter_rx_init(v27ter_rx_state_t *s, int bit_rate, span_put_bit_func_t put_bit, void *user_data);
+int v27ter_rx_restart(v27ter_rx_state_t *s, int bit_rate, bool old_train);
+int v27ter_rx_release(v27ter_rx_state_t *s);
+int v27ter_rx_free(v27ter_rx_state_t *s);
+logging_state_t *v27ter_rx_get_logging_state(v27ter_rx_state_t *s);
+void v27ter_rx_set_put_bit(v27ter_rx_state_t *s, span_put_bit_func_t put_bit, void *user_data);
+void v27ter_rx_set_modem_status_handler(v27ter_rx_state_t *s, span_modem_status_func_t handler, void *user_data);
+int v27ter_rx(v27ter_rx_state_t *s, const int16_t amp[], int len);
+int v27ter_rx_fillin(v27ter_rx_state_t *s, int len);
+int v27ter_rx_equalizer_state(v27ter_rx_state_t *s, complexf_t **coeffs);
+float v27ter_rx_carrier_frequency(v27ter_rx_state_t *s);
+float v27ter_rx_symbol_timing_correction(v27ter_rx_state_t *s);
+float v27ter_rx_signal_power(v27ter_rx_state_t *s);
+void v27ter_rx_set_signal_cutoff(v27ter_rx_state_t *s, float cutoff);
+void v27ter_rx_set_qam_report_handler(v27ter_rx_state_t *s, qam_report_handler_t handler, void *user_data);
+
 #if defined(__cplusplus)
 }
 #endif

@@ -303,6 +303,60 @@ def v17_tables(lib, fn_name):
     return {"rrc_re": re, "rrc_im": im, "godard": g, "ints": it, "constellations": con, "maps": maps, "map4800": m48}
 
 
+def v27ter_generate(o, n, bit_rate=4800, tep=False, power_dbm0=-13.0, lfsr_seed=1, lead=0, burst1=-1, gap=0, burst2=0,
+                    noise_seed=1234567, noise_dbm0=-50.0):
+    """v27ter_tx of PRBS data (+ awgn): silence, a burst, optionally a gap and a second burst."""
+    amp = np.zeros(n, dtype=np.int16)
+    o.lib.ref_v27ter_generate.restype = C.c_int
+    rc = o.lib.ref_v27ter_generate(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(bit_rate), C.c_int(int(tep)), C.c_float(power_dbm0),
+                                   C.c_uint32(lfsr_seed), C.c_int(lead), C.c_int(burst1), C.c_int(gap), C.c_int(burst2),
+                                   C.c_int(noise_seed), C.c_float(noise_dbm0))
+    if rc < 0:
+        raise RuntimeError("ref_v27ter_generate failed")
+    return amp
+
+
+def v27ter_run(o, amp, bit_rate=4800, chunk=160, cutoff=-100.0, want_qam=True, restart_at=-1, restart_old_train=0):
+    """One channel through the reference's v27ter_rx.  Gardner hops (qam_report with NULL pointers) appear as
+    symbols with NaN coordinates and state = the integrator value.  Returns dict(bits, syms, eq_coeff[64], final[10])."""
+    amp = np.ascontiguousarray(amp, dtype=np.int16)
+    n = len(amp)
+    bits = np.zeros(n * 2 + 64, dtype=np.int8)
+    syms = np.zeros(n * 2 // 5 + 16, dtype=V29_SYM_DTYPE)
+    nb = C.c_int32(0)
+    ns = C.c_int32(0)
+    eq = np.zeros(64, dtype=np.float32)
+    fin = np.zeros(10, dtype=np.int32)
+    o.lib.ref_v27ter_run.restype = C.c_int
+    rc = o.lib.ref_v27ter_run(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(bit_rate), C.c_float(cutoff), C.c_int(int(want_qam)),
+                              C.c_int(restart_at), C.c_int(restart_old_train),
+                              C.c_void_p(bits.ctypes.data), C.c_int(bits.size), C.byref(nb), C.c_void_p(syms.ctypes.data), C.c_int(syms.size),
+                              C.byref(ns), C.c_void_p(eq.ctypes.data), C.c_void_p(fin.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("ref_v27ter_run failed")
+    return {"bits": bits[:nb.value].copy(), "syms": syms[:ns.value].copy(), "eq_coeff": eq, "final": fin}
+
+
+def v27ter_run_batch(o, amp, bit_rate=4800, chunk=160, cutoff=-100.0, nthreads=1):
+    """Many channels, timing only (CPU baseline).  Returns seconds."""
+    amp = np.asarray(amp)
+    assert amp.dtype == np.int16 and amp.ndim == 2 and amp.strides[1] == 2
+    o.lib.ref_v27ter_run_batch.restype = C.c_double
+    return o.lib.ref_v27ter_run_batch(C.c_void_p(amp.ctypes.data), C.c_int64(amp.strides[0] // 2), C.c_int(amp.shape[0]), C.c_int(amp.shape[1]),
+                                      C.c_int(chunk), C.c_int(bit_rate), C.c_float(cutoff), C.c_int(nthreads))
+
+
+def v27ter_tables(lib, fn_name):
+    r48 = np.zeros(8 * 27, np.float32)
+    i48 = np.zeros(8 * 27, np.float32)
+    r24 = np.zeros(12 * 27, np.float32)
+    i24 = np.zeros(12 * 27, np.float32)
+    it = np.zeros(8, np.int32)
+    getattr(lib, fn_name)(C.c_void_p(r48.ctypes.data), C.c_void_p(i48.ctypes.data), C.c_void_p(r24.ctypes.data), C.c_void_p(i24.ctypes.data),
+                          C.c_void_p(it.ctypes.data))
+    return {"rrc4800_re": r48, "rrc4800_im": i48, "rrc2400_re": r24, "rrc2400_im": i24, "ints": it}
+
+
 _cache = {}
 
 

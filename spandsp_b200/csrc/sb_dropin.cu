@@ -17,6 +17,7 @@
 #include "../../include/spandsp_b200_dropin.h"
 #include "../../include/spandsp_b200_v29.h"
 #include "../../include/spandsp_b200_v17.h"
+#include "../../include/spandsp_b200_v27ter.h"
 #pragma GCC visibility pop
 
 #define SB_MAGIC    0x5350414E42323030ULL       /* "SPANB200" */
@@ -1310,4 +1311,213 @@ extern "C" float v17_rx_signal_power(v17_rx_state_t *s)
 extern "C" void v17_rx_set_signal_cutoff(v17_rx_state_t *s, float cutoff)
 {
     span_b200_v17_bank_set_signal_cutoff(s->bank, 0, 1, cutoff);
+}
+
+// ------------------------------------------------------------------------------------------
+// V.27ter receiver, one bank of one per state object (src/v27ter_rx.c:137-189,863-1210)
+struct v27ter_rx_state_s
+{
+    unsigned long long magic;
+    span_b200_v27ter_bank_t *bank;
+    int heap;
+    int bit_rate;
+    span_put_bit_func_t put_bit;
+    void *put_bit_user_data;
+    span_modem_status_func_t status_handler;
+    void *status_user_data;
+    qam_report_handler_t qam_report;
+    void *qam_user_data;
+    complexf_t eq_coeff[32];
+    std::vector<int8_t> *bits;
+    std::vector<span_b200_v27ter_symbol_t> *syms;
+};
+
+static_assert(sizeof(v27ter_rx_state_s) <= 1184, "must fit the reference's v27ter_rx_state_t (private/v27ter_rx.h)");
+
+extern "C" v27ter_rx_state_t *v27ter_rx_init(v27ter_rx_state_t *s, int bit_rate, span_put_bit_func_t put_bit, void *user_data)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (bit_rate != 4800  &&  bit_rate != 2400)
+        return NULL;                                        // src/v27ter_rx.c:1163-1171
+    span_b200_ctx_t *ctx = span_b200_default_ctx();
+    if (ctx == NULL)
+        return NULL;
+    int heap = 0;
+    if (s != NULL  &&  s->magic == SB_MAGIC  &&  s->bank != NULL)
+    {
+        span_b200_v27ter_bank_destroy(s->bank);
+        delete s->bits;
+        delete s->syms;
+        heap = s->heap;
+    }
+    else if (s == NULL)
+    {
+        if ((s = (v27ter_rx_state_t *) calloc(1, sizeof(*s))) == NULL)
+            return NULL;
+        heap = 1;
+    }
+    memset(s, 0, sizeof(*s));
+    s->bank = span_b200_v27ter_bank_create(ctx, 1, bit_rate, 1);
+    if (s->bank == NULL)
+    {
+        if (heap)
+            free(s);
+        return NULL;
+    }
+    s->magic = SB_MAGIC;
+    s->heap = heap;
+    s->bit_rate = bit_rate;
+    s->put_bit = put_bit;
+    s->put_bit_user_data = user_data;
+    s->bits = new std::vector<int8_t>();
+    s->syms = new std::vector<span_b200_v27ter_symbol_t>();
+    return s;
+}
+
+extern "C" int v27ter_rx_restart(v27ter_rx_state_t *s, int bit_rate, bool old_train)
+{
+    if (bit_rate != 4800  &&  bit_rate != 2400)
+        return -1;                                          // src/v27ter_rx.c:1095-1103
+    s->bit_rate = bit_rate;
+    return span_b200_v27ter_bank_restart(s->bank, 0, 1, bit_rate, (old_train)  ?  1  :  0);
+}
+
+static int v27ter_close(v27ter_rx_state_t *s, int do_free)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (s == NULL  ||  s->magic != SB_MAGIC)
+        return 0;
+    span_b200_v27ter_bank_destroy(s->bank);
+    delete s->bits;
+    delete s->syms;
+    const int heap = s->heap;
+    s->magic = 0;
+    s->bank = NULL;
+    if (do_free  &&  heap)
+        free(s);
+    return 0;
+}
+
+extern "C" int v27ter_rx_release(v27ter_rx_state_t *s) { return v27ter_close(s, 0); }
+extern "C" int v27ter_rx_free(v27ter_rx_state_t *s) { return v27ter_close(s, 1); }
+extern "C" logging_state_t *v27ter_rx_get_logging_state(v27ter_rx_state_t *s) { (void) s; return NULL; }
+
+extern "C" void v27ter_rx_set_put_bit(v27ter_rx_state_t *s, span_put_bit_func_t put_bit, void *user_data)
+{
+    s->put_bit = put_bit;
+    s->put_bit_user_data = user_data;
+}
+
+extern "C" void v27ter_rx_set_modem_status_handler(v27ter_rx_state_t *s, span_modem_status_func_t handler, void *user_data)
+{
+    s->status_handler = handler;
+    s->status_user_data = user_data;
+}
+
+extern "C" void v27ter_rx_set_qam_report_handler(v27ter_rx_state_t *s, qam_report_handler_t handler, void *user_data)
+{
+    s->qam_report = handler;
+    s->qam_user_data = user_data;
+}
+
+// One entry of the put_bit stream: data bits go to put_bit, status codes to the status handler if one
+// is installed, else to put_bit (src/v27ter_rx.c:166-174).
+static void v27ter_deliver(v27ter_rx_state_t *s, int v)
+{
+    if (v < 0  &&  s->status_handler)
+        s->status_handler(s->status_user_data, v);
+    else if (s->put_bit)
+        s->put_bit(s->put_bit_user_data, v);
+}
+
+extern "C" int v27ter_rx(v27ter_rx_state_t *s, const int16_t amp[], int len)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (len <= 0)
+        return 0;
+    if (span_b200_v27ter_bank_rx_host(s->bank, amp, len, len, NULL) != 0)
+        return 0;
+    int32_t nb = 0;
+    int32_t ns = 0;
+    if (span_b200_v27ter_bank_counts(s->bank, &nb, &ns) != 0)
+        return 0;
+    s->bits->resize((size_t) std::max(nb, 1));
+    s->syms->resize((size_t) std::max(ns, 1));
+    if (nb > 0)
+        span_b200_v27ter_bank_bits(s->bank, 0, s->bits->data(), nb);
+    if (ns > 0)
+        span_b200_v27ter_bank_symbols(s->bank, 0, s->syms->data(), ns);
+    // Replay in the reference's order: the bits of a baud come before that baud's qam report.
+    int done = 0;
+    for (int k = 0;  k < ns;  k++)
+    {
+        const span_b200_v27ter_symbol_t &y = (*s->syms)[k];
+        for (  ;  done < y.bit_pos  &&  done < nb;  done++)
+            v27ter_deliver(s, (*s->bits)[done]);
+        if (s->qam_report)
+        {
+            if (y.re != y.re)
+            {
+                // A Gardner timing hop: the reference passes NULL pointers and the integrator value (src/v27ter_rx.c:517-518)
+                s->qam_report(s->qam_user_data, NULL, NULL, y.state);
+            }
+            else
+            {
+                const complexf_t z = {y.re, y.im};
+                const complexf_t t = {y.target_re, y.target_im};
+                s->qam_report(s->qam_user_data, &z, &t, y.state);
+            }
+        }
+    }
+    for (  ;  done < nb;  done++)
+        v27ter_deliver(s, (*s->bits)[done]);
+    return 0;                                               // src/v27ter_rx.c:1026
+}
+
+extern "C" int v27ter_rx_fillin(v27ter_rx_state_t *s, int len)
+{
+    return (span_b200_v27ter_bank_fillin(s->bank, 0, 1, len) == 0)  ?  0  :  0;
+}
+
+extern "C" int v27ter_rx_equalizer_state(v27ter_rx_state_t *s, complexf_t **coeffs)
+{
+    float eq[64];
+    span_b200_v27ter_bank_channel_state(s->bank, 0, eq, NULL);
+    for (int i = 0;  i < 32;  i++)
+    {
+        s->eq_coeff[i].re = eq[2*i];
+        s->eq_coeff[i].im = eq[2*i + 1];
+    }
+    *coeffs = s->eq_coeff;
+    return 32;                                              // V27TER_EQUALIZER_LEN
+}
+
+extern "C" float v27ter_rx_carrier_frequency(v27ter_rx_state_t *s)
+{
+    int32_t info[12];
+    span_b200_v27ter_bank_channel_state(s->bank, 0, NULL, info);
+    return (float) info[1]*(float) 8000/(65536.0f*65536.0f);           // dds_frequencyf, src/dds_float.c:2115-2118
+}
+
+extern "C" float v27ter_rx_symbol_timing_correction(v27ter_rx_state_t *s)
+{
+    int32_t info[12];
+    span_b200_v27ter_bank_channel_state(s->bank, 0, NULL, info);
+    const int steps_per_symbol = (info[11] == 4800)  ?  8*5  :  12*20/3;
+    return (float) info[5]/(float) steps_per_symbol;                    // src/v27ter_rx.c:143-149
+}
+
+extern "C" float v27ter_rx_signal_power(v27ter_rx_state_t *s)
+{
+    int32_t info[12];
+    span_b200_v27ter_bank_channel_state(s->bank, 0, NULL, info);
+    // power_meter_current_dbm0() + 3.98f: src/power_meter.c:115-122, src/v27ter_rx.c:152-155
+    if (info[10] <= 0)
+        return (-96.329f + (3.14f + 3.02f)) + 3.98f;
+    return (10.0f*log10f((float) info[10]/(32767.0f*32767.0f) + 1.0e-10f) + (3.14f + 3.02f)) + 3.98f;
+}
+
+extern "C" void v27ter_rx_set_signal_cutoff(v27ter_rx_state_t *s, float cutoff)
+{
+    span_b200_v27ter_bank_set_signal_cutoff(s->bank, 0, 1, cutoff);
 }

@@ -227,14 +227,15 @@ static inline void dit_transform(cplx *data, cplx *temp, int n, const std::vecto
 
 // Root raised cosine prototype by frequency sampling (src/filter_tools.c:126-190), then the polyphase
 // band-pass sets (src/make_modem_filter.c:155-271).  V.29: 48 sets x 27 taps at 1700 Hz (:401-413);
-// V.17: 192 sets x 27 taps at 1800 Hz (:319-332); both 2400 baud, excess bandwidth 0.5.
-static inline void make_rx_rrc(std::vector<float> &re, std::vector<float> &im, int coeff_sets, double carrier_hz)
+// V.17: 192 sets x 27 taps at 1800 Hz (:319-332); both 2400 baud, excess bandwidth 0.5.  V.27ter: 12 sets at
+// 1200 baud and 8 sets at 1600 baud, 1800 Hz, excess bandwidth 0.5 (:375-400).
+static inline void make_rx_rrc(std::vector<float> &re, std::vector<float> &im, int coeff_sets, double carrier_hz, double baud_rate = 2400.0)
 {
     const int SEQ_LEN = 8192;
     const double GEN_PI = 3.1415926535;
     const int per_filter = SBM_FILTER_STEPS;
     const int total = coeff_sets*per_filter + 1;
-    const double alpha = 2400.0/(2.0*(double) (coeff_sets*8000));
+    const double alpha = baud_rate/(2.0*(double) (coeff_sets*8000));
     const double beta = 0.5;
     const double f1 = (1.0 - beta)*alpha;
     const double f2 = (1.0 + beta)*alpha;
@@ -454,10 +455,15 @@ struct StateStorer
 // One receiver.  Scalars live in registers; the per-channel arrays live in shared memory,
 // lane-interleaved (element e of lane l at [e*32 + l]) so that any per-lane index is conflict-free.
 // D is the concrete receiver (CRTP): it supplies restart_after_carrier_down() and process_baud().
-template <class D, int COEFF_SETS>
+template <class D, int COEFF_SETS, int EQ_LEN = SBM_EQ_LEN>
 struct RxCore
 {
     static const int SETS = COEFF_SETS;
+    static const int EQ_TAPS = EQ_LEN;      // equalizer length (33: V.29, V.17; 32: V.27ter); arrays are sized for 33
+    // Symbol clock of xxx_rx_fillin(): coefficient-set steps per sample and per T/2 (a receiver with several
+    // baud rates overrides these)
+    static int fillin_sets(int) { return COEFF_SETS; }
+    static int fillin_half_baud(int) { return COEFF_SETS*10/(3*2); }
     // float state
     float agc_scaling, agc_scaling_save, eq_delta, training_error, track_p, track_i;
     float lbe0, lbe1, hbe0, hbe1, dc0, dc1, baud_phase;
@@ -520,7 +526,7 @@ struct RxCore
         v.f(F_DC0, dc0);
         v.f(F_DC1, dc1);
         v.f(F_BAUD_PHASE, baud_phase);
-        for (int k = 0;  k < SBM_EQ_LEN;  k++)
+        for (int k = 0;  k < EQ_LEN;  k++)
         {
             v.f(F_EQ_COEFF + 2*k, eq_coeff[k*32].x);
             v.f(F_EQ_COEFF + 2*k + 1, eq_coeff[k*32].y);
@@ -559,8 +565,8 @@ struct RxCore
     // After loading: fill the second copy of the two rings
     SB_HD void mirror_rings()
     {
-        for (int k = 0;  k < SBM_EQ_LEN;  k++)
-            eq_buf[(k + SBM_EQ_LEN)*32] = eq_buf[k*32];
+        for (int k = 0;  k < EQ_LEN;  k++)
+            eq_buf[(k + EQ_LEN)*32] = eq_buf[k*32];
         for (int k = 0;  k < SBM_FILTER_STEPS;  k++)
             rrc[(k + SBM_FILTER_STEPS)*32] = rrc[k*32];
     }
@@ -607,9 +613,9 @@ struct RxCore
     // src/v29rx.c:214-258, src/v17rx.c:219-264
     SB_HD void equalizer_reset()
     {
-        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < EQ_LEN;  i++)
             eq_coeff[i*32] = make_float2(0.0f, 0.0f);
-        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < 2*EQ_LEN;  i++)
             eq_buf[i*32] = make_float2(0.0f, 0.0f);
         eq_coeff[SBM_EQ_PRE_LEN*32] = make_float2(3.0f, 0.0f);
         eq_put_step = COEFF_SETS*10/(3*2) - 1;
@@ -618,12 +624,12 @@ struct RxCore
 
     SB_HD void equalizer_restore()
     {
-        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < EQ_LEN;  i++)
         {
             eq_coeff[i*32] = make_float2(fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c],
                                          fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i + 1)*channels + c]);
         }
-        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < 2*EQ_LEN;  i++)
             eq_buf[i*32] = make_float2(0.0f, 0.0f);
         eq_put_step = COEFF_SETS*10/(3*2) - 1;
         eq_step = 0;
@@ -631,7 +637,7 @@ struct RxCore
 
     SB_HD void equalizer_save()
     {
-        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < EQ_LEN;  i++)
         {
             const float2 y = eq_coeff[i*32];
             fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c] = y.x;
@@ -695,10 +701,10 @@ struct RxCore
     SB_HD void equalizer_get(float &zre, float &zim)
     {
         float are = 0.0f, aim = 0.0f, bre = 0.0f, bim = 0.0f;
-        const int first = SBM_EQ_LEN - eq_step;
+        const int first = EQ_LEN - eq_step;
         const float2 *xb = eq_buf + eq_step*32;
 #pragma unroll
-        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < EQ_LEN;  i++)
         {
             const float2 x = xb[i*32];
             const float2 y = eq_coeff[i*32];
@@ -726,7 +732,7 @@ struct RxCore
         const float eim = fmul(fsub(tim, zim), eq_delta);
         const float2 *xb = eq_buf + eq_step*32;
 #pragma unroll
-        for (int i = 0;  i < SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < EQ_LEN;  i++)
         {
             const float2 x = xb[i*32];
             float2 y = eq_coeff[i*32];
@@ -742,7 +748,7 @@ struct RxCore
         const float p = phase_to_radians(phase_step);
         const float cr = host_cosf(p);
         const float ci = -host_sinf(p);
-        for (int q = 0;  q < 2*SBM_EQ_LEN;  q++)
+        for (int q = 0;  q < 2*EQ_LEN;  q++)
         {
             const float2 x = eq_buf[q*32];
             eq_buf[q*32] = make_float2(fsub(fmul(x.x, cr), fmul(x.y, ci)), fadd(fmul(x.x, ci), fmul(x.y, cr)));
@@ -911,8 +917,8 @@ struct RxCore
         eq_put_step += COEFF_SETS*10/(3*2);
         // process_half_baud, first part (src/v29rx.c:516-525, src/v17rx.c:638-647)
         eq_buf[eq_step*32] = make_float2(zzre, zzim);
-        eq_buf[(eq_step + SBM_EQ_LEN)*32] = make_float2(zzre, zzim);
-        if (++eq_step >= SBM_EQ_LEN)
+        eq_buf[(eq_step + EQ_LEN)*32] = make_float2(zzre, zzim);
+        if (++eq_step >= EQ_LEN)
             eq_step = 0;
         if ((baud_half ^= 1))
         {
@@ -951,57 +957,77 @@ struct RxCore
     template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 #endif
 
-    template <class K> SB_HD void run(const K &k, const float *s_rrc_re, const float *s_rrc_im, const int16_t *row, int n)
+    bool feed_staged;
+    int feed_fill;
+    const int16_t *feed_row;
+    int feed_n;
+
+    SB_HD void feed_open(const int16_t *row, int n)
     {
-        int pos = 0;
+        feed_row = row;
+        feed_n = n;
+        feed_fill = 0;
+        feed_staged = false;
 #if defined(__CUDA_ARCH__)
-        const bool staged = (((size_t) row) & 15) == 0;
-        int fill = 0;
-        if (staged)
+        feed_staged = (((size_t) row) & 15) == 0;
+        if (feed_staged)
         {
             for (int g = 0;  g < (SBM_IN_RING - 8)/8;  g++)
             {
-                if (fill < n)
+                if (feed_fill < n)
                 {
-                    cp_async16(in_ring + (fill & (SBM_IN_RING - 1)), row + fill, (n - fill >= 8)  ?  16  :  2*(n - fill));
-                    fill += 8;
+                    cp_async16(in_ring + (feed_fill & (SBM_IN_RING - 1)), row + feed_fill, (n - feed_fill >= 8)  ?  16  :  2*(n - feed_fill));
+                    feed_fill += 8;
                 }
             }
             cp_async_commit();
             cp_async_wait<0>();
         }
 #endif
+    }
+
+    // The four samples at pos .. pos + 3, packed (zeros beyond the end of the row); tops the ring up by eight
+    SB_HD unsigned long long feed_peek4(int pos)
+    {
+        unsigned long long cur;
+#if defined(__CUDA_ARCH__)
+        if (feed_staged)
+        {
+            if (feed_fill < feed_n  &&  feed_fill - pos <= SBM_IN_RING - 8)
+            {
+                cp_async16(in_ring + (feed_fill & (SBM_IN_RING - 1)), feed_row + feed_fill, (feed_n - feed_fill >= 8)  ?  16  :  2*(feed_n - feed_fill));
+                feed_fill += 8;
+            }
+            cp_async_commit();
+            cp_async_wait<2>();
+            const unsigned int a0 = (unsigned short) in_ring[pos & (SBM_IN_RING - 1)];
+            const unsigned int a1 = (unsigned short) in_ring[(pos + 1) & (SBM_IN_RING - 1)];
+            const unsigned int a2 = (unsigned short) in_ring[(pos + 2) & (SBM_IN_RING - 1)];
+            const unsigned int a3 = (unsigned short) in_ring[(pos + 3) & (SBM_IN_RING - 1)];
+            cur = (unsigned long long) (a0 | (a1 << 16)) | ((unsigned long long) (a2 | (a3 << 16)) << 32);
+        }
+        else
+#endif
+        {
+            cur = 0;
+            for (int i = 0;  i < 4;  i++)
+            {
+                if (pos + i < feed_n)
+                    cur |= (unsigned long long) (unsigned short) ldg(feed_row + pos + i) << (16*i);
+            }
+        }
+        return cur;
+    }
+
+    template <class K> SB_HD void run(const K &k, const float *s_rrc_re, const float *s_rrc_im, const int16_t *row, int n)
+    {
+        int pos = 0;
+        feed_open(row, n);
 #pragma unroll 1
         while (pos < n)
         {
             // The (up to) four samples of this trip, packed
-            unsigned long long cur;
-#if defined(__CUDA_ARCH__)
-            if (staged)
-            {
-                if (fill < n  &&  fill - pos <= SBM_IN_RING - 8)
-                {
-                    cp_async16(in_ring + (fill & (SBM_IN_RING - 1)), row + fill, (n - fill >= 8)  ?  16  :  2*(n - fill));
-                    fill += 8;
-                }
-                cp_async_commit();
-                cp_async_wait<2>();
-                const unsigned int a0 = (unsigned short) in_ring[pos & (SBM_IN_RING - 1)];
-                const unsigned int a1 = (unsigned short) in_ring[(pos + 1) & (SBM_IN_RING - 1)];
-                const unsigned int a2 = (unsigned short) in_ring[(pos + 2) & (SBM_IN_RING - 1)];
-                const unsigned int a3 = (unsigned short) in_ring[(pos + 3) & (SBM_IN_RING - 1)];
-                cur = (unsigned long long) (a0 | (a1 << 16)) | ((unsigned long long) (a2 | (a3 << 16)) << 32);
-            }
-            else
-#endif
-            {
-                cur = 0;
-                for (int i = 0;  i < 4;  i++)
-                {
-                    if (pos + i < n)
-                        cur |= (unsigned long long) (unsigned short) ldg(row + pos + i) << (16*i);
-                }
-            }
+            unsigned long long cur = feed_peek4(pos);
 #pragma unroll 1
             for (int h = 0;  h < 2;  h++)
             {

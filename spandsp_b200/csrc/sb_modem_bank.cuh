@@ -1,4 +1,4 @@
-// sb_modem_bank.cuh - host side of the modem receiver banks (V.29, V.17): device tables, per-channel
+// sb_modem_bank.cuh - host side of the modem receiver banks (V.29, V.17, V.27ter): device tables, per-channel
 // state arrays, launches, result read-back.  The C ABI functions of include/spandsp_b200_v29.h and
 // include/spandsp_b200_v17.h are thin wrappers over these templates.
 #pragma once
@@ -73,14 +73,23 @@ static int modem_upload(std::vector<void *> &owned, const T **dst, const void *s
 
 // Tables every receiver needs: RRC sets, sine table, sqrt table, Godard descriptor, carrier constants.
 template <class RX>
-static int modem_core_tables(ModemBank<RX> *b, double carrier_hz, double godard_fine_trigger, int godard_coarse_step, float agc_target)
+static int modem_core_tables(ModemBank<RX> *b, double carrier_hz, double godard_fine_trigger, int godard_coarse_step, float agc_target,
+                             float agc_reference = 735.0f, const std::vector<float> *rrc_re_rows = NULL, const std::vector<float> *rrc_im_rows = NULL)
 {
     std::vector<float> re;
     std::vector<float> im;
     std::vector<float> st;
     std::vector<unsigned short> sq;
     godard_desc_t g;
-    make_rx_rrc(re, im, RX::SETS, carrier_hz);
+    if (rrc_re_rows)
+    {
+        re = *rrc_re_rows;          // [RX::SETS][27], prepared by the caller
+        im = *rrc_im_rows;
+    }
+    else
+    {
+        make_rx_rrc(re, im, RX::SETS, carrier_hz);
+    }
     make_sine_table(st);
     make_sqrt_table(sq);
     make_godard(g, carrier_hz, godard_fine_trigger, godard_coarse_step);
@@ -109,7 +118,7 @@ static int modem_core_tables(ModemBank<RX> *b, double carrier_hz, double godard_
     b->k.rate_low = host_dds_phase_rate(carrier - 20.0f);
     b->k.rate_high = host_dds_phase_rate(carrier + 20.0f);
     b->k.agc_target = agc_target/1.000000f;                 // RX_PULSESHAPER_GAIN is 1.0 in the float build
-    b->k.agc_initial = (agc_target/1.000000f)/735.0f;       // src/v29rx.c:1078, src/v17rx.c:1474
+    b->k.agc_initial = (agc_target/1.000000f)/agc_reference;    // src/v29rx.c:1078, src/v17rx.c:1474, src/v27ter_rx.c:1141
     return 0;
 }
 
@@ -241,7 +250,7 @@ static int modem_set_signal_cutoff(ModemBank<RX> *b, int first, int count, float
     return 0;
 }
 
-// xxx_rx_fillin(): integer bookkeeping only (src/v29rx.c:967-996, src/v17rx.c:1313-1343); done on the
+// xxx_rx_fillin(): integer bookkeeping only (src/v29rx.c:967-996, src/v17rx.c:1313-1343, src/v27ter_rx.c:1030-1068); done on the
 // host copy of four fields.
 template <class RX>
 static int modem_fillin(ModemBank<RX> *b, int first, int count, int samples)
@@ -254,7 +263,8 @@ static int modem_fillin(ModemBank<RX> *b, int first, int count, int samples)
     if (modem_quiesce(b) != 0)
         return -1;
     const size_t C = b->channels;
-    std::vector<int> present(count), stage(count), phase(count), rate(count), put(count);
+    std::vector<int> present(count), stage(count), phase(count), rate(count), put(count), bps(count);
+    CK(cudaMemcpy(bps.data(), b->istate + I_BIT_RATE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(present.data(), b->istate + I_SIGNAL_PRESENT*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(stage.data(), b->istate + I_STAGE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(phase.data(), b->istate + I_CARRIER_PHASE*C + first, sizeof(int)*count, cudaMemcpyDeviceToHost));
@@ -268,9 +278,9 @@ static int modem_fillin(ModemBank<RX> *b, int first, int count, int samples)
         for (int i = 0;  i < samples;  i++)
         {
             ph += (unsigned int) rate[c];
-            put[c] -= RX::SETS;
+            put[c] -= RX::fillin_sets(bps[c]);
             if (put[c] <= 0)
-                put[c] += RX::SETS*10/(3*2);
+                put[c] += RX::fillin_half_baud(bps[c]);
         }
         phase[c] = (int) ph;
     }
@@ -426,10 +436,11 @@ static int modem_output_layout(ModemBank<RX> *b, const int8_t **d_bits, int64_t 
     return 0;
 }
 
-// eq_coeff: 33 complex taps; info[i] = istate field fields[i] (or, for fields[i] < 0, the float field
+// eq_coeff: eq_len complex taps; info[i] = istate field fields[i] (or, for fields[i] < 0, the float field
 // -1 - fields[i] as its bit pattern).
 template <class RX>
-static int modem_channel_state(ModemBank<RX> *b, int channel, float *eq_coeff, int32_t *info, const int *fields, int nfields)
+static int modem_channel_state(ModemBank<RX> *b, int channel, float *eq_coeff, int32_t *info, const int *fields, int nfields,
+                               int eq_len = SBM_EQ_LEN)
 {
     if (channel < 0  ||  channel >= b->channels)
         return -1;
@@ -438,7 +449,7 @@ static int modem_channel_state(ModemBank<RX> *b, int channel, float *eq_coeff, i
     const size_t C = b->channels;
     if (eq_coeff)
     {
-        for (int i = 0;  i < 2*SBM_EQ_LEN;  i++)
+        for (int i = 0;  i < 2*eq_len;  i++)
             CK(cudaMemcpy(&eq_coeff[i], b->fstate + (size_t) (F_EQ_COEFF + i)*C + channel, sizeof(float), cudaMemcpyDeviceToHost));
     }
     if (info)

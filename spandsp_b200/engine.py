@@ -102,6 +102,19 @@ def lib():
         "span_b200_v17_bank_symbols": (i64, [vp, i32, vp, i64]),
         "span_b200_v17_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_v17_tables": (i32, [vp, vp, vp, vp, vp, vp, vp]),
+        "span_b200_v27ter_bank_create": (vp, [vp, i32, i32, i32]),
+        "span_b200_v27ter_bank_destroy": (None, [vp]),
+        "span_b200_v27ter_bank_channels": (i32, [vp]),
+        "span_b200_v27ter_bank_restart": (i32, [vp, i32, i32, i32, i32]),
+        "span_b200_v27ter_bank_set_signal_cutoff": (i32, [vp, i32, i32, f32]),
+        "span_b200_v27ter_bank_fillin": (i32, [vp, i32, i32, i32]),
+        "span_b200_v27ter_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_v27ter_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_v27ter_bank_counts": (i32, [vp, vp, vp]),
+        "span_b200_v27ter_bank_bits": (i64, [vp, i32, vp, i64]),
+        "span_b200_v27ter_bank_symbols": (i64, [vp, i32, vp, i64]),
+        "span_b200_v27ter_bank_channel_state": (i32, [vp, i32, vp, vp]),
+        "span_b200_v27ter_tables": (i32, [vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -344,7 +357,7 @@ class V29Bank:
         return rc
 
     def restart(self, bit_rate, first=0, count=None, mode=0):
-        """mode: V.29 old_train (0/1); V.17 short_train (0/1/2)."""
+        """mode: V.29 and V.27ter old_train (0/1); V.17 short_train (0/1/2)."""
         n = self.channels - first if count is None else count
         if self.PREFIX == "span_b200_v29_bank_":
             self._ck(lib().span_b200_v29_bank_restart_ex(self.h, first, n, bit_rate, mode))
@@ -402,6 +415,15 @@ class V17Bank(V29Bank):
     INFO = 12
 
     def __init__(self, ctx, channels, bit_rate=14400, want_symbols=False):
+        V29Bank.__init__(self, ctx, channels, bit_rate, want_symbols)
+
+
+class V27terBank(V29Bank):
+    """N V.27ter receivers (span_b200_v27ter_bank_create)."""
+    PREFIX = "span_b200_v27ter_bank_"
+    INFO = 12
+
+    def __init__(self, ctx, channels, bit_rate=4800, want_symbols=False):
         V29Bank.__init__(self, ctx, channels, bit_rate, want_symbols)
 
 

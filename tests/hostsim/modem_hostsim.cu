@@ -6,6 +6,7 @@
 #include "../../spandsp_b200/csrc/sb_modem.cuh"
 #include "../../spandsp_b200/csrc/sb_v29_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_v17_rx.cuh"
+#include "../../spandsp_b200/csrc/sb_v27ter_rx.cuh"
 
 using namespace sbm;
 
@@ -257,6 +258,44 @@ EXPORT int hostsim_v29_run(const int16_t *amp, int n, int chunk, int bit_rate, f
         final[5] = ch.istate[I_TOTAL_TIMING];
         final[6] = ch.istate[RxV29::I_CONSTELLATION];
         final[7] = ch.istate[I_CARRIER_PHASE];
+    }
+    return 0;
+}
+
+// final[]: as oracle ref_v27ter_run: {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling bits,
+//           total_baud_timing_correction, constellation_state, carrier_phase, gardner_integrate, gardner_step}
+EXPORT int hostsim_v27ter_run(const int16_t *amp, int n, int chunk, int bit_rate, float cutoff, int restart_at, int restart_old_train,
+                              int8_t *bits, int bits_cap, int32_t *nbits, span_b200_v29_symbol_t *syms, int sym_cap, int32_t *nsyms,
+                              float *eq_coeff, int32_t *final)
+{
+    static HostTables h;
+    HostChannel<RxV27ter> ch;
+    core_consts(ch.k, h, V27TER_SETS_4800, 1800.0, 30.0, 5, 1.414f);
+    make_v27ter_rrc(h.re, h.im);
+    ch.k.rrc_re = h.re.data();
+    ch.k.rrc_im = h.im.data();
+    ch.k.agc_initial = (1.414f/1.000000f)/283.0f;
+    ch.k.phase_p45 = host_dds_phase(45.0f);
+    ch.k.phase_m45 = host_dds_phase(-45.0f);
+    ch.k.phase_180 = host_dds_phase(180.0f);
+    ch.k.eq_delta = 0.25f/V27TER_EQ_LEN;
+    ch.setup();
+    if (cutoff <= -99.0f)
+        cutoff = -45.5f;
+    ch.init(bit_rate, (int32_t) (host_power_meter_level_dbm0(cutoff + 2.5f)*0.4f), (int32_t) (host_power_meter_level_dbm0(cutoff - 2.5f)*0.4f));
+    run_channel(ch, amp, n, chunk, bit_rate, restart_at, restart_old_train, bits, bits_cap, nbits, syms, sym_cap, nsyms, eq_coeff);
+    if (final)
+    {
+        final[0] = ch.istate[I_STAGE];
+        final[1] = ch.istate[I_PHASE_RATE];
+        final[2] = ch.istate[I_EQ_PUT_STEP];
+        final[3] = ch.istate[I_SIGNAL_PRESENT];
+        memcpy(&final[4], &ch.fstate[F_AGC], 4);
+        final[5] = ch.istate[I_TOTAL_TIMING];
+        final[6] = ch.istate[RxV27ter::I_CONSTELLATION];
+        final[7] = ch.istate[I_CARRIER_PHASE];
+        final[8] = ch.istate[RxV27ter::I_GARDNER_INTEGRATE];
+        final[9] = ch.istate[RxV27ter::I_GARDNER_STEP];
     }
     return 0;
 }

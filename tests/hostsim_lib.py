@@ -14,7 +14,7 @@ SYM_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     subprocess.run([os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
@@ -33,7 +33,7 @@ def lib():
 
 
 def run(modem, amp, bit_rate, chunk=160, cutoff=-100.0, restart_at=-1, restart_mode=1):
-    """modem: 'v17' or 'v29'.  Same result layout as pyoracle.v17_run / v29_run."""
+    """modem: 'v17', 'v29' or 'v27ter'.  Same result layout as pyoracle.v17_run / v29_run."""
     amp = np.ascontiguousarray(amp, dtype=np.int16)
     n = len(amp)
     bits = np.zeros(n * 2 + 64, dtype=np.int8)

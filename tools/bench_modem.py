@@ -1,6 +1,6 @@
 """cfg4 of BASELINE.json (8 192-channel V.29 9600 bit/s receive) and the same for V.17 14400 bit/s:
 Msamples/s of the receiver bank on the GPU with the reference's own build on the host cores beside it.
-MODEM=v29|v17, MODEM_CHANNELS, MODEM_SAMPLES, MODEM_RATE from the environment."""
+MODEM=v29|v17|v27ter, MODEM_CHANNELS, MODEM_SAMPLES, MODEM_RATE from the environment."""
 import json
 import os
 import sys
@@ -17,7 +17,7 @@ from spandsp_b200 import engine  # noqa: E402
 MODEM = os.environ.get("MODEM", "v29")
 C = int(os.environ.get("MODEM_CHANNELS", os.environ.get("V29_CHANNELS", "8192")))
 T = int(os.environ.get("MODEM_SAMPLES", os.environ.get("V29_SAMPLES", "80000")))
-RATE = int(os.environ.get("MODEM_RATE", "9600" if MODEM == "v29" else "14400"))
+RATE = int(os.environ.get("MODEM_RATE", {"v29": "9600", "v17": "14400", "v27ter": "4800"}[MODEM]))
 CPU = int(os.environ.get("MODEM_CPU", "1"))
 S = po.load("strict") if po.available("strict") else None
 F = po.load("fast") if po.available("fast") else None
@@ -27,6 +27,9 @@ t0 = time.time()
 if MODEM == "v29":
     sig = np.stack([po.v29_generate(S, T, RATE, False, -13.0, c + 1, (c * 37) % 400, 1234567 + c, -50.0) for c in range(base)])
     Bank = engine.V29Bank
+elif MODEM == "v27ter":
+    sig = np.stack([po.v27ter_generate(S, T, RATE, False, -13.0, c + 1, (c * 37) % 400, -1, 0, 0, 1234567 + c, -50.0) for c in range(base)])
+    Bank = engine.V27terBank
 else:
     sig = np.stack([po.v17_generate(S, T, RATE, False, -13.0, c + 1, (c * 37) % 400, -1, 0, 0, 1234567 + c, -50.0) for c in range(base)])
     Bank = engine.V17Bank
@@ -62,7 +65,7 @@ for want in (0, 1):
 if CPU:
     threads = len(os.sched_getaffinity(0))
     chans = min(C, threads * 16)
-    run = po.v29_run_batch if MODEM == "v29" else po.v17_run_batch
+    run = {"v29": po.v29_run_batch, "v17": po.v17_run_batch, "v27ter": po.v27ter_run_batch}[MODEM]
     secs = run(F or S, amp[:chans], RATE, T, -100.0, threads)
     out["cpu_reference"] = {"msamples_s": chans * T / secs / 1e6, "threads": threads, "channels": chans, "kind": "fast" if F else "strict"}
     print(json.dumps(out["cpu_reference"]), flush=True)
