@@ -295,6 +295,83 @@ struct Runner
         }
     }
 
+    // Eight samples with exactly one block boundary inside: k (1..7) samples finish the open block, the
+    // other 8 - k start the next one.  k is warp-uniform in the staged kernel.  The tail of the old block is a
+    // straight-line chain of steps left early after k of them; the head of the new block is the same chain
+    // entered late (fall-through switch) - no per-sample loop, and the resonator registers rotate by renaming
+    // except for one fix-up at the exit.  Needs B >= 8.
+    template <bool FILT, int I>
+    __device__ __forceinline__ void tail_chain(const float (&x)[8], int k)
+    {
+        step<FILT>(x[I]);
+        if constexpr (I < 6)
+        {
+            if (k > I + 1)
+                tail_chain<FILT, I + 1>(x, k);
+        }
+    }
+
+    template <bool FILT>
+    __device__ __forceinline__ void straddle8(const float (&x)[8], int k, const BankArgs<DET> &a)
+    {
+        tail_chain<FILT, 0>(x, k);
+        block_end(a);
+        zero_after_block();
+        switch (k)
+        {
+        case 1:
+            step<FILT>(x[1]);
+            [[fallthrough]];
+        case 2:
+            step<FILT>(x[2]);
+            [[fallthrough]];
+        case 3:
+            step<FILT>(x[3]);
+            [[fallthrough]];
+        case 4:
+            step<FILT>(x[4]);
+            [[fallthrough]];
+        case 5:
+            step<FILT>(x[5]);
+            [[fallthrough]];
+        case 6:
+            step<FILT>(x[6]);
+            [[fallthrough]];
+        default:
+            step<FILT>(x[7]);
+            break;
+        }
+        cs = 8 - k;
+    }
+
+    template <bool FILT>
+    __device__ __forceinline__ void straddle8_i16(const uint4 &v, int k, const BankArgs<DET> &a)
+    {
+        float x[8];
+        x[0] = sample_of<0>(v);
+        x[1] = sample_of<1>(v);
+        x[2] = sample_of<2>(v);
+        x[3] = sample_of<3>(v);
+        x[4] = sample_of<4>(v);
+        x[5] = sample_of<5>(v);
+        x[6] = sample_of<6>(v);
+        x[7] = sample_of<7>(v);
+        straddle8<FILT>(x, k, a);
+    }
+
+    template <bool FILT>
+    __device__ __forceinline__ void straddle8_g711(unsigned int w0, unsigned int w1, const float *lut, int k, const BankArgs<DET> &a)
+    {
+        float x[8];
+#pragma unroll
+        for (int i = 0;  i < 4;  i++)
+        {
+            x[i] = lut[(w0 >> (8*i)) & 0xFFu];
+            x[4 + i] = lut[(w1 >> (8*i)) & 0xFFu];
+        }
+        straddle8<FILT>(x, k, a);
+    }
+
     // A whole vector.  The common case - no block boundary inside a group of eight samples - takes the
     // unrolled path.  All conditions are warp-uniform in the staged kernel.
     template <bool FILT, bool IN8>
@@ -312,6 +389,10 @@ struct Runner
                     block_end(a);
                     zero_after_block();
                 }
+            }
+            else if (B >= 8)
+            {
+                straddle8_i16<FILT>(v, B - cs, a);
             }
             else
             {
@@ -331,6 +412,10 @@ struct Runner
                     zero_after_block();
                 }
             }
+            else if (B >= 8)
+            {
+                straddle8_g711<FILT>(v.x, v.y, lut, B - cs, a);
+            }
             else
             {
                 partial<FILT, true>(v, 0, 8, a, lut);
@@ -344,6 +429,10 @@ struct Runner
                     block_end(a);
                     zero_after_block();
                 }
+            }
+            else if (B >= 8)
+            {
+                straddle8_g711<FILT>(v.z, v.w, lut, B - cs, a);
             }
             else
             {
@@ -374,7 +463,9 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // The broadcast tells the compiler that the warp index - and with it the slice geometry and the block
+    // phase - is warp-uniform: uniform registers and plain branches instead of divergence bookkeeping.
+    const int warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
     // 8-bit input: the 256-entry expansion table sits in front of the rings (1 KB per CTA)
     const float *lut = (const float *) smem_raw;
     if (IN8)
