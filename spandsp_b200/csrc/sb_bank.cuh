@@ -295,8 +295,8 @@ struct Runner
         }
     }
 
-    // Eight samples with exactly one block boundary inside: k (1..7) samples finish the open block, the
-    // other 8 - k start the next one.  k is warp-uniform in the staged kernel.  The tail of the old block is a
+    // Eight samples with a block boundary inside or right after them: k (1..8) samples finish the open block,
+    // the other 8 - k start the next one.  k is warp-uniform in the staged kernel.  The tail of the old block is a
     // straight-line chain of steps left early after k of them; the head of the new block is the same chain
     // entered late (fall-through switch) - no per-sample loop, and the resonator registers rotate by renaming
     // except for one fix-up at the exit.  Needs B >= 8.
@@ -304,7 +304,7 @@ struct Runner
     __device__ __forceinline__ void tail_chain(const float (&x)[8], int k)
     {
         step<FILT>(x[I]);
-        if constexpr (I < 6)
+        if constexpr (I < 7)
         {
             if (k > I + 1)
                 tail_chain<FILT, I + 1>(x, k);
@@ -337,8 +337,10 @@ struct Runner
         case 6:
             step<FILT>(x[6]);
             [[fallthrough]];
-        default:
+        case 7:
             step<FILT>(x[7]);
+            break;
+        default:
             break;
         }
         cs = 8 - k;
@@ -380,17 +382,12 @@ struct Runner
         const int B = block_len(a);
         if (!IN8)
         {
-            if (cs + 8 <= B)
+            if (cs + 8 < B)
             {
                 fast8<FILT>(v);
                 cs += 8;
-                if (cs == B)
-                {
-                    block_end(a);
-                    zero_after_block();
-                }
             }
-            else if (B >= 8)
+            else if (DET::BLOCK > 0  ||  B >= 8)
             {
                 straddle8_i16<FILT>(v, B - cs, a);
             }
@@ -402,41 +399,24 @@ struct Runner
         else
         {
             // two groups of eight companded samples
-            if (cs + 8 <= B)
+#pragma unroll 1
+            for (int h = 0;  h < 2;  h++)
             {
-                fast8_g711<FILT>(v.x, v.y, lut);
-                cs += 8;
-                if (cs == B)
+                const unsigned int w0 = (h)  ?  v.z  :  v.x;
+                const unsigned int w1 = (h)  ?  v.w  :  v.y;
+                if (cs + 8 < B)
                 {
-                    block_end(a);
-                    zero_after_block();
+                    fast8_g711<FILT>(w0, w1, lut);
+                    cs += 8;
                 }
-            }
-            else if (B >= 8)
-            {
-                straddle8_g711<FILT>(v.x, v.y, lut, B - cs, a);
-            }
-            else
-            {
-                partial<FILT, true>(v, 0, 8, a, lut);
-            }
-            if (cs + 8 <= B)
-            {
-                fast8_g711<FILT>(v.z, v.w, lut);
-                cs += 8;
-                if (cs == B)
+                else if (DET::BLOCK > 0  ||  B >= 8)
                 {
-                    block_end(a);
-                    zero_after_block();
+                    straddle8_g711<FILT>(w0, w1, lut, B - cs, a);
                 }
-            }
-            else if (B >= 8)
-            {
-                straddle8_g711<FILT>(v.z, v.w, lut, B - cs, a);
-            }
-            else
-            {
-                partial<FILT, true>(v, 8, 16, a, lut);
+                else
+                {
+                    partial<FILT, true>(v, 8*h, 8*h + 8, a, lut);
+                }
             }
         }
     }
@@ -453,7 +433,8 @@ struct StageCfg
     static_assert(SEG_VEC == 8  ||  SEG_VEC == 16  ||  SEG_VEC == 32, "SEG_VEC lanes copy one row segment");
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK, bool IN8>
+// FILTK: this instantiation carries the DTMF dial-tone notch (used when any channel of the bank has it on).
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK, bool IN8, bool FILTK>
 __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankArgs<DET> a)
 {
     constexpr int VSH = (IN8)  ?  4  :  3;          // log2(samples per 16-byte vector)
@@ -521,13 +502,11 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
         r.zero_state();
         r.cs = 0;
     }
-    bool any_filter = false;
-    if (DET::FILTER)
+    constexpr bool any_filter = DET::FILTER  &&  FILTK;
+    if (any_filter)
     {
         r.filt = DET::filter_on(a.det, r.c);
-        any_filter = __any_sync(0xFFFFFFFFu, r.filt);
-        if (any_filter)
-            DET::load_filter(a.det, r.c, a.channels, r.z);
+        DET::load_filter(a.det, r.c, a.channels, r.z);
     }
 
     // ---- staging geometry ----
@@ -554,26 +533,28 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     {
         if (g < g_hi)
         {
-            const int V = g*SEG_VEC + cp_vec;
             const long long off = (long long) g*(SEG_VEC*16);
-            long long nbytes = row_bytes - (off + cp_vec*16);
-            int sb = (nbytes >= 16)  ?  16  :  (nbytes > 0)  ?  (int) nbytes  :  0;
-            if (V < v_lo  ||  V >= v_hi)
-                sb = 0;
             uint32_t dst = cp_dst0 + (g % NSTAGE)*(SEG_VEC*16);
-            if (full_group)
+            // Interior segment of a full group of rows: every 16-byte piece lies inside the slice and the row
+            const bool interior = full_group  &&  g*SEG_VEC >= v_lo  &&  (g + 1)*SEG_VEC <= v_hi  &&  off + SEG_VEC*16 <= row_bytes;
+            if (interior)
             {
                 const char *src = cp_src0 + off;
 #pragma unroll
                 for (int i = 0;  i < SEG_VEC;  i++)
                 {
-                    cp_async_16(dst, src, sb);
+                    cp_async_16_full(dst, src);
                     src += cp_step;
                     dst += RPI*cfg::ROW_BYTES;
                 }
             }
             else
             {
+                const int V = g*SEG_VEC + cp_vec;
+                long long nbytes = row_bytes - (off + cp_vec*16);
+                int sb = (nbytes >= 16)  ?  16  :  (nbytes > 0)  ?  (int) nbytes  :  0;
+                if (V < v_lo  ||  V >= v_hi)
+                    sb = 0;
 #pragma unroll 1
                 for (int i = 0;  i < SEG_VEC;  i++)
                 {
@@ -592,47 +573,68 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     for (int s = 0;  s < NSTAGE - 1;  s++)
         issue(g_lo + s);
 
-    auto consume = [&](auto filt_tag)
+    // Vector roles inside the slice.  A slice starts on a block boundary with all-zero resonators, for which
+    // zero samples are exact no-ops: the leading samples of its first vector (they belong to the previous
+    // slice) are masked to zero and the block phase starts negative, so the first vector runs through full()
+    // like any other.  A slice that is not the last one ends on a block boundary: what full() computes past
+    // it (the head of a block that belongs to the next slice) is never emitted or stored.  Only the last
+    // vector of the last slice must stop exactly at `end`: that one takes partial().  (8-bit input keeps
+    // partial() for the head too: A-law has no code for zero.)
+    const int lead = start & VMASK;
+    const bool head_partial = (IN8  &&  lead != 0);
+    const bool tail_exact = (last  &&  (end & VMASK) != 0);
+    const int vf_lo = (head_partial)  ?  (v_lo + 1)  :  v_lo;          // vectors [vf_lo, vf_hi) go through full()
+    const int vf_hi = (tail_exact)  ?  (v_hi - 1)  :  v_hi;
+    constexpr bool FILT = any_filter;
+    for (int g = g_lo;  g < g_hi;  g++)
     {
-        constexpr bool FILT = decltype(filt_tag)::value;
-        for (int g = g_lo;  g < g_hi;  g++)
+        cp_async_wait<NSTAGE - 2>();
+        __syncwarp();
+        issue(g + NSTAGE - 1);
+        const uint32_t stage = my_row + (g % NSTAGE)*SEG_VEC*16;
+        const int Vbase = g*SEG_VEC;
+        if (head_partial  &&  v_lo >= Vbase  &&  v_lo < Vbase + SEG_VEC)
         {
-            cp_async_wait<NSTAGE - 2>();
-            __syncwarp();
-            issue(g + NSTAGE - 1);
-            const uint32_t stage = my_row + (g % NSTAGE)*SEG_VEC*16;
-            const int Vbase = g*SEG_VEC;
-            const int j0 = (v_lo > Vbase)  ?  (v_lo - Vbase)  :  0;
-            const int j1 = (v_hi < Vbase + SEG_VEC)  ?  (v_hi - Vbase)  :  SEG_VEC;
-            // The slice's first and last vectors may be partial; peel them so that the interior
-            // loop carries no per-vector bounds logic.
-            const int jh = (v_lo >= Vbase  &&  v_lo < Vbase + SEG_VEC)  ?  (v_lo - Vbase)  :  -1;
-            const int jt = (v_hi - 1 >= Vbase  &&  v_hi - 1 < Vbase + SEG_VEC  &&  v_hi - 1 != v_lo)  ?  (v_hi - 1 - Vbase)  :  -1;
-            const int ja = (jh >= 0)  ?  (jh + 1)  :  j0;
-            const int jb = (jt >= 0)  ?  jt  :  j1;
-            if (jh >= 0)
-            {
-                const int hi_h = (v_hi - 1 == v_lo)  ?  (((end - 1) & VMASK) + 1)  :  (VMASK + 1);
-                r.template partial<FILT, IN8>(lds128(stage + jh*16), start & VMASK, hi_h, a, lut);
-            }
-            int j = ja;
-            for (  ;  j + 2 <= jb;  j += 2)
-            {
-                const uint4 v0 = lds128(stage + j*16);
-                const uint4 v1 = lds128(stage + j*16 + 16);
-                r.template full<FILT, IN8>(v0, a, lut);
-                r.template full<FILT, IN8>(v1, a, lut);
-            }
-            if (j < jb)
-                r.template full<FILT, IN8>(lds128(stage + j*16), a, lut);
-            if (jt >= 0)
-                r.template partial<FILT, IN8>(lds128(stage + jt*16), 0, ((end - 1) & VMASK) + 1, a, lut);
+            const int hi_h = (v_hi - 1 == v_lo)  ?  (((end - 1) & VMASK) + 1)  :  (VMASK + 1);
+            r.template partial<FILT, IN8>(lds128(stage + (v_lo - Vbase)*16), lead, hi_h, a, lut);
         }
-    };
-    if (DET::FILTER  &&  any_filter)
-        consume(std::true_type());
-    else
-        consume(std::false_type());
+        const int ja = (vf_lo > Vbase)  ?  (vf_lo - Vbase)  :  0;
+        const int jb = (vf_hi < Vbase + SEG_VEC)  ?  (vf_hi - Vbase)  :  SEG_VEC;
+        if (ja < jb)
+        {
+            uint4 cur = lds128(stage + ja*16);
+            if (!IN8  &&  lead != 0  &&  Vbase + ja == v_lo)
+            {
+                // mask the `lead` samples that precede the slice
+                cur.x = (lead >= 2)  ?  0u  :  (cur.x & 0xFFFF0000u);
+                cur.y = (lead >= 4)  ?  0u  :  (lead == 3)  ?  (cur.y & 0xFFFF0000u)  :  cur.y;
+                cur.z = (lead >= 6)  ?  0u  :  (lead == 5)  ?  (cur.z & 0xFFFF0000u)  :  cur.z;
+                cur.w = (lead == 7)  ?  (cur.w & 0xFFFF0000u)  :  cur.w;
+                r.cs = -lead;
+            }
+            // Two vectors per trip, each fetched while the previous one is processed (the fetch after the last
+            // vector of a stage lands in the 16 bytes of padding that follow the ring, or in the next stage;
+            // its value is not used).  Ping-pong between the two register sets: no copies.
+            int j = ja;
+#pragma unroll 1
+            for (;;)
+            {
+                const uint4 nxt = lds128(stage + j*16 + 16);
+                r.template full<FILT, IN8>(cur, a, lut);
+                if (++j >= jb)
+                    break;
+                cur = lds128(stage + j*16 + 16);
+                r.template full<FILT, IN8>(nxt, a, lut);
+                if (++j >= jb)
+                    break;
+            }
+        }
+        if (tail_exact  &&  v_hi - 1 >= Vbase  &&  v_hi - 1 < Vbase + SEG_VEC  &&  !(head_partial  &&  v_hi - 1 == v_lo))
+        {
+            const int lo_t = (v_hi - 1 == v_lo)  ?  lead  :  0;
+            r.template partial<FILT, IN8>(lds128(stage + (v_hi - 1 - Vbase)*16), lo_t, ((end - 1) & VMASK) + 1, a, lut);
+        }
+    }
     cp_async_wait<0>();
 
     if (last  &&  !DET::RAW)

@@ -93,6 +93,11 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *gptr
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
 }
 
+__device__ __forceinline__ void cp_async_16_full(uint32_t smem_addr, const void *gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(smem_addr), "l"(gptr) : "memory");
+}
+
 __device__ __forceinline__ void cp_async_commit()
 {
     asm volatile("cp.async.commit_group;\n" ::: "memory");

@@ -860,12 +860,12 @@ struct Geometry
     bool staged;
 };
 
-template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK, bool IN8 = false>
-static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK, bool IN8, bool FILTK>
+static int launch_staged_k(const BankArgs<DET> &a, cudaStream_t st)
 {
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
     const int smem = cfg::WARP_BYTES*WARPS + ((IN8)  ?  1024  :  0);
-    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK, IN8>;
+    auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK, IN8, FILTK>;
     static bool configured = false;
     if (!configured)
     {
@@ -880,24 +880,41 @@ static int launch_staged(const BankArgs<DET> &a, cudaStream_t st)
     return 0;
 }
 
-template <class DET, int NPACK>
-static int launch_variant(const BankArgs<DET> &a, int variant, cudaStream_t st)
+// `filter`: some channel of the bank has the DTMF dial-tone notch on (only DtmfDet has an instantiation for it)
+template <class DET, int SEG_VEC, int NSTAGE, int WARPS, int MINB, int NPACK, bool IN8 = false>
+static int launch_staged(const BankArgs<DET> &a, bool filter, cudaStream_t st)
 {
-    // (row bytes per stage = SEG_VEC*16, stages, warps per CTA, min CTAs per SM).  The round-1 sweep
-    // (profiles/r01_sweep_dtmf*.json) covered nine shapes; the two ends of it are kept.
-    switch (variant)
+    if constexpr (DET::FILTER)
     {
-    case 8:
-        return launch_staged<DET, 16, 3, 4, 2, NPACK>(a, st);       // 784 B/row, 8 warps/SM
-    default:
-        // Fastest in the sweep: 128-byte row segments, 2 stages, 16-20 resident warps per SM.
-        return launch_staged<DET, 8, 2, 4, 4, NPACK>(a, st);        // 272 B/row
+        if (filter)
+            return launch_staged_k<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK, IN8, true>(a, st);
     }
+    return launch_staged_k<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK, IN8, false>(a, st);
+}
+
+template <class DET, int NPACK>
+static int launch_variant(const BankArgs<DET> &a, bool filter, cudaStream_t st, int variant = 0)
+{
+    // Occupancy experiments (DTMF only, tuning knob 1): more resident warps per SM at a lower register cap
+    if constexpr (std::is_same<DET, DtmfDet>::value  &&  NPACK == DET::NPAIRS)
+    {
+        if (variant == 1)
+            return launch_staged<DET, 8, 2, 4, 6, NPACK>(a, filter, st);    // 24 warps/SM, <= 80 registers
+        if (variant == 2)
+            return launch_staged<DET, 8, 2, 8, 3, NPACK>(a, filter, st);    // 24 warps/SM in 3 CTAs of 8 warps
+        if (variant == 3)
+            return launch_staged<DET, 8, 2, 2, 10, NPACK>(a, filter, st);   // 20 warps/SM in 10 CTAs of 2 warps
+    }
+    // (row bytes per stage = SEG_VEC*16, stages, warps per CTA, min CTAs per SM).  The round-1 sweep
+    // (profiles/r01_sweep_dtmf*.json) covered nine shapes; the fastest is kept: 128-byte row segments,
+    // 2 stages, 16-20 resident warps per SM.
+    return launch_staged<DET, 8, 2, 4, 4, NPACK>(a, filter, st);        // 272 B/row
 }
 
 template <class DET>
 static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g, cudaStream_t st, bool all_variants)
 {
+    const bool filter = (b->det == SPAN_B200_DET_DTMF  &&  b->n_filter > 0);
     if (a.lut)
     {
         // 8-bit companded input: one staged shape, or the direct kernel
@@ -908,7 +925,7 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
         if (g.staged)
         {
             b->last_path = "staged";
-            return launch_staged<DET, 8, 2, 4, 4, DET::NPAIRS, true>(a, st);
+            return launch_staged<DET, 8, 2, 4, 4, DET::NPAIRS, true>(a, filter, st);
         }
         b->last_path = "direct";
         bank_kernel_direct<DET, DET::NPAIRS, true><<<(a.channels + 127)/128, 128, 0, st>>>(a);
@@ -922,12 +939,11 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
     if (g.staged)
     {
         b->last_path = "staged";
-        const int variant = (all_variants)  ?  b->tune_variant  :  0;
         // Knob 3 = 0 selects scalar FADDs instead of FADD2 (DTMF only; kept for the comparison in
         // packed is 7-9 % faster, mixing packed and scalar pairs brings nothing).
         if (all_variants  &&  b->tune_packed == 0)
-            return launch_variant<DET, 0>(a, variant, st);
-        return launch_variant<DET, DET::NPAIRS>(a, variant, st);
+            return launch_variant<DET, 0>(a, filter, st);
+        return launch_variant<DET, DET::NPAIRS>(a, filter, st, (all_variants)  ?  b->tune_variant  :  0);
     }
     b->last_path = "direct";
     const int grid = (a.channels + 127)/128;
@@ -1432,7 +1448,7 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
             L = 16;
         a.slice_blocks = (nb > L)  ?  L  :  (nb + 1);
         a.nslices = (nb > L)  ?  ((nb + L - 1)/L)  :  1;
-        return launch_staged<RawDet<NP>, 8, 2, 4, 4, NP>(a, st);
+        return launch_staged<RawDet<NP>, 8, 2, 4, 4, NP>(a, false, st);
     }
     bank_kernel_direct<RawDet<NP>, NP, false><<<(channels + 127)/128, 128, 0, st>>>(a);
     CK(cudaGetLastError());
