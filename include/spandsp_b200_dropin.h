@@ -200,6 +200,49 @@ float v27ter_rx_signal_power(v27ter_rx_state_t *s);
 void v27ter_rx_set_signal_cutoff(v27ter_rx_state_t *s, float cutoff);
 void v27ter_rx_set_qam_report_handler(v27ter_rx_state_t *s, qam_report_handler_t handler, void *user_data);
 
+/* ---- FSK receiver (V.21, V.23, Bell 103/202, Weitbrecht): src/spandsp/fsk.h:92-269, src/fsk.c:60-156,271-760 ---- */
+typedef struct
+{
+    const char *name;
+    int freq_zero;
+    int freq_one;
+    int tx_level;
+    int min_level;
+    int baud_rate;
+} fsk_spec_t;                                                           /* src/spandsp/fsk.h:92-106 */
+
+enum
+{
+    FSK_V21CH1 = 0, FSK_V21CH2, FSK_V23CH1, FSK_V23CH2, FSK_BELL103CH1, FSK_BELL103CH2, FSK_BELL202,
+    FSK_WEITBRECHT_4545, FSK_WEITBRECHT_50, FSK_WEITBRECHT_476, FSK_V21CH1_110
+};                                                                      /* src/spandsp/fsk.h:108-121 */
+
+enum
+{
+    FSK_FRAME_MODE_ASYNC = 0,
+    FSK_FRAME_MODE_SYNC = 1,
+    FSK_FRAME_MODE_FRAMED = 2
+};                                                                      /* src/spandsp/fsk.h:124-129 */
+
+extern const fsk_spec_t preset_fsk_specs[];                             /* src/spandsp/fsk.h:131 */
+
+typedef struct fsk_rx_state_s fsk_rx_state_t;
+
+/* Synchronous, one receiver per state (a bank of one).  Banks of many receivers: spandsp_b200_fsk.h. */
+fsk_rx_state_t *fsk_rx_init(fsk_rx_state_t *s, const fsk_spec_t *spec, int framing_mode, span_put_bit_func_t put_bit, void *user_data);
+int fsk_rx_restart(fsk_rx_state_t *s, const fsk_spec_t *spec, int framing_mode);
+int fsk_rx_release(fsk_rx_state_t *s);
+int fsk_rx_free(fsk_rx_state_t *s);
+int fsk_rx(fsk_rx_state_t *s, const int16_t *amp, int len);
+int fsk_rx_fillin(fsk_rx_state_t *s, int len);
+void fsk_rx_set_put_bit(fsk_rx_state_t *s, span_put_bit_func_t put_bit, void *user_data);
+void fsk_rx_set_modem_status_handler(fsk_rx_state_t *s, span_modem_status_func_t handler, void *user_data);
+void fsk_rx_set_signal_cutoff(fsk_rx_state_t *s, float cutoff);
+float fsk_rx_signal_power(fsk_rx_state_t *s);
+void fsk_rx_set_frame_parameters(fsk_rx_state_t *s, int data_bits, int parity, int stop_bits);
+int fsk_rx_get_parity_errors(fsk_rx_state_t *s, bool reset);
+int fsk_rx_get_framing_errors(fsk_rx_state_t *s, bool reset);
+
 #if defined(__cplusplus)
 }
 #endif

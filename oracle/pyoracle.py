@@ -357,6 +357,56 @@ def v27ter_tables(lib, fn_name):
     return {"rrc4800_re": r48, "rrc4800_im": i48, "rrc2400_re": r24, "rrc2400_im": i24, "ints": it}
 
 
+FSK_FINAL = 28
+
+
+def fsk_generate(o, n, spec=1, level_dbm0=1.0, lfsr_seed=1, char_bits=0, parity=0, idle=2, lead=0, burst=-1, noise_seed=1234567, noise_dbm0=-100.0):
+    """fsk_tx of PRBS data (raw bits, or start-stop characters when char_bits > 0) + awgn.  level_dbm0 > 0: the spec's tx level."""
+    amp = np.zeros(n, dtype=np.int16)
+    o.lib.ref_fsk_generate.restype = C.c_int
+    rc = o.lib.ref_fsk_generate(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(spec), C.c_float(level_dbm0), C.c_uint32(lfsr_seed),
+                                C.c_int(char_bits), C.c_int(parity), C.c_int(idle), C.c_int(lead), C.c_int(burst),
+                                C.c_int(noise_seed), C.c_float(noise_dbm0))
+    if rc < 0:
+        raise RuntimeError("ref_fsk_generate failed")
+    return amp
+
+
+def fsk_run(o, amp, spec=1, framing_mode=1, chunk=160, cutoff=-100.0, frame=(0, 0, 0), restart=(-1, 0, 0), fillin=(-1, 0)):
+    """One channel through the reference's fsk_rx.  Returns dict(out int16[], final int32[28], window int32[2,128,2])."""
+    amp = np.ascontiguousarray(amp, dtype=np.int16)
+    n = len(amp)
+    out = np.zeros(n * 2 + 64, dtype=np.int16)
+    nout = C.c_int32(0)
+    fin = np.zeros(FSK_FINAL, dtype=np.int32)
+    win = np.zeros((2, 128, 2), dtype=np.int32)
+    o.lib.ref_fsk_run.restype = C.c_int
+    rc = o.lib.ref_fsk_run(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(spec), C.c_int(framing_mode), C.c_float(cutoff),
+                           C.c_int(frame[0]), C.c_int(frame[1]), C.c_int(frame[2]),
+                           C.c_int(restart[0]), C.c_int(restart[1]), C.c_int(restart[2]), C.c_int(fillin[0]), C.c_int(fillin[1]),
+                           C.c_void_p(out.ctypes.data), C.c_int(out.size), C.byref(nout), C.c_void_p(fin.ctypes.data), C.c_void_p(win.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("ref_fsk_run failed")
+    return {"out": out[:nout.value].copy(), "final": fin, "window": win}
+
+
+def fsk_run_batch(o, amp, spec=1, framing_mode=1, chunk=160, nthreads=1):
+    """Many channels, timing only (CPU baseline).  Returns seconds."""
+    amp = np.asarray(amp)
+    assert amp.dtype == np.int16 and amp.ndim == 2 and amp.strides[1] == 2
+    o.lib.ref_fsk_run_batch.restype = C.c_double
+    return o.lib.ref_fsk_run_batch(C.c_void_p(amp.ctypes.data), C.c_int64(amp.strides[0] // 2), C.c_int(amp.shape[0]), C.c_int(amp.shape[1]),
+                                   C.c_int(chunk), C.c_int(spec), C.c_int(framing_mode), C.c_int(nthreads))
+
+
+def fsk_tables(o):
+    sine = np.zeros(257, np.int16)
+    derived = np.zeros((11, 4), np.int32)
+    presets = np.zeros((11, 5), np.int32)
+    o.lib.ref_fsk_tables(C.c_void_p(sine.ctypes.data), C.c_void_p(derived.ctypes.data), C.c_void_p(presets.ctypes.data))
+    return {"sine": sine, "derived": derived, "presets": presets}
+
+
 _cache = {}
 
 

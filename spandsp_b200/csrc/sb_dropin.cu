@@ -18,6 +18,7 @@
 #include "../../include/spandsp_b200_v29.h"
 #include "../../include/spandsp_b200_v17.h"
 #include "../../include/spandsp_b200_v27ter.h"
+#include "../../include/spandsp_b200_fsk.h"
 #pragma GCC visibility pop
 
 #define SB_MAGIC    0x5350414E42323030ULL       /* "SPANB200" */
@@ -1520,4 +1521,170 @@ extern "C" float v27ter_rx_signal_power(v27ter_rx_state_t *s)
 extern "C" void v27ter_rx_set_signal_cutoff(v27ter_rx_state_t *s, float cutoff)
 {
     span_b200_v27ter_bank_set_signal_cutoff(s->bank, 0, 1, cutoff);
+}
+
+// ------------------------------------------------------------------------------------------
+// FSK receiver, one bank of one per state object (src/fsk.c:271-354,396-760)
+struct fsk_rx_state_s
+{
+    unsigned long long magic;
+    span_b200_fsk_bank_t *bank;
+    int heap;
+    span_put_bit_func_t put_bit;
+    void *put_bit_user_data;
+    span_modem_status_func_t status_handler;
+    void *status_user_data;
+    std::vector<int16_t> *out;
+};
+
+static_assert(sizeof(fsk_rx_state_s) <= 2200, "must fit the reference's fsk_rx_state_t (private/fsk.h)");
+static_assert(sizeof(fsk_spec_t) == sizeof(span_b200_fsk_spec_t), "fsk_spec_t layout");
+
+// preset_fsk_specs[] (src/fsk.c:60-156), exported as data like the reference's (src/spandsp/fsk.h:131)
+extern "C" __attribute__((visibility("default"))) const fsk_spec_t preset_fsk_specs[] =
+{
+    {"V21 ch 1", 1080 + 100, 1080 - 100, -14, -30, 300*100},
+    {"V21 ch 2", 1750 + 100, 1750 - 100, -14, -30, 300*100},
+    {"V23 ch 1", 1700 + 400, 1700 - 400, -14, -30, 1200*100},
+    {"V23 ch 2", 420 + 30, 420 - 30, -14, -30, 75*100},
+    {"Bell103 ch 1", 1170 - 100, 1170 + 100, -14, -30, 300*100},
+    {"Bell103 ch 2", 2125 - 100, 2125 + 100, -14, -30, 300*100},
+    {"Bell202", 1700 + 500, 1700 - 500, -14, -30, 1200*100},
+    {"Weitbrecht 45.45", 1600 + 200, 1600 - 200, -14, -30, 4545},
+    {"Weitbrecht 50", 1600 + 200, 1600 - 200, -14, -30, 50*100},
+    {"Weitbrecht 47.6", 1600 + 200, 1600 - 200, -14, -30, 4760},
+    {"V21 (110bps) ch 1", 1080 + 100, 1080 - 100, -14, -30, 110*100}
+};
+
+extern "C" fsk_rx_state_t *fsk_rx_init(fsk_rx_state_t *s, const fsk_spec_t *spec, int framing_mode, span_put_bit_func_t put_bit, void *user_data)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (spec == NULL)
+        return NULL;
+    span_b200_ctx_t *ctx = span_b200_default_ctx();
+    if (ctx == NULL)
+        return NULL;
+    int heap = 0;
+    if (s != NULL  &&  s->magic == SB_MAGIC  &&  s->bank != NULL)
+    {
+        span_b200_fsk_bank_destroy(s->bank);
+        delete s->out;
+        heap = s->heap;
+    }
+    else if (s == NULL)
+    {
+        if ((s = (fsk_rx_state_t *) calloc(1, sizeof(*s))) == NULL)
+            return NULL;
+        heap = 1;
+    }
+    memset(s, 0, sizeof(*s));
+    s->bank = span_b200_fsk_bank_create(ctx, 1, (const span_b200_fsk_spec_t *) spec, framing_mode);
+    if (s->bank == NULL)
+    {
+        if (heap)
+            free(s);
+        return NULL;
+    }
+    s->magic = SB_MAGIC;
+    s->heap = heap;
+    s->put_bit = put_bit;
+    s->put_bit_user_data = user_data;
+    s->out = new std::vector<int16_t>();
+    return s;
+}
+
+extern "C" int fsk_rx_restart(fsk_rx_state_t *s, const fsk_spec_t *spec, int framing_mode)
+{
+    span_b200_fsk_bank_restart(s->bank, 0, 1, (const span_b200_fsk_spec_t *) spec, framing_mode);
+    return 0;                                               // src/fsk.c:721
+}
+
+static int fsk_close(fsk_rx_state_t *s, int do_free)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (s == NULL  ||  s->magic != SB_MAGIC)
+        return 0;
+    span_b200_fsk_bank_destroy(s->bank);
+    delete s->out;
+    const int heap = s->heap;
+    s->magic = 0;
+    s->bank = NULL;
+    if (do_free  &&  heap)
+        free(s);
+    return 0;
+}
+
+extern "C" int fsk_rx_release(fsk_rx_state_t *s) { return fsk_close(s, 0); }
+extern "C" int fsk_rx_free(fsk_rx_state_t *s) { return fsk_close(s, 1); }
+
+extern "C" void fsk_rx_set_put_bit(fsk_rx_state_t *s, span_put_bit_func_t put_bit, void *user_data)
+{
+    s->put_bit = put_bit;
+    s->put_bit_user_data = user_data;
+}
+
+extern "C" void fsk_rx_set_modem_status_handler(fsk_rx_state_t *s, span_modem_status_func_t handler, void *user_data)
+{
+    s->status_handler = handler;
+    s->status_user_data = user_data;
+}
+
+extern "C" void fsk_rx_set_signal_cutoff(fsk_rx_state_t *s, float cutoff)
+{
+    span_b200_fsk_bank_set_signal_cutoff(s->bank, 0, 1, cutoff);
+}
+
+extern "C" float fsk_rx_signal_power(fsk_rx_state_t *s)
+{
+    return span_b200_fsk_bank_signal_power(s->bank, 0);
+}
+
+extern "C" void fsk_rx_set_frame_parameters(fsk_rx_state_t *s, int data_bits, int parity, int stop_bits)
+{
+    span_b200_fsk_bank_set_frame_parameters(s->bank, 0, 1, data_bits, parity, stop_bits);
+}
+
+extern "C" int fsk_rx_get_parity_errors(fsk_rx_state_t *s, bool reset)
+{
+    int32_t e = 0;
+    span_b200_fsk_bank_errors(s->bank, 0, &e, NULL, (reset)  ?  1  :  0);
+    return e;
+}
+
+extern "C" int fsk_rx_get_framing_errors(fsk_rx_state_t *s, bool reset)
+{
+    int32_t e = 0;
+    span_b200_fsk_bank_errors(s->bank, 0, NULL, &e, (reset)  ?  1  :  0);
+    return e;
+}
+
+extern "C" int fsk_rx(fsk_rx_state_t *s, const int16_t *amp, int len)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (len <= 0)
+        return 0;
+    if (span_b200_fsk_bank_rx_host(s->bank, amp, len, len, NULL) != 0)
+        return 0;
+    int32_t n = 0;
+    if (span_b200_fsk_bank_counts(s->bank, &n) != 0)
+        return 0;
+    s->out->resize((size_t) std::max(n, 1));
+    if (n > 0)
+        n = (int32_t) span_b200_fsk_bank_output(s->bank, 0, s->out->data(), n);
+    for (int i = 0;  i < n;  i++)
+    {
+        const int v = (*s->out)[i];
+        // status reports go to the status handler if one is installed, else through put_bit (src/fsk.c:347-354)
+        if (v < 0  &&  s->status_handler)
+            s->status_handler(s->status_user_data, v);
+        else if (s->put_bit)
+            s->put_bit(s->put_bit_user_data, v);
+    }
+    return 0;                                               // src/fsk.c:625
+}
+
+extern "C" int fsk_rx_fillin(fsk_rx_state_t *s, int len)
+{
+    span_b200_fsk_bank_fillin(s->bank, 0, 1, len);
+    return 0;
 }

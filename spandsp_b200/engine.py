@@ -115,6 +115,22 @@ def lib():
         "span_b200_v27ter_bank_symbols": (i64, [vp, i32, vp, i64]),
         "span_b200_v27ter_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_v27ter_tables": (i32, [vp, vp, vp, vp, vp]),
+        "span_b200_fsk_preset": (vp, [i32]),
+        "span_b200_fsk_bank_create": (vp, [vp, i32, vp, i32]),
+        "span_b200_fsk_bank_destroy": (None, [vp]),
+        "span_b200_fsk_bank_channels": (i32, [vp]),
+        "span_b200_fsk_bank_restart": (i32, [vp, i32, i32, vp, i32]),
+        "span_b200_fsk_bank_set_signal_cutoff": (i32, [vp, i32, i32, f32]),
+        "span_b200_fsk_bank_set_frame_parameters": (i32, [vp, i32, i32, i32, i32, i32]),
+        "span_b200_fsk_bank_fillin": (i32, [vp, i32, i32, i32]),
+        "span_b200_fsk_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_fsk_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_fsk_bank_counts": (i32, [vp, vp]),
+        "span_b200_fsk_bank_output": (i64, [vp, i32, vp, i64]),
+        "span_b200_fsk_bank_errors": (i32, [vp, i32, vp, vp, i32]),
+        "span_b200_fsk_bank_signal_power": (f32, [vp, i32]),
+        "span_b200_fsk_bank_channel_state": (i32, [vp, i32, vp, vp]),
+        "span_b200_dds_int_table": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -425,6 +441,95 @@ class V27terBank(V29Bank):
 
     def __init__(self, ctx, channels, bit_rate=4800, want_symbols=False):
         V29Bank.__init__(self, ctx, channels, bit_rate, want_symbols)
+
+
+class FskSpec(C.Structure):
+    """span_b200_fsk_spec_t (= the reference's fsk_spec_t)."""
+    _fields_ = [("name", C.c_char_p), ("freq_zero", C.c_int), ("freq_one", C.c_int), ("tx_level", C.c_int),
+                ("min_level", C.c_int), ("baud_rate", C.c_int)]
+
+
+def fsk_preset(which):
+    p = lib().span_b200_fsk_preset(which)
+    if not p:
+        raise EngineError("no such FSK preset")
+    return C.cast(p, C.POINTER(FskSpec)).contents
+
+
+class FskBank:
+    """N FSK receivers (span_b200_fsk_bank_create).  spec: a preset index or an FskSpec."""
+
+    def __init__(self, ctx, channels, spec=1, framing_mode=1):
+        self.ctx = ctx
+        self._spec = fsk_preset(spec) if isinstance(spec, int) else spec
+        self.h = lib().span_b200_fsk_bank_create(ctx.h, channels, C.addressof(self._spec), framing_mode)
+        if not self.h:
+            raise EngineError(_err())
+        self.channels = channels
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    def _range(self, first, count):
+        return first, (self.channels - first if count is None else count)
+
+    def restart(self, spec, framing_mode, first=0, count=None):
+        sp = fsk_preset(spec) if isinstance(spec, int) else spec
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_fsk_bank_restart(self.h, f, n, C.addressof(sp), framing_mode))
+
+    def set_signal_cutoff(self, cutoff, first=0, count=None):
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_fsk_bank_set_signal_cutoff(self.h, f, n, cutoff))
+
+    def set_frame_parameters(self, data_bits, parity, stop_bits, first=0, count=None):
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_fsk_bank_set_frame_parameters(self.h, f, n, data_bits, parity, stop_bits))
+
+    def fillin(self, samples, first=0, count=None):
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_fsk_bank_fillin(self.h, f, n, samples))
+
+    def rx_device(self, d_ptr, stride, samples, stream=None):
+        self._ck(lib().span_b200_fsk_bank_rx_device(self.h, d_ptr, stride, samples, stream))
+
+    def rx_host(self, amp, stream=None):
+        assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
+        self._ck(lib().span_b200_fsk_bank_rx_host(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
+
+    def counts(self):
+        n = np.zeros(self.channels, dtype=np.int32)
+        self._ck(lib().span_b200_fsk_bank_counts(self.h, n.ctypes.data))
+        return n
+
+    def output(self, channel, cap=1 << 22):
+        out = np.zeros(cap, dtype=np.int16)
+        n = lib().span_b200_fsk_bank_output(self.h, channel, out.ctypes.data, cap)
+        if n < 0:
+            raise EngineError(_err())
+        return out[:n]
+
+    def errors(self, channel, reset=False):
+        p = C.c_int32(0)
+        f = C.c_int32(0)
+        self._ck(lib().span_b200_fsk_bank_errors(self.h, channel, C.addressof(p), C.addressof(f), int(reset)))
+        return p.value, f.value
+
+    def signal_power(self, channel):
+        return lib().span_b200_fsk_bank_signal_power(self.h, channel)
+
+    def channel_state(self, channel):
+        info = np.zeros(28, dtype=np.int32)
+        win = np.zeros((2, 128, 2), dtype=np.int32)
+        self._ck(lib().span_b200_fsk_bank_channel_state(self.h, channel, info.ctypes.data, win.ctypes.data))
+        return info, win
+
+    def close(self):
+        if self.h:
+            lib().span_b200_fsk_bank_destroy(self.h)
+            self.h = None
 
 
 def events_by_channel(ev, channels):

@@ -7,6 +7,7 @@
 #include "../../spandsp_b200/csrc/sb_v29_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_v17_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_v27ter_rx.cuh"
+#include "../../spandsp_b200/csrc/sb_fsk_rx.cuh"
 
 using namespace sbm;
 
@@ -298,4 +299,84 @@ EXPORT int hostsim_v27ter_run(const int16_t *amp, int n, int chunk, int bit_rate
         final[9] = ch.istate[RxV27ter::I_GARDNER_STEP];
     }
     return 0;
+}
+
+// ---- FSK receiver (sb_fsk_rx.cuh) on the host: same call sequence as oracle ref_fsk_run ----------------------
+// spec5 = {freq_zero, freq_one, tx_level, min_level, baud_rate}; rspec5: the spec of the restart (if restart_at >= 0)
+static void fsk_host_restart(sbf::FskRx &r, const int32_t *spec5, int mode)
+{
+    const float cutoff = (float) spec5[3];
+    r.restart(spec5[4], mode, sbf::host_dds_int_phase_rate((float) spec5[0]), sbf::host_dds_int_phase_rate((float) spec5[1]),
+              sbf::host_level_dbm0(cutoff + 2.5f - 5.3f), sbf::host_level_dbm0(cutoff - 2.5f - 5.3f));
+}
+
+EXPORT int hostsim_fsk_run(const int16_t *amp, int n, int chunk, const int32_t *spec5, int framing_mode, float cutoff,
+                           int data_bits, int parity, int stop_bits,
+                           int restart_at, const int32_t *rspec5, int restart_mode, int fillin_at, int fillin_len,
+                           int16_t *out, int out_cap, int32_t *nout, int32_t *final, int32_t *window)
+{
+    static std::vector<short> sine;
+    if (sine.empty())
+        sbf::make_dds_int_table(sine);
+    std::vector<int2> win(2*SBF_MAX_WINDOW, make_int2(0, 0));
+    std::vector<int> state(sbf::K_COUNT, 0);
+    sbf::FskRx r;
+    sbf::FskLoader ld = {state.data(), 1, 0};
+    r.visit(ld);
+    r.win = win.data();
+    r.wspan = SBF_MAX_WINDOW;
+    r.ls = 1;
+    r.sine = sine.data();
+    r.out = out;
+    r.out_cap = out_cap;
+    r.nout = 0;
+    fsk_host_restart(r, spec5, framing_mode);
+    if (cutoff > -99.0f)
+    {
+        r.on_power = sbf::host_level_dbm0(cutoff + 2.5f - 5.3f);
+        r.off_power = sbf::host_level_dbm0(cutoff - 2.5f - 5.3f);
+    }
+    if (data_bits > 0)
+        r.set_frame_parameters(data_bits, parity, stop_bits);
+    if (chunk <= 0)
+        chunk = n;
+    int len;
+    for (int pos = 0;  pos < n;  pos += len)
+    {
+        if (restart_at >= 0  &&  pos >= restart_at)
+        {
+            fsk_host_restart(r, rspec5, restart_mode);
+            restart_at = -1;
+        }
+        len = (n - pos < chunk)  ?  (n - pos)  :  chunk;
+        // every chunk goes through the state arrays, as every kernel launch does
+        sbf::FskStorer st = {state.data(), 1, 0};
+        r.visit(st);
+        r.visit(ld);
+        if (fillin_at >= 0  &&  pos >= fillin_at  &&  pos < fillin_at + fillin_len)
+        {
+            for (int i = 0;  i < len;  i++)
+                r.fillin_sample();
+        }
+        else
+        {
+            for (int i = 0;  i < len;  i++)
+                r.sample(amp[pos + i]);
+        }
+    }
+    *nout = r.nout;
+    sbf::FskStorer st = {state.data(), 1, 0};
+    r.visit(st);
+    if (final)
+        memcpy(final, state.data(), sizeof(int)*sbf::K_COUNT);
+    if (window)
+        memcpy(window, win.data(), sizeof(int2)*2*SBF_MAX_WINDOW);
+    return 0;
+}
+
+EXPORT void hostsim_fsk_tables(int16_t *sine)
+{
+    std::vector<short> t;
+    sbf::make_dds_int_table(t);
+    memcpy(sine, t.data(), sizeof(short)*257);
 }

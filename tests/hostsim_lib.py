@@ -14,7 +14,7 @@ SYM_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     subprocess.run([os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
@@ -51,3 +51,25 @@ def run(modem, amp, bit_rate, chunk=160, cutoff=-100.0, restart_at=-1, restart_m
     if rc != 0:
         raise RuntimeError("hostsim run failed")
     return {"bits": bits[:nb.value].copy(), "syms": syms[:ns.value].copy(), "eq_coeff": eq, "final": fin}
+
+
+def fsk_run(amp, spec5, framing_mode=1, chunk=160, cutoff=-100.0, frame=(0, 0, 0), restart=(-1, None, 0), fillin=(-1, 0)):
+    """The FSK receiver of sb_fsk_rx.cuh on the host; same result layout as pyoracle.fsk_run.
+    spec5 = (freq_zero, freq_one, tx_level, min_level, baud_rate x 100)."""
+    amp = np.ascontiguousarray(amp, dtype=np.int16)
+    n = len(amp)
+    out = np.zeros(n * 2 + 64, dtype=np.int16)
+    nout = C.c_int32(0)
+    fin = np.zeros(28, dtype=np.int32)
+    win = np.zeros((2, 128, 2), dtype=np.int32)
+    s5 = np.asarray(spec5, dtype=np.int32)
+    r5 = np.asarray(restart[1] if restart[1] is not None else spec5, dtype=np.int32)
+    fn = lib().hostsim_fsk_run
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_void_p(s5.ctypes.data), C.c_int(framing_mode), C.c_float(cutoff),
+            C.c_int(frame[0]), C.c_int(frame[1]), C.c_int(frame[2]),
+            C.c_int(restart[0]), C.c_void_p(r5.ctypes.data), C.c_int(restart[2]), C.c_int(fillin[0]), C.c_int(fillin[1]),
+            C.c_void_p(out.ctypes.data), C.c_int(out.size), C.byref(nout), C.c_void_p(fin.ctypes.data), C.c_void_p(win.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("hostsim fsk run failed")
+    return {"out": out[:nout.value].copy(), "final": fin, "window": win}

@@ -1,6 +1,6 @@
 """cfg4 of BASELINE.json (8 192-channel V.29 9600 bit/s receive) and the same for V.17 14400 bit/s:
 Msamples/s of the receiver bank on the GPU with the reference's own build on the host cores beside it.
-MODEM=v29|v17|v27ter, MODEM_CHANNELS, MODEM_SAMPLES, MODEM_RATE from the environment."""
+MODEM=v29|v17|v27ter|fsk, MODEM_CHANNELS, MODEM_SAMPLES, MODEM_RATE from the environment."""
 import json
 import os
 import sys
@@ -17,7 +17,7 @@ from spandsp_b200 import engine  # noqa: E402
 MODEM = os.environ.get("MODEM", "v29")
 C = int(os.environ.get("MODEM_CHANNELS", os.environ.get("V29_CHANNELS", "8192")))
 T = int(os.environ.get("MODEM_SAMPLES", os.environ.get("V29_SAMPLES", "80000")))
-RATE = int(os.environ.get("MODEM_RATE", {"v29": "9600", "v17": "14400", "v27ter": "4800"}[MODEM]))
+RATE = int(os.environ.get("MODEM_RATE", {"v29": "9600", "v17": "14400", "v27ter": "4800", "fsk": "1"}[MODEM]))    # fsk: preset index
 CPU = int(os.environ.get("MODEM_CPU", "1"))
 S = po.load("strict") if po.available("strict") else None
 F = po.load("fast") if po.available("fast") else None
@@ -27,6 +27,9 @@ t0 = time.time()
 if MODEM == "v29":
     sig = np.stack([po.v29_generate(S, T, RATE, False, -13.0, c + 1, (c * 37) % 400, 1234567 + c, -50.0) for c in range(base)])
     Bank = engine.V29Bank
+elif MODEM == "fsk":
+    sig = np.stack([po.fsk_generate(S, T, RATE, 1.0, c + 1, 0, 0, 2, (c * 37) % 400, -1, 1234567 + c, -40.0) for c in range(base)])
+    Bank = None
 elif MODEM == "v27ter":
     sig = np.stack([po.v27ter_generate(S, T, RATE, False, -13.0, c + 1, (c * 37) % 400, -1, 0, 0, 1234567 + c, -50.0) for c in range(base)])
     Bank = engine.V27terBank
@@ -42,13 +45,16 @@ ws = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(ws)
 stream = ws.cuda_stream
 out = {"modem": MODEM, "bit_rate": RATE, "channels": C, "samples": T}
-for want in (0, 1):
-    bank = Bank(ctx, C, RATE, want_symbols=bool(want))
+for want in ((0,) if MODEM == "fsk" else (0, 1)):
+    bank = engine.FskBank(ctx, C, RATE, 1) if MODEM == "fsk" else Bank(ctx, C, RATE, want_symbols=bool(want))
     bank.rx_device(d.data_ptr(), T, T, stream)          # warm (allocations)
     torch.cuda.synchronize()
     times = []
     for _ in range(3):
-        bank.restart(RATE)
+        if MODEM == "fsk":
+            bank.restart(RATE, 1)
+        else:
+            bank.restart(RATE)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -56,7 +62,7 @@ for want in (0, 1):
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
-    nb, ns = bank.counts()
+    nb, ns = (bank.counts(), [0]) if MODEM == "fsk" else bank.counts()
     ms = min(times)
     out["symbols_%d" % want] = {"ms": ms, "msamples_s": C * T / ms / 1e3, "hbm_read_gbs": 2.0 * C * T / ms / 1e6,
                                 "bits_per_channel": int(nb[0]), "syms": int(ns[0])}
@@ -65,8 +71,11 @@ for want in (0, 1):
 if CPU:
     threads = len(os.sched_getaffinity(0))
     chans = min(C, threads * 16)
-    run = {"v29": po.v29_run_batch, "v17": po.v17_run_batch, "v27ter": po.v27ter_run_batch}[MODEM]
-    secs = run(F or S, amp[:chans], RATE, T, -100.0, threads)
+    if MODEM == "fsk":
+        secs = po.fsk_run_batch(F or S, amp[:chans], RATE, 1, T, threads)
+    else:
+        run = {"v29": po.v29_run_batch, "v17": po.v17_run_batch, "v27ter": po.v27ter_run_batch}[MODEM]
+        secs = run(F or S, amp[:chans], RATE, T, -100.0, threads)
     out["cpu_reference"] = {"msamples_s": chans * T / secs / 1e6, "threads": threads, "channels": chans, "kind": "fast" if F else "strict"}
     print(json.dumps(out["cpu_reference"]), flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bench_%s.json" % MODEM), "w"), indent=1)
