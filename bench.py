@@ -307,29 +307,41 @@ def main():
 
     ev_cap = C * (T // 102 // 2 + 1)
     d_events = None
+    comm_stream = None
     if world > 1:
-        # two buffers: the NCCL gather of step k-1 runs while the kernels of step k execute
+        # Two record buffers and a side stream for NCCL: the gather of step k-1 travels over NVLink while the
+        # kernels of step k execute.  ready[i]: buffer i holds a step's records (recorded on the work stream
+        # BEFORE the next step is launched, so the gather does not wait for that next step); done[i]: the
+        # gather that read buffer i has finished (the work stream waits for it before overwriting the buffer).
         d_events = [torch.empty((ev_cap, 6), dtype=torch.int32, device=dev) for _ in range(2)]
-    pending = {"n": None, "buf": None, "total": 0}
+        comm_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [None, None]
+    pending = {"n": None, "buf": None, "slot": 0, "total": 0}
 
-    def gather_events(buf, n_local):
+    def gather_events(buf, n_local, slot):
         """NCCL: event counts all-gathered, records gathered to rank 0 (padded to the max count)."""
-        cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        counts = [int(c.item()) for c in allc]
-        mx = max(max(counts), 1)
-        send = buf[:mx]
-        if rank == 0:
-            bufs = [torch.empty_like(send) for _ in range(world)]
-            dist.gather(send, bufs, dst=0)
-        else:
-            dist.gather(send, None, dst=0)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ready[slot])
+            cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
+            allc = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(allc, cnt)
+            counts = [int(c.item()) for c in allc]
+            mx = max(max(counts), 1)
+            send = buf[:mx]
+            if rank == 0:
+                bufs = [torch.empty_like(send) for _ in range(world)]
+                dist.gather(send, bufs, dst=0)
+            else:
+                dist.gather(send, None, dst=0)
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+            done[slot] = ev
         return sum(counts)
 
     def flush_gather():
         if pending["n"] is not None:
-            pending["total"] = gather_events(pending["buf"], pending["n"])
+            pending["total"] = gather_events(pending["buf"], pending["n"], pending["slot"])
             pending["n"] = None
 
     step_no = [0]
@@ -338,10 +350,15 @@ def main():
         bank.rx_device(d_amp.data_ptr(), T, T, stream)
         if world > 1:
             flush_gather()                                  # step k-1's records travel while step k computes
-            buf = d_events[step_no[0] & 1]
+            slot = step_no[0] & 1
+            buf = d_events[slot]
             step_no[0] += 1
+            if done[slot] is not None:
+                work_stream.wait_event(done[slot])          # the gather of step k-2 has released this buffer
             pending["n"] = bank.events_to_device(buf.data_ptr(), ev_cap, stream)
+            ready[slot].record(work_stream)
             pending["buf"] = buf
+            pending["slot"] = slot
             return pending["total"]
         n, ov = bank.event_count()
         return n
@@ -371,6 +388,7 @@ def main():
     if world > 1:
         flush_gather()
         total_events = pending["total"]
+        work_stream.wait_stream(comm_stream)                # the last gather is inside the timed region
     e1.record()
     barrier()
     sampler.mark_end()

@@ -118,7 +118,7 @@ def test_dtmf_random(gpu_ctx, engine_lib, torch_mod, port, chunk, mode):
     bank.close()
 
 
-@pytest.mark.parametrize("knob", [("variant", 8), ("packed", 0),
+@pytest.mark.parametrize("knob", [("variant", 1), ("variant", 2), ("variant", 3), ("packed", 0),
                                   ("direct", 1), ("slice", 3), ("slice", 1)])
 def test_dtmf_kernel_variants(gpu_ctx, engine_lib, torch_mod, port, knob):
     """Every staging variant, the scalar-add build, the direct kernel and odd slice lengths give
@@ -131,6 +131,68 @@ def test_dtmf_kernel_variants(gpu_ctx, engine_lib, torch_mod, port, knob):
     check(bank, amp, 16320, oracle_rows(ev, False), torch_mod)
     assert bank.last_path == ("direct" if knob[0] == "direct" else "staged")
     bank.close()
+
+
+def feed(bank, amp, cuts, g711=None):
+    """Feed amp in calls that end at the positions in `cuts` (host input, so every call is 16-byte aligned);
+    returns the events as rows in per-channel time order."""
+    per = [[] for _ in range(amp.shape[0])]
+    pos = 0
+    for end in list(cuts) + [amp.shape[1]]:
+        if end <= pos:
+            continue
+        if g711 is None:
+            bank.rx_host(np.ascontiguousarray(amp[:, pos:end]))
+        else:
+            bank.rx_host_g711(np.ascontiguousarray(amp[:, pos:end]), alaw=g711)
+        for e in bank.events():
+            per[int(e["channel"])].append((int(e["channel"]), int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])))
+        pos = end
+    return [r for ch in per for r in ch]
+
+
+@pytest.mark.parametrize("first", [37, 100, 5, 1001])
+def test_slices_off_the_vector_grid(gpu_ctx, engine_lib, torch_mod, port, first):
+    """A short first call leaves the block phase off the 8-sample vector grid, so in the long call that follows
+    every time slice starts inside a vector (masked slice head) and block boundaries fall at odd positions of the
+    straddling vectors.  The staged kernel must give what the direct kernel (per-sample loop) gives on the same
+    calls, and - for the chunk-invariant realtime events - what the oracle gives on the whole buffer."""
+    n = 20000
+    amp, _ = synth.dtmf_channels(40, n, seed=900 + first)
+    ev, fin, _ = port.run(po.make_params(po.DET_DTMF, po.MODE_REALTIME, n), amp)
+    rows = {}
+    for direct in (0, 1):
+        bank = engine_lib.Bank.dtmf(gpu_ctx, 40)
+        bank.dtmf_realtime(True)
+        bank.tune(2, direct)
+        rows[direct] = feed(bank, amp, [first])
+        assert bank.last_path == ("direct" if direct else "staged")
+        assert (bank.status() == fin["status"]).all()
+        bank.close()
+    assert rows[0] == rows[1]
+    assert rows[0] == normalise(oracle_rows(ev, False))
+    # the other block lengths (120, 133, 128) and companded input (its slice head takes the rolled loop)
+    amp = synth.mf_channels(33, n, synth.R2_FWD_FREQS, seed=first)
+    for make in (lambda: engine_lib.Bank.r2_mf(gpu_ctx, 33, True), lambda: engine_lib.Bank.bell_mf(gpu_ctx, 33)):
+        rows = {}
+        for direct in (0, 1):
+            bank = make()
+            bank.tune(2, direct)
+            rows[direct] = feed(bank, amp, [first])
+            bank.close()
+        assert rows[0] == rows[1] and len(rows[0]) > 0
+    amp, _ = synth.dtmf_channels(40, n, seed=901 + first)
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g711_golden.npz"))
+    data = G["encode_alaw"][amp.astype(np.int32) + 32768]
+    rows = {}
+    for direct in (0, 1):
+        bank = engine_lib.Bank.dtmf(gpu_ctx, 40)
+        bank.dtmf_realtime(True)
+        bank.tune(2, direct)
+        rows[direct] = feed(bank, data, [first], g711=True)
+        bank.close()
+    assert rows[0] == rows[1] and len(rows[0]) > 0
 
 
 def test_dtmf_host_input_and_unaligned(gpu_ctx, engine_lib, torch_mod, port):
