@@ -243,6 +243,38 @@ void fsk_rx_set_frame_parameters(fsk_rx_state_t *s, int data_bits, int parity, i
 int fsk_rx_get_parity_errors(fsk_rx_state_t *s, bool reset);
 int fsk_rx_get_framing_errors(fsk_rx_state_t *s, bool reset);
 
+/* ---- Modem connect tone detector (FAX CNG, CED / ANS and its variants, Bell ANS, calling tone, V.21 preamble):
+        src/spandsp/modem_connect_tones.h:57-188, src/modem_connect_tones.c:74-118,419-892 ---- */
+enum
+{
+    MODEM_CONNECT_TONES_NONE = 0,
+    MODEM_CONNECT_TONES_FAX_CNG = 1,
+    MODEM_CONNECT_TONES_ANS = 2,
+    MODEM_CONNECT_TONES_ANS_PR = 3,
+    MODEM_CONNECT_TONES_ANSAM = 4,
+    MODEM_CONNECT_TONES_ANSAM_PR = 5,
+    MODEM_CONNECT_TONES_FAX_PREAMBLE = 6,
+    MODEM_CONNECT_TONES_FAX_CED_OR_PREAMBLE = 7,
+    MODEM_CONNECT_TONES_BELL_ANS = 8,
+    MODEM_CONNECT_TONES_CALLING_TONE = 9,
+    MODEM_CONNECT_TONES_REAL_TIME_REPORTS = 0x1000
+};                                                                      /* src/spandsp/modem_connect_tones.h:57-90 */
+#define MODEM_CONNECT_TONES_FAX_CED MODEM_CONNECT_TONES_ANS             /* src/spandsp/modem_connect_tones.h:93 */
+
+typedef struct modem_connect_tones_rx_state_s modem_connect_tones_rx_state_t;
+
+/* Synchronous, one detector per state (a bank of one).  Banks of many detectors: spandsp_b200_mct.h.
+   With a tone_callback every change of the detected tone is reported through it, (user_data, tone, level, 0);
+   without one the last tone declared is kept for modem_connect_tones_rx_get(). */
+modem_connect_tones_rx_state_t *modem_connect_tones_rx_init(modem_connect_tones_rx_state_t *s, int tone_type,
+                                                            span_tone_report_func_t tone_callback, void *user_data);
+int modem_connect_tones_rx_release(modem_connect_tones_rx_state_t *s);
+int modem_connect_tones_rx_free(modem_connect_tones_rx_state_t *s);
+int modem_connect_tones_rx(modem_connect_tones_rx_state_t *s, const int16_t amp[], int len);
+int modem_connect_tones_rx_fillin(modem_connect_tones_rx_state_t *s, int len);
+int modem_connect_tones_rx_get(modem_connect_tones_rx_state_t *s);
+const char *modem_connect_tone_to_str(int tone);
+
 #if defined(__cplusplus)
 }
 #endif

@@ -407,6 +407,53 @@ def fsk_tables(o):
     return {"sine": sine, "derived": derived, "presets": presets}
 
 
+MCT_FINAL = 16
+
+
+def mct_generate(o, n, tone_type, freq=0.0, level_dbm0=1.0, mod_freq=0.0, lead=0, burst=-1, flags=40, lfsr_seed=1,
+                 noise_seed=1234567, noise_dbm0=-100.0, into=None):
+    """modem_connect_tones_tx (types 1..5, 8, 9) or V.21 ch 2 flags + data (type 6) ADDED into a buffer, then awgn.
+    level_dbm0 > 0 / freq <= 0 / mod_freq <= 0: the generator's defaults."""
+    amp = np.zeros(n, dtype=np.int16) if into is None else into
+    assert amp.dtype == np.int16 and len(amp) == n and amp.flags["C_CONTIGUOUS"]
+    o.lib.ref_mct_generate.restype = C.c_int
+    rc = o.lib.ref_mct_generate(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(tone_type), C.c_float(freq), C.c_float(level_dbm0),
+                                C.c_float(mod_freq), C.c_int(lead), C.c_int(burst), C.c_int(flags), C.c_uint32(lfsr_seed),
+                                C.c_int(noise_seed), C.c_float(noise_dbm0))
+    if rc < 0:
+        raise RuntimeError("ref_mct_generate failed")
+    return amp
+
+
+def mct_run(o, amp, tone_type, chunk=160, use_callback=True):
+    """One channel through the reference's modem_connect_tones_rx.  Returns dict(ev int32[n,3] = (call, tone, level),
+    final int32[16], fsk_final int32[28])."""
+    amp = np.ascontiguousarray(amp, dtype=np.int16)
+    n = len(amp)
+    cap = 4096
+    ev = np.zeros((cap, 3), dtype=np.int32)
+    nev = C.c_int32(0)
+    fin = np.zeros(MCT_FINAL, dtype=np.int32)
+    ffin = np.zeros(FSK_FINAL, dtype=np.int32)
+    o.lib.ref_mct_run.restype = C.c_int
+    rc = o.lib.ref_mct_run(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(tone_type), C.c_int(1 if use_callback else 0),
+                           C.c_void_p(ev.ctypes.data), C.c_int(cap), C.byref(nev), C.c_void_p(fin.ctypes.data), C.c_void_p(ffin.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("ref_mct_run failed")
+    if nev.value > cap:
+        raise RuntimeError("mct event buffer overflow")
+    return {"ev": ev[:nev.value].copy(), "final": fin, "fsk_final": ffin}
+
+
+def mct_run_batch(o, amp, tone_type, chunk=160, nthreads=1):
+    """Many channels, timing only (CPU baseline).  Returns seconds."""
+    amp = np.asarray(amp)
+    assert amp.dtype == np.int16 and amp.ndim == 2 and amp.strides[1] == 2
+    o.lib.ref_mct_run_batch.restype = C.c_double
+    return o.lib.ref_mct_run_batch(C.c_void_p(amp.ctypes.data), C.c_int64(amp.strides[0] // 2), C.c_int(amp.shape[0]), C.c_int(amp.shape[1]),
+                                   C.c_int(chunk), C.c_int(tone_type), C.c_int(nthreads))
+
+
 _cache = {}
 
 

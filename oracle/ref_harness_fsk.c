@@ -154,7 +154,7 @@ static void fsk_put_bit(void *user, int bit)
     r->n++;
 }
 
-static void fsk_final(fsk_rx_state_t *rx, int32_t *final, int32_t *window)
+void ref_fsk_final(fsk_rx_state_t *rx, int32_t *final, int32_t *window)
 {
     int j;
     int k;
@@ -245,7 +245,7 @@ EXPORT int ref_fsk_run(const int16_t *amp, int n, int chunk, int spec, int frami
             fsk_rx(rx, amp + pos, len);
     }
     *nout = rec.n;
-    fsk_final(rx, final, window);
+    ref_fsk_final(rx, final, window);
     fsk_rx_free(rx);
     return 0;
 }

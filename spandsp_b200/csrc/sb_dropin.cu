@@ -19,6 +19,7 @@
 #include "../../include/spandsp_b200_v17.h"
 #include "../../include/spandsp_b200_v27ter.h"
 #include "../../include/spandsp_b200_fsk.h"
+#include "../../include/spandsp_b200_mct.h"
 #pragma GCC visibility pop
 
 #define SB_MAGIC    0x5350414E42323030ULL       /* "SPANB200" */
@@ -1687,4 +1688,142 @@ extern "C" int fsk_rx_fillin(fsk_rx_state_t *s, int len)
 {
     span_b200_fsk_bank_fillin(s->bank, 0, 1, len);
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Modem connect tone detector, one bank of one per state object (src/modem_connect_tones.c:74-118,419-892)
+struct modem_connect_tones_rx_state_s
+{
+    unsigned long long magic;
+    span_b200_mct_bank_t *bank;
+    int heap;
+    int hit;
+    span_tone_report_func_t tone_callback;
+    void *callback_data;
+    std::vector<span_b200_mct_event_t> *ev;
+};
+
+static_assert(sizeof(modem_connect_tones_rx_state_s) <= 2300, "must fit the reference's modem_connect_tones_rx_state_t");
+
+extern "C" const char *modem_connect_tone_to_str(int tone)
+{
+    switch (tone)                                           // src/modem_connect_tones.c:74-103
+    {
+    case MODEM_CONNECT_TONES_NONE:
+        return "No tone";
+    case MODEM_CONNECT_TONES_FAX_CNG:
+        return "FAX CNG";
+    case MODEM_CONNECT_TONES_ANS:
+        return "ANS or FAX CED";
+    case MODEM_CONNECT_TONES_ANS_PR:
+        return "ANS/";
+    case MODEM_CONNECT_TONES_ANSAM:
+        return "ANSam";
+    case MODEM_CONNECT_TONES_ANSAM_PR:
+        return "ANSam/";
+    case MODEM_CONNECT_TONES_FAX_PREAMBLE:
+        return "FAX preamble";
+    case MODEM_CONNECT_TONES_FAX_CED_OR_PREAMBLE:
+        return "FAX CED or preamble";
+    case MODEM_CONNECT_TONES_BELL_ANS:
+        return "Bell ANS";
+    case MODEM_CONNECT_TONES_CALLING_TONE:
+        return "Calling tone";
+    }
+    return "???";
+}
+
+extern "C" modem_connect_tones_rx_state_t *modem_connect_tones_rx_init(modem_connect_tones_rx_state_t *s, int tone_type,
+                                                                       span_tone_report_func_t tone_callback, void *user_data)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    span_b200_ctx_t *ctx = span_b200_default_ctx();
+    if (ctx == NULL)
+        return NULL;
+    int heap = 0;
+    if (s != NULL  &&  s->magic == SB_MAGIC  &&  s->bank != NULL)
+    {
+        // a second init of a live state keeps its bank (the reference re-initialises in place)
+        if (span_b200_mct_bank_init(s->bank, 0, 1, tone_type) != 0)
+            return NULL;
+        s->hit = MODEM_CONNECT_TONES_NONE;
+        s->tone_callback = tone_callback;
+        s->callback_data = user_data;
+        return s;
+    }
+    if (s == NULL)
+    {
+        if ((s = (modem_connect_tones_rx_state_t *) calloc(1, sizeof(*s))) == NULL)
+            return NULL;
+        heap = 1;
+    }
+    memset(s, 0, sizeof(*s));
+    s->bank = span_b200_mct_bank_create(ctx, 1, tone_type);
+    if (s->bank == NULL)
+    {
+        if (heap)
+            free(s);
+        return NULL;
+    }
+    s->magic = SB_MAGIC;
+    s->heap = heap;
+    s->hit = MODEM_CONNECT_TONES_NONE;
+    s->tone_callback = tone_callback;
+    s->callback_data = user_data;
+    s->ev = new std::vector<span_b200_mct_event_t>();
+    return s;
+}
+
+static int mct_close(modem_connect_tones_rx_state_t *s, int do_free)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (s == NULL  ||  s->magic != SB_MAGIC)
+        return 0;
+    span_b200_mct_bank_destroy(s->bank);
+    delete s->ev;
+    const int heap = s->heap;
+    s->magic = 0;
+    s->bank = NULL;
+    if (do_free  &&  heap)
+        free(s);
+    return 0;
+}
+
+extern "C" int modem_connect_tones_rx_release(modem_connect_tones_rx_state_t *s) { return mct_close(s, 0); }
+extern "C" int modem_connect_tones_rx_free(modem_connect_tones_rx_state_t *s) { return mct_close(s, 1); }
+
+extern "C" int modem_connect_tones_rx(modem_connect_tones_rx_state_t *s, const int16_t amp[], int len)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (len <= 0)
+        return 0;
+    if (span_b200_mct_bank_rx_host(s->bank, amp, len, len, NULL) != 0)
+        return 0;
+    int64_t n = span_b200_mct_bank_events(s->bank, NULL, 0);
+    if (n <= 0)
+        return 0;
+    s->ev->resize((size_t) n);
+    n = span_b200_mct_bank_events(s->bank, s->ev->data(), n);
+    for (int64_t i = 0;  i < n;  i++)
+    {
+        const span_b200_mct_event_t &e = (*s->ev)[(size_t) i];
+        // report_tone_state() (src/modem_connect_tones.c:419-438): the callback, or else the hit
+        if (s->tone_callback)
+            s->tone_callback(s->callback_data, e.tone, e.level, 0);
+        else if (e.tone != MODEM_CONNECT_TONES_NONE)
+            s->hit = e.tone;
+    }
+    return 0;                                               // src/modem_connect_tones.c:803
+}
+
+extern "C" int modem_connect_tones_rx_fillin(modem_connect_tones_rx_state_t *s, int len)
+{
+    return 0;                                               // src/modem_connect_tones.c:806-809: nothing is done
+}
+
+extern "C" int modem_connect_tones_rx_get(modem_connect_tones_rx_state_t *s)
+{
+    const int x = s->hit;                                   // src/modem_connect_tones.c:812-820
+    s->hit = MODEM_CONNECT_TONES_NONE;
+    return x;
 }

@@ -487,6 +487,8 @@ constexpr int fsk_smem_bytes(int wspan)
     return (SBF_SINE_PAD/2 + 2)*4 + wspan*2*32*8;
 }
 
+#if !defined(SBF_NO_FSK_KERNELS)       // sb_mct.cu embeds the receiver in its own kernel and does not want these
+
 // fsk_rx() for 32 channels per CTA (one warp), one thread per channel: the receiver is a short sequential
 // integer state machine per sample; the per-channel correlation windows sit in shared memory lane-interleaved
 // (conflict-free for any per-lane window position), samples arrive as 16-byte loads per lane.
@@ -569,6 +571,8 @@ __global__ void __launch_bounds__(32) fsk_ctl_kernel(const FskArgs a, int first,
     FskStorer st = {a.state, (size_t) a.channels, (size_t) c};
     r.visit(st);
 }
+
+#endif  // SBF_NO_FSK_KERNELS
 
 #endif  // __CUDACC__
 

@@ -131,6 +131,15 @@ def lib():
         "span_b200_fsk_bank_signal_power": (f32, [vp, i32]),
         "span_b200_fsk_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_dds_int_table": (i32, [vp]),
+        "span_b200_mct_bank_create": (vp, [vp, i32, i32]),
+        "span_b200_mct_bank_destroy": (None, [vp]),
+        "span_b200_mct_bank_channels": (i32, [vp]),
+        "span_b200_mct_bank_init": (i32, [vp, i32, i32, i32]),
+        "span_b200_mct_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_mct_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_mct_bank_events": (i64, [vp, vp, i64]),
+        "span_b200_mct_bank_get": (i32, [vp, i32, i32, vp]),
+        "span_b200_mct_bank_channel_state": (i32, [vp, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -529,6 +538,59 @@ class FskBank:
     def close(self):
         if self.h:
             lib().span_b200_fsk_bank_destroy(self.h)
+            self.h = None
+
+
+MCT_EVENT_DTYPE = np.dtype([("channel", "<i4"), ("tone", "<i4"), ("level", "<i4")])
+
+
+class MctBank:
+    """N modem connect tone detectors (span_b200_mct_bank_create); tone_type as the reference's MODEM_CONNECT_TONES_*."""
+
+    def __init__(self, ctx, channels, tone_type):
+        self.ctx = ctx
+        self.h = lib().span_b200_mct_bank_create(ctx.h, channels, tone_type)
+        if not self.h:
+            raise EngineError(_err())
+        self.channels = channels
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    def init(self, tone_type, first=0, count=None):
+        self._ck(lib().span_b200_mct_bank_init(self.h, first, self.channels - first if count is None else count, tone_type))
+
+    def rx_device(self, d_ptr, stride, samples, stream=None):
+        self._ck(lib().span_b200_mct_bank_rx_device(self.h, d_ptr, stride, samples, stream))
+
+    def rx_host(self, amp, stream=None):
+        assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
+        self._ck(lib().span_b200_mct_bank_rx_host(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
+
+    def events(self):
+        n = self._ck(lib().span_b200_mct_bank_events(self.h, None, 0))
+        ev = np.zeros(n, dtype=MCT_EVENT_DTYPE)
+        if n:
+            self._ck(lib().span_b200_mct_bank_events(self.h, ev.ctypes.data, n))
+        return ev
+
+    def get(self, first=0, count=None):
+        n = self.channels - first if count is None else count
+        hits = np.zeros(n, dtype=np.int32)
+        self._ck(lib().span_b200_mct_bank_get(self.h, first, n, hits.ctypes.data))
+        return hits
+
+    def channel_state(self, channel):
+        info = np.zeros(17, dtype=np.int32)
+        fsk = np.zeros(28, dtype=np.int32)
+        self._ck(lib().span_b200_mct_bank_channel_state(self.h, channel, info.ctypes.data, fsk.ctypes.data))
+        return info, fsk
+
+    def close(self):
+        if self.h:
+            lib().span_b200_mct_bank_destroy(self.h)
             self.h = None
 
 

@@ -8,6 +8,7 @@
 #include "../../spandsp_b200/csrc/sb_v17_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_v27ter_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_fsk_rx.cuh"
+#include "../../spandsp_b200/csrc/sb_mct_rx.cuh"
 
 using namespace sbm;
 
@@ -371,6 +372,77 @@ EXPORT int hostsim_fsk_run(const int16_t *amp, int n, int chunk, const int32_t *
         memcpy(final, state.data(), sizeof(int)*sbf::K_COUNT);
     if (window)
         memcpy(window, win.data(), sizeof(int2)*2*SBF_MAX_WINDOW);
+    return 0;
+}
+
+// modem_connect_tones_rx() in `chunk`-sample calls on the host: ev[] = {call index, tone, level} per report;
+// final[17] = the M_* fields, fsk_final[28] = the K_* fields of the embedded V.21 receiver
+EXPORT int hostsim_mct_run(const int16_t *amp, int n, int chunk, int tone_type, int32_t *ev, int ev_cap, int32_t *nev,
+                           int32_t *final, int32_t *fsk_final)
+{
+    static std::vector<short> sine;
+    if (sine.empty())
+        sbf::make_dds_int_table(sine);
+    std::vector<int2> win(2*SBF_MAX_WINDOW, make_int2(0, 0));
+    std::vector<int> state(sbf::M_COUNT, 0);
+    std::vector<int2> rep(64);
+    sbf::MctRx r;
+    sbf::FskLoader ld = {state.data(), 1, 0};
+    sbf::FskStorer st = {state.data(), 1, 0};
+    r.fsk.visit(ld);
+    r.visit_own(ld, true);
+    r.fsk.win = win.data();
+    r.fsk.wspan = SBF_MAX_WINDOW;
+    r.fsk.ls = 1;
+    r.fsk.sine = sine.data();
+    r.init(tone_type);
+    if (r.uses_v21())
+    {
+        r.fsk.restart(300*100, sbf::FRAME_MODE_SYNC, sbf::host_dds_int_phase_rate(1850.0f), sbf::host_dds_int_phase_rate(1650.0f),
+                      sbf::host_level_dbm0(-45.5f + 2.5f - 5.3f), sbf::host_level_dbm0(-45.5f - 2.5f - 5.3f));
+    }
+    if (chunk <= 0)
+        chunk = n;
+    int len;
+    int total = 0;
+    int call = 0;
+    for (int pos = 0;  pos < n;  pos += len, call++)
+    {
+        len = (n - pos < chunk)  ?  (n - pos)  :  chunk;
+        // every chunk goes through the state arrays, as every kernel launch does
+        r.fsk.visit(st);
+        r.visit_own(st, false);
+        r.fsk.visit(ld);
+        r.visit_own(ld, true);
+        r.ev = rep.data();
+        r.ev_cap = (int) rep.size();
+        r.nev = 0;
+        if (r.uses_v21())
+        {
+            for (int i = 0;  i < len;  i++)
+                r.preamble_sample(amp[pos + i]);
+        }
+        for (int i = 0;  i < len;  i++)
+            r.tone_sample(amp[pos + i]);
+        if (r.nev > r.ev_cap)
+            return -1;
+        for (int i = 0;  i < r.nev;  i++, total++)
+        {
+            if (total < ev_cap)
+            {
+                ev[3*total] = call;
+                ev[3*total + 1] = rep[i].x & 0xFFFF;
+                ev[3*total + 2] = sbf::host_mct_level(rep[i].x >> 16, rep[i].y);
+            }
+        }
+    }
+    *nev = total;
+    r.fsk.visit(st);
+    r.visit_own(st, false);
+    if (final)
+        memcpy(final, state.data() + sbf::K_COUNT, sizeof(int)*(sbf::M_COUNT - sbf::K_COUNT));
+    if (fsk_final)
+        memcpy(fsk_final, state.data(), sizeof(int)*sbf::K_COUNT);
     return 0;
 }
 

@@ -14,7 +14,7 @@ SYM_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh", "sb_mct_rx.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     subprocess.run([os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
@@ -73,3 +73,22 @@ def fsk_run(amp, spec5, framing_mode=1, chunk=160, cutoff=-100.0, frame=(0, 0, 0
     if rc != 0:
         raise RuntimeError("hostsim fsk run failed")
     return {"out": out[:nout.value].copy(), "final": fin, "window": win}
+
+
+def mct_run(amp, tone_type, chunk=160):
+    """The modem connect tone detector of sb_mct_rx.cuh on the host; same result layout as pyoracle.mct_run
+    (final has a 17th entry, the accumulated hit)."""
+    amp = np.ascontiguousarray(amp, dtype=np.int16)
+    n = len(amp)
+    cap = 4096
+    ev = np.zeros((cap, 3), dtype=np.int32)
+    nev = C.c_int32(0)
+    fin = np.zeros(17, dtype=np.int32)
+    ffin = np.zeros(28, dtype=np.int32)
+    fn = lib().hostsim_mct_run
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_int(tone_type), C.c_void_p(ev.ctypes.data), C.c_int(cap),
+            C.byref(nev), C.c_void_p(fin.ctypes.data), C.c_void_p(ffin.ctypes.data))
+    if rc != 0 or nev.value > cap:
+        raise RuntimeError("hostsim mct run failed")
+    return {"ev": ev[:nev.value].copy(), "final": fin, "fsk_final": ffin}
