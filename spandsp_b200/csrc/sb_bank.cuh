@@ -139,6 +139,27 @@ struct Runner
         return famp;
     }
 
+    // The resonators of all bins, one sample
+    __device__ __forceinline__ void bins(float x)
+    {
+        // The first NPACK pairs use the 2-wide add/sub (FADD2), the rest scalar FADDs: the mix is a
+        // tuning knob (FADD2 saves issue slots but is not spread over the FP32 sub-pipes like FADD).
+        // NPACK > NP: the multiply is 2-wide as well (FFMA2 with a zero addend, sb_common.cuh): 3 issue slots
+        // per pair and sample instead of 4.
+#pragma unroll
+        for (int p = 0;  p < NP;  p++)
+        {
+            const pair_t v1 = v2[p];
+            v2[p] = v3[p];
+            if (NPACK > NP)
+                v3[p] = padd_scalar<true>(psub<true>(pmul_packed(fac[p], v2[p]), v1), x);
+            else if (p < NPACK)
+                v3[p] = padd_scalar<true>(psub<true>(pmul(fac[p], v2[p]), v1), x);
+            else
+                v3[p] = padd_scalar<false>(psub<false>(pmul(fac[p], v2[p]), v1), x);
+        }
+    }
+
     template <bool FILT>
     __device__ __forceinline__ void step(float x)
     {
@@ -149,18 +170,7 @@ struct Runner
         }
         if (DET::ENERGY)
             energy = fadd(energy, fmul(x, x));              // src/dtmf.c:189, super_tone_rx.c:477
-        // The first NPACK pairs use the 2-wide add/sub (FADD2), the rest scalar FADDs: the mix is a
-        // tuning knob (FADD2 saves issue slots but is not spread over the FP32 sub-pipes like FADD).
-#pragma unroll
-        for (int p = 0;  p < NP;  p++)
-        {
-            const pair_t v1 = v2[p];
-            v2[p] = v3[p];
-            if (p < NPACK)
-                v3[p] = padd_scalar<true>(psub<true>(pmul(fac[p], v2[p]), v1), x);
-            else
-                v3[p] = padd_scalar<false>(psub<false>(pmul(fac[p], v2[p]), v1), x);
-        }
+        bins(x);
     }
 
     // End of a detection block: finish the bins, decide, emit, reset.
@@ -209,9 +219,34 @@ struct Runner
     template <bool FILT>
     __device__ __forceinline__ void fast8f(const float (&x)[8])
     {
+        if constexpr (DET::ENERGY  &&  (NPACK > NP)  &&  !(DET::FILTER  &&  FILT))
+        {
+            // The squares for the block energy two at a time (a square is never -0, so pmul_packed is exact);
+            // the sum itself stays sequential, in the reference's order
+            float sq[8];
 #pragma unroll
-        for (int i = 0;  i < 8;  i++)
-            step<FILT>(x[i]);
+            for (int i = 0;  i < 8;  i += 2)
+            {
+                pair_t xx;
+                xx.x = x[i];
+                xx.y = x[i + 1];
+                const pair_t q = pmul_packed(xx, xx);
+                sq[i] = q.x;
+                sq[i + 1] = q.y;
+            }
+#pragma unroll
+            for (int i = 0;  i < 8;  i++)
+            {
+                energy = fadd(energy, sq[i]);
+                bins(x[i]);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0;  i < 8;  i++)
+                step<FILT>(x[i]);
+        }
     }
 
     template <bool FILT>

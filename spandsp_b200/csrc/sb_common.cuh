@@ -23,9 +23,10 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 
 // ---- two-bin packed state --------------------------------------------------------------
 // A pair holds two independent Goertzel bins (for DTMF: row_i in .x, col_i in .y).  On sm_100a
-// add/sub have a 2-wide form (FADD2) that halves the issue slots of the recurrence.  The
-// multiply stays scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + sub.rn.f32x2 into a
-// single FFMA2 even with explicit .rn and --fmad=false, which would change the rounding.
+// add/sub have a 2-wide form (FADD2) that halves the issue slots of the recurrence.  The 2-wide
+// multiply cannot be written as mul.rn.f32x2: ptxas 12.9 contracts mul.rn.f32x2 + sub.rn.f32x2 into a
+// single FFMA2 even with explicit .rn and --fmad=false, which would change the rounding.  pmul_packed()
+// below gets the 2-wide multiply another way.
 struct pair_t
 {
     float x;
@@ -85,6 +86,20 @@ __device__ __forceinline__ pair_t pmul(pair_t a, pair_t b)
     r.x = fmul(a.x, b.x);
     r.y = fmul(a.y, b.y);
     return r;
+}
+
+// The 2-wide multiply as an explicit FMA with a +0 addend: fma(a, b, +0) rounds the exact product once, i.e. it IS
+// the IEEE product, except that a product of -0 comes out as +0.  ptxas keeps it as FFMA2 Rd, Ra, Rb, RZ (it has
+// nothing to contract it with).  The one caller is the Goertzel recurrence v3 = (fac*v2 - v1) + x, where the sign
+// of a zero product cannot reach v3: (+-0 - v1) differs only for v1 = +0 (giving -0 vs +0), and adding x - a
+// sample, never -0 - maps both to the same value.
+__device__ __forceinline__ pair_t pmul_packed(pair_t a, pair_t b)
+{
+    u64 r;
+    u64 z;
+    asm("mov.b64 %0, 0;" : "=l"(z));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)), "l"(z));
+    return unpack2(r);
 }
 
 // ---- cp.async (LDGSTS) 16-byte copies with zero fill ------------------------------------

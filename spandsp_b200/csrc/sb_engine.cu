@@ -360,7 +360,7 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
     b->bins = bins;
     b->npairs = (bins + 1)/2;
     b->uniform_cs = 0;
-    b->tune_packed = 4;
+    b->tune_packed = 5;
     b->last_path = "";
     const size_t C = channels;
     CKP(cudaMalloc(&b->v2, sizeof(float)*2*b->npairs*C));
@@ -925,10 +925,10 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
         if (g.staged)
         {
             b->last_path = "staged";
-            return launch_staged<DET, 8, 2, 4, 4, DET::NPAIRS, true>(a, filter, st);
+            return launch_staged<DET, 8, 2, 4, 4, DET::NPAIRS + 1, true>(a, filter, st);
         }
         b->last_path = "direct";
-        bank_kernel_direct<DET, DET::NPAIRS, true><<<(a.channels + 127)/128, 128, 0, st>>>(a);
+        bank_kernel_direct<DET, DET::NPAIRS + 1, true><<<(a.channels + 127)/128, 128, 0, st>>>(a);
         CK(cudaGetLastError());
         return 0;
     }
@@ -939,16 +939,22 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
     if (g.staged)
     {
         b->last_path = "staged";
-        // Knob 3 = 0 selects scalar FADDs instead of FADD2 (DTMF only; kept for the comparison in
-        // packed is 7-9 % faster, mixing packed and scalar pairs brings nothing).
-        if (all_variants  &&  b->tune_packed == 0)
-            return launch_variant<DET, 0>(a, filter, st);
-        return launch_variant<DET, DET::NPAIRS>(a, filter, st, (all_variants)  ?  b->tune_variant  :  0);
+        // Default: 2-wide multiply, subtract and add (NPACK = NPAIRS + 1).  DTMF keeps the earlier forms behind
+        // knob 3 for the comparison in DESIGN.md: 0 = all scalar, 4 = scalar FMUL + FADD2 (also what the
+        // occupancy variants of knob 1 are built with).
+        if constexpr (std::is_same<DET, DtmfDet>::value)
+        {
+            if (all_variants  &&  b->tune_packed == 0)
+                return launch_variant<DET, 0>(a, filter, st);
+            if (all_variants  &&  (b->tune_packed == 4  ||  b->tune_variant != 0))
+                return launch_variant<DET, DET::NPAIRS>(a, filter, st, b->tune_variant);
+        }
+        return launch_variant<DET, DET::NPAIRS + 1>(a, filter, st);
     }
     b->last_path = "direct";
     const int grid = (a.channels + 127)/128;
     if (b->tune_packed  ||  !all_variants)
-        bank_kernel_direct<DET, DET::NPAIRS, false><<<grid, 128, 0, st>>>(a);
+        bank_kernel_direct<DET, DET::NPAIRS + 1, false><<<grid, 128, 0, st>>>(a);
     else
         bank_kernel_direct<DET, 0, false><<<grid, 128, 0, st>>>(a);
     CK(cudaGetLastError());
@@ -1450,7 +1456,7 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
         a.nslices = (nb > L)  ?  ((nb + L - 1)/L)  :  1;
         return launch_staged<RawDet<NP>, 8, 2, 4, 4, NP>(a, false, st);
     }
-    bank_kernel_direct<RawDet<NP>, NP, false><<<(channels + 127)/128, 128, 0, st>>>(a);
+    bank_kernel_direct<RawDet<NP>, RawDet<NP>::NPAIRS + 1, false><<<(channels + 127)/128, 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return 0;
 }
