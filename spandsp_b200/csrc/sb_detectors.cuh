@@ -57,23 +57,28 @@ struct EventSink
 
     __device__ __forceinline__ EventSink(const SeqCommon &qq, int warp_global) : q(qq)
     {
-        base = (EMIT)  ?  qq.offsets[warp_global]  :  0;
+        // (a CTA's trailing warps may lie wholly beyond the last channel: they have no slot in offsets[] / counts[])
+        base = (EMIT  &&  warp_global*32 < qq.channels)  ?  qq.offsets[warp_global]  :  0;
         lt = (1u << (threadIdx.x & 31)) - 1u;
     }
 
-    __device__ __forceinline__ void push(bool has, int c, int blk, int kind, int a, int b, int cc)
+    // Returns the position the event was written to (emit pass, has == true), else 0
+    __device__ __forceinline__ unsigned int push(bool has, int c, int blk, int kind, int a, int b, int cc)
     {
+        unsigned int pos = 0;
         if (EMIT)
         {
             const unsigned int m = __ballot_sync(0xFFFFFFFFu, has);
+            pos = base + __popc(m & lt);
             if (has)
-                put_event(q, base + __popc(m & lt), c, blk, kind, a, b, cc);
+                put_event(q, pos, c, blk, kind, a, b, cc);
             base += __popc(m);
         }
         else
         {
             base += (has)  ?  1u  :  0u;        // count pass: per lane, reduced once at the end
         }
+        return pos;
     }
 
     __device__ __forceinline__ void finish(int warp_global)
@@ -81,7 +86,7 @@ struct EventSink
         if (!EMIT)
         {
             const unsigned int total = __reduce_add_sync(0xFFFFFFFFu, base);
-            if ((threadIdx.x & 31) == 0)
+            if ((threadIdx.x & 31) == 0  &&  warp_global*32 < q.channels)
                 q.counts[warp_global] = total;
         }
     }
@@ -227,10 +232,80 @@ __device__ __forceinline__ int dtmf_level(const DtmfSeqArgs &s, float energy)
     return s.level_min + lo;
 }
 
-// src/dtmf.c:201-207 (duration) and 304-347 (two-block debounce).
+// One block decision through the debounce / duration logic of src/dtmf.c:201-207,304-347
+// DEFER: the level of a "tone on" report is not computed here (it needs the block energy from global memory and a
+// table search, neither of which the state machine depends on); need_level tells the caller to fill it in later.
+template <bool EMIT, bool DEFER>
+__device__ __forceinline__ void dtmf_seq_block(const DtmfSeqArgs &s, int c, int b, int len, int hit, bool realtime,
+                                               int &in_digit, int &last_hit, int &dur,
+                                               bool &ev, int &ev_kind, int &ev_a, int &ev_b, int &ev_c, bool &need_level)
+{
+    if (dur < INT_MAX - len)
+        dur += len;
+    if (hit != in_digit  &&  last_hit != in_digit)
+    {
+        hit = (hit  &&  hit == last_hit)  ?  hit  :  0;
+        if (realtime)
+        {
+            if (in_digit  ||  hit)
+            {
+                ev = true;
+                ev_kind = SPAN_B200_EV_TONE;
+                ev_a = hit;
+                ev_c = dur;
+                if (in_digit  &&  !hit)
+                    ev_b = -99;
+                else if (EMIT  &&  DEFER)
+                    need_level = true;
+                else if (EMIT)
+                    ev_b = dtmf_level(s, s.eout[(size_t) b*s.q.channels + c]);
+                dur = 0;
+            }
+        }
+        else if (hit)
+        {
+            ev = true;
+            ev_kind = SPAN_B200_EV_DIGIT;
+            ev_a = hit;
+        }
+        in_digit = hit;
+    }
+    last_hit = hit;
+}
+
+#define SB_SEQ_TILE     112             // block rows staged per tile (cfg2: 784 blocks = 7 tiles)
+#define SB_SEQ_LEVELS   1024            // level table entries kept in shared memory (the table has ~830)
+#define SB_SEQ_QUEUE    16              // deferred levels per thread and tile
+
+// dtmf_level() over a copy of the table in shared memory
+__device__ __forceinline__ int dtmf_level_tab(const float *tab, int n, int level_min, float energy)
+{
+    int lo = 0;
+    int hi = n;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid] <= energy)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return level_min + lo;
+}
+
+// The per-channel sequencer is a short serial state machine over the block decisions; left to itself it is bound
+// by the latency of its one-byte loads (the round-1 version took 0.25 ms per pass for 51 MB of codes).  Where the
+// bank has one block phase and a channel count that keeps the rows 16-byte aligned, the CTA stages the decisions
+// of its 128 channels through shared memory in tiles of SB_SEQ_TILE block rows (16-byte cp.async, double
+// buffered): a handful of memory round trips per CTA instead of one or more per block.
 template <bool EMIT>
 __global__ void __launch_bounds__(128) dtmf_sequencer(const DtmfSeqArgs s)
 {
+    __shared__ __align__(16) unsigned char tile[2][SB_SEQ_TILE*128];
+    // Emit pass: the level table, and per thread a short queue of "tone on" reports whose level is still owed
+    __shared__ float lvl_tab[(EMIT)  ?  SB_SEQ_LEVELS  :  1];
+    __shared__ unsigned int q_pos[(EMIT)  ?  SB_SEQ_QUEUE  :  1][128];
+    __shared__ unsigned short q_row[(EMIT)  ?  SB_SEQ_QUEUE  :  1][128];
     const int gc = blockIdx.x*blockDim.x + threadIdx.x;
     const int wg = gc >> 5;
     const bool live = (gc < s.q.channels);
@@ -238,67 +313,128 @@ __global__ void __launch_bounds__(128) dtmf_sequencer(const DtmfSeqArgs s)
     const int B = DtmfDet::BLOCK;
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
     const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
-    const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
     const bool realtime = (s.flags[c] & SB_DTMF_FLAG_REALTIME) != 0;
     int in_digit = s.in_digit[c];
     int last_hit = s.last_hit[c];
     int dur = s.duration[c];
     EventSink<EMIT> sink(s.q, wg);
 
-    // The decision codes of a group of blocks are fetched together: the loads do not depend on the
-    // state machine, and issuing them back to back hides the memory latency a one-by-one walk exposes.
-    constexpr int G = 16;
-    for (int b0 = 0;  b0 < nb_max;  b0 += G)
+    if (s.q.cs0 >= 0  &&  (s.q.channels & 15) == 0  &&  s.level_n <= SB_SEQ_LEVELS)
     {
-        unsigned char codes[G];
-#pragma unroll
-        for (int i = 0;  i < G;  i++)
-            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*s.q.channels + c]  :  (unsigned char) 0;
-#pragma unroll
-        for (int i = 0;  i < G;  i++)
+        if (EMIT)
         {
-            const int b = b0 + i;
-            bool ev = false;
-            int ev_kind = 0;
-            int ev_a = 0;
-            int ev_b = 0;
-            int ev_c = 0;
-            if (b < nb)
+            for (int i = threadIdx.x;  i < s.level_n;  i += 128)
+                lvl_tab[i] = s.level_thr[i];                // visible after the first __syncthreads() below
+        }
+        int qn = 0;
+        const int nbu = (s.q.cs0 + s.q.n)/B;                // the same for every channel
+        const int ntiles = (nbu + SB_SEQ_TILE - 1)/SB_SEQ_TILE;
+        const int c0 = blockIdx.x*128;
+        auto issue = [&](int t)
+        {
+            if (t < ntiles)
             {
-                const int len = (b == 0)  ?  (B - cs_old)  :  B;
-                if (dur < INT_MAX - len)
-                    dur += len;
-                int hit = codes[i];
-                if (hit != in_digit  &&  last_hit != in_digit)
+                const uint32_t dst0 = (uint32_t) __cvta_generic_to_shared(tile[t & 1]);
+                for (int k = threadIdx.x;  k < SB_SEQ_TILE*8;  k += 128)
                 {
-                    hit = (hit  &&  hit == last_hit)  ?  hit  :  0;
-                    if (realtime)
-                    {
-                        if (in_digit  ||  hit)
-                        {
-                            ev = true;
-                            ev_kind = SPAN_B200_EV_TONE;
-                            ev_a = hit;
-                            ev_c = dur;
-                            if (in_digit  &&  !hit)
-                                ev_b = -99;
-                            else if (EMIT)
-                                ev_b = dtmf_level(s, s.eout[(size_t) b*s.q.channels + c]);
-                            dur = 0;
-                        }
-                    }
-                    else if (hit)
-                    {
-                        ev = true;
-                        ev_kind = SPAN_B200_EV_DIGIT;
-                        ev_a = hit;
-                    }
-                    in_digit = hit;
+                    const int row = k >> 3;
+                    const int piece = k & 7;
+                    const int b = t*SB_SEQ_TILE + row;
+                    const bool ok = (b < nbu  &&  c0 + 16*piece < s.q.channels);
+                    const unsigned char *src = (ok)  ?  (s.code + (size_t) b*s.q.channels + c0 + 16*piece)  :  s.code;
+                    cp_async_16(dst0 + row*128 + piece*16, src, (ok)  ?  16  :  0);
                 }
-                last_hit = hit;
             }
-            if (b < nb_max)
-                sink.push(ev, c, b, ev_kind, ev_a, ev_b, ev_c);
+            cp_async_commit();
+        };
+        issue(0);
+        for (int t = 0;  t < ntiles;  t++)
+        {
+            issue(t + 1);
+            cp_async_wait<1>();
+            __syncthreads();
+            const unsigned char *col = tile[t & 1] + threadIdx.x;
+            const int rows = (nbu - t*SB_SEQ_TILE < SB_SEQ_TILE)  ?  (nbu - t*SB_SEQ_TILE)  :  SB_SEQ_TILE;
+#pragma unroll 4
+            for (int row = 0;  row < rows;  row++)
+            {
+                const int b = t*SB_SEQ_TILE + row;
+                bool ev = false;
+                int ev_kind = 0;
+                int ev_a = 0;
+                int ev_b = 0;
+                int ev_c = 0;
+                bool need_level = false;
+                if (live)
+                    dtmf_seq_block<EMIT, true>(s, c, b, (b == 0)  ?  (B - cs_old)  :  B, col[row*128], realtime, in_digit, last_hit, dur,
+                                               ev, ev_kind, ev_a, ev_b, ev_c, need_level);
+                const unsigned int pos = sink.push(ev, c, b, ev_kind, ev_a, ev_b, ev_c);
+                if (EMIT  &&  need_level)
+                {
+                    if (qn < SB_SEQ_QUEUE)
+                    {
+                        q_pos[qn][threadIdx.x] = pos;
+                        q_row[qn][threadIdx.x] = (unsigned short) row;
+                        qn++;
+                    }
+                    else if ((long long) pos < s.q.capacity)
+                    {
+                        s.q.events[pos].b = dtmf_level_tab(lvl_tab, s.level_n, s.level_min, s.eout[(size_t) b*s.q.channels + c]);
+                    }
+                }
+            }
+            if (EMIT)
+            {
+                // The levels owed for this tile: all energy loads first (independent, one memory round trip), then
+                // the table searches and the 4-byte stores into the records written above
+                float en[SB_SEQ_QUEUE];
+#pragma unroll
+                for (int i = 0;  i < SB_SEQ_QUEUE;  i++)
+                    en[i] = (i < qn)  ?  s.eout[(size_t) (t*SB_SEQ_TILE + q_row[i][threadIdx.x])*s.q.channels + c]  :  0.0f;
+#pragma unroll
+                for (int i = 0;  i < SB_SEQ_QUEUE;  i++)
+                {
+                    if (i < qn)
+                    {
+                        const unsigned int pos = q_pos[i][threadIdx.x];
+                        if ((long long) pos < s.q.capacity)
+                            s.q.events[pos].b = dtmf_level_tab(lvl_tab, s.level_n, s.level_min, en[i]);
+                    }
+                }
+                qn = 0;
+            }
+            __syncthreads();
+        }
+        cp_async_wait<0>();
+    }
+    else
+    {
+        const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
+        // The decision codes of a group of blocks are fetched together: the loads do not depend on the
+        // state machine, and issuing them back to back hides the memory latency a one-by-one walk exposes.
+        constexpr int G = 16;
+        for (int b0 = 0;  b0 < nb_max;  b0 += G)
+        {
+            unsigned char codes[G];
+#pragma unroll
+            for (int i = 0;  i < G;  i++)
+                codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*s.q.channels + c]  :  (unsigned char) 0;
+#pragma unroll
+            for (int i = 0;  i < G;  i++)
+            {
+                const int b = b0 + i;
+                bool ev = false;
+                int ev_kind = 0;
+                int ev_a = 0;
+                int ev_b = 0;
+                int ev_c = 0;
+                bool need_level = false;
+                if (b < nb)
+                    dtmf_seq_block<EMIT, false>(s, c, b, (b == 0)  ?  (B - cs_old)  :  B, codes[i], realtime, in_digit, last_hit, dur,
+                                                ev, ev_kind, ev_a, ev_b, ev_c, need_level);
+                if (b < nb_max)
+                    sink.push(ev, c, b, ev_kind, ev_a, ev_b, ev_c);
+            }
         }
     }
     sink.finish(wg);

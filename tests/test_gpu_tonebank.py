@@ -118,6 +118,22 @@ def test_dtmf_random(gpu_ctx, engine_lib, torch_mod, port, chunk, mode):
     bank.close()
 
 
+@pytest.mark.parametrize("chunk", [16320, 160, 2040])
+@pytest.mark.parametrize("mode", [po.MODE_DIGITS_CB, po.MODE_REALTIME])
+def test_dtmf_staged_sequencer(gpu_ctx, engine_lib, torch_mod, port, chunk, mode):
+    """A channel count that is a multiple of 16 takes the sequencer path that stages the block decisions through
+    shared memory and fills in the report levels afterwards (176 = one full CTA + a partial one; 16320 samples =
+    two tiles of block rows, the second partial)."""
+    amp, _ = synth.dtmf_channels(176, 16320, seed=300 + chunk)
+    ev, fin, _ = port.run(po.make_params(po.DET_DTMF, mode, chunk), amp)
+    bank = engine_lib.Bank.dtmf(gpu_ctx, amp.shape[0])
+    if mode == po.MODE_REALTIME:
+        bank.dtmf_realtime(True)
+    check(bank, amp, chunk, oracle_rows(ev, False), torch_mod)
+    assert (bank.status() == fin["status"]).all()
+    bank.close()
+
+
 @pytest.mark.parametrize("knob", [("variant", 1), ("variant", 2), ("variant", 3), ("packed", 0), ("packed", 5),
                                   ("direct", 1), ("slice", 3), ("slice", 1)])
 def test_dtmf_kernel_variants(gpu_ctx, engine_lib, torch_mod, port, knob):
