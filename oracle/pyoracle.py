@@ -454,6 +454,45 @@ def mct_run_batch(o, amp, tone_type, chunk=160, nthreads=1):
                                    C.c_int(chunk), C.c_int(tone_type), C.c_int(nthreads))
 
 
+def dtmf_tx_calls(o, max_lens, digits, digits2=None, put2_before_call=0, level=None, timing=None, fill=0x5555):
+    """The reference's dtmf_tx(): one put, then len(max_lens) calls.  Returns (amp with `fill` where nothing was
+    written, lens returned, put results)."""
+    max_lens = np.asarray(max_lens, dtype=np.int32)
+    amp = np.full(int(max_lens.sum()), fill, dtype=np.int16)
+    out_lens = np.zeros(len(max_lens), dtype=np.int32)
+    puts = np.zeros(2, dtype=np.int32)
+    o.lib.ref_dtmf_tx_calls.restype = C.c_int
+    rc = o.lib.ref_dtmf_tx_calls(C.c_void_p(amp.ctypes.data), C.c_void_p(max_lens.ctypes.data), C.c_int(len(max_lens)),
+                                 C.c_char_p(digits.encode()), C.c_char_p(digits2.encode()) if digits2 is not None else None,
+                                 C.c_int(put2_before_call),
+                                 C.c_int(0 if level is None else 1), C.c_int(0 if level is None else level[0]), C.c_int(0 if level is None else level[1]),
+                                 C.c_int(0 if timing is None else 1), C.c_int(0 if timing is None else timing[0]), C.c_int(0 if timing is None else timing[1]),
+                                 C.c_void_p(out_lens.ctypes.data), C.c_void_p(puts.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("ref_dtmf_tx_calls failed")
+    return amp, out_lens, puts
+
+
+def awgn_run(o, n, seed, level, dbov=False, into=None):
+    """n x the reference's awgn(); added (saturating) to `into` if given."""
+    amp = np.zeros(n, dtype=np.int16) if into is None else into
+    assert amp.dtype == np.int16 and len(amp) == n and amp.flags["C_CONTIGUOUS"]
+    o.lib.ref_awgn_run.restype = C.c_int
+    rc = o.lib.ref_awgn_run(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(seed), C.c_float(level), C.c_int(1 if dbov else 0),
+                            C.c_int(0 if into is None else 1))
+    if rc != 0:
+        raise RuntimeError("ref_awgn_run failed")
+    return amp
+
+
+def gen_tables(o):
+    sine = np.zeros(2048, np.float32)
+    rates = np.zeros(8, np.int32)
+    gains = np.zeros(3, np.float32)
+    o.lib.ref_gen_tables(C.c_void_p(sine.ctypes.data), C.c_void_p(rates.ctypes.data), C.c_void_p(gains.ctypes.data))
+    return {"sine": sine, "rates": rates, "gains": gains}
+
+
 _cache = {}
 
 

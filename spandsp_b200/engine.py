@@ -131,6 +131,25 @@ def lib():
         "span_b200_fsk_bank_signal_power": (f32, [vp, i32]),
         "span_b200_fsk_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_dds_int_table": (i32, [vp]),
+        "span_b200_dtmf_tx_bank_create": (vp, [vp, i32]),
+        "span_b200_dtmf_tx_bank_destroy": (None, [vp]),
+        "span_b200_dtmf_tx_bank_channels": (i32, [vp]),
+        "span_b200_dtmf_tx_bank_init": (i32, [vp, i32, i32]),
+        "span_b200_dtmf_tx_bank_set_level": (i32, [vp, i32, i32, i32, i32]),
+        "span_b200_dtmf_tx_bank_set_timing": (i32, [vp, i32, i32, i32, i32]),
+        "span_b200_dtmf_tx_bank_put": (i32, [vp, i32, i32, C.c_char_p, i32]),
+        "span_b200_dtmf_tx_bank_put_each": (i32, [vp, i32, i32, vp, i64, vp]),
+        "span_b200_dtmf_tx_bank_tx_device": (i32, [vp, vp, i64, i32, i32, vp]),
+        "span_b200_dtmf_tx_bank_tx_host": (i32, [vp, vp, i64, i32, i32]),
+        "span_b200_dtmf_tx_bank_lens": (i32, [vp, vp]),
+        "span_b200_awgn_bank_create": (vp, [vp, i32, vp, i32, f32]),
+        "span_b200_awgn_bank_destroy": (None, [vp]),
+        "span_b200_awgn_bank_channels": (i32, [vp]),
+        "span_b200_awgn_bank_init_dbm0": (i32, [vp, i32, i32, vp, i32, f32]),
+        "span_b200_awgn_bank_init_dbov": (i32, [vp, i32, i32, vp, i32, f32]),
+        "span_b200_awgn_bank_add_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_awgn_bank_fill_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_dds_float_table": (i32, [vp]),
         "span_b200_mct_bank_create": (vp, [vp, i32, i32]),
         "span_b200_mct_bank_destroy": (None, [vp]),
         "span_b200_mct_bank_channels": (i32, [vp]),
@@ -591,6 +610,111 @@ class MctBank:
     def close(self):
         if self.h:
             lib().span_b200_mct_bank_destroy(self.h)
+            self.h = None
+
+
+class DtmfTxBank:
+    """N DTMF transmitters (span_b200_dtmf_tx_bank_create): dtmf_tx_init/put/set_level/set_timing/dtmf_tx per channel."""
+
+    def __init__(self, ctx, channels):
+        self.ctx = ctx
+        self.h = lib().span_b200_dtmf_tx_bank_create(ctx.h, channels)
+        if not self.h:
+            raise EngineError(_err())
+        self.channels = channels
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    def _range(self, first, count):
+        return first, (self.channels - first if count is None else count)
+
+    def init(self, first=0, count=None):
+        self._ck(lib().span_b200_dtmf_tx_bank_init(self.h, *self._range(first, count)))
+
+    def set_level(self, level, twist, first=0, count=None):
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_dtmf_tx_bank_set_level(self.h, f, n, level, twist))
+
+    def set_timing(self, on_time, off_time, first=0, count=None):
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_dtmf_tx_bank_set_timing(self.h, f, n, on_time, off_time))
+
+    def put(self, digits, first=0, count=None):
+        f, n = self._range(first, count)
+        return self._ck(lib().span_b200_dtmf_tx_bank_put(self.h, f, n, digits.encode(), -1))
+
+    def put_each(self, strings, first=0):
+        """One digit string per channel, channels [first, first + len(strings))."""
+        n = len(strings)
+        stride = max(1, max(len(x) for x in strings))
+        buf = np.zeros((n, stride), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.int32)
+        for i, x in enumerate(strings):
+            b = np.frombuffer(x.encode(), dtype=np.uint8)
+            buf[i, :len(b)] = b
+            lens[i] = len(b)
+        return self._ck(lib().span_b200_dtmf_tx_bank_put_each(self.h, first, n, buf.ctypes.data, stride, lens.ctypes.data))
+
+    def tx_device(self, d_ptr, stride, max_samples, zero_fill=False, stream=None):
+        self._ck(lib().span_b200_dtmf_tx_bank_tx_device(self.h, d_ptr, stride, max_samples, int(zero_fill), stream))
+
+    def tx_host(self, amp, zero_fill=False):
+        assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
+        self._ck(lib().span_b200_dtmf_tx_bank_tx_host(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], int(zero_fill)))
+
+    def lens(self):
+        n = np.zeros(self.channels, dtype=np.int32)
+        self._ck(lib().span_b200_dtmf_tx_bank_lens(self.h, n.ctypes.data))
+        return n
+
+    def close(self):
+        if self.h:
+            lib().span_b200_dtmf_tx_bank_destroy(self.h)
+            self.h = None
+
+
+class AwgnBank:
+    """N noise sources (span_b200_awgn_bank_create): awgn_init_dbm0(seed) / awgn() per channel."""
+
+    def __init__(self, ctx, channels, level_dbm0, seeds=None, seed0=0):
+        self.ctx = ctx
+        sp = None
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+            assert len(self._seeds) == channels
+            sp = self._seeds.ctypes.data
+        self.h = lib().span_b200_awgn_bank_create(ctx.h, channels, sp, seed0, level_dbm0)
+        if not self.h:
+            raise EngineError(_err())
+        self.channels = channels
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    def init(self, level, seeds=None, seed0=0, first=0, count=None, dbov=False):
+        n = self.channels - first if count is None else count
+        sp = None
+        if seeds is not None:
+            s = np.ascontiguousarray(seeds, dtype=np.int32)
+            assert len(s) == n
+            sp = s.ctypes.data
+        fn = lib().span_b200_awgn_bank_init_dbov if dbov else lib().span_b200_awgn_bank_init_dbm0
+        self._ck(fn(self.h, first, n, sp, seed0, level))
+
+    def add_device(self, d_ptr, stride, samples, stream=None):
+        self._ck(lib().span_b200_awgn_bank_add_device(self.h, d_ptr, stride, samples, stream))
+
+    def fill_device(self, d_ptr, stride, samples, stream=None):
+        self._ck(lib().span_b200_awgn_bank_fill_device(self.h, d_ptr, stride, samples, stream))
+
+    def close(self):
+        if self.h:
+            lib().span_b200_awgn_bank_destroy(self.h)
             self.h = None
 
 

@@ -9,6 +9,7 @@
 #include "../../spandsp_b200/csrc/sb_v27ter_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_fsk_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_mct_rx.cuh"
+#include "../../spandsp_b200/csrc/sb_gen.cuh"
 
 using namespace sbm;
 
@@ -451,4 +452,100 @@ EXPORT void hostsim_fsk_tables(int16_t *sine)
     std::vector<short> t;
     sbf::make_dds_int_table(t);
     memcpy(sine, t.data(), sizeof(short)*257);
+}
+
+// ------------------------------------------------------------------------------------------
+// The signal sources of sb_gen.cuh on the host (same layout of arguments as oracle/ref_harness_gen.c)
+
+EXPORT int hostsim_dtmf_tx_calls(int16_t *amp, const int32_t *max_lens, int ncalls, const char *digits, const char *digits2, int put2_before_call,
+                                 int set_level, int level, int twist, int set_timing, int on_ms, int off_ms,
+                                 int32_t *out_lens, int32_t *put_results)
+{
+    static std::vector<float> sine;
+    if (sine.empty())
+    {
+        sine.resize(SBG_SINE_WORDS);
+        sbg::host_make_sine_table(sine.data());
+    }
+    static const int row[4] = {697, 770, 852, 941};
+    static const int col[4] = {1209, 1336, 1477, 1633};
+    int rates[8];
+    for (int i = 0;  i < 4;  i++)
+    {
+        rates[i] = sbg::host_dds_phase_ratef((float) row[i]);
+        rates[4 + i] = sbg::host_dds_phase_ratef((float) col[i]);
+    }
+    std::vector<unsigned char> queue(SBG_QUEUE, 0);
+    std::vector<int> state(sbg::D_COUNT, 0);
+    sbg::GenLoader ld = {state.data(), 1, 0};
+    sbg::GenStorer st = {state.data(), 1, 0};
+    sbg::DtmfTx t;
+    t.tones.sine = sine.data();
+    t.queue = queue.data();
+    t.qstride = 1;
+    t.row_rate = rates;
+    t.col_rate = rates + 4;
+    t.init(sbg::host_dds_scaling_dbm0f(-10.0f));
+    if (set_level)
+    {
+        t.low_level = sbg::host_dds_scaling_dbm0f((float) level);
+        t.high_level = sbg::host_dds_scaling_dbm0f((float) (level + twist));
+    }
+    if (set_timing)
+    {
+        t.on_time = ((on_ms >= 0)  ?  on_ms  :  50)*8;
+        t.off_time = ((off_ms >= 0)  ?  off_ms  :  55)*8;
+    }
+    auto put = [&](const char *d) -> int
+    {
+        const int len = (int) strlen(d);
+        if (len == 0)
+            return 0;
+        const int space = SBG_QUEUE - t.qcnt;
+        if (space < len)
+            return len - space;
+        for (int i = 0;  i < len;  i++)
+            queue[(t.qrd + t.qcnt + i) & (SBG_QUEUE - 1)] = (unsigned char) d[i];
+        t.qcnt += len;
+        return 0;
+    };
+    put_results[0] = put(digits);
+    put_results[1] = 0;
+    int pos = 0;
+    for (int k = 0;  k < ncalls;  k++)
+    {
+        if (digits2  &&  k == put2_before_call)
+            put_results[1] = put(digits2);
+        // every call goes through the state arrays, as every kernel launch does
+        t.store(st);
+        t.load(ld);
+        sbg::RowOut out;
+        out.begin(amp + pos);
+        out_lens[k] = t.tx(out, max_lens[k]);
+        out.flush();
+        pos += max_lens[k];
+    }
+    return 0;
+}
+
+EXPORT int hostsim_awgn_run(int16_t *amp, int n, int seed, float level, int dbov, int add)
+{
+    std::vector<double> r(SBG_RAN_TABLE);
+    sbg::Awgn g;
+    g.r = r.data();
+    g.rs = 1;
+    g.ran_init(seed);
+    if (!dbov)
+        level = level - (3.14f + 3.02f);
+    g.rms = pow(10.0, level/20.0)*32768.0;
+    g.amp2 = 0.0;
+    g.odd = 1;
+    for (int i = 0;  i < n;  i++)
+        amp[i] = (int16_t) ((add)  ?  sbg::sat_add16(amp[i], g.sample())  :  g.sample());
+    return 0;
+}
+
+EXPORT void hostsim_gen_tables(float *sine)
+{
+    sbg::host_make_sine_table(sine);
 }

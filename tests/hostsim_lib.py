@@ -14,7 +14,7 @@ SYM_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh", "sb_mct_rx.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh", "sb_mct_rx.cuh", "sb_gen.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     subprocess.run([os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
@@ -92,3 +92,32 @@ def mct_run(amp, tone_type, chunk=160):
     if rc != 0 or nev.value > cap:
         raise RuntimeError("hostsim mct run failed")
     return {"ev": ev[:nev.value].copy(), "final": fin, "fsk_final": ffin}
+
+
+def dtmf_tx_calls(max_lens, digits, digits2=None, put2_before_call=0, level=None, timing=None, fill=0x5555):
+    """The DTMF transmitter of sb_gen.cuh on the host; same arguments and results as pyoracle.dtmf_tx_calls."""
+    max_lens = np.asarray(max_lens, dtype=np.int32)
+    amp = np.full(int(max_lens.sum()), fill, dtype=np.int16)
+    out_lens = np.zeros(len(max_lens), dtype=np.int32)
+    puts = np.zeros(2, dtype=np.int32)
+    fn = lib().hostsim_dtmf_tx_calls
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(amp.ctypes.data), C.c_void_p(max_lens.ctypes.data), C.c_int(len(max_lens)),
+            C.c_char_p(digits.encode()), C.c_char_p(digits2.encode()) if digits2 is not None else None, C.c_int(put2_before_call),
+            C.c_int(0 if level is None else 1), C.c_int(0 if level is None else level[0]), C.c_int(0 if level is None else level[1]),
+            C.c_int(0 if timing is None else 1), C.c_int(0 if timing is None else timing[0]), C.c_int(0 if timing is None else timing[1]),
+            C.c_void_p(out_lens.ctypes.data), C.c_void_p(puts.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("hostsim dtmf_tx failed")
+    return amp, out_lens, puts
+
+
+def awgn_run(n, seed, level, dbov=False, into=None):
+    """The noise source of sb_gen.cuh on the host; same arguments and results as pyoracle.awgn_run."""
+    amp = np.zeros(n, dtype=np.int16) if into is None else into
+    fn = lib().hostsim_awgn_run
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(seed), C.c_float(level), C.c_int(1 if dbov else 0), C.c_int(0 if into is None else 1))
+    if rc != 0:
+        raise RuntimeError("hostsim awgn failed")
+    return amp

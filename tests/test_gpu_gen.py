@@ -1,0 +1,167 @@
+"""GPU parity of the signal source banks (dtmf_tx / tone_gen / awgn on the device) against the reference (golden
+vectors from the strict build; the compiled reference itself where it is present), and the loop-back they exist for:
+generated on the device, detected on the device, digits out = digits in."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gen_golden.npz")
+ALPHABET = "123A456B789C*0#D"
+
+
+def cases():
+    spec = importlib.util.spec_from_file_location("make_golden_gen", os.path.join(os.path.dirname(GOLD), "make_golden_gen.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    return mk
+
+
+def run_tx(torch, bank, nch, max_lens, digits2=None, put2_before_call=0, zero_fill=False, fill=0x5555):
+    """Calls of dtmf_tx() for every channel; returns (amp [nch][sum], lens [calls][nch], result of the second put)."""
+    total = int(np.sum(max_lens))
+    row = (total + 7) // 8 * 8 + 8
+    d = torch.full((nch, row), fill, dtype=torch.int16, device="cuda")
+    lens = []
+    put2 = 0
+    pos = 0
+    for k, m in enumerate(max_lens):
+        if digits2 is not None and k == put2_before_call:
+            put2 = bank.put(digits2)
+        bank.tx_device(d.data_ptr() + 2 * pos, row, int(m), zero_fill)
+        lens.append(bank.lens().copy())
+        pos += int(m)
+    return d.cpu().numpy()[:, :total], np.asarray(lens), put2
+
+
+def test_dtmf_tx_golden(gpu_ctx, engine_lib):
+    import torch
+    g = np.load(GOLD)
+    mk = cases()
+    for k, c in enumerate(mk.TX_CASES):
+        bank = engine_lib.DtmfTxBank(gpu_ctx, 3)
+        if c.get("level") is not None:
+            bank.set_level(*c["level"])
+        if c.get("timing") is not None:
+            bank.set_timing(*c["timing"])
+        put1 = bank.put(c["digits"]) if c["digits"] else 0
+        amp, lens, put2 = run_tx(torch, bank, 3, c["max_lens"], c.get("digits2"), c.get("put2_before_call", 0))
+        assert [put1, put2] == g["tx_puts%d" % k].tolist(), k
+        for ch in range(3):
+            assert (lens[:, ch] == g["tx_lens%d" % k]).all(), k
+            assert (amp[ch] == g["tx_amp%d" % k]).all(), k
+        bank.close()
+
+
+def test_dtmf_tx_bank_vs_reference(gpu_ctx, engine_lib, oracles):
+    """200 transmitters with their own digit strings (put_each), levels and timings per range, uneven call sizes
+    (odd offsets: the unaligned store path), zero fill after the last digit."""
+    import torch
+    if "strict" not in oracles:
+        pytest.skip("compiled reference not available here")
+    S = oracles["strict"]
+    rng = np.random.default_rng(66)
+    nch = 200
+    strings = ["".join(ALPHABET[i] for i in rng.integers(0, 16, int(rng.integers(0, 40)))) for _ in range(nch)]
+    strings[5] = "9" * 128
+    strings[6] = "12 3z4"
+    ranges = [(0, 50, None, None), (50, 70, (-20, 4), None), (120, 80, (-3, -2), (30, 70))]
+    calls = [1000, 77, 4001, 160, 8000, 3]
+    bank = engine_lib.DtmfTxBank(gpu_ctx, nch)
+    for first, count, level, timing in ranges:
+        if level:
+            bank.set_level(level[0], level[1], first, count)
+        if timing:
+            bank.set_timing(timing[0], timing[1], first, count)
+    assert bank.put_each(strings) == 0
+    amp, lens, _ = run_tx(torch, bank, nch, calls)
+    for first, count, level, timing in ranges:
+        for c in range(first, first + count):
+            ra, rl, _ = po.dtmf_tx_calls(S, calls, strings[c], level=level, timing=timing)
+            assert (lens[:, c] == rl).all(), c
+            assert (amp[c] == ra).all(), c
+    # zero fill: what follows the last digit is silence instead of the caller's contents
+    bank.init()
+    bank.put("42")
+    amp, lens, _ = run_tx(torch, bank, nch, [4000], zero_fill=True)
+    ra, rl, _ = po.dtmf_tx_calls(S, [4000], "42", fill=0)
+    assert (lens[0] == rl[0]).all() and (amp == ra[None, :]).all()
+    # a queue that cannot take the digits leaves the channel unchanged and reports the deficit
+    bank.init()
+    assert bank.put("1" * 100) == 0
+    assert bank.put("2" * 40) == 12
+    assert bank.put("3" * 28) == 0
+    bank.close()
+
+
+def test_awgn_golden(gpu_ctx, engine_lib):
+    import torch
+    g = np.load(GOLD)
+    mk = cases()
+    n = 40000
+    nch = len(mk.NOISE_CASES)
+    bank = engine_lib.AwgnBank(gpu_ctx, nch, -30.0, seed0=1)
+    for c, (seed, level, dbov) in enumerate(mk.NOISE_CASES):
+        bank.init(level, seeds=[seed], first=c, count=1, dbov=dbov)
+    d = torch.zeros((nch, n), dtype=torch.int16, device="cuda")
+    bank.fill_device(d.data_ptr(), n, 16000)
+    bank.fill_device(d.data_ptr() + 2 * 16000, n, 24000 - 3)          # state carries across calls
+    bank.fill_device(d.data_ptr() + 2 * (40000 - 3), n, 3)            # unaligned tail
+    got = d.cpu().numpy()
+    for c in range(nch):
+        assert (got[c] == g["noise%d" % c]).all(), c
+    # saturating add on top of a signal
+    base = g["add_base"]
+    bank2 = engine_lib.AwgnBank(gpu_ctx, 40, -3.0, seeds=[5] * 40)
+    d = torch.from_numpy(np.tile(base, (40, 1))).cuda()
+    bank2.add_device(d.data_ptr(), len(base), len(base))
+    assert (d.cpu().numpy() == g["add_out"][None, :]).all()
+    bank.close()
+    bank2.close()
+
+
+def test_awgn_seed_sequence(gpu_ctx, engine_lib, oracles):
+    """seed0 + channel seeding (the cfg2 rule: seed 1234567 + c), 70 channels (partial warps)."""
+    import torch
+    if "strict" not in oracles:
+        pytest.skip("compiled reference not available here")
+    S = oracles["strict"]
+    n = 8000
+    bank = engine_lib.AwgnBank(gpu_ctx, 70, -30.0, seed0=1234567)
+    d = torch.zeros((70, n), dtype=torch.int16, device="cuda")
+    bank.fill_device(d.data_ptr(), n, n)
+    got = d.cpu().numpy()
+    for c in range(70):
+        assert (got[c] == po.awgn_run(S, n, 1234567 + c, -30.0)).all(), c
+    bank.close()
+
+
+def test_loopback_on_device(gpu_ctx, engine_lib):
+    """BASELINE cfg1 at scale, without the host: 1024 channels, each dtmf_tx's its own permutation of the sixteen
+    digits, -30 dBm0 noise added, and the DTMF bank reads the same device buffer: digits out = digits in."""
+    import torch
+    rng = np.random.default_rng(77)
+    nch = 1024
+    n = 13440
+    strings = ["".join(ALPHABET[i] for i in rng.permutation(16)) for _ in range(nch)]
+    tx = engine_lib.DtmfTxBank(gpu_ctx, nch)
+    noise = engine_lib.AwgnBank(gpu_ctx, nch, -30.0, seed0=1234567)
+    rx = engine_lib.Bank.dtmf(gpu_ctx, nch)
+    assert tx.put_each(strings) == 0
+    d = torch.empty((nch, n), dtype=torch.int16, device="cuda")
+    tx.tx_device(d.data_ptr(), n, n, True)
+    assert (tx.lens() == n).all()
+    noise.add_device(d.data_ptr(), n, n)
+    rx.rx_device(d.data_ptr(), n, n)
+    got = [[] for _ in range(nch)]
+    for e in rx.events():
+        assert int(e["kind"]) == 1
+        got[int(e["channel"])].append(chr(int(e["a"])))
+    assert ["".join(x) for x in got] == strings
+    for b in (tx, noise, rx):
+        b.close()
