@@ -50,6 +50,9 @@ int span_b200_dtmf_tx_bank_tx_device(span_b200_dtmf_tx_bank_t *bank, int16_t *d_
                                      void *stream);
 int span_b200_dtmf_tx_bank_tx_host(span_b200_dtmf_tx_bank_t *bank, int16_t *h_amp, int64_t stride, int max_samples, int zero_fill);
 int span_b200_dtmf_tx_bank_lens(span_b200_dtmf_tx_bank_t *bank, int32_t *lens);
+/* The *_device calls are asynchronous on the stream given (NULL: the context's own non-blocking stream, which is
+   not ordered with the legacy default stream).  Wait for the bank's last call to finish: */
+int span_b200_dtmf_tx_bank_sync(span_b200_dtmf_tx_bank_t *bank);
 
 /* awgn_init_dbm0(NULL, seed, level) x channels (src/awgn.c:152-155); channel i is seeded with seeds[i], or with
    seed0 + i when seeds is NULL. */
@@ -63,6 +66,7 @@ int span_b200_awgn_bank_init_dbov(span_b200_awgn_bank_t *bank, int first, int co
    put noise on a line - or amp[i] = awgn(). */
 int span_b200_awgn_bank_add_device(span_b200_awgn_bank_t *bank, int16_t *d_amp, int64_t stride, int samples, void *stream);
 int span_b200_awgn_bank_fill_device(span_b200_awgn_bank_t *bank, int16_t *d_amp, int64_t stride, int samples, void *stream);
+int span_b200_awgn_bank_sync(span_b200_awgn_bank_t *bank);
 
 /* The 2048-entry float sine table of the DDS (src/dds_float.c:51-2101) as computed by this library, for verification */
 int span_b200_dds_float_table(float *table);

@@ -339,6 +339,13 @@ extern "C" int span_b200_dtmf_tx_bank_lens(span_b200_dtmf_tx_bank_t *b, int32_t 
     return 0;
 }
 
+extern "C" int span_b200_dtmf_tx_bank_sync(span_b200_dtmf_tx_bank_t *b)
+{
+    if (b == NULL)
+        return -1;
+    return tx_quiesce(b);
+}
+
 // ------------------------------------------------------------------------------------------
 struct span_b200_awgn_bank_s
 {
@@ -477,4 +484,14 @@ extern "C" int span_b200_awgn_bank_add_device(span_b200_awgn_bank_t *b, int16_t 
 extern "C" int span_b200_awgn_bank_fill_device(span_b200_awgn_bank_t *b, int16_t *d_amp, int64_t stride, int samples, void *stream)
 {
     return awgn_run(b, d_amp, stride, samples, 0, stream);
+}
+
+extern "C" int span_b200_awgn_bank_sync(span_b200_awgn_bank_t *b)
+{
+    if (b == NULL)
+        return -1;
+    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    return 0;
 }

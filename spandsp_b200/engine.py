@@ -150,6 +150,8 @@ def lib():
         "span_b200_awgn_bank_add_device": (i32, [vp, vp, i64, i32, vp]),
         "span_b200_awgn_bank_fill_device": (i32, [vp, vp, i64, i32, vp]),
         "span_b200_dds_float_table": (i32, [vp]),
+        "span_b200_dtmf_tx_bank_sync": (i32, [vp]),
+        "span_b200_awgn_bank_sync": (i32, [vp]),
         "span_b200_mct_bank_create": (vp, [vp, i32, i32]),
         "span_b200_mct_bank_destroy": (None, [vp]),
         "span_b200_mct_bank_channels": (i32, [vp]),
@@ -670,6 +672,9 @@ class DtmfTxBank:
         self._ck(lib().span_b200_dtmf_tx_bank_lens(self.h, n.ctypes.data))
         return n
 
+    def sync(self):
+        self._ck(lib().span_b200_dtmf_tx_bank_sync(self.h))
+
     def close(self):
         if self.h:
             lib().span_b200_dtmf_tx_bank_destroy(self.h)
@@ -711,6 +716,9 @@ class AwgnBank:
 
     def fill_device(self, d_ptr, stride, samples, stream=None):
         self._ck(lib().span_b200_awgn_bank_fill_device(self.h, d_ptr, stride, samples, stream))
+
+    def sync(self):
+        self._ck(lib().span_b200_awgn_bank_sync(self.h))
 
     def close(self):
         if self.h:
