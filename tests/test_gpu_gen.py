@@ -27,7 +27,8 @@ def run_tx(torch, bank, nch, max_lens, digits2=None, put2_before_call=0, zero_fi
     total = int(np.sum(max_lens))
     row = (total + 7) // 8 * 8 + 8
     d = torch.full((nch, row), fill, dtype=torch.int16, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream         # the buffer is filled and read back on torch's stream
+    torch.cuda.synchronize()            # the banks run on the context's own non-blocking stream (stream = NULL)
+    stream = None
     lens = []
     put2 = 0
     pos = 0
@@ -109,11 +110,13 @@ def test_awgn_golden(gpu_ctx, engine_lib):
     bank = engine_lib.AwgnBank(gpu_ctx, nch, -30.0, seed0=1)
     for c, (seed, level, dbov) in enumerate(mk.NOISE_CASES):
         bank.init(level, seeds=[seed], first=c, count=1, dbov=dbov)
-    stream = torch.cuda.current_stream().cuda_stream         # the buffer is made and read back on torch's stream
+    stream = None                       # the context's own non-blocking stream: order it with torch's by hand
     d = torch.zeros((nch, n), dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
     bank.fill_device(d.data_ptr(), n, 16000, stream)
     bank.fill_device(d.data_ptr() + 2 * 16000, n, 24000 - 3, stream)  # state carries across calls
     bank.fill_device(d.data_ptr() + 2 * (40000 - 3), n, 3, stream)    # unaligned tail
+    bank.sync()
     got = d.cpu().numpy()
     for c in range(nch):
         assert (got[c] == g["noise%d" % c]).all(), c
@@ -122,6 +125,7 @@ def test_awgn_golden(gpu_ctx, engine_lib):
     bank2 = engine_lib.AwgnBank(gpu_ctx, 40, -3.0, seeds=[5] * 40)
     d = torch.from_numpy(np.tile(base, (40, 1))).cuda()
     bank2.add_device(d.data_ptr(), len(base), len(base), stream)
+    bank2.sync()
     assert (d.cpu().numpy() == g["add_out"][None, :]).all()
     bank.close()
     bank2.close()
@@ -136,7 +140,9 @@ def test_awgn_seed_sequence(gpu_ctx, engine_lib, oracles):
     n = 8000
     bank = engine_lib.AwgnBank(gpu_ctx, 70, -30.0, seed0=1234567)
     d = torch.zeros((70, n), dtype=torch.int16, device="cuda")
-    bank.fill_device(d.data_ptr(), n, n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    bank.fill_device(d.data_ptr(), n, n)
+    bank.sync()
     got = d.cpu().numpy()
     for c in range(70):
         assert (got[c] == po.awgn_run(S, n, 1234567 + c, -30.0)).all(), c
@@ -156,7 +162,8 @@ def test_loopback_on_device(gpu_ctx, engine_lib):
     rx = engine_lib.Bank.dtmf(gpu_ctx, nch)
     assert tx.put_each(strings) == 0
     d = torch.empty((nch, n), dtype=torch.int16, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    stream = None                       # all three banks on the context's stream: ordered among themselves
     tx.tx_device(d.data_ptr(), n, n, True, stream)
     assert (tx.lens() == n).all()
     noise.add_device(d.data_ptr(), n, n, stream)
