@@ -275,6 +275,38 @@ int modem_connect_tones_rx_fillin(modem_connect_tones_rx_state_t *s, int len);
 int modem_connect_tones_rx_get(modem_connect_tones_rx_state_t *s);
 const char *modem_connect_tone_to_str(int tone);
 
+/* ---- In-band signalling tone receiver (2280 Hz, 2600 Hz, 2400 + 2600 Hz): src/spandsp/sig_tone.h:56-134,
+        src/sig_tone.c:402-734 ---- */
+enum
+{
+    SIG_TONE_2280HZ = 1,
+    SIG_TONE_2600HZ,
+    SIG_TONE_2400HZ_2600HZ
+};                                                                      /* src/spandsp/sig_tone.h:56-64 */
+
+enum
+{
+    SIG_TONE_1_PRESENT = 0x001,
+    SIG_TONE_1_CHANGE = 0x002,
+    SIG_TONE_2_PRESENT = 0x004,
+    SIG_TONE_2_CHANGE = 0x008,
+    SIG_TONE_TX_PASSTHROUGH = 0x010,
+    SIG_TONE_RX_PASSTHROUGH = 0x040,
+    SIG_TONE_RX_FILTER_TONE = 0x080,
+    SIG_TONE_TX_UPDATE_REQUEST = 0x100,
+    SIG_TONE_RX_UPDATE_REQUEST = 0x200
+};                                                                      /* src/spandsp/sig_tone.h:67-88 */
+
+typedef struct sig_tone_rx_state_s sig_tone_rx_state_t;
+
+/* Synchronous, one receiver per state (a bank of one); amp[] is rewritten in place as in the reference, and
+   sig_update(user_data, signalling_state, 0, duration) is called for every change.  Banks: spandsp_b200_sig.h. */
+sig_tone_rx_state_t *sig_tone_rx_init(sig_tone_rx_state_t *s, int tone_type, span_tone_report_func_t sig_update, void *user_data);
+int sig_tone_rx_release(sig_tone_rx_state_t *s);
+int sig_tone_rx_free(sig_tone_rx_state_t *s);
+int sig_tone_rx(sig_tone_rx_state_t *s, int16_t amp[], int len);
+void sig_tone_rx_set_mode(sig_tone_rx_state_t *s, int mode, int duration);
+
 #if defined(__cplusplus)
 }
 #endif

@@ -493,6 +493,42 @@ def gen_tables(o):
     return {"sine": sine, "rates": rates, "gains": gains}
 
 
+SIG_FINAL = 31
+
+
+def sig_generate(o, n, tone_type, steps, tone_db=-100.0, freq_offset=0.0, noise_seed=1234567, noise_dbm0=-100.0, into=None):
+    """sig_tone_tx() script ADDED into a buffer: steps = [(mode bits, samples), ...]; then awgn."""
+    amp = np.zeros(n, dtype=np.int16) if into is None else into
+    assert amp.dtype == np.int16 and len(amp) == n and amp.flags["C_CONTIGUOUS"]
+    st = np.asarray(steps, dtype=np.int32).reshape(-1, 2)
+    o.lib.ref_sig_generate.restype = C.c_int
+    rc = o.lib.ref_sig_generate(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(tone_type), C.c_void_p(st.ctypes.data), C.c_int(len(st)),
+                                C.c_float(tone_db), C.c_float(freq_offset), C.c_int(noise_seed), C.c_float(noise_dbm0))
+    if rc < 0:
+        raise RuntimeError("ref_sig_generate failed")
+    return amp
+
+
+def sig_run(o, amp, tone_type, chunk=160, lens=None, modes=((0, 0x40),)):
+    """One channel through the reference's sig_tone_rx (a copy of amp is processed in place).  modes = ((call, mode), ...).
+    Returns dict(out int16[], ev int32[n,3] = (call, signalling_state, duration), final int32[31])."""
+    out = np.array(amp, dtype=np.int16, copy=True)
+    n = len(out)
+    cap = 8192
+    ev = np.zeros((cap, 3), dtype=np.int32)
+    nev = C.c_int32(0)
+    fin = np.zeros(SIG_FINAL, dtype=np.int32)
+    md = np.asarray(modes, dtype=np.int32).reshape(-1, 2)
+    ln = None if lens is None else np.asarray(lens, dtype=np.int32)
+    o.lib.ref_sig_run.restype = C.c_int
+    rc = o.lib.ref_sig_run(C.c_void_p(out.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_void_p(ln.ctypes.data) if ln is not None else None,
+                           C.c_int(0 if ln is None else len(ln)), C.c_int(tone_type), C.c_void_p(md.ctypes.data), C.c_int(len(md)),
+                           C.c_void_p(ev.ctypes.data), C.c_int(cap), C.byref(nev), C.c_void_p(fin.ctypes.data))
+    if rc != 0 or nev.value > cap:
+        raise RuntimeError("ref_sig_run failed")
+    return {"out": out, "ev": ev[:nev.value].copy(), "final": fin}
+
+
 _cache = {}
 
 

@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-shared",
 ]
 
-SOURCES = ["sb_engine.cu", "sb_v29.cu", "sb_v17.cu", "sb_v27ter.cu", "sb_fsk.cu", "sb_mct.cu", "sb_gen.cu", "sb_dropin.cu"]
+SOURCES = ["sb_engine.cu", "sb_v29.cu", "sb_v17.cu", "sb_v27ter.cu", "sb_fsk.cu", "sb_mct.cu", "sb_gen.cu", "sb_sig.cu", "sb_dropin.cu"]
 
 
 def sources():

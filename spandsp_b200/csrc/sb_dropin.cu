@@ -20,6 +20,7 @@
 #include "../../include/spandsp_b200_v27ter.h"
 #include "../../include/spandsp_b200_fsk.h"
 #include "../../include/spandsp_b200_mct.h"
+#include "../../include/spandsp_b200_sig.h"
 #pragma GCC visibility pop
 
 #define SB_MAGIC    0x5350414E42323030ULL       /* "SPANB200" */
@@ -1826,4 +1827,102 @@ extern "C" int modem_connect_tones_rx_get(modem_connect_tones_rx_state_t *s)
     const int x = s->hit;                                   // src/modem_connect_tones.c:812-820
     s->hit = MODEM_CONNECT_TONES_NONE;
     return x;
+}
+
+// ------------------------------------------------------------------------------------------
+// In-band signalling tone receiver, one bank of one per state object (src/sig_tone.c:402-734)
+struct sig_tone_rx_state_s
+{
+    unsigned long long magic;
+    span_b200_sig_bank_t *bank;
+    int heap;
+    span_tone_report_func_t sig_update;
+    void *user_data;
+    std::vector<span_b200_sig_event_t> *ev;
+};
+
+static_assert(sizeof(sig_tone_rx_state_s) <= 160, "must fit the reference's sig_tone_rx_state_t (private/sig_tone.h)");
+
+extern "C" sig_tone_rx_state_t *sig_tone_rx_init(sig_tone_rx_state_t *s, int tone_type, span_tone_report_func_t sig_update, void *user_data)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (sig_update == NULL  ||  tone_type < 1  ||  tone_type > 3)
+        return NULL;                                        // src/sig_tone.c:679-680
+    span_b200_ctx_t *ctx = span_b200_default_ctx();
+    if (ctx == NULL)
+        return NULL;
+    int heap = 0;
+    if (s != NULL  &&  s->magic == SB_MAGIC  &&  s->bank != NULL)
+    {
+        if (span_b200_sig_bank_init(s->bank, 0, 1, tone_type) != 0)
+            return NULL;
+        s->sig_update = sig_update;
+        s->user_data = user_data;
+        return s;
+    }
+    if (s == NULL)
+    {
+        if ((s = (sig_tone_rx_state_t *) calloc(1, sizeof(*s))) == NULL)
+            return NULL;
+        heap = 1;
+    }
+    memset(s, 0, sizeof(*s));
+    s->bank = span_b200_sig_bank_create(ctx, 1, tone_type);
+    if (s->bank == NULL)
+    {
+        if (heap)
+            free(s);
+        return NULL;
+    }
+    s->magic = SB_MAGIC;
+    s->heap = heap;
+    s->sig_update = sig_update;
+    s->user_data = user_data;
+    s->ev = new std::vector<span_b200_sig_event_t>();
+    return s;
+}
+
+static int sig_close(sig_tone_rx_state_t *s, int do_free)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (s == NULL  ||  s->magic != SB_MAGIC)
+        return 0;
+    span_b200_sig_bank_destroy(s->bank);
+    delete s->ev;
+    const int heap = s->heap;
+    s->magic = 0;
+    s->bank = NULL;
+    if (do_free  &&  heap)
+        free(s);
+    return 0;
+}
+
+extern "C" int sig_tone_rx_release(sig_tone_rx_state_t *s) { return sig_close(s, 0); }
+extern "C" int sig_tone_rx_free(sig_tone_rx_state_t *s) { return sig_close(s, 1); }
+
+extern "C" void sig_tone_rx_set_mode(sig_tone_rx_state_t *s, int mode, int duration)
+{
+    span_b200_sig_bank_set_mode(s->bank, 0, 1, mode);       // the duration is not used on the receive side (src/sig_tone.c:666-669)
+}
+
+extern "C" int sig_tone_rx(sig_tone_rx_state_t *s, int16_t amp[], int len)
+{
+    std::lock_guard<std::recursive_mutex> lk(g_lock);
+    if (len <= 0)
+        return len;
+    if (span_b200_sig_bank_rx_host(s->bank, amp, len, len, NULL) != 0)
+        return len;
+    int64_t n = span_b200_sig_bank_events(s->bank, NULL, 0);
+    if (n > 0)
+    {
+        s->ev->resize((size_t) n);
+        n = span_b200_sig_bank_events(s->bank, s->ev->data(), n);
+        for (int64_t i = 0;  i < n;  i++)
+        {
+            const span_b200_sig_event_t &e = (*s->ev)[(size_t) i];
+            if (s->sig_update)
+                s->sig_update(s->user_data, e.signalling_state, 0, e.duration);
+        }
+    }
+    return len;                                             // src/sig_tone.c:663
 }

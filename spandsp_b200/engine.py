@@ -152,6 +152,15 @@ def lib():
         "span_b200_dds_float_table": (i32, [vp]),
         "span_b200_dtmf_tx_bank_sync": (i32, [vp]),
         "span_b200_awgn_bank_sync": (i32, [vp]),
+        "span_b200_sig_bank_create": (vp, [vp, i32, i32]),
+        "span_b200_sig_bank_destroy": (None, [vp]),
+        "span_b200_sig_bank_channels": (i32, [vp]),
+        "span_b200_sig_bank_init": (i32, [vp, i32, i32, i32]),
+        "span_b200_sig_bank_set_mode": (i32, [vp, i32, i32, i32]),
+        "span_b200_sig_bank_rx_device": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_sig_bank_rx_host": (i32, [vp, vp, i64, i32, vp]),
+        "span_b200_sig_bank_events": (i64, [vp, vp, i64]),
+        "span_b200_sig_bank_channel_state": (i32, [vp, i32, vp]),
         "span_b200_mct_bank_create": (vp, [vp, i32, i32]),
         "span_b200_mct_bank_destroy": (None, [vp]),
         "span_b200_mct_bank_channels": (i32, [vp]),
@@ -612,6 +621,57 @@ class MctBank:
     def close(self):
         if self.h:
             lib().span_b200_mct_bank_destroy(self.h)
+            self.h = None
+
+
+SIG_EVENT_DTYPE = np.dtype([("channel", "<i4"), ("signalling_state", "<i4"), ("duration", "<i4")])
+
+
+class SigBank:
+    """N in-band signalling tone receivers (span_b200_sig_bank_create); tone_type 1 = 2280 Hz, 2 = 2600 Hz, 3 = 2400 + 2600 Hz.
+    rx_* rewrite the audio in place, as sig_tone_rx() does."""
+
+    def __init__(self, ctx, channels, tone_type):
+        self.ctx = ctx
+        self.h = lib().span_b200_sig_bank_create(ctx.h, channels, tone_type)
+        if not self.h:
+            raise EngineError(_err())
+        self.channels = channels
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    def init(self, tone_type, first=0, count=None):
+        self._ck(lib().span_b200_sig_bank_init(self.h, first, self.channels - first if count is None else count, tone_type))
+
+    def set_mode(self, mode, first=0, count=None):
+        self._ck(lib().span_b200_sig_bank_set_mode(self.h, first, self.channels - first if count is None else count, mode))
+
+    def rx_device(self, d_ptr, stride, samples, stream=None):
+        self._ck(lib().span_b200_sig_bank_rx_device(self.h, d_ptr, stride, samples, stream))
+
+    def rx_host(self, amp, stream=None):
+        assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
+        assert amp.flags["WRITEABLE"]
+        self._ck(lib().span_b200_sig_bank_rx_host(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
+
+    def events(self):
+        n = self._ck(lib().span_b200_sig_bank_events(self.h, None, 0))
+        ev = np.zeros(n, dtype=SIG_EVENT_DTYPE)
+        if n:
+            self._ck(lib().span_b200_sig_bank_events(self.h, ev.ctypes.data, n))
+        return ev
+
+    def channel_state(self, channel):
+        info = np.zeros(31, dtype=np.int32)
+        self._ck(lib().span_b200_sig_bank_channel_state(self.h, channel, info.ctypes.data))
+        return info
+
+    def close(self):
+        if self.h:
+            lib().span_b200_sig_bank_destroy(self.h)
             self.h = None
 
 

@@ -10,6 +10,7 @@
 #include "../../spandsp_b200/csrc/sb_fsk_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_mct_rx.cuh"
 #include "../../spandsp_b200/csrc/sb_gen.cuh"
+#include "../../spandsp_b200/csrc/sb_sig_rx.cuh"
 
 using namespace sbm;
 
@@ -548,4 +549,59 @@ EXPORT int hostsim_awgn_run(int16_t *amp, int n, int seed, float level, int dbov
 EXPORT void hostsim_gen_tables(float *sine)
 {
     sbg::host_make_sine_table(sine);
+}
+
+// ------------------------------------------------------------------------------------------
+// The signalling tone receiver of sb_sig_rx.cuh on the host (same arguments as oracle/ref_harness_sig.c: ref_sig_run)
+EXPORT int hostsim_sig_run(int16_t *amp, int n, int chunk, const int32_t *lens, int ncalls, int tone_type, const int32_t *modes, int nmodes,
+                           int32_t *ev, int ev_cap, int32_t *nev, int32_t *final)
+{
+    if (tone_type < 1  ||  tone_type > 3)
+        return -1;
+    std::vector<int> state(sbs::T_COUNT, 0);
+    std::vector<int2> rep(16384);
+    sbs::SigLoader ld = {state.data(), 1, 0};
+    sbs::SigStorer st = {state.data(), 1, 0};
+    sbs::SigRx r;
+    int32_t thr[3];
+    sbs::host_sig_thresholds(tone_type, thr);
+    r.init(tone_type, thr[0], thr[1], thr[2]);
+    if (chunk <= 0)
+        chunk = n;
+    int len;
+    int call = 0;
+    int total = 0;
+    for (int pos = 0;  (lens)  ?  (call < ncalls)  :  (pos < n);  pos += len, call++)
+    {
+        for (int m = 0;  m < nmodes;  m++)
+        {
+            if (modes[2*m] == call)
+                r.current_rx_tone = modes[2*m + 1];
+        }
+        len = (lens)  ?  lens[call]  :  ((n - pos < chunk)  ?  (n - pos)  :  chunk);
+        // every call goes through the state arrays, as every kernel launch does
+        r.store(st);
+        r.load(ld);
+        r.ev = rep.data();
+        r.ev_cap = (int) rep.size();
+        r.nev = 0;
+        for (int i = 0;  i < len;  i++)
+            amp[pos + i] = (int16_t) r.sample(amp[pos + i]);
+        if (r.nev > r.ev_cap)
+            return -1;
+        for (int i = 0;  i < r.nev;  i++, total++)
+        {
+            if (total < ev_cap)
+            {
+                ev[3*total] = call;
+                ev[3*total + 1] = rep[i].x;
+                ev[3*total + 2] = rep[i].y;
+            }
+        }
+    }
+    *nev = total;
+    r.store(st);
+    if (final)
+        memcpy(final, state.data(), sizeof(int)*sbs::T_COUNT);
+    return 0;
 }

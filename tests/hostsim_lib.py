@@ -14,7 +14,7 @@ SYM_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh", "sb_mct_rx.cuh", "sb_gen.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh", "sb_mct_rx.cuh", "sb_gen.cuh", "sb_sig_rx.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     subprocess.run([os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
@@ -121,3 +121,23 @@ def awgn_run(n, seed, level, dbov=False, into=None):
     if rc != 0:
         raise RuntimeError("hostsim awgn failed")
     return amp
+
+
+def sig_run(amp, tone_type, chunk=160, lens=None, modes=((0, 0x40),)):
+    """The signalling tone receiver of sb_sig_rx.cuh on the host; same arguments and results as pyoracle.sig_run."""
+    out = np.array(amp, dtype=np.int16, copy=True)
+    n = len(out)
+    cap = 8192
+    ev = np.zeros((cap, 3), dtype=np.int32)
+    nev = C.c_int32(0)
+    fin = np.zeros(31, dtype=np.int32)
+    md = np.asarray(modes, dtype=np.int32).reshape(-1, 2)
+    ln = None if lens is None else np.asarray(lens, dtype=np.int32)
+    fn = lib().hostsim_sig_run
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(out.ctypes.data), C.c_int(n), C.c_int(chunk), C.c_void_p(ln.ctypes.data) if ln is not None else None,
+            C.c_int(0 if ln is None else len(ln)), C.c_int(tone_type), C.c_void_p(md.ctypes.data), C.c_int(len(md)),
+            C.c_void_p(ev.ctypes.data), C.c_int(cap), C.byref(nev), C.c_void_p(fin.ctypes.data))
+    if rc != 0 or nev.value > cap:
+        raise RuntimeError("hostsim sig run failed")
+    return {"out": out, "ev": ev[:nev.value].copy(), "final": fin}
