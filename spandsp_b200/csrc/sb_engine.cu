@@ -866,11 +866,15 @@ static int launch_staged_k(const BankArgs<DET> &a, cudaStream_t st)
     typedef StageCfg<SEG_VEC, NSTAGE> cfg;
     const int smem = cfg::WARP_BYTES*WARPS + ((IN8)  ?  1024  :  0);
     auto kern = bank_kernel_staged<DET, SEG_VEC, NSTAGE, WARPS, MINB, NPACK, IN8, FILTK>;
-    static bool configured = false;
-    if (!configured)
+    // function attributes are per device: one flag per device ordinal, not one per process
+    static bool configured[64] = {false};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0  ||  dev >= 64  ||  !configured[dev])
     {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        if (dev >= 0  &&  dev < 64)
+            configured[dev] = true;
     }
     const long long ngroups = (a.channels + 31)/32;
     const long long items = ngroups*a.nslices;

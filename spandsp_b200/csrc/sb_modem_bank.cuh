@@ -145,13 +145,17 @@ static KernelArgs<RX> modem_args(ModemBank<RX> *b, const int16_t *d_amp, int64_t
 template <class RX>
 static int modem_configure()
 {
-    static bool configured = false;
-    if (!configured)
+    // function attributes are per device: one flag per device ordinal, not one per process
+    static bool configured[64] = {false};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0  ||  dev >= 64  ||  !configured[dev])
     {
         const int smem = (int) sizeof(float)*modem_smem_words<RX>();
         CK(cudaFuncSetAttribute(modem_rx_kernel<RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(modem_init_kernel<RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        if (dev >= 0  &&  dev < 64)
+            configured[dev] = true;
     }
     return 0;
 }
@@ -162,6 +166,7 @@ static int modem_init_channels(ModemBank<RX> *b, int first, int count, int bit_r
 {
     if (count <= 0)
         return 0;
+    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
     if (modem_configure<RX>() != 0)
         return -1;
     const int smem = (int) sizeof(float)*modem_smem_words<RX>();
