@@ -1,5 +1,5 @@
 #!/bin/bash
-# Session 4, last call: the signalling tone tests, then the whole GPU suite for one consistent log
+# Session 4, last call: smoke() and the whole GPU suite on the final tree
 mkdir -p gpurun_out
-timeout 120 python -m pytest tests/test_gpu_sig.py -q 2>&1 | tail -12 | tee gpurun_out/pytest_gpu_sig.log
-timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.log
+timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
