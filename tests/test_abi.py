@@ -61,3 +61,45 @@ def test_product_does_not_touch_oracle():
                 assert "oracle" not in txt.replace("CPU oracle", "").replace("strict CPU oracle", "").lower() \
                     or f == "sb_common.cuh" or "oracle/" not in txt, "%s mentions oracle/" % f
                 assert "tonebank_oracle" not in txt and "pyoracle" not in txt and "libspandsp_ref" not in txt, f
+
+
+def declared_prototypes(path):
+    """name -> number of parameters, for every function prototype in a header."""
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//.*", "", txt)
+    out = {}
+    for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(([^;{}()]*(?:\([^()]*\)[^;{}()]*)*)\)\s*;", txt):
+        name, args = m.group(1), m.group(2).strip()
+        if name in ("defined", "sizeof", "__attribute__") or name.endswith("_t"):
+            continue
+        depth = 0
+        n = 1
+        for ch in args:
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "," and depth == 0:
+                n += 1
+        out[name] = 0 if args in ("", "void") else n
+    return out
+
+
+def test_python_binding_matches_headers(engine_lib):
+    """Every entry of the ctypes signature table in spandsp_b200/engine.py has as many arguments as the prototype in
+    include/*.h declares (a drifted binding would corrupt the call without any error)."""
+    L = engine_lib.lib()
+    inc = os.path.join(ROOT, "include")
+    protos = {}
+    for h in sorted(os.listdir(inc)):
+        if h.endswith(".h") and h != "spandsp_b200_dropin.h":
+            protos.update(declared_prototypes(os.path.join(inc, h)))
+    checked = 0
+    for name, nargs in protos.items():
+        fn = getattr(L, name, None)
+        if fn is None or fn.argtypes is None:
+            continue
+        assert len(fn.argtypes) == nargs, "%s: header declares %d parameters, binding passes %d" % (name, nargs, len(fn.argtypes))
+        checked += 1
+    assert checked > 100
