@@ -1,0 +1,108 @@
+"""CPU: the reference's own DTMF receiver test procedures (tests/dtmf_rx_tests.c:mitel_cm7291_side_1_tests, the Mitel
+CM7291 tape: decode check, recognition bandwidth, twist, dynamic range, guard time, signal to noise) with the
+reference's own pass criteria, run on the pinned oracle (the compiled reference) AND on the plain-C restatement
+(oracle/tonebank_oracle.c).  The stimulus is made exactly as the test makes it (tone_gen_descriptor_init with integer
+frequencies, one tone_gen() per burst, awgn seed 1234567); the two oracles must agree burst for burst and both must
+meet the criteria - this is how the oracle is pinned to the reference's test suite, which stores no vectors
+(SURVEY 8c).  Talk-off (test 8) needs the Bellcore tapes, which are not in the tree."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+DIGITS = "123A456B789C*0#D"                     # dtmf_positions: row = index // 4, column = index % 4
+ROW = [697.0, 770.0, 852.0, 941.0]
+COL = [1209.0, 1336.0, 1477.0, 1633.0]
+
+
+def fudged(freq, permille):
+    """dtmf_row[row]*(1.0f + fudge) as tests/dtmf_rx_tests.c:165-180 computes it in float, truncated by the int
+    parameter of tone_gen_descriptor_init()."""
+    fudge = np.float32(permille) / np.float32(1000.0)
+    return int(np.float32(freq) * (np.float32(1.0) + fudge))
+
+
+def burst(S, digit, low_pm=0, low_level=-4, high_pm=0, high_level=-4, on_ms=50, off_ms=50):
+    k = DIGITS.index(digit)
+    return po.tone_burst(S, fudged(ROW[k // 4], low_pm), low_level, fudged(COL[k % 4], high_pm), high_level, on_ms, off_ms)
+
+
+def detect(oracles_list, stream, chunk):
+    """Digit events of every oracle, as [(call index, digit), ...]; all oracles must agree."""
+    out = None
+    for o in oracles_list:
+        ev, _, _ = o.run(po.make_params(po.DET_DTMF, po.MODE_DIGITS_CB, chunk), stream[None, :])
+        got = [(int(e["chunk"]), chr(int(e["a"]))) for e in ev[0]]
+        if out is None:
+            out = got
+        else:
+            assert got == out, "the restatement and the compiled reference disagree"
+    return out
+
+
+@pytest.fixture(scope="module")
+def both(oracles):
+    if "strict" not in oracles:
+        pytest.skip("compiled reference not available here (it makes the stimulus)")
+    return oracles["strict"], [oracles["strict"], oracles["port"]]
+
+
+def test_2_decode_check(both):
+    S, os_ = both
+    stream = np.concatenate([burst(S, d) for d in DIGITS for _ in range(10)])
+    got = detect(os_, stream, 800)
+    assert got == [(10 * i + j, d) for i, d in enumerate(DIGITS) for j in range(10)]
+
+
+def test_3_recognition_bandwidth(both):
+    S, os_ = both
+    for digit in "159D":
+        for which in ("low", "high"):
+            counts = []
+            for sign in (1, -1):
+                kw = {"%s_pm" % which: 0}
+                stream = np.concatenate([burst(S, digit, low_level=-17, high_level=-17, **{"%s_pm" % which: sign * i})
+                                         for i in range(1, 61)])
+                counts.append(len(detect(os_, stream, 800)))
+            nplus, nminus = counts
+            rrb = (nplus + nminus) / 10.0
+            rcfo = (nplus - nminus) / 10.0
+            assert not (rrb < 3.0 + rcfo or rrb >= 15.0 + rcfo), (digit, which, rrb, rcfo)     # dtmf_rx_tests.c:446,479
+
+
+def test_4_twist(both):
+    S, os_ = both
+    for digit in "159D":
+        # C integer division truncates toward zero: i/10 for i = -30 .. -230
+        levels = [-(abs(i) // 10) for i in range(-30, -231, -1)]
+        nplus = len(detect(os_, np.concatenate([burst(S, digit, low_level=-3, high_level=lv) for lv in levels]), 800))
+        nminus = len(detect(os_, np.concatenate([burst(S, digit, low_level=lv, high_level=-3) for lv in levels]), 800))
+        assert nplus >= 80 and nminus >= 40, (digit, nplus, nminus)                           # dtmf_rx_tests.c:529,546
+
+
+def test_5_dynamic_range(both):
+    S, os_ = both
+    stream = np.concatenate([burst(S, "1", low_level=i, high_level=i) for i in range(3, -51, -1)])
+    assert len(detect(os_, stream, 800)) >= 35                                                # dtmf_rx_tests.c:579
+
+
+def test_6_guard_time(both):
+    """No pass criterion in the reference; the figure itself is compared between the oracles (inside detect())."""
+    S, os_ = both
+    stream = np.concatenate([burst(S, "1", low_level=-3, high_level=-3, on_ms=i // 10) for i in range(490, 99, -1)])
+    n = len(detect(os_, stream, 102))
+    assert 10 <= (500 - n) // 10 <= 40              # the receiver needs two 12.75 ms blocks: a guard time of 2x-4x that
+
+
+def test_7_signal_to_noise(both):
+    S, os_ = both
+    one = burst(S, "1")
+    clean = np.tile(one, 1000)
+    acceptable = None
+    for j in range(-13, -50, -1):
+        stream = po.awgn_run(S, len(clean), 1234567, float(j), into=clean.copy())
+        got = detect(os_, stream, 800)
+        if got == [(i, "1") for i in range(1000)]:
+            acceptable = -4 - j
+            break
+    assert acceptable is not None and acceptable <= 26                                       # dtmf_rx_tests.c:650
