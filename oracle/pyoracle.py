@@ -529,11 +529,11 @@ def sig_run(o, amp, tone_type, chunk=160, lens=None, modes=((0, 0x40),)):
     return {"out": out, "ev": ev[:nev.value].copy(), "final": fin}
 
 
-def tone_burst(o, f1, l1, f2, l2, on_ms, off_ms):
-    """One test burst of tests/dtmf_rx_tests.c (my_dtmf_gen_init + my_dtmf_generate), reference tone_gen()."""
-    amp = np.zeros(1000, dtype=np.int16)
+def tone_burst(o, f1, l1, f2, l2, on_ms, off_ms, max_samples=1000):
+    """One test burst of tests/dtmf_rx_tests.c / bell_mf_rx_tests.c (my_*_gen_init + my_*_generate), reference tone_gen()."""
+    amp = np.zeros(max_samples, dtype=np.int16)
     o.lib.ref_tone_burst.restype = C.c_int
-    n = o.lib.ref_tone_burst(C.c_void_p(amp.ctypes.data), C.c_int(int(f1)), C.c_int(int(l1)), C.c_int(int(f2)), C.c_int(int(l2)),
+    n = o.lib.ref_tone_burst(C.c_void_p(amp.ctypes.data), C.c_int(max_samples), C.c_int(int(f1)), C.c_int(int(l1)), C.c_int(int(f2)), C.c_int(int(l2)),
                              C.c_int(int(on_ms)), C.c_int(int(off_ms)))
     return amp[:n]
 

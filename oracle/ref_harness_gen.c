@@ -106,13 +106,13 @@ EXPORT void ref_gen_tables(float *sine, int32_t *rates, float *gains)
 
 /* One burst as tests/dtmf_rx_tests.c:my_dtmf_gen_init() + my_dtmf_generate() make it: tone_gen_descriptor_init(f1, l1,
    f2, l2, on_ms, off_ms, 0, 0, false) - frequencies as int, like the test passes them - then one tone_gen() of at most
-   1000 samples.  Returns the samples written. */
-EXPORT int ref_tone_burst(int16_t *amp, int f1, int l1, int f2, int l2, int on_ms, int off_ms)
+   max_samples samples (1000 in dtmf_rx_tests.c, 9999 in bell_mf_rx_tests.c).  Returns the samples written. */
+EXPORT int ref_tone_burst(int16_t *amp, int max_samples, int f1, int l1, int f2, int l2, int on_ms, int off_ms)
 {
     tone_gen_descriptor_t desc;
     tone_gen_state_t tone;
 
     tone_gen_descriptor_init(&desc, f1, l1, f2, l2, on_ms, off_ms, 0, 0, false);
     tone_gen_init(&tone, &desc);
-    return tone_gen(&tone, amp, 1000);
+    return tone_gen(&tone, amp, max_samples);
 }

@@ -106,3 +106,77 @@ def test_7_signal_to_noise(both):
             acceptable = -4 - j
             break
     assert acceptable is not None and acceptable <= 26                                       # dtmf_rx_tests.c:650
+
+
+# ---- Bell MF: tests/bell_mf_rx_tests.c:mitel_cm7291_side_1_tests ------------------------------------------------
+
+MF_CODES = "1234567890CA*B#"                    # bell_mf_tone_codes
+MF_TONES = [(700, 900), (700, 1100), (900, 1100), (700, 1300), (900, 1300), (1100, 1300), (700, 1500), (900, 1500),
+            (1100, 1500), (1300, 1500), (700, 1700), (900, 1700), (1100, 1700), (1300, 1700), (1500, 1700)]
+
+
+def mf_fudged(freq, permille):
+    """bell_mf_tones[i].f1*(1.0 + low_fudge) (bell_mf_rx_tests.c:141-145): float fudge, double product, int parameter."""
+    fudge = float(np.float32(permille / 1000.0))
+    return int(float(np.float32(freq)) * (1.0 + fudge))
+
+
+def mf_burst(S, code, low_pm=0, low_level=-3, high_pm=0, high_level=-3, duration=68, gap=68):
+    i = MF_CODES.index(code)
+    f1, f2 = MF_TONES[i]
+    return po.tone_burst(S, mf_fudged(f1, low_pm), low_level, mf_fudged(f2, high_pm), high_level,
+                         3 * duration // 2 if i == 12 else duration, gap, max_samples=9999)
+
+
+def mf_detect(oracles_list, stream):
+    out = None
+    for o in oracles_list:
+        ev, _, _ = o.run(po.make_params(po.DET_BELL_MF, po.MODE_DIGITS_CB, 160), stream[None, :])
+        got = "".join(chr(int(e["a"])) for e in ev[0])
+        if out is None:
+            out = got
+        else:
+            assert got == out, "the restatement and the compiled reference disagree"
+    return out
+
+
+def test_bell_mf_2_decode_check(both):
+    S, os_ = both
+    for code in MF_CODES:
+        assert mf_detect(os_, np.concatenate([mf_burst(S, code) for _ in range(10)])) == code * 10
+
+
+def test_bell_mf_3_recognition_bandwidth(both):
+    S, os_ = both
+    for j, code in enumerate(MF_CODES):
+        for which, f in (("low", MF_TONES[j][0]), ("high", MF_TONES[j][1])):
+            counts = []
+            for sign in (1, -1):
+                stream = np.concatenate([mf_burst(S, code, low_level=-17, high_level=-17, **{"%s_pm" % which: sign * i})
+                                         for i in range(1, 61)])
+                counts.append(len(mf_detect(os_, stream)))
+            nplus, nminus = counts
+            rrb = (nplus + nminus) / 10.0
+            rcfo = (nplus - nminus) / 10.0
+            assert not (rrb < 3.0 + rcfo + 2.0 * 100.0 * 10.0 / f or rrb >= 15.0 + rcfo), (code, which, rrb, rcfo)   # :334,367
+
+
+def test_bell_mf_4_twist(both):
+    S, os_ = both
+    levels = [-(abs(i) // 10) for i in range(-50, -251, -1)]
+    for code in MF_CODES:
+        nplus = len(mf_detect(os_, np.concatenate([mf_burst(S, code, low_level=-5, high_level=lv) for lv in levels])))
+        nminus = len(mf_detect(os_, np.concatenate([mf_burst(S, code, low_level=lv, high_level=-5) for lv in levels])))
+        assert nplus >= 60 and nminus >= 60, (code, nplus, nminus)                                                  # :400,417
+
+
+def test_bell_mf_7_signal_to_noise(both):
+    S, os_ = both
+    clean = np.tile(np.concatenate([mf_burst(S, c) for c in MF_CODES]), 500)
+    acceptable = None
+    for i in range(-10, -50, -1):
+        stream = po.awgn_run(S, len(clean), 1234567, float(i), into=clean.copy())
+        if mf_detect(os_, stream) == MF_CODES * 500:
+            acceptable = -3 - i
+            break
+    assert acceptable is not None and acceptable <= 26                                                              # :543
