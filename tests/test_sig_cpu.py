@@ -87,3 +87,42 @@ def test_sig_random_vs_reference(oracles):
         same(got, ref["out"], ref["ev"], ref["final"])
         reports += len(ref["ev"])
     assert reports > 60
+
+
+def handler_rule(ev):
+    """tests/sig_tone_tests.c:rx_handler(): a CHANGE bit must come with a toggled PRESENT bit, no CHANGE bit with an
+    unchanged one (the test exits with failure otherwise)."""
+    present = {1: 0, 4: 0}
+    for _, what, _ in ev.tolist():
+        for p, ch in ((1, 2), (4, 8)):
+            x = what & p
+            if what & ch:
+                assert x != present[p]
+                present[p] = x
+            else:
+                assert x == present[p]
+    return present
+
+
+def test_sig_tone_tests_sequence(oracles):
+    """The signalling sequence of tests/sig_tone_tests.c:sequence_tests(): tone(s) on over -20 dBm0 noise (seed 1234567),
+    a 100 ms seize, then dial pulses 33 / 67 ms (one-tone types) or tone 1, both, tone 2 for 100 ms each (the SS5
+    pair); 4000 samples in 160-sample calls, receiver in pass-through.  Criterion of the test = its rx_handler's
+    consistency rule; plus: the kernel code compiled for the host gives the reference's reports, audio and state."""
+    if "strict" not in oracles:
+        pytest.skip("compiled reference not available here")
+    S = oracles["strict"]
+    P1, P2 = 1, 4
+    for t in (1, 2, 3):
+        steps = [(P1 | P2, 800), (0, 800)]
+        steps += [(P1, 264), (0, 536)] * 3 if t != 3 else [(P1, 800), (P1 | P2, 800), (P2, 800)]
+        assert sum(x[1] for x in steps) == 4000
+        # -20 dBm0 is the test's own noise level: 10 dB under the tones, where the receiver (rightly) reports nothing -
+        # the test's handler rule holds vacuously.  -40 dBm0 is added here so that the rule is exercised.
+        for noise in (-20.0, -40.0):
+            amp = po.sig_generate(S, 4000, t, steps, noise_seed=1234567, noise_dbm0=noise)
+            ref = po.sig_run(S, amp, t, 160, None, ((0, 0x40),))
+            same(hs.sig_run(amp, t, 160, None, ((0, 0x40),)), ref["out"], ref["ev"], ref["final"])
+            handler_rule(ref["ev"])
+            if noise < -30.0:
+                assert len(ref["ev"]) >= 4             # at least: on, seize off, and one more on / off
