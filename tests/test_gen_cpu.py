@@ -86,3 +86,13 @@ def test_random_vs_reference(oracles):
         seed = int(rng.integers(-2**31 + 1, 2**31 - 1))
         level = float(rng.uniform(-60, 3))
         assert (po.awgn_run(S, 50000, seed, level) == hs.awgn_run(50000, seed, level)).all(), (seed, level)
+
+
+def test_awgn_tests_rms_procedure():
+    """tests/awgn_tests.c:69-107: a million samples at each level from -50 to -5 dBm0 in 5 dB steps, seed 1234567; the
+    measured RMS must be within 0.2 % of the generator's rms - run on the kernel code compiled for the host."""
+    for level in range(-50, 0, 5):
+        x = hs.awgn_run(1000000, 1234567, float(level)).astype(np.float64)
+        rms = 10.0 ** ((np.float32(level) - np.float32(3.14 + 3.02)) / 20.0) * 32768.0
+        error = 100.0 * (1.0 - np.sqrt((x * x).mean()) / rms)
+        assert abs(error) <= 0.2, (level, error)
