@@ -103,3 +103,17 @@ def test_python_binding_matches_headers(engine_lib):
         assert len(fn.argtypes) == nargs, "%s: header declares %d parameters, binding passes %d" % (name, nargs, len(fn.argtypes))
         checked += 1
     assert checked > 100
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI for C callers: every header under include/ must compile as C99 on its own."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for h in sorted(os.listdir(inc)):
+        if not h.endswith(".h"):
+            continue
+        src = tmp_path / "use.c"
+        src.write_text('#include "%s"\nint main(void) { return 0; }\n' % h)
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, "%s: %s" % (h, r.stderr[:500])
