@@ -117,3 +117,56 @@ def test_headers_are_plain_c(tmp_path):
         r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
                            capture_output=True, text=True)
         assert r.returncode == 0, "%s: %s" % (h, r.stderr[:500])
+
+
+def test_c_program_links_against_dropin(tmp_path, engine_lib):
+    """A plain C caller written against the reference's names links against the library; without a GPU the
+    constructors return NULL and the library says why (no fallback)."""
+    import subprocess
+    import torch
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "spandsp_b200_dropin.h"
+
+static void digits(void *user, const char *d, int len) { (void) user; (void) d; (void) len; }
+static void tone(void *user, int code, int level, int delay) { (void) user; (void) code; (void) level; (void) delay; }
+
+int main(void)
+{
+    int16_t amp[160];
+    char buf[8];
+    dtmf_rx_state_t *s;
+    modem_connect_tones_rx_state_t *m;
+    sig_tone_rx_state_t *g;
+
+    memset(amp, 0, sizeof(amp));
+    s = dtmf_rx_init(NULL, digits, NULL);
+    m = modem_connect_tones_rx_init(NULL, MODEM_CONNECT_TONES_FAX_CNG, tone, NULL);
+    g = sig_tone_rx_init(NULL, SIG_TONE_2280HZ, tone, NULL);
+    if (s == NULL  ||  m == NULL  ||  g == NULL)
+    {
+        printf("no-gpu: %s\n", span_b200_last_error());
+        return (s == NULL  &&  m == NULL  &&  g == NULL)  ?  3  :  4;
+    }
+    dtmf_rx(s, amp, 160);
+    modem_connect_tones_rx(m, amp, 160);
+    sig_tone_rx(g, amp, 160);
+    printf("digits=%d hit=%d\n", (int) dtmf_rx_get(s, buf, 7), modem_connect_tones_rx_get(m));
+    dtmf_rx_free(s);
+    modem_connect_tones_rx_free(m);
+    sig_tone_rx_free(g);
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(engine_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                        "-L", libdir, "-lspandsp_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:800]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "digits=0 hit=0" in r.stdout, (r.returncode, r.stdout, r.stderr)
+    else:
+        assert r.returncode == 3 and "no-gpu:" in r.stdout and len(r.stdout.strip()) > len("no-gpu:"), (r.returncode, r.stdout)
