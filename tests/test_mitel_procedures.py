@@ -218,3 +218,75 @@ def test_dtmf_callback_delivery_modes(both):
         else:
             assert signal == ord(DIGITS[(roll >> 1) % 16])
             assert -11 <= level <= -9                                           # DEFAULT_DTMF_TX_LEVEL +- 1 (:299-303)
+
+
+# ---- MFC/R2: tests/r2_mf_rx_tests.c:mitel_cm7291_side_1_tests, forward and backward sets -------------------------
+
+R2_CODES = "1234567890BCDEF"
+R2_FWD = [(1380, 1500), (1380, 1620), (1500, 1620), (1380, 1740), (1500, 1740), (1620, 1740), (1380, 1860), (1500, 1860),
+          (1620, 1860), (1740, 1860), (1380, 1980), (1500, 1980), (1620, 1980), (1740, 1980), (1860, 1980)]
+R2_BACK = [(1140, 1020), (1140, 900), (1020, 900), (1140, 780), (1020, 780), (900, 780), (1140, 660), (1020, 660),
+           (900, 660), (780, 660), (1140, 540), (1020, 540), (900, 540), (780, 540), (660, 540)]
+
+
+def r2_burst(S, fwd, code, low_pm=0, low_level=-3, high_pm=0, high_level=-3):
+    f1, f2 = (R2_FWD if fwd else R2_BACK)[R2_CODES.index(code)]
+    return po.tone_burst(S, mf_fudged(f1, low_pm), low_level, mf_fudged(f2, high_pm), high_level, 68, 0, max_samples=9999)
+
+
+def r2_gets(oracles_list, stream, fwd, nbursts):
+    """What r2_mf_rx_get() returns after each 544-sample burst: the code of the last change report so far."""
+    out = None
+    for o in oracles_list:
+        ev, _, _ = o.run(po.make_params(po.DET_R2_MF, po.MODE_REALTIME, 544, r2_fwd=int(fwd)), stream[None, :])
+        cur = 0
+        k = 0
+        got = []
+        changes = [(int(e["chunk"]), int(e["a"])) for e in ev[0]]
+        for b in range(nbursts):
+            while k < len(changes) and changes[k][0] <= b:
+                cur = changes[k][1]
+                k += 1
+            got.append(cur)
+        if out is None:
+            out = got
+        else:
+            assert got == out, "the restatement and the compiled reference disagree"
+    return out
+
+
+@pytest.mark.parametrize("fwd", [True, False])
+def test_r2_mf_2_decode_check(both, fwd):
+    S, os_ = both
+    for code in R2_CODES:
+        stream = np.concatenate([r2_burst(S, fwd, code) for _ in range(10)])
+        assert len(stream) == 10 * 544
+        assert r2_gets(os_, stream, fwd, 10) == [ord(code)] * 10
+
+
+@pytest.mark.parametrize("fwd", [True, False])
+def test_r2_mf_3_recognition_bandwidth(both, fwd):
+    S, os_ = both
+    for j, code in enumerate(R2_CODES):
+        for which, f in (("low", R2_FWD[j][0]), ("high", R2_FWD[j][1])):       # the test divides by the forward set's frequency (:350,387)
+            counts = []
+            for sign in (1, -1):
+                stream = np.concatenate([r2_burst(S, fwd, code, low_level=-17, high_level=-17, **{"%s_pm" % which: sign * i})
+                                         for i in range(1, 61)])
+                counts.append(sum(1 for g in r2_gets(os_, stream, fwd, 60) if g == ord(code)))
+            nplus, nminus = counts
+            rrb = (nplus + nminus) / 10.0
+            rcfo = (nplus - nminus) / 10.0
+            assert not (rrb < rcfo + 2.0 * 100.0 * 14.0 / f or rrb >= 15.0 + rcfo), (fwd, code, which, rrb, rcfo)
+
+
+@pytest.mark.parametrize("fwd", [True, False])
+def test_r2_mf_4_twist(both, fwd):
+    S, os_ = both
+    levels = [-(abs(i) // 10) for i in range(-50, -251, -1)]
+    for code in R2_CODES:
+        up = np.concatenate([r2_burst(S, fwd, code, low_level=-5, high_level=lv) for lv in levels])
+        dn = np.concatenate([r2_burst(S, fwd, code, low_level=lv, high_level=-5) for lv in levels])
+        nplus = sum(1 for g in r2_gets(os_, up, fwd, len(levels)) if g == ord(code))
+        nminus = sum(1 for g in r2_gets(os_, dn, fwd, len(levels)) if g == ord(code))
+        assert nplus >= 70 and nminus >= 70, (fwd, code, nplus, nminus)                               # :421,440
