@@ -538,6 +538,16 @@ def tone_burst(o, f1, l1, f2, l2, on_ms, off_ms, max_samples=1000):
     return amp[:n]
 
 
+def super_tone_range_stimulus(o, first_level=-80, last_level=-1, chunks=100):
+    """The dial tone sweep of tests/super_tone_rx_tests.c:detection_range_tests()."""
+    n = (last_level - first_level + 1) * chunks * 160
+    amp = np.zeros(n, dtype=np.int16)
+    o.lib.ref_super_tone_range_stimulus.restype = C.c_int
+    got = o.lib.ref_super_tone_range_stimulus(C.c_void_p(amp.ctypes.data), C.c_int(n), C.c_int(first_level), C.c_int(last_level), C.c_int(chunks))
+    assert got == n
+    return amp
+
+
 _cache = {}
 
 

@@ -116,3 +116,39 @@ EXPORT int ref_tone_burst(int16_t *amp, int max_samples, int f1, int l1, int f2,
     tone_gen_init(&tone, &desc);
     return tone_gen(&tone, amp, max_samples);
 }
+
+/* The stimulus of tests/super_tone_rx_tests.c:detection_range_tests(): 350 Hz + 440 Hz from the integer DDS with
+   running phases, at every level from first_level to last_level dBm0 in 1 dB steps, `chunks` chunks of 160 samples per
+   level.  Returns the samples written. */
+EXPORT int ref_super_tone_range_stimulus(int16_t *amp, int max_samples, int first_level, int last_level, int chunks)
+{
+    uint32_t phase[2];
+    int32_t phase_inc[2];
+    int scale;
+    int level;
+    int i;
+    int j;
+    int n;
+
+    phase[0] = 0;
+    phase_inc[0] = dds_phase_rate(350.0f);
+    phase[1] = 0;
+    phase_inc[1] = dds_phase_rate(440.0f);
+    n = 0;
+    for (level = first_level;  level <= last_level;  level++)
+    {
+        scale = dds_scaling_dbm0(level);
+        for (j = 0;  j < chunks;  j++)
+        {
+            for (i = 0;  i < 160;  i++)
+            {
+                if (n >= max_samples)
+                    return n;
+                amp[n] = (dds(&phase[0], phase_inc[0])*scale) >> 15;
+                amp[n] += (dds(&phase[1], phase_inc[1])*scale) >> 15;
+                n++;
+            }
+        }
+    }
+    return n;
+}
