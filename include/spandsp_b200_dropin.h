@@ -50,7 +50,8 @@ typedef struct logging_state_s logging_state_t;
 typedef struct span_b200_group_s span_b200_group_t;
 
 /* detector: SPAN_B200_DET_*; arg: R2 MF forward flag, or for super-tone a super_tone_rx_descriptor_t
-   passed through `desc`.  max_samples bounds the samples one member may stage between flushes. */
+   passed through `desc`.  max_samples sizes the pinned staging area (samples one member stages between flushes); it grows when a
+   member is fed more than that, audio is never dropped. */
 span_b200_group_t *span_b200_group_create(span_b200_ctx_t *ctx, int detector, int members, int max_samples,
                                           int arg, super_tone_rx_descriptor_t *desc);
 /* Member i as the detector's state type (cast to dtmf_rx_state_t * etc.).  Members are created in

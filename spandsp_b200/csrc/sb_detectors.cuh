@@ -702,7 +702,8 @@ __global__ void __launch_bounds__(128) r2_mf_sequencer(const MfSeqArgs s)
 
 // ==========================================================================================
 // Supervisory tones  (reference: src/super_tone_rx.c)
-#define SB_ST_MAX_PAIRS     16          // up to 32 monitored bins in one pass
+#define SB_ST_MAX_PAIRS     32          // 64 monitored bins: the reference's limit (src/spandsp/private/super_tone_rx.h:29,44)
+#define SB_RAW_MAX_BINS     32          // raw Goertzel banks
 
 struct StParams
 {

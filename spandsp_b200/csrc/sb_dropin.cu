@@ -401,9 +401,16 @@ extern "C" int span_b200_group_flush(span_b200_group_t *g)
     }
     if (span_b200_bank_rx_host(g->bank, g->h_stage, g->max_samples, n, NULL) != 0)
         return -1;
-    const int64_t total = span_b200_bank_event_count(g->bank, NULL);
+    int overflow = 0;
+    const int64_t total = span_b200_bank_event_count(g->bank, &overflow);
     if (total < 0)
         return -1;
+    if (overflow)
+    {
+        // Cannot happen with the default (worst case) event capacity; a caller-set capacity was too small.
+        // The reports that fit are still delivered below, but the flush is reported as failed.
+        sb_set_error("group flush: the bank's event buffer overflowed; reports were lost");
+    }
     g->events.resize((size_t) total);
     if (total > 0  &&  span_b200_bank_events(g->bank, g->events.data(), total) < 0)
         return -1;
@@ -424,7 +431,7 @@ extern "C" int span_b200_group_flush(span_b200_group_t *g)
             fired += trailing_flush((bell_mf_rx_state_s *) m);
         m->staged = 0;
     }
-    return fired;
+    return (overflow)  ?  -1  :  fired;
 }
 
 static int stage_samples(sb_member_t *m, const int16_t amp[], int samples)
@@ -435,12 +442,9 @@ static int stage_samples(sb_member_t *m, const int16_t amp[], int samples)
         return 0;
     if (m->staged + samples > g->max_samples)
     {
-        if (!g->single)
-        {
-            sb_set_error("group member %d: %d samples staged + %d exceed max_samples %d; flush more often",
-                         m->index, m->staged, samples, g->max_samples);
-            return -1;
-        }
+        // More audio than the staging area holds (a group that is flushed less often than its max_samples
+        // suggests, or a long call on a plain state): grow it, keeping what every member has staged.  Audio is
+        // never dropped; the only failure left is running out of pinned memory.
         if (alloc_stage(g, std::max(2*g->max_samples, m->staged + samples)) != 0)
             return -1;
     }
@@ -564,8 +568,9 @@ extern "C" void dtmf_rx_parms(dtmf_rx_state_t *s, int filter_dialtone, float twi
 
 extern "C" int dtmf_rx(dtmf_rx_state_t *s, const int16_t amp[], int samples)
 {
-    stage_samples(&s->m, amp, samples);
-    return 0;                                   // src/dtmf.c:360
+    // "The number of samples unprocessed" (src/spandsp/dtmf.h:176): 0 as in src/dtmf.c:360, or all of them when
+    // the device path failed (span_b200_last_error() says why)
+    return (stage_samples(&s->m, amp, samples) == 0)  ?  0  :  samples;
 }
 
 extern "C" int dtmf_rx_fillin(dtmf_rx_state_t *s, int samples)
@@ -633,8 +638,7 @@ extern "C" int bell_mf_rx_free(bell_mf_rx_state_t *s) { return state_close(s, 1)
 
 extern "C" int bell_mf_rx(bell_mf_rx_state_t *s, const int16_t amp[], int samples)
 {
-    stage_samples(&s->m, amp, samples);
-    return 0;
+    return (stage_samples(&s->m, amp, samples) == 0)  ?  0  :  samples;         // unprocessed samples
 }
 
 extern "C" size_t bell_mf_rx_get(bell_mf_rx_state_t *s, char *buf, int max)
@@ -662,8 +666,7 @@ extern "C" int r2_mf_rx_free(r2_mf_rx_state_t *s) { return state_close(s, 1); }
 
 extern "C" int r2_mf_rx(r2_mf_rx_state_t *s, const int16_t amp[], int samples)
 {
-    stage_samples(&s->m, amp, samples);
-    return 0;
+    return (stage_samples(&s->m, amp, samples) == 0)  ?  0  :  samples;         // unprocessed samples
 }
 
 extern "C" int r2_mf_rx_get(r2_mf_rx_state_t *s)
@@ -755,8 +758,9 @@ extern "C" void super_tone_rx_segment_callback(super_tone_rx_state_t *s, tone_se
 
 extern "C" int super_tone_rx(super_tone_rx_state_t *s, const int16_t amp[], int samples)
 {
-    stage_samples(&s->m, amp, samples);
-    return samples;                             // src/super_tone_rx.c:489
+    // "The number of samples processed" (src/spandsp/super_tone_rx.h:154): all of them (src/super_tone_rx.c:489), or
+    // none when the device path failed
+    return (stage_samples(&s->m, amp, samples) == 0)  ?  samples  :  0;
 }
 
 extern "C" int super_tone_rx_fillin(super_tone_rx_state_t *s, int samples)
@@ -848,7 +852,7 @@ static int gz_prepare(int n)
     span_b200_ctx_t *ctx = span_b200_default_ctx();
     if (ctx == NULL)
         return -1;
-    cudaSetDevice(span_b200_ctx_device(ctx));
+    sb_device_guard sb_dg_(span_b200_ctx_device(ctx));
     if (g_gz_state == NULL  &&  cudaMalloc(&g_gz_state, sizeof(float)*4) != cudaSuccess)
         return -1;
     if (n > g_gz_cap)

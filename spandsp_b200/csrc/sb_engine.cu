@@ -53,6 +53,34 @@ void sb_set_error(const char *fmt, ...)
     } \
     while (0)
 
+// Inside a *_create function, once the object exists: a failure releases what was already acquired
+// (the destroy functions tolerate NULL members)
+#define CKB(call) \
+    do \
+    { \
+        cudaError_t e_ = (call); \
+        if (e_ != cudaSuccess) \
+        { \
+            sb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            span_b200_bank_destroy(b); \
+            return NULL; \
+        } \
+    } \
+    while (0)
+
+#define CKC(call) \
+    do \
+    { \
+        cudaError_t e_ = (call); \
+        if (e_ != cudaSuccess) \
+        { \
+            sb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            span_b200_ctx_destroy(ctx); \
+            return NULL; \
+        } \
+    } \
+    while (0)
+
 extern "C" const char *span_b200_last_error(void)
 {
     return g_err;
@@ -201,27 +229,30 @@ extern "C" span_b200_ctx_t *span_b200_ctx_create(int device)
         sb_set_error("device %d is sm_%d%d; spandsp_b200 kernels are built for sm_100a only", device, prop.major, prop.minor);
         return NULL;
     }
-    CKP(cudaSetDevice(device));
+    SB_DEVICE_CKP(device);
     span_b200_ctx_t *ctx = new span_b200_ctx_s();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int) prop.sharedMemPerBlockOptin;
-    CKP(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     if (upload_constants(device) != 0)
+    {
+        span_b200_ctx_destroy(ctx);
         return NULL;
+    }
     std::vector<float> thr;
     build_level_table(thr, ctx->level_min);
     ctx->level_n = (int) thr.size();
-    CKP(cudaMalloc(&ctx->d_level_thr, sizeof(float)*thr.size()));
-    CKP(cudaMemcpy(ctx->d_level_thr, thr.data(), sizeof(float)*thr.size(), cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&ctx->d_level_thr, sizeof(float)*thr.size()));
+    CKC(cudaMemcpy(ctx->d_level_thr, thr.data(), sizeof(float)*thr.size(), cudaMemcpyHostToDevice));
     float lut[512];
     for (int i = 0;  i < 256;  i++)
     {
         lut[i] = (float) sb_ulaw_to_linear((unsigned char) i);
         lut[256 + i] = (float) sb_alaw_to_linear((unsigned char) i);
     }
-    CKP(cudaMalloc(&ctx->d_g711_lut, sizeof(lut)));
-    CKP(cudaMemcpy(ctx->d_g711_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&ctx->d_g711_lut, sizeof(lut)));
+    CKC(cudaMemcpy(ctx->d_g711_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     return ctx;
 }
 
@@ -229,11 +260,13 @@ extern "C" void span_b200_ctx_destroy(span_b200_ctx_t *ctx)
 {
     if (ctx == NULL)
         return;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sb_device_guard sb_dg_(ctx->device);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_level_thr);
     cudaFree(ctx->d_g711_lut);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -344,6 +377,21 @@ static int ensure(void **p, size_t *have, size_t want)
     return 0;
 }
 
+// The super-tone bank kernel is instantiated for a fixed list of pair counts; a descriptor runs on the next larger
+// one (the surplus bins have a zero coefficient and are never read by the decision).  The carried state arrays
+// must have the rows of the instantiation that runs, not of the descriptor: load_carry()/store_carry() touch
+// all 2*NPAIRS rows.
+static int st_template_pairs(int npairs)
+{
+    static const int sizes[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
+    for (size_t i = 0;  i < sizeof(sizes)/sizeof(sizes[0]);  i++)
+    {
+        if (npairs <= sizes[i])
+            return sizes[i];
+    }
+    return -1;
+}
+
 static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels, int block, int bins)
 {
     if (ctx == NULL  ||  channels <= 0)
@@ -351,7 +399,7 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
         sb_set_error("bad bank arguments");
         return NULL;
     }
-    CKP(cudaSetDevice(ctx->device));
+    SB_DEVICE_CKP(ctx->device);
     span_b200_bank_t *b = new span_b200_bank_s();
     b->ctx = ctx;
     b->det = det;
@@ -359,18 +407,20 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
     b->block = block;
     b->bins = bins;
     b->npairs = (bins + 1)/2;
+    if (det == SPAN_B200_DET_SUPER_TONE)
+        b->npairs = st_template_pairs(b->npairs);
     b->uniform_cs = 0;
     b->tune_packed = 5;
     b->last_path = "";
     const size_t C = channels;
-    CKP(cudaMalloc(&b->v2, sizeof(float)*2*b->npairs*C));
-    CKP(cudaMalloc(&b->v3, sizeof(float)*2*b->npairs*C));
-    CKP(cudaMalloc(&b->energy, sizeof(float)*C));
-    CKP(cudaMalloc(&b->cs, sizeof(int)*C));
-    CKP(cudaMalloc(&b->counts, sizeof(unsigned int)*((C + 31)/32 + 1)));
-    CKP(cudaMalloc(&b->offsets, sizeof(unsigned int)*((C + 31)/32 + 1)));
-    CKP(cudaMalloc(&b->d_total, sizeof(unsigned long long)));
-    CKP(cudaMallocHost(&b->h_total, sizeof(unsigned long long)));
+    CKB(cudaMalloc(&b->v2, sizeof(float)*2*b->npairs*C));
+    CKB(cudaMalloc(&b->v3, sizeof(float)*2*b->npairs*C));
+    CKB(cudaMalloc(&b->energy, sizeof(float)*C));
+    CKB(cudaMalloc(&b->cs, sizeof(int)*C));
+    CKB(cudaMalloc(&b->counts, sizeof(unsigned int)*((C + 31)/32 + 1)));
+    CKB(cudaMalloc(&b->offsets, sizeof(unsigned int)*((C + 31)/32 + 1)));
+    CKB(cudaMalloc(&b->d_total, sizeof(unsigned long long)));
+    CKB(cudaMallocHost(&b->h_total, sizeof(unsigned long long)));
     b->h_total[0] = 0;
     return b;
 }
@@ -384,7 +434,7 @@ extern "C" int span_b200_bank_reset(span_b200_bank_t *b, int first, int count)
     }
     if (count == 0)
         return 0;
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     const size_t C = b->channels;
@@ -451,21 +501,24 @@ extern "C" span_b200_bank_t *span_b200_dtmf_bank_create(span_b200_ctx_t *ctx, in
     if (b == NULL)
         return NULL;
     const size_t C = channels;
-    CKP(cudaMalloc(&b->thr, sizeof(float)*C));
-    CKP(cudaMalloc(&b->ntw, sizeof(float)*C));
-    CKP(cudaMalloc(&b->rtw, sizeof(float)*C));
-    CKP(cudaMalloc(&b->flags, C));
-    CKP(cudaMalloc(&b->z, sizeof(float)*4*C));
-    CKP(cudaMalloc(&b->last_hit, C));
-    CKP(cudaMalloc(&b->in_digit, C));
-    CKP(cudaMalloc(&b->duration, sizeof(int)*C));
+    CKB(cudaMalloc(&b->thr, sizeof(float)*C));
+    CKB(cudaMalloc(&b->ntw, sizeof(float)*C));
+    CKB(cudaMalloc(&b->rtw, sizeof(float)*C));
+    CKB(cudaMalloc(&b->flags, C));
+    CKB(cudaMalloc(&b->z, sizeof(float)*4*C));
+    CKB(cudaMalloc(&b->last_hit, C));
+    CKB(cudaMalloc(&b->in_digit, C));
+    CKB(cudaMalloc(&b->duration, sizeof(int)*C));
     b->h_thr.assign(C, 0.0f);
     b->h_ntw.assign(C, 0.0f);
     b->h_rtw.assign(C, 0.0f);
     b->h_flags.assign(C, 0);
     b->n_filter = 0;
     if (span_b200_bank_reset(b, 0, channels) != 0)
+    {
+        span_b200_bank_destroy(b);
         return NULL;
+    }
     return b;
 }
 
@@ -474,9 +527,12 @@ extern "C" span_b200_bank_t *span_b200_bell_mf_bank_create(span_b200_ctx_t *ctx,
     span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_BELL_MF, channels, 120, 6);
     if (b == NULL)
         return NULL;
-    CKP(cudaMalloc(&b->hits, (size_t) 5*channels));
+    CKB(cudaMalloc(&b->hits, (size_t) 5*channels));
     if (span_b200_bank_reset(b, 0, channels) != 0)
+    {
+        span_b200_bank_destroy(b);
         return NULL;
+    }
     return b;
 }
 
@@ -486,9 +542,12 @@ extern "C" span_b200_bank_t *span_b200_r2_mf_bank_create(span_b200_ctx_t *ctx, i
     if (b == NULL)
         return NULL;
     b->fwd = (fwd != 0);
-    CKP(cudaMalloc(&b->hits, (size_t) channels));
+    CKB(cudaMalloc(&b->hits, (size_t) channels));
     if (span_b200_bank_reset(b, 0, channels) != 0)
+    {
+        span_b200_bank_destroy(b);
         return NULL;
+    }
     return b;
 }
 
@@ -574,8 +633,8 @@ extern "C" span_b200_bank_t *span_b200_super_tone_bank_create(span_b200_ctx_t *c
     }
     if (bd.monitored > 2*SB_ST_MAX_PAIRS)
     {
-        sb_set_error("super-tone descriptors with more than %d monitored frequencies are not supported yet (got %d)",
-                     2*SB_ST_MAX_PAIRS, bd.monitored);
+        sb_set_error("super-tone descriptor monitors %d frequencies; the limit is %d (src/spandsp/private/super_tone_rx.h:44)",
+                     bd.monitored, 2*SB_ST_MAX_PAIRS);
         return NULL;
     }
     span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_SUPER_TONE, channels, 128, bd.monitored);
@@ -589,22 +648,25 @@ extern "C" span_b200_bank_t *span_b200_super_tone_bank_create(span_b200_ctx_t *c
     b->h_fac.assign(bd.fac, bd.fac + bd.monitored);
     b->tones = desc->tones;
     const size_t C = channels;
-    CKP(cudaMalloc(&b->segments, sizeof(int)*33*C));
-    CKP(cudaMalloc(&b->detected, sizeof(int)*C));
-    CKP(cudaMalloc(&b->rotation, sizeof(int)*C));
-    CKP(cudaMalloc(&b->pending, C));
-    CKP(cudaMalloc(&b->d_tone_segs, sizeof(int)*(desc->tones + 1)));
-    CKP(cudaMalloc(&b->d_tone_first, sizeof(int)*(desc->tones + 1)));
-    CKP(cudaMalloc(&b->d_elements, sizeof(int4)*(elements.size() + 1)));
+    CKB(cudaMalloc(&b->segments, sizeof(int)*33*C));
+    CKB(cudaMalloc(&b->detected, sizeof(int)*C));
+    CKB(cudaMalloc(&b->rotation, sizeof(int)*C));
+    CKB(cudaMalloc(&b->pending, C));
+    CKB(cudaMalloc(&b->d_tone_segs, sizeof(int)*(desc->tones + 1)));
+    CKB(cudaMalloc(&b->d_tone_first, sizeof(int)*(desc->tones + 1)));
+    CKB(cudaMalloc(&b->d_elements, sizeof(int4)*(elements.size() + 1)));
     if (desc->tones)
     {
-        CKP(cudaMemcpy(b->d_tone_segs, desc->tone_segs, sizeof(int)*desc->tones, cudaMemcpyHostToDevice));
-        CKP(cudaMemcpy(b->d_tone_first, tone_first.data(), sizeof(int)*desc->tones, cudaMemcpyHostToDevice));
+        CKB(cudaMemcpy(b->d_tone_segs, desc->tone_segs, sizeof(int)*desc->tones, cudaMemcpyHostToDevice));
+        CKB(cudaMemcpy(b->d_tone_first, tone_first.data(), sizeof(int)*desc->tones, cudaMemcpyHostToDevice));
     }
     if (!elements.empty())
-        CKP(cudaMemcpy(b->d_elements, elements.data(), sizeof(int4)*elements.size(), cudaMemcpyHostToDevice));
+        CKB(cudaMemcpy(b->d_elements, elements.data(), sizeof(int4)*elements.size(), cudaMemcpyHostToDevice));
     if (span_b200_bank_reset(b, 0, channels) != 0)
+    {
+        span_b200_bank_destroy(b);
         return NULL;
+    }
     return b;
 }
 
@@ -612,7 +674,7 @@ extern "C" void span_b200_bank_destroy(span_b200_bank_t *b)
 {
     if (b == NULL)
         return;
-    cudaSetDevice(b->ctx->device);
+    sb_device_guard sb_dg_(b->ctx->device);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->v2);
@@ -728,7 +790,7 @@ extern "C" int span_b200_dtmf_bank_parms(span_b200_bank_t *b, int first, int cou
         return -1;
     if (count == 0)
         return 0;
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     const size_t C = b->channels;
@@ -771,7 +833,7 @@ extern "C" int span_b200_dtmf_bank_realtime(span_b200_bank_t *b, int first, int 
         return -1;
     if (count == 0)
         return 0;
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     for (int i = first;  i < first + count;  i++)
@@ -791,7 +853,7 @@ extern "C" int span_b200_dtmf_bank_fillin(span_b200_bank_t *b, int first, int co
         return -1;
     if (count == 0)
         return 0;
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     const size_t C = b->channels;
@@ -819,7 +881,7 @@ extern "C" int span_b200_bank_status(span_b200_bank_t *b, int first, int count, 
     }
     if (count == 0)
         return 0;
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     std::vector<unsigned char> a(count);
@@ -912,7 +974,12 @@ static int launch_variant(const BankArgs<DET> &a, bool filter, cudaStream_t st, 
     // (row bytes per stage = SEG_VEC*16, stages, warps per CTA, min CTAs per SM).  The round-1 sweep
     // (profiles/r01_sweep_dtmf*.json) covered nine shapes; the fastest is kept: 128-byte row segments,
     // 2 stages, 16-20 resident warps per SM.
-    return launch_staged<DET, 8, 2, 4, 4, NPACK>(a, filter, st);        // 272 B/row
+    // More than 32 bins (super-tone descriptors with 33..64 monitored frequencies): the resonators alone need
+    // 4*NPAIRS registers, so two CTAs per SM instead of four
+    if constexpr (DET::NPAIRS > 16)
+        return launch_staged<DET, 8, 2, 4, 2, NPACK>(a, filter, st);
+    else
+        return launch_staged<DET, 8, 2, 4, 4, NPACK>(a, filter, st);    // 272 B/row
 }
 
 template <class DET>
@@ -929,7 +996,10 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
         if (g.staged)
         {
             b->last_path = "staged";
-            return launch_staged<DET, 8, 2, 4, 4, DET::NPAIRS + 1, true>(a, filter, st);
+            if constexpr (DET::NPAIRS > 16)
+                return launch_staged<DET, 8, 2, 4, 2, DET::NPAIRS + 1, true>(a, filter, st);
+            else
+                return launch_staged<DET, 8, 2, 4, 4, DET::NPAIRS + 1, true>(a, filter, st);
         }
         b->last_path = "direct";
         bank_kernel_direct<DET, DET::NPAIRS + 1, true><<<(a.channels + 127)/128, 128, 0, st>>>(a);
@@ -1004,7 +1074,10 @@ static long long worst_case_events(const span_b200_bank_t *b, int nb)
     switch (b->det)
     {
     case SPAN_B200_DET_DTMF:
-        return C*(nb/2 + 1);            // an event needs two consecutive differing blocks
+        // An event needs two consecutive blocks that differ from in_digit, and it leaves last_hit == in_digit
+        // (src/dtmf.c:304-346: last_hit takes the debounced hit), so the block after an event cannot fire:
+        // at most one event per two blocks in either mode.
+        return C*(nb/2 + 1);
     case SPAN_B200_DET_BELL_MF:
         return C*(nb/2 + 1);
     case SPAN_B200_DET_R2_MF:
@@ -1022,7 +1095,7 @@ static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, in
         sb_set_error("bad rx arguments");
         return -1;
     }
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
@@ -1149,8 +1222,14 @@ static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, in
                 rc = run_st<10>(b, d_amp, stride, n, g, st, lut);
             else if (b->npairs <= 12)
                 rc = run_st<12>(b, d_amp, stride, n, g, st, lut);
-            else
+            else if (b->npairs <= 16)
                 rc = run_st<16>(b, d_amp, stride, n, g, st, lut);
+            else if (b->npairs <= 20)
+                rc = run_st<20>(b, d_amp, stride, n, g, st, lut);
+            else if (b->npairs <= 24)
+                rc = run_st<24>(b, d_amp, stride, n, g, st, lut);
+            else
+                rc = run_st<32>(b, d_amp, stride, n, g, st, lut);
             break;
         }
         if (rc != 0)
@@ -1279,7 +1358,7 @@ extern "C" int span_b200_bank_rx_host_g711(span_b200_bank_t *b, const uint8_t *h
         sb_set_error("bad rx arguments");
         return -1;
     }
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
@@ -1304,7 +1383,7 @@ extern "C" int span_b200_bank_rx_host(span_b200_bank_t *b, const int16_t *h_amp,
         sb_set_error("bad rx arguments");
         return -1;
     }
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
@@ -1334,7 +1413,7 @@ extern "C" int64_t span_b200_bank_event_count(span_b200_bank_t *b, int *overflow
         *overflow = 0;
     if (!b->have_last)
         return 0;
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     CK(cudaStreamSynchronize(b->last_stream));
     long long total = (long long) b->h_total[0];
     if (total > b->ev_cap)
@@ -1376,7 +1455,8 @@ extern "C" double span_b200_bank_kernel_ms(span_b200_bank_t *b, int *launches)
     double ms = 0.0;
     if (launches)
         *launches = 0;
-    if (cudaSetDevice(b->ctx->device) != cudaSuccess)
+    sb_device_guard sb_dg_(b->ctx->device);
+    if (!sb_dg_.ok())
         return -1.0;
     if (b->have_last  &&  cudaStreamSynchronize(b->last_stream) != cudaSuccess)
         return -1.0;
@@ -1401,7 +1481,7 @@ extern "C" int span_b200_bank_block_codes(span_b200_bank_t *b, uint16_t *codes, 
 {
     if (!b->have_last)
         return 0;
-    CK(cudaSetDevice(b->ctx->device));
+    SB_DEVICE_CK(b->ctx->device);
     CK(cudaStreamSynchronize(b->last_stream));
     const int64_t total = (int64_t) b->last_nb*b->channels;
     const int64_t n = (total < max)  ?  total  :  max;
@@ -1469,12 +1549,12 @@ extern "C" int span_b200_goertzel_blocks_device(span_b200_ctx_t *ctx, const floa
                                                 const int16_t *d_amp, int64_t stride, int channels, int n,
                                                 float *d_out, int64_t out_capacity, void *stream)
 {
-    if (ctx == NULL  ||  fac == NULL  ||  bins < 1  ||  bins > 2*SB_ST_MAX_PAIRS  ||  block_len < 1  ||  channels < 1  ||  n < 0)
+    if (ctx == NULL  ||  fac == NULL  ||  bins < 1  ||  bins > SB_RAW_MAX_BINS  ||  block_len < 1  ||  channels < 1  ||  n < 0)
     {
-        sb_set_error("bad goertzel bank arguments (1..%d bins)", 2*SB_ST_MAX_PAIRS);
+        sb_set_error("bad goertzel bank arguments (1..%d bins)", SB_RAW_MAX_BINS);
         return -1;
     }
-    CK(cudaSetDevice(ctx->device));
+    SB_DEVICE_CK(ctx->device);
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  ctx->stream;
     const int np = (bins + 1)/2;
     int rc;

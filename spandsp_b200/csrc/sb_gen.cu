@@ -73,7 +73,7 @@ static DtmfTxArgs tx_args(span_b200_dtmf_tx_bank_t *b, int16_t *d_amp, int64_t s
 
 static int tx_quiesce(span_b200_dtmf_tx_bank_t *b)
 {
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     return 0;
@@ -125,7 +125,7 @@ extern "C" void span_b200_dtmf_tx_bank_destroy(span_b200_dtmf_tx_bank_t *b)
 {
     if (b == NULL)
         return;
-    cudaSetDevice(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->state);
@@ -146,11 +146,7 @@ extern "C" span_b200_dtmf_tx_bank_t *span_b200_dtmf_tx_bank_create(span_b200_ctx
         sb_set_error("bad DTMF transmitter bank arguments");
         return NULL;
     }
-    if (cudaSetDevice(span_b200_ctx_device(ctx)) != cudaSuccess)
-    {
-        sb_set_error("cudaSetDevice failed");
-        return NULL;
-    }
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
     span_b200_dtmf_tx_bank_t *b = new span_b200_dtmf_tx_bank_s();
     memset(b, 0, sizeof(*b));
     b->ctx = ctx;
@@ -284,7 +280,7 @@ extern "C" int span_b200_dtmf_tx_bank_tx_device(span_b200_dtmf_tx_bank_t *b, int
         sb_set_error("bad tx arguments");
         return -1;
     }
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
@@ -380,7 +376,7 @@ static int awgn_init(span_b200_awgn_bank_t *b, int first, int count, const int32
     }
     if (count == 0)
         return 0;
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     if (seeds)
@@ -409,7 +405,7 @@ extern "C" void span_b200_awgn_bank_destroy(span_b200_awgn_bank_t *b)
 {
     if (b == NULL)
         return;
-    cudaSetDevice(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->istate);
@@ -425,11 +421,7 @@ extern "C" span_b200_awgn_bank_t *span_b200_awgn_bank_create(span_b200_ctx_t *ct
         sb_set_error("bad noise bank arguments");
         return NULL;
     }
-    if (cudaSetDevice(span_b200_ctx_device(ctx)) != cudaSuccess)
-    {
-        sb_set_error("cudaSetDevice failed");
-        return NULL;
-    }
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
     span_b200_awgn_bank_t *b = new span_b200_awgn_bank_s();
     memset(b, 0, sizeof(*b));
     b->ctx = ctx;
@@ -464,7 +456,7 @@ static int awgn_run(span_b200_awgn_bank_t *b, int16_t *d_amp, int64_t stride, in
         sb_set_error("bad noise arguments");
         return -1;
     }
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
@@ -490,7 +482,7 @@ extern "C" int span_b200_awgn_bank_sync(span_b200_awgn_bank_t *b)
 {
     if (b == NULL)
         return -1;
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     return 0;

@@ -68,7 +68,7 @@ static MctArgs mct_args(span_b200_mct_bank_t *b, const int16_t *d_amp, int64_t s
 
 static int mct_quiesce(span_b200_mct_bank_t *b)
 {
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     return 0;
@@ -118,7 +118,7 @@ extern "C" void span_b200_mct_bank_destroy(span_b200_mct_bank_t *b)
 {
     if (b == NULL)
         return;
-    cudaSetDevice(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->state);
@@ -139,11 +139,7 @@ extern "C" span_b200_mct_bank_t *span_b200_mct_bank_create(span_b200_ctx_t *ctx,
         sb_set_error("bad modem connect tone bank arguments");
         return NULL;
     }
-    if (cudaSetDevice(span_b200_ctx_device(ctx)) != cudaSuccess)
-    {
-        sb_set_error("cudaSetDevice failed");
-        return NULL;
-    }
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
     span_b200_mct_bank_t *b = new span_b200_mct_bank_s();
     memset(b, 0, sizeof(*b));
     b->ctx = ctx;
@@ -194,7 +190,7 @@ extern "C" int span_b200_mct_bank_rx_device(span_b200_mct_bank_t *b, const int16
         sb_set_error("bad rx arguments");
         return -1;
     }
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
@@ -229,7 +225,7 @@ extern "C" int span_b200_mct_bank_rx_host(span_b200_mct_bank_t *b, const int16_t
         sb_set_error("bad rx arguments");
         return -1;
     }
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));

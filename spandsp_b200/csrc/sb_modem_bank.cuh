@@ -166,7 +166,7 @@ static int modem_init_channels(ModemBank<RX> *b, int first, int count, int bit_r
 {
     if (count <= 0)
         return 0;
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     if (modem_configure<RX>() != 0)
         return -1;
     const int smem = (int) sizeof(float)*modem_smem_words<RX>();
@@ -198,7 +198,7 @@ static void modem_destroy(ModemBank<RX> *b)
 {
     if (b == NULL)
         return;
-    cudaSetDevice(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->fstate);
@@ -216,7 +216,7 @@ static void modem_destroy(ModemBank<RX> *b)
 template <class RX>
 static int modem_quiesce(ModemBank<RX> *b)
 {
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     return 0;
@@ -311,7 +311,7 @@ static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t strid
         sb_set_error("bad rx arguments");
         return -1;
     }
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
@@ -353,7 +353,7 @@ static int modem_rx_host(ModemBank<RX> *b, const int16_t *h_amp, int64_t stride,
         sb_set_error("bad rx arguments");
         return -1;
     }
-    CK(cudaSetDevice(span_b200_ctx_device(b->ctx)));
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));

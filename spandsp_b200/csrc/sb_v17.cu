@@ -68,7 +68,7 @@ extern "C" span_b200_v17_bank_t *span_b200_v17_bank_create(span_b200_ctx_t *ctx,
         sb_set_error("bad V.17 bank arguments (bit rate must be 14400, 12000, 9600, 7200 or 4800)");    // src/v17rx.c:1498-1510
         return NULL;
     }
-    CKP(cudaSetDevice(span_b200_ctx_device(ctx)));
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
     span_b200_v17_bank_t *b = new span_b200_v17_bank_s();
     b->ctx = ctx;
     b->channels = channels;

@@ -48,7 +48,7 @@ extern "C" span_b200_v27ter_bank_t *span_b200_v27ter_bank_create(span_b200_ctx_t
         sb_set_error("bad V.27ter bank arguments (bit rate must be 4800 or 2400)");         // src/v27ter_rx.c:1163-1171
         return NULL;
     }
-    CKP(cudaSetDevice(span_b200_ctx_device(ctx)));
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
     span_b200_v27ter_bank_t *b = new span_b200_v27ter_bank_s();
     b->ctx = ctx;
     b->channels = channels;

@@ -58,7 +58,7 @@ extern "C" span_b200_v29_bank_t *span_b200_v29_bank_create(span_b200_ctx_t *ctx,
         sb_set_error("bad V.29 bank arguments (bit rate must be 9600, 7200 or 4800)");      // src/v29rx.c:1102-1111
         return NULL;
     }
-    CKP(cudaSetDevice(span_b200_ctx_device(ctx)));
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
     span_b200_v29_bank_t *b = new span_b200_v29_bank_s();
     b->ctx = ctx;
     b->channels = channels;
