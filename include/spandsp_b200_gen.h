@@ -68,6 +68,67 @@ int span_b200_awgn_bank_add_device(span_b200_awgn_bank_t *bank, int16_t *d_amp, 
 int span_b200_awgn_bank_fill_device(span_b200_awgn_bank_t *bank, int16_t *d_amp, int64_t stride, int samples, void *stream);
 int span_b200_awgn_bank_sync(span_b200_awgn_bank_t *bank);
 
+/* ---- cadenced tone generators: tone_gen() (src/tone_generate.c:60-230) ------------------------------------------ */
+typedef struct span_b200_tone_gen_bank_s span_b200_tone_gen_bank_t;
+
+/* What tone_gen_descriptor_init() takes (src/spandsp/tone_generate.h): frequencies in Hz (f2 < 0: f1 amplitude
+   modulated by |f2|, l2 = depth in percent), levels in dBm0, four durations in ms (on, off, on, off), repeat. */
+typedef struct
+{
+    int32_t f1;
+    int32_t l1;
+    int32_t f2;
+    int32_t l2;
+    int32_t d1;
+    int32_t d2;
+    int32_t d3;
+    int32_t d4;
+    int32_t repeat;
+} span_b200_tone_desc_t;
+
+/* N idle generators (they produce nothing until initialised). */
+span_b200_tone_gen_bank_t *span_b200_tone_gen_bank_create(span_b200_ctx_t *ctx, int channels);
+void span_b200_tone_gen_bank_destroy(span_b200_tone_gen_bank_t *bank);
+int span_b200_tone_gen_bank_channels(const span_b200_tone_gen_bank_t *bank);
+/* tone_gen_descriptor_init() + tone_gen_init() for channels [first, first+count): the same descriptor for all of them,
+   or descs[i] for channel first + i. */
+int span_b200_tone_gen_bank_init(span_b200_tone_gen_bank_t *bank, int first, int count, const span_b200_tone_desc_t *desc);
+int span_b200_tone_gen_bank_init_each(span_b200_tone_gen_bank_t *bank, int first, int count, const span_b200_tone_desc_t *descs);
+/* tone_gen(s, amp, max_samples) for every channel (src/tone_generate.c:125-230); a generator without repeat stops at
+   the end of its cadence and leaves the rest of its row alone unless zero_fill is set. */
+int span_b200_tone_gen_bank_tx_device(span_b200_tone_gen_bank_t *bank, int16_t *d_amp, int64_t stride, int max_samples, int zero_fill,
+                                      void *stream);
+int span_b200_tone_gen_bank_lens(span_b200_tone_gen_bank_t *bank, int32_t *lens);
+int span_b200_tone_gen_bank_sync(span_b200_tone_gen_bank_t *bank);
+
+/* ---- V.29 transmitters: v29_tx() (src/v29tx.c:100-470) ------------------------------------------------------------- */
+typedef struct span_b200_v29_tx_bank_s span_b200_v29_tx_bank_t;
+
+/* v29_tx_init(NULL, bit_rate, tep, get_bit, ...) x channels (src/v29tx.c:401-429): -14 dBm0, training from the start.
+   The data bits a get_bit callback would supply come from a per-channel source on the device: by default a
+   maximal-length sequence x^23 + x^18 + 1 seeded with channel + 1 (see *_set_prbs / *_set_bits). */
+span_b200_v29_tx_bank_t *span_b200_v29_tx_bank_create(span_b200_ctx_t *ctx, int channels, int bit_rate, int tep);
+void span_b200_v29_tx_bank_destroy(span_b200_v29_tx_bank_t *bank);
+int span_b200_v29_tx_bank_channels(const span_b200_v29_tx_bank_t *bank);
+/* v29_tx_restart() (src/v29tx.c:362-398), v29_tx_power() (:323-338) for channels [first, first+count) */
+int span_b200_v29_tx_bank_restart(span_b200_v29_tx_bank_t *bank, int first, int count, int bit_rate, int tep);
+int span_b200_v29_tx_bank_power(span_b200_v29_tx_bank_t *bank, int first, int count, float power_dbm0);
+/* Data source: the 23-bit sequence, channel first + i seeded with seeds[i] (or seed0 + i when seeds is NULL; 0 -> 1) */
+int span_b200_v29_tx_bank_set_prbs(span_b200_v29_tx_bank_t *bank, int first, int count, const uint32_t *seeds, uint32_t seed0);
+/* Data source: caller bits, LSB first, channel first + i takes nbits[i] bits from bits + i*stride_bytes (host memory,
+   copied).  When they run out the transmitter gets SIG_STATUS_END_OF_DATA (src/v29tx.c:109-119) and shuts down. */
+int span_b200_v29_tx_bank_set_bits(span_b200_v29_tx_bank_t *bank, int first, int count, const uint8_t *bits, int64_t stride_bytes,
+                                   const int32_t *nbits);
+/* v29_tx(s, amp, max_samples) for every channel (src/v29tx.c:226-296); lens = what each call returned */
+int span_b200_v29_tx_bank_tx_device(span_b200_v29_tx_bank_t *bank, int16_t *d_amp, int64_t stride, int max_samples, int zero_fill,
+                                    void *stream);
+int span_b200_v29_tx_bank_lens(span_b200_v29_tx_bank_t *bank, int32_t *lens);
+/* Per channel: bit 0 = SIG_STATUS_END_OF_DATA seen, bit 1 = SIG_STATUS_SHUTDOWN_COMPLETE reported */
+int span_b200_v29_tx_bank_status(span_b200_v29_tx_bank_t *bank, int32_t *status);
+int span_b200_v29_tx_bank_sync(span_b200_v29_tx_bank_t *bank);
+/* The transmit pulse shaper [10][9] (src/v29tx_rrc.h, generated by src/make_modem_filter.c) as computed by this library */
+int span_b200_v29_tx_tables(float *shaper);
+
 /* The 2048-entry float sine table of the DDS (src/dds_float.c:51-2101) as computed by this library, for verification */
 int span_b200_dds_float_table(float *table);
 

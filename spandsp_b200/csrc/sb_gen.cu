@@ -4,6 +4,7 @@
 
 #include "sb_engine.h"
 #include "sb_gen.cuh"
+#include "sb_modem.cuh"          // host generators of the modem filter tables (make_tx_rrc)
 
 #pragma GCC visibility push(default)
 #include "../../include/spandsp_b200_gen.h"
@@ -486,4 +487,427 @@ extern "C" int span_b200_awgn_bank_sync(span_b200_awgn_bank_t *b)
     if (b->have_last)
         CK(cudaStreamSynchronize(b->last_stream));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic bank plumbing shared by the tone_gen and V.29 transmitter banks
+struct gen_bank_base
+{
+    span_b200_ctx_t *ctx;
+    int channels;
+    int *state;
+    float *sine;
+    int *lens;
+    cudaStream_t last_stream;
+    bool have_last;
+};
+
+static int gen_quiesce(gen_bank_base *b)
+{
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    return 0;
+}
+
+static int gen_range_ok(const gen_bank_base *b, int first, int count)
+{
+    if (b == NULL  ||  first < 0  ||  count < 0  ||  first + count > b->channels)
+    {
+        sb_set_error("channel range out of bounds");
+        return 0;
+    }
+    return 1;
+}
+
+static bool gen_base_alloc(gen_bank_base *b, span_b200_ctx_t *ctx, int channels, int fields)
+{
+    b->ctx = ctx;
+    b->channels = channels;
+    std::vector<float> t(SBG_SINE_WORDS);
+    host_make_sine_table(t.data());
+    const size_t C = channels;
+    return cudaMalloc(&b->state, sizeof(int)*(size_t) fields*C) == cudaSuccess
+           &&  cudaMemset(b->state, 0, sizeof(int)*(size_t) fields*C) == cudaSuccess
+           &&  cudaMalloc(&b->sine, sizeof(float)*SBG_SINE_WORDS) == cudaSuccess
+           &&  cudaMalloc(&b->lens, sizeof(int)*C) == cudaSuccess
+           &&  cudaMemcpy(b->sine, t.data(), sizeof(float)*SBG_SINE_WORDS, cudaMemcpyHostToDevice) == cudaSuccess
+           &&  cudaMemset(b->lens, 0, sizeof(int)*C) == cudaSuccess;
+}
+
+static void gen_base_free(gen_bank_base *b)
+{
+    if (b->have_last)
+        cudaStreamSynchronize(b->last_stream);
+    cudaFree(b->state);
+    cudaFree(b->sine);
+    cudaFree(b->lens);
+}
+
+static int gen_lens(gen_bank_base *b, int32_t *lens)
+{
+    if (b == NULL  ||  lens == NULL)
+        return -1;
+    if (gen_quiesce(b) != 0)
+        return -1;
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    CK(cudaMemcpy(lens, b->lens, sizeof(int)*(size_t) b->channels, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// tone_gen banks
+struct span_b200_tone_gen_bank_s : gen_bank_base
+{
+    ToneDesc *d_descs;
+    size_t d_descs_n;
+};
+
+static ToneGenArgs tg_args(span_b200_tone_gen_bank_t *b, int16_t *d_amp, int64_t stride, int max_samples, int zero_fill)
+{
+    ToneGenArgs a;
+    a.amp = d_amp;
+    a.stride = stride;
+    a.max_samples = max_samples;
+    a.channels = b->channels;
+    a.zero_fill = zero_fill;
+    a.state = b->state;
+    a.sine = b->sine;
+    a.lens = b->lens;
+    return a;
+}
+
+extern "C" void span_b200_tone_gen_bank_destroy(span_b200_tone_gen_bank_t *b)
+{
+    if (b == NULL)
+        return;
+    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    gen_base_free(b);
+    cudaFree(b->d_descs);
+    delete b;
+}
+
+extern "C" span_b200_tone_gen_bank_t *span_b200_tone_gen_bank_create(span_b200_ctx_t *ctx, int channels)
+{
+    if (ctx == NULL  ||  channels <= 0)
+    {
+        sb_set_error("bad tone generator bank arguments");
+        return NULL;
+    }
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
+    span_b200_tone_gen_bank_t *b = new span_b200_tone_gen_bank_s();
+    memset(b, 0, sizeof(*b));
+    if (!gen_base_alloc(b, ctx, channels, T_COUNT))
+    {
+        sb_set_error("tone generator bank allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        span_b200_tone_gen_bank_destroy(b);
+        return NULL;
+    }
+    // idle: tone_gen() returns 0 while current_section < 0 (src/tone_generate.c:139-140)
+    std::vector<int> idle((size_t) channels, -1);
+    if (cudaMemcpy(b->state + (size_t) T_SECTION*channels, idle.data(), sizeof(int)*(size_t) channels, cudaMemcpyHostToDevice) != cudaSuccess)
+    {
+        sb_set_error("tone generator bank setup failed");
+        span_b200_tone_gen_bank_destroy(b);
+        return NULL;
+    }
+    return b;
+}
+
+extern "C" int span_b200_tone_gen_bank_channels(const span_b200_tone_gen_bank_t *b)
+{
+    return b->channels;
+}
+
+static int tg_init(span_b200_tone_gen_bank_t *b, int first, int count, const span_b200_tone_desc_t *descs, int same)
+{
+    if (!gen_range_ok(b, first, count)  ||  descs == NULL)
+    {
+        sb_set_error("bad tone generator init arguments");
+        return -1;
+    }
+    if (count == 0)
+        return 0;
+    if (gen_quiesce(b) != 0)
+        return -1;
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    const size_t n = (same)  ?  1  :  (size_t) count;
+    std::vector<ToneDesc> h(n);
+    for (size_t i = 0;  i < n;  i++)
+        host_tone_descriptor(h[i], descs[i].f1, descs[i].l1, descs[i].f2, descs[i].l2, descs[i].d1, descs[i].d2, descs[i].d3, descs[i].d4, descs[i].repeat);
+    if (b->d_descs_n < n)
+    {
+        if (gen_realloc((void **) &b->d_descs, sizeof(ToneDesc)*n) != 0)
+            return -1;
+        b->d_descs_n = n;
+    }
+    CK(cudaMemcpy(b->d_descs, h.data(), sizeof(ToneDesc)*n, cudaMemcpyHostToDevice));
+    cudaStream_t st = (cudaStream_t) sb_ctx_stream(b->ctx);
+    tone_gen_init_kernel<<<(count + 127)/128, 128, 0, st>>>(tg_args(b, NULL, 0, 0, 0), first, count, b->d_descs, same);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int span_b200_tone_gen_bank_init(span_b200_tone_gen_bank_t *b, int first, int count, const span_b200_tone_desc_t *desc)
+{
+    return tg_init(b, first, count, desc, 1);
+}
+
+extern "C" int span_b200_tone_gen_bank_init_each(span_b200_tone_gen_bank_t *b, int first, int count, const span_b200_tone_desc_t *descs)
+{
+    return tg_init(b, first, count, descs, 0);
+}
+
+extern "C" int span_b200_tone_gen_bank_tx_device(span_b200_tone_gen_bank_t *b, int16_t *d_amp, int64_t stride, int max_samples, int zero_fill,
+                                                  void *stream)
+{
+    if (b == NULL  ||  max_samples < 0  ||  (max_samples > 0  &&  d_amp == NULL))
+    {
+        sb_set_error("bad tx arguments");
+        return -1;
+    }
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
+    if (b->have_last  &&  b->last_stream != st)
+        CK(cudaStreamSynchronize(b->last_stream));
+    tone_gen_kernel<<<(b->channels + 127)/128, 128, 0, st>>>(tg_args(b, d_amp, stride, max_samples, zero_fill));
+    CK(cudaGetLastError());
+    b->last_stream = st;
+    b->have_last = true;
+    return 0;
+}
+
+extern "C" int span_b200_tone_gen_bank_lens(span_b200_tone_gen_bank_t *b, int32_t *lens)
+{
+    return gen_lens(b, lens);
+}
+
+extern "C" int span_b200_tone_gen_bank_sync(span_b200_tone_gen_bank_t *b)
+{
+    return (b)  ?  gen_quiesce(b)  :  -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// V.29 transmitter banks
+struct span_b200_v29_tx_bank_s : gen_bank_base
+{
+    float *shaper;
+    unsigned char *bits;
+    int64_t bits_stride;
+    unsigned int *d_seeds;
+    int *d_counts;
+};
+
+extern "C" int span_b200_v29_tx_tables(float *shaper)
+{
+    std::vector<float> t;
+    sbm::make_tx_rrc(t, SBG_V29_TX_SETS, SBG_V29_TX_STEPS, 0.25);          // src/make_modem_filter.c:401-413
+    memcpy(shaper, t.data(), sizeof(float)*t.size());
+    return 0;
+}
+
+static V29TxArgs vt_args(span_b200_v29_tx_bank_t *b, int16_t *d_amp, int64_t stride, int max_samples, int zero_fill)
+{
+    V29TxArgs a;
+    a.amp = d_amp;
+    a.stride = stride;
+    a.max_samples = max_samples;
+    a.channels = b->channels;
+    a.zero_fill = zero_fill;
+    a.state = b->state;
+    a.bits = b->bits;
+    a.bits_stride = b->bits_stride;
+    a.sine = b->sine;
+    a.shaper = b->shaper;
+    a.lens = b->lens;
+    a.carrier_phase_rate = host_dds_phase_ratef(1700.0f);                   // CARRIER_NOMINAL_FREQ, src/v29tx.c:79
+    return a;
+}
+
+// v29_tx_power() (src/v29tx.c:323-338), float build: TX_PULSESHAPER_GAIN is 1
+static float v29_tx_base_gain(float power)
+{
+    return powf(10.0f, (power - 3.14f)/20.0f)*32768.0f/1.000000f;
+}
+
+static int vt_ctl(span_b200_v29_tx_bank_t *b, int first, int count, int mode, float ga, int ia, int ib, const unsigned int *seeds, const int *counts)
+{
+    if (!gen_range_ok(b, first, count))
+        return -1;
+    if (count == 0)
+        return 0;
+    if (gen_quiesce(b) != 0)
+        return -1;
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    cudaStream_t st = (cudaStream_t) sb_ctx_stream(b->ctx);
+    v29_tx_ctl_kernel<<<(count + 127)/128, 128, 0, st>>>(vt_args(b, NULL, 0, 0, 0), first, count, mode, ga, ia, ib, seeds, counts);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static bool v29_rate_ok(int bit_rate)
+{
+    return bit_rate == 9600  ||  bit_rate == 7200  ||  bit_rate == 4800;
+}
+
+extern "C" void span_b200_v29_tx_bank_destroy(span_b200_v29_tx_bank_t *b)
+{
+    if (b == NULL)
+        return;
+    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    gen_base_free(b);
+    cudaFree(b->shaper);
+    cudaFree(b->bits);
+    cudaFree(b->d_seeds);
+    cudaFree(b->d_counts);
+    delete b;
+}
+
+extern "C" span_b200_v29_tx_bank_t *span_b200_v29_tx_bank_create(span_b200_ctx_t *ctx, int channels, int bit_rate, int tep)
+{
+    if (ctx == NULL  ||  channels <= 0  ||  !v29_rate_ok(bit_rate))
+    {
+        sb_set_error("bad V.29 transmitter bank arguments");        // src/v29tx.c:403-412: unknown rates are refused
+        return NULL;
+    }
+    SB_DEVICE_CKP(span_b200_ctx_device(ctx));
+    span_b200_v29_tx_bank_t *b = new span_b200_v29_tx_bank_s();
+    memset(b, 0, sizeof(*b));
+    float shaper[SBG_V29_TX_SETS*SBG_V29_TX_STEPS];
+    span_b200_v29_tx_tables(shaper);
+    const size_t C = channels;
+    bool ok = gen_base_alloc(b, ctx, channels, X_COUNT)
+              &&  cudaMalloc(&b->shaper, sizeof(shaper)) == cudaSuccess
+              &&  cudaMemcpy(b->shaper, shaper, sizeof(shaper), cudaMemcpyHostToDevice) == cudaSuccess
+              &&  cudaMalloc(&b->d_seeds, sizeof(unsigned int)*C) == cudaSuccess
+              &&  cudaMalloc(&b->d_counts, sizeof(int)*C) == cudaSuccess;
+    if (!ok)
+    {
+        sb_set_error("V.29 transmitter bank allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        span_b200_v29_tx_bank_destroy(b);
+        return NULL;
+    }
+    if (vt_ctl(b, 0, channels, 0, v29_tx_base_gain(-14.0f), bit_rate, tep != 0, NULL, NULL) != 0
+        ||  vt_ctl(b, 0, channels, 3, 0.0f, 1, 0, NULL, NULL) != 0)
+    {
+        span_b200_v29_tx_bank_destroy(b);
+        return NULL;
+    }
+    return b;
+}
+
+extern "C" int span_b200_v29_tx_bank_channels(const span_b200_v29_tx_bank_t *b)
+{
+    return b->channels;
+}
+
+extern "C" int span_b200_v29_tx_bank_restart(span_b200_v29_tx_bank_t *b, int first, int count, int bit_rate, int tep)
+{
+    if (!v29_rate_ok(bit_rate))
+    {
+        sb_set_error("V.29 bit rate %d", bit_rate);
+        return -1;                                              // src/v29tx.c:377-378
+    }
+    return vt_ctl(b, first, count, 1, 0.0f, bit_rate, tep != 0, NULL, NULL);
+}
+
+extern "C" int span_b200_v29_tx_bank_power(span_b200_v29_tx_bank_t *b, int first, int count, float power)
+{
+    return vt_ctl(b, first, count, 2, v29_tx_base_gain(power), 0, 0, NULL, NULL);
+}
+
+extern "C" int span_b200_v29_tx_bank_set_prbs(span_b200_v29_tx_bank_t *b, int first, int count, const uint32_t *seeds, uint32_t seed0)
+{
+    if (!gen_range_ok(b, first, count))
+        return -1;
+    if (count == 0)
+        return 0;
+    if (seeds)
+    {
+        if (gen_quiesce(b) != 0)
+            return -1;
+        SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+        CK(cudaMemcpy(b->d_seeds, seeds, sizeof(unsigned int)*(size_t) count, cudaMemcpyHostToDevice));
+    }
+    return vt_ctl(b, first, count, 3, 0.0f, (int) seed0, 0, (seeds)  ?  b->d_seeds  :  NULL, NULL);
+}
+
+extern "C" int span_b200_v29_tx_bank_set_bits(span_b200_v29_tx_bank_t *b, int first, int count, const uint8_t *bits, int64_t stride_bytes,
+                                               const int32_t *nbits)
+{
+    if (!gen_range_ok(b, first, count)  ||  bits == NULL  ||  nbits == NULL  ||  stride_bytes < 0)
+    {
+        sb_set_error("bad bit source arguments");
+        return -1;
+    }
+    if (count == 0)
+        return 0;
+    if (gen_quiesce(b) != 0)
+        return -1;
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    int64_t need = 1;
+    for (int i = 0;  i < count;  i++)
+    {
+        if (nbits[i] < 0  ||  ((int64_t) nbits[i] + 7)/8 > stride_bytes)
+        {
+            sb_set_error("channel %d: %d bits do not fit a stride of %lld bytes", first + i, nbits[i], (long long) stride_bytes);
+            return -1;
+        }
+        need = std::max(need, ((int64_t) nbits[i] + 7)/8);
+    }
+    if (b->bits == NULL  ||  b->bits_stride < need)
+    {
+        // one pitch for the whole bank; a wider request re-creates the buffer (sources of other channels are lost:
+        // set the widest first)
+        if (gen_realloc((void **) &b->bits, (size_t) need*b->channels) != 0)
+            return -1;
+        CK(cudaMemset(b->bits, 0, (size_t) need*b->channels));
+        b->bits_stride = need;
+    }
+    CK(cudaMemcpy2D(b->bits + (size_t) first*b->bits_stride, (size_t) b->bits_stride, bits, (size_t) stride_bytes, (size_t) need, (size_t) count,
+                    cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->d_counts, nbits, sizeof(int)*(size_t) count, cudaMemcpyHostToDevice));
+    return vt_ctl(b, first, count, 4, 0.0f, 0, 0, NULL, b->d_counts);
+}
+
+extern "C" int span_b200_v29_tx_bank_tx_device(span_b200_v29_tx_bank_t *b, int16_t *d_amp, int64_t stride, int max_samples, int zero_fill,
+                                                void *stream)
+{
+    if (b == NULL  ||  max_samples < 0  ||  (max_samples > 0  &&  d_amp == NULL))
+    {
+        sb_set_error("bad tx arguments");
+        return -1;
+    }
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
+    if (b->have_last  &&  b->last_stream != st)
+        CK(cudaStreamSynchronize(b->last_stream));
+    v29_tx_kernel<<<(b->channels + 127)/128, 128, 0, st>>>(vt_args(b, d_amp, stride, max_samples, zero_fill));
+    CK(cudaGetLastError());
+    b->last_stream = st;
+    b->have_last = true;
+    return 0;
+}
+
+extern "C" int span_b200_v29_tx_bank_lens(span_b200_v29_tx_bank_t *b, int32_t *lens)
+{
+    return gen_lens(b, lens);
+}
+
+extern "C" int span_b200_v29_tx_bank_status(span_b200_v29_tx_bank_t *b, int32_t *status)
+{
+    if (b == NULL  ||  status == NULL)
+        return -1;
+    if (gen_quiesce(b) != 0)
+        return -1;
+    SB_DEVICE_CK(span_b200_ctx_device(b->ctx));
+    CK(cudaMemcpy(status, b->state + (size_t) X_STATUS*b->channels, sizeof(int)*(size_t) b->channels, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int span_b200_v29_tx_bank_sync(span_b200_v29_tx_bank_t *b)
+{
+    return (b)  ?  gen_quiesce(b)  :  -1;
 }

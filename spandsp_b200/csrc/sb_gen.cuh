@@ -513,6 +513,405 @@ struct AwgnArgs
     double *dstate;                 // [2 + SBG_RAN_TABLE][channels]: amp2, rms, r[]
 };
 
+// ------------------------------------------------------------------------------------------
+// Cadenced tone generator banks: tone_gen_descriptor_init() + tone_gen_init() + tone_gen() per channel
+// (src/tone_generate.c:60-230).  Per-channel state, one int per field, [field][channel]; floats as their bits.
+enum
+{
+    T_SECTION = 0, T_POSITION, T_REPEAT,
+    T_PHASE0, T_RATE0 = T_PHASE0 + 4, T_GAIN0 = T_RATE0 + 4, T_DUR0 = T_GAIN0 + 4, T_COUNT = T_DUR0 + 4
+};
+
+SB_HD void tone_gen_load(ToneGen &t, const GenLoader &ld)
+{
+    t.section = ld(T_SECTION);
+    t.position = ld(T_POSITION);
+    t.repeat = ld(T_REPEAT);
+    for (int i = 0;  i < 4;  i++)
+    {
+        t.phase[i] = (unsigned int) ld(T_PHASE0 + i);
+        t.rate[i] = ld(T_RATE0 + i);
+        t.gain[i] = g_bitsf(ld(T_GAIN0 + i));
+        t.duration[i] = ld(T_DUR0 + i);
+    }
+}
+
+SB_HD void tone_gen_store(const ToneGen &t, const GenStorer &st)
+{
+    st(T_SECTION, t.section);
+    st(T_POSITION, t.position);
+    st(T_REPEAT, t.repeat);
+    for (int i = 0;  i < 4;  i++)
+    {
+        st(T_PHASE0 + i, (int) t.phase[i]);
+        st(T_RATE0 + i, t.rate[i]);
+        st(T_GAIN0 + i, g_fbits(t.gain[i]));
+        st(T_DUR0 + i, t.duration[i]);
+    }
+}
+
+// What tone_gen_descriptor_init() computes on the host (libm powf), per channel
+struct ToneDesc
+{
+    int rate[2];
+    float gain[2];
+    int duration[4];
+    int repeat;
+};
+
+static inline void host_tone_descriptor(ToneDesc &d, int f1, int l1, int f2, int l2, int d1, int d2, int d3, int d4, int repeat)
+{
+    memset(&d, 0, sizeof(d));
+    if (f1)
+    {
+        d.rate[0] = host_dds_phase_ratef((float) f1);
+        if (f2 < 0)
+            d.rate[0] = -d.rate[0];
+        d.gain[0] = host_dds_scaling_dbm0f((float) l1);
+    }
+    if (f2)
+    {
+        d.rate[1] = host_dds_phase_ratef((float) abs(f2));
+        d.gain[1] = (f2 < 0)  ?  ((float) l2/100.0f)  :  host_dds_scaling_dbm0f((float) l2);
+    }
+    d.duration[0] = d1*8000/1000;
+    d.duration[1] = d2*8000/1000;
+    d.duration[2] = d3*8000/1000;
+    d.duration[3] = d4*8000/1000;
+    d.repeat = repeat;
+}
+
+// tone_gen_init() (src/tone_generate.c:232-270): copy the descriptor, zero the phases, start at section 0
+SB_HD void tone_gen_start(ToneGen &t, const ToneDesc &d)
+{
+    for (int i = 0;  i < 4;  i++)
+    {
+        t.rate[i] = (i < 2)  ?  d.rate[i]  :  0;
+        t.gain[i] = (i < 2)  ?  d.gain[i]  :  0.0f;
+        t.phase[i] = 0;
+        t.duration[i] = d.duration[i];
+    }
+    t.repeat = d.repeat;
+    t.section = 0;
+    t.position = 0;
+}
+
+struct ToneGenArgs
+{
+    int16_t *amp;
+    long long stride;
+    int max_samples;
+    int channels;
+    int zero_fill;
+    int *state;                     // [T_COUNT][channels]
+    const float *sine;
+    int *lens;
+};
+
+// ------------------------------------------------------------------------------------------
+// v29_tx() (src/v29tx.c:100-322), float build.  The data bits come from a per-channel source on the device: a
+// maximal-length sequence (x^23 + x^18 + 1, the generator the oracle harness feeds the reference with) or a buffer
+// of caller bits; when the buffer runs out the transmitter sees SIG_STATUS_END_OF_DATA and shuts down as the
+// reference does (32 bauds of scrambled ones, then silence).
+#define SBG_V29_TX_STEPS        9       // V29_TX_FILTER_STEPS, src/spandsp/private/v29tx.h:30
+#define SBG_V29_TX_SETS         10      // TX_PULSESHAPER_COEFF_SETS
+
+enum
+{
+    X_BIT_RATE = 0, X_RRC_STEP, X_SCRAMBLE, X_TRAIN_SCRAMBLE, X_IN_TRAINING, X_TRAINING_STEP, X_TRAINING_OFFSET,
+    X_CARRIER_PHASE, X_BAUD_PHASE, X_CONSTELLATION, X_REAL_BITS, X_SRC_MODE, X_LFSR, X_BIT_POS, X_BIT_COUNT,
+    X_STATUS, X_GAIN, X_BASE_GAIN, X_RRC_RE, X_RRC_IM = X_RRC_RE + SBG_V29_TX_STEPS, X_COUNT = X_RRC_IM + SBG_V29_TX_STEPS
+};
+
+struct V29Tx
+{
+    int bit_rate;
+    int rrc_step;
+    unsigned int scramble_reg;
+    unsigned int training_scramble_reg;
+    int in_training;
+    int training_step;
+    int training_offset;
+    unsigned int carrier_phase;
+    int carrier_phase_rate;
+    int baud_phase;
+    int constellation_state;
+    int real_bits;                  // current_get_bit == get_bit (else fake_get_bit)
+    int src_mode;                   // 0: PRBS, 1: caller bits
+    unsigned int lfsr;
+    int bit_pos;
+    int bit_count;
+    int status;                     // bit 0: SIG_STATUS_END_OF_DATA reported, bit 1: SIG_STATUS_SHUTDOWN_COMPLETE reported
+    float gain;
+    float base_gain;
+    float rrc_re[SBG_V29_TX_STEPS];
+    float rrc_im[SBG_V29_TX_STEPS];
+    const unsigned char *bits;      // caller bits of this channel, LSB first
+    const float *sine;              // [2048]
+    const float *shaper;            // [10][9]
+
+    SB_HD void load(const GenLoader &ld)
+    {
+        bit_rate = ld(X_BIT_RATE);
+        rrc_step = ld(X_RRC_STEP);
+        scramble_reg = (unsigned int) ld(X_SCRAMBLE);
+        training_scramble_reg = (unsigned int) ld(X_TRAIN_SCRAMBLE);
+        in_training = ld(X_IN_TRAINING);
+        training_step = ld(X_TRAINING_STEP);
+        training_offset = ld(X_TRAINING_OFFSET);
+        carrier_phase = (unsigned int) ld(X_CARRIER_PHASE);
+        baud_phase = ld(X_BAUD_PHASE);
+        constellation_state = ld(X_CONSTELLATION);
+        real_bits = ld(X_REAL_BITS);
+        src_mode = ld(X_SRC_MODE);
+        lfsr = (unsigned int) ld(X_LFSR);
+        bit_pos = ld(X_BIT_POS);
+        bit_count = ld(X_BIT_COUNT);
+        status = ld(X_STATUS);
+        gain = g_bitsf(ld(X_GAIN));
+        base_gain = g_bitsf(ld(X_BASE_GAIN));
+        for (int i = 0;  i < SBG_V29_TX_STEPS;  i++)
+        {
+            rrc_re[i] = g_bitsf(ld(X_RRC_RE + i));
+            rrc_im[i] = g_bitsf(ld(X_RRC_IM + i));
+        }
+    }
+
+    SB_HD void store(const GenStorer &st) const
+    {
+        st(X_BIT_RATE, bit_rate);
+        st(X_RRC_STEP, rrc_step);
+        st(X_SCRAMBLE, (int) scramble_reg);
+        st(X_TRAIN_SCRAMBLE, (int) training_scramble_reg);
+        st(X_IN_TRAINING, in_training);
+        st(X_TRAINING_STEP, training_step);
+        st(X_TRAINING_OFFSET, training_offset);
+        st(X_CARRIER_PHASE, (int) carrier_phase);
+        st(X_BAUD_PHASE, baud_phase);
+        st(X_CONSTELLATION, constellation_state);
+        st(X_REAL_BITS, real_bits);
+        st(X_SRC_MODE, src_mode);
+        st(X_LFSR, (int) lfsr);
+        st(X_BIT_POS, bit_pos);
+        st(X_BIT_COUNT, bit_count);
+        st(X_STATUS, status);
+        st(X_GAIN, g_fbits(gain));
+        st(X_BASE_GAIN, g_fbits(base_gain));
+        for (int i = 0;  i < SBG_V29_TX_STEPS;  i++)
+        {
+            st(X_RRC_RE + i, g_fbits(rrc_re[i]));
+            st(X_RRC_IM + i, g_fbits(rrc_im[i]));
+        }
+    }
+
+    // set_working_gain() (src/v29tx.c:299-319)
+    SB_HD void set_working_gain()
+    {
+        if (bit_rate == 9600)
+            gain = g_fmul(0.387f, base_gain);
+        else if (bit_rate == 7200)
+            gain = g_fmul(0.605f, base_gain);
+        else if (bit_rate == 4800)
+            gain = g_fmul(0.470f, base_gain);
+    }
+
+    // v29_tx_restart() (src/v29tx.c:362-398)
+    SB_HD int restart(int rate, int tep)
+    {
+        bit_rate = rate;
+        set_working_gain();
+        if (rate == 9600)
+            training_offset = 0;
+        else if (rate == 7200)
+            training_offset = 2;
+        else if (rate == 4800)
+            training_offset = 4;
+        else
+            return -1;
+        for (int i = 0;  i < SBG_V29_TX_STEPS;  i++)
+            rrc_re[i] = rrc_im[i] = 0.0f;
+        rrc_step = 0;
+        scramble_reg = 0;
+        training_scramble_reg = 0x2A;
+        in_training = 1;
+        training_step = (tep)  ?  0  :  480;        // V29_TRAINING_SEG_TEP / V29_TRAINING_SEG_1
+        carrier_phase = 0;
+        baud_phase = 0;
+        constellation_state = 0;
+        real_bits = 0;
+        return 0;
+    }
+
+    // The caller's get_bit: 0/1, or -1 for SIG_STATUS_END_OF_DATA
+    SB_HD int source_bit()
+    {
+        if (src_mode == 0)
+        {
+            const int bit = (int) ((lfsr >> 22) ^ (lfsr >> 17)) & 1;
+            lfsr = ((lfsr << 1) | (unsigned int) bit) & 0x7FFFFFu;
+            return bit;
+        }
+        if (bit_pos >= bit_count)
+            return -1;
+        const int bit = (bits[bit_pos >> 3] >> (bit_pos & 7)) & 1;
+        bit_pos++;
+        return bit;
+    }
+
+    // get_scrambled_bit() (src/v29tx.c:104-125)
+    SB_HD int get_scrambled_bit()
+    {
+        int bit = 1;                                    // fake_get_bit()
+        if (real_bits)
+        {
+            bit = source_bit();
+            if (bit < 0)
+            {
+                status |= 1;
+                real_bits = 0;
+                in_training = 1;
+                bit = 1;
+            }
+        }
+        const int out_bit = (bit ^ (int) (scramble_reg >> (18 - 1)) ^ (int) (scramble_reg >> (23 - 1))) & 1;
+        scramble_reg = (scramble_reg << 1) | (unsigned int) out_bit;
+        return out_bit;
+    }
+
+    // getbaud() (src/v29tx.c:128-222); constellations: src/v29tx_constellation_maps.h:28-79
+    SB_HD void getbaud(float &vre, float &vim)
+    {
+        const float c16[16][2] =
+        {
+            { 3.0f,  0.0f}, { 1.0f,  1.0f}, { 0.0f,  3.0f}, {-1.0f,  1.0f}, {-3.0f,  0.0f}, {-1.0f, -1.0f}, { 0.0f, -3.0f}, { 1.0f, -1.0f},
+            { 5.0f,  0.0f}, { 3.0f,  3.0f}, { 0.0f,  5.0f}, {-3.0f,  3.0f}, {-5.0f,  0.0f}, {-3.0f, -3.0f}, { 0.0f, -5.0f}, { 3.0f, -3.0f}
+        };
+        const float abab[6][2] = {{3.0f, -3.0f}, {-3.0f, 0.0f}, {1.0f, -1.0f}, {-3.0f, 0.0f}, {0.0f, -3.0f}, {-3.0f, 0.0f}};
+        const float cdcd[6][2] = {{3.0f, 0.0f}, {-3.0f, 3.0f}, {3.0f, 0.0f}, {-1.0f, 1.0f}, {3.0f, 0.0f}, {0.0f, 3.0f}};
+        const int steps_9600[8] = {1, 0, 2, 3, 6, 7, 5, 4};
+        const int steps_4800[4] = {0, 2, 6, 4};
+
+        if (in_training)
+        {
+            if (++training_step <= 480 + 48 + 128 + 384)            // V29_TRAINING_SEG_4
+            {
+                if (training_step <= 480 + 48 + 128)                // V29_TRAINING_SEG_3
+                {
+                    if (training_step <= 480)                       // talker echo protection: unmodulated carrier
+                    {
+                        vre = c16[0][0];
+                        vim = c16[0][1];
+                        return;
+                    }
+                    if (training_step <= 480 + 48)                  // segment 1: silence
+                    {
+                        vre = vim = 0.0f;
+                        return;
+                    }
+                    const int k = (training_step & 1) + training_offset;       // segment 2: ABAB
+                    vre = abab[k][0];
+                    vim = abab[k][1];
+                    return;
+                }
+                // segment 3: CDCD through the 1 + x^-6 + x^-7 training scrambler (the register is a uint8_t)
+                const int bit = (int) (training_scramble_reg & 1);
+                training_scramble_reg >>= 1;
+                training_scramble_reg |= ((((unsigned int) bit ^ training_scramble_reg) & 1) << 6);
+                training_scramble_reg &= 0xFFu;
+                vre = cdcd[bit + training_offset][0];
+                vim = cdcd[bit + training_offset][1];
+                return;
+            }
+            if (training_step == 480 + 48 + 128 + 384 + 48 + 1)     // V29_TRAINING_END + 1: over to the real bits
+            {
+                real_bits = 1;
+                in_training = 0;
+            }
+            if (training_step == 480 + 48 + 128 + 384 + 48 + 32)    // V29_TRAINING_SHUTDOWN_END
+                status |= 2;
+        }
+        int amp = 0;
+        if (bit_rate == 9600  &&  get_scrambled_bit())
+            amp = 8;
+        int b = get_scrambled_bit();
+        b = (b << 1) | get_scrambled_bit();
+        if (bit_rate == 4800)
+        {
+            b = steps_4800[b];
+        }
+        else
+        {
+            b = (b << 1) | get_scrambled_bit();
+            b = steps_9600[b];
+        }
+        constellation_state = (constellation_state + b) & 7;
+        vre = c16[amp | constellation_state][0];
+        vim = c16[amp | constellation_state][1];
+    }
+
+    // vec_circular_dot_prodf() with the scalar vec_dot_prodf() (src/vector_float.c:890-939)
+    SB_HD float shape(const float *x, const float *y) const
+    {
+        float za = 0.0f;
+        float zb = 0.0f;
+        const int first = SBG_V29_TX_STEPS - rrc_step;
+        for (int i = 0;  i < SBG_V29_TX_STEPS;  i++)
+        {
+            if (i < first)
+                za = g_fadd(za, g_fmul(x[rrc_step + i], y[i]));
+            else
+                zb = g_fadd(zb, g_fmul(x[i - first], y[i]));
+        }
+        return g_fadd(za, zb);
+    }
+
+    // v29_tx() (src/v29tx.c:226-296)
+    template <class OUT> SB_HD int tx(OUT &out, int len)
+    {
+        if (training_step >= 480 + 48 + 128 + 384 + 48 + 32)
+            return 0;
+        for (int sample = 0;  sample < len;  sample++)
+        {
+            if ((baud_phase += 3) >= 10)
+            {
+                baud_phase -= 10;
+                float vre;
+                float vim;
+                getbaud(vre, vim);
+                rrc_re[rrc_step] = vre;
+                rrc_im[rrc_step] = vim;
+                if (++rrc_step >= SBG_V29_TX_STEPS)
+                    rrc_step = 0;
+            }
+            const float *row = shaper + (SBG_V29_TX_SETS - 1 - baud_phase)*SBG_V29_TX_STEPS;
+            const float xre = shape(rrc_re, row);
+            const float xim = shape(rrc_im, row);
+            const float zre = sine[(carrier_phase + (1u << 30)) >> 21];        // dds_complexf(), src/dds_float.c:2183-2190
+            const float zim = sine[carrier_phase >> 21];
+            carrier_phase += (unsigned int) carrier_phase_rate;
+            const float famp = g_fadd(g_fmul(xre, zre), -g_fmul(xim, zim));
+            out.put(ToneGen::to_amp(g_fmul(famp, gain)));
+        }
+        return len;
+    }
+};
+
+struct V29TxArgs
+{
+    int16_t *amp;
+    long long stride;
+    int max_samples;
+    int channels;
+    int zero_fill;
+    int *state;                     // [X_COUNT][channels]
+    const unsigned char *bits;      // [channels][bits_stride] caller bits, or NULL
+    long long bits_stride;
+    const float *sine;
+    const float *shaper;
+    int *lens;
+    int carrier_phase_rate;         // dds_phase_ratef(1700.0f)
+};
+
 #if defined(__CUDACC__)
 
 // dtmf_tx() for every channel: thread per channel, the sine table in shared memory
@@ -678,6 +1077,134 @@ __global__ void awgn_init_kernel(const AwgnArgs a, int first, int count, const i
     a.istate[3*C + c] = 1;          // odd = true
     a.dstate[c] = 0.0;              // amp2
     a.dstate[C + c] = rms;
+}
+
+// tone_gen() for every channel
+__global__ void __launch_bounds__(128) tone_gen_kernel(const ToneGenArgs a)
+{
+    __shared__ float s_sine[SBG_SINE_WORDS];
+    for (int i = threadIdx.x;  i < SBG_SINE_WORDS;  i += blockDim.x)
+        s_sine[i] = a.sine[i];
+    __syncthreads();
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= a.channels)
+        return;
+    ToneGen t;
+    GenLoader ld = {a.state, (size_t) a.channels, (size_t) c};
+    tone_gen_load(t, ld);
+    t.sine = s_sine;
+    RowOut out;
+    out.begin(a.amp + (long long) c*a.stride);
+    const int len = t.run(out, a.max_samples);
+    if (a.zero_fill)
+    {
+        for (int i = len;  i < a.max_samples;  i++)
+            out.put(0);
+    }
+    out.flush();
+    GenStorer st = {a.state, (size_t) a.channels, (size_t) c};
+    tone_gen_store(t, st);
+    a.lens[c] = len;
+}
+
+// tone_gen_init() with descs[idx] (or descs[0] for every channel when `same`) for channels [first, first + count)
+__global__ void tone_gen_init_kernel(const ToneGenArgs a, int first, int count, const ToneDesc *descs, int same)
+{
+    const int idx = blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= count)
+        return;
+    ToneGen t;
+    tone_gen_start(t, descs[(same)  ?  0  :  idx]);
+    GenStorer st = {a.state, (size_t) a.channels, (size_t) (first + idx)};
+    tone_gen_store(t, st);
+}
+
+// v29_tx() for every channel
+__global__ void __launch_bounds__(128) v29_tx_kernel(const V29TxArgs a)
+{
+    __shared__ float s_sine[SBG_SINE_WORDS];
+    __shared__ float s_shaper[SBG_V29_TX_SETS*SBG_V29_TX_STEPS];
+    for (int i = threadIdx.x;  i < SBG_SINE_WORDS;  i += blockDim.x)
+        s_sine[i] = a.sine[i];
+    for (int i = threadIdx.x;  i < SBG_V29_TX_SETS*SBG_V29_TX_STEPS;  i += blockDim.x)
+        s_shaper[i] = a.shaper[i];
+    __syncthreads();
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= a.channels)
+        return;
+    V29Tx t;
+    GenLoader ld = {a.state, (size_t) a.channels, (size_t) c};
+    t.load(ld);
+    t.sine = s_sine;
+    t.shaper = s_shaper;
+    t.carrier_phase_rate = a.carrier_phase_rate;
+    t.bits = (a.bits)  ?  (a.bits + (long long) c*a.bits_stride)  :  NULL;
+    RowOut out;
+    out.begin(a.amp + (long long) c*a.stride);
+    const int len = t.tx(out, a.max_samples);
+    if (a.zero_fill)
+    {
+        for (int i = len;  i < a.max_samples;  i++)
+            out.put(0);
+    }
+    out.flush();
+    GenStorer st = {a.state, (size_t) a.channels, (size_t) c};
+    t.store(st);
+    a.lens[c] = len;
+}
+
+// mode 0: v29_tx_init() (all state zeroed, power = base gain `ga`, restart); 1: v29_tx_restart(ia = bit rate, ib = tep);
+// 2: v29_tx_power (ga = base gain); 3: PRBS source, seed seeds[idx] or ia + idx; 4: caller bits, counts[idx] of them
+__global__ void v29_tx_ctl_kernel(const V29TxArgs a, int first, int count, int mode, float ga, int ia, int ib,
+                                  const unsigned int *seeds, const int *counts)
+{
+    const int idx = blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= count)
+        return;
+    const int c = first + idx;
+    V29Tx t;
+    GenLoader ld = {a.state, (size_t) a.channels, (size_t) c};
+    GenStorer st = {a.state, (size_t) a.channels, (size_t) c};
+    if (mode == 0)
+    {
+        t.scramble_reg = 0;
+        t.status = 0;
+        t.src_mode = 0;
+        t.lfsr = 1;
+        t.bit_pos = 0;
+        t.bit_count = 0;
+        t.base_gain = ga;
+        t.gain = 0.0f;
+        t.bit_rate = ia;
+        t.restart(ia, ib);
+    }
+    else
+    {
+        t.load(ld);
+        if (mode == 1)
+        {
+            t.restart(ia, ib);
+        }
+        else if (mode == 2)
+        {
+            t.base_gain = ga;
+            t.set_working_gain();
+        }
+        else if (mode == 3)
+        {
+            const unsigned int seed = ((seeds)  ?  seeds[idx]  :  (unsigned int) (ia + idx)) & 0x7FFFFFu;
+            t.src_mode = 0;
+            t.lfsr = (seed)  ?  seed  :  1u;
+        }
+        else
+        {
+            t.src_mode = 1;
+            t.bit_pos = 0;
+            t.bit_count = counts[idx];
+            t.status &= ~1;
+        }
+    }
+    t.store(st);
 }
 
 #endif  // __CUDACC__

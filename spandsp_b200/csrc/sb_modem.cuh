@@ -229,14 +229,10 @@ static inline void dit_transform(cplx *data, cplx *temp, int n, const std::vecto
 // band-pass sets (src/make_modem_filter.c:155-271).  V.29: 48 sets x 27 taps at 1700 Hz (:401-413);
 // V.17: 192 sets x 27 taps at 1800 Hz (:319-332); both 2400 baud, excess bandwidth 0.5.  V.27ter: 12 sets at
 // 1200 baud and 8 sets at 1600 baud, 1800 Hz, excess bandwidth 0.5 (:375-400).
-static inline void make_rx_rrc(std::vector<float> &re, std::vector<float> &im, int coeff_sets, double carrier_hz, double baud_rate = 2400.0)
+static inline void rrc_prototype(std::vector<double> &coeffs, int coeff_sets, int total, double alpha, double beta)
 {
     const int SEQ_LEN = 8192;
     const double GEN_PI = 3.1415926535;
-    const int per_filter = SBM_FILTER_STEPS;
-    const int total = coeff_sets*per_filter + 1;
-    const double alpha = baud_rate/(2.0*(double) (coeff_sets*8000));
-    const double beta = 0.5;
     const double f1 = (1.0 - beta)*alpha;
     const double f2 = (1.0 + beta)*alpha;
     const double tau = 0.5/alpha;
@@ -272,15 +268,25 @@ static inline void make_rx_rrc(std::vector<float> &re, std::vector<float> &im, i
         circle[i].im = sin(x);
     }
     dit_transform(vec.data(), temp.data(), SEQ_LEN, circle, SEQ_LEN);
-    std::vector<double> coeffs(total);
+    coeffs.resize(total);
     const int h = (total - 1)/2;
     for (int i = 0;  i < total;  i++)
         coeffs[i] = vec[(SEQ_LEN - h + i) % SEQ_LEN].re/(double) SEQ_LEN;
+    // unity DC gain (src/make_modem_filter.c:77-86,175-184)
     double gain = 0.0;
     for (int i = coeff_sets/2;  i < total;  i += coeff_sets)
         gain += coeffs[i];
     for (int i = 0;  i < total;  i++)
         coeffs[i] /= gain;
+}
+
+static inline void make_rx_rrc(std::vector<float> &re, std::vector<float> &im, int coeff_sets, double carrier_hz, double baud_rate = 2400.0)
+{
+    const double GEN_PI = 3.1415926535;
+    const int per_filter = SBM_FILTER_STEPS;
+    const int total = coeff_sets*per_filter + 1;
+    std::vector<double> coeffs;
+    rrc_prototype(coeffs, coeff_sets, total, baud_rate/(2.0*(double) (coeff_sets*8000)), 0.5);
     double carrier = carrier_hz;
     carrier *= 2.0*GEN_PI/8000;
     re.assign(coeff_sets*per_filter, 0.0f);
@@ -294,6 +300,21 @@ static inline void make_rx_rrc(std::vector<float> &re, std::vector<float> &im, i
             re[j*per_filter + i] = decimal_roundtrip(coeffs[x]*cos(carrier*m), 10);
             im[j*per_filter + i] = decimal_roundtrip(coeffs[x]*sin(carrier*m), 10);
         }
+    }
+}
+
+// The transmit pulse shaper (src/make_modem_filter.c:48-151): baseband root raised cosine, `coeff_sets` polyphase
+// sets of `per_filter` taps, alpha = 1/(2*coeff_sets).  V.29: 10 sets x 9 taps, excess bandwidth 0.25 (:401-413).
+static inline void make_tx_rrc(std::vector<float> &taps, int coeff_sets, int per_filter, double excess_bandwidth)
+{
+    const int total = coeff_sets*per_filter + 1;
+    std::vector<double> coeffs;
+    rrc_prototype(coeffs, coeff_sets, total, 1.0/(2.0*(double) coeff_sets), excess_bandwidth);
+    taps.assign(coeff_sets*per_filter, 0.0f);
+    for (int j = 0;  j < coeff_sets;  j++)
+    {
+        for (int i = 0;  i < per_filter;  i++)
+            taps[j*per_filter + i] = decimal_roundtrip(coeffs[i*coeff_sets + j], 10);
     }
 }
 

@@ -151,6 +151,26 @@ def lib():
         "span_b200_awgn_bank_fill_device": (i32, [vp, vp, i64, i32, vp]),
         "span_b200_dds_float_table": (i32, [vp]),
         "span_b200_dtmf_tx_bank_sync": (i32, [vp]),
+        "span_b200_tone_gen_bank_create": (vp, [vp, i32]),
+        "span_b200_tone_gen_bank_destroy": (None, [vp]),
+        "span_b200_tone_gen_bank_channels": (i32, [vp]),
+        "span_b200_tone_gen_bank_init": (i32, [vp, i32, i32, vp]),
+        "span_b200_tone_gen_bank_init_each": (i32, [vp, i32, i32, vp]),
+        "span_b200_tone_gen_bank_tx_device": (i32, [vp, vp, i64, i32, i32, vp]),
+        "span_b200_tone_gen_bank_lens": (i32, [vp, vp]),
+        "span_b200_tone_gen_bank_sync": (i32, [vp]),
+        "span_b200_v29_tx_bank_create": (vp, [vp, i32, i32, i32]),
+        "span_b200_v29_tx_bank_destroy": (None, [vp]),
+        "span_b200_v29_tx_bank_channels": (i32, [vp]),
+        "span_b200_v29_tx_bank_restart": (i32, [vp, i32, i32, i32, i32]),
+        "span_b200_v29_tx_bank_power": (i32, [vp, i32, i32, f32]),
+        "span_b200_v29_tx_bank_set_prbs": (i32, [vp, i32, i32, vp, C.c_uint32]),
+        "span_b200_v29_tx_bank_set_bits": (i32, [vp, i32, i32, vp, i64, vp]),
+        "span_b200_v29_tx_bank_tx_device": (i32, [vp, vp, i64, i32, i32, vp]),
+        "span_b200_v29_tx_bank_lens": (i32, [vp, vp]),
+        "span_b200_v29_tx_bank_status": (i32, [vp, vp]),
+        "span_b200_v29_tx_bank_sync": (i32, [vp]),
+        "span_b200_v29_tx_tables": (i32, [vp]),
         "span_b200_awgn_bank_sync": (i32, [vp]),
         "span_b200_sig_bank_create": (vp, [vp, i32, i32]),
         "span_b200_sig_bank_destroy": (None, [vp]),
@@ -784,6 +804,118 @@ class AwgnBank:
         if self.h:
             lib().span_b200_awgn_bank_destroy(self.h)
             self.h = None
+
+
+class ToneGenBank:
+    """N cadenced tone generators (span_b200_tone_gen_bank_create): tone_gen_descriptor_init / tone_gen_init / tone_gen."""
+
+    def __init__(self, ctx, channels):
+        self.ctx = ctx
+        self.h = lib().span_b200_tone_gen_bank_create(ctx.h, channels)
+        if not self.h:
+            raise EngineError(_err())
+        self.channels = channels
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    def init(self, desc, first=0, count=None):
+        """desc = (f1, l1, f2, l2, d1, d2, d3, d4, repeat) for every channel of the range."""
+        d = np.asarray(desc, dtype=np.int32).reshape(9)
+        n = self.channels - first if count is None else count
+        self._ck(lib().span_b200_tone_gen_bank_init(self.h, first, n, d.ctypes.data))
+
+    def init_each(self, descs, first=0):
+        d = np.ascontiguousarray(descs, dtype=np.int32).reshape(-1, 9)
+        self._ck(lib().span_b200_tone_gen_bank_init_each(self.h, first, len(d), d.ctypes.data))
+
+    def tx_device(self, d_ptr, stride, max_samples, zero_fill=False, stream=None):
+        self._ck(lib().span_b200_tone_gen_bank_tx_device(self.h, d_ptr, stride, max_samples, int(zero_fill), stream))
+
+    def lens(self):
+        n = np.zeros(self.channels, dtype=np.int32)
+        self._ck(lib().span_b200_tone_gen_bank_lens(self.h, n.ctypes.data))
+        return n
+
+    def sync(self):
+        self._ck(lib().span_b200_tone_gen_bank_sync(self.h))
+
+    def close(self):
+        if self.h:
+            lib().span_b200_tone_gen_bank_destroy(self.h)
+            self.h = None
+
+
+class V29TxBank:
+    """N V.29 transmitters (span_b200_v29_tx_bank_create): v29_tx_init / restart / power / v29_tx per channel."""
+
+    def __init__(self, ctx, channels, bit_rate=9600, tep=False):
+        self.ctx = ctx
+        self.h = lib().span_b200_v29_tx_bank_create(ctx.h, channels, bit_rate, int(tep))
+        if not self.h:
+            raise EngineError(_err())
+        self.channels = channels
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError(_err())
+        return rc
+
+    def _range(self, first, count):
+        return first, (self.channels - first if count is None else count)
+
+    def restart(self, bit_rate, tep=False, first=0, count=None):
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_v29_tx_bank_restart(self.h, f, n, bit_rate, int(tep)))
+
+    def power(self, dbm0, first=0, count=None):
+        f, n = self._range(first, count)
+        self._ck(lib().span_b200_v29_tx_bank_power(self.h, f, n, dbm0))
+
+    def set_prbs(self, seeds=None, seed0=1, first=0, count=None):
+        f, n = self._range(first, count)
+        sp = None
+        if seeds is not None:
+            s = np.ascontiguousarray(seeds, dtype=np.uint32)
+            assert len(s) == n
+            sp = s.ctypes.data
+        self._ck(lib().span_b200_v29_tx_bank_set_prbs(self.h, f, n, sp, seed0))
+
+    def set_bits(self, bits, nbits, first=0):
+        """bits: uint8 [count][bytes], LSB first; nbits: bits per channel."""
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        nb = np.ascontiguousarray(nbits, dtype=np.int32)
+        assert b.ndim == 2 and len(nb) == b.shape[0]
+        self._ck(lib().span_b200_v29_tx_bank_set_bits(self.h, first, b.shape[0], b.ctypes.data, b.shape[1], nb.ctypes.data))
+
+    def tx_device(self, d_ptr, stride, max_samples, zero_fill=False, stream=None):
+        self._ck(lib().span_b200_v29_tx_bank_tx_device(self.h, d_ptr, stride, max_samples, int(zero_fill), stream))
+
+    def lens(self):
+        n = np.zeros(self.channels, dtype=np.int32)
+        self._ck(lib().span_b200_v29_tx_bank_lens(self.h, n.ctypes.data))
+        return n
+
+    def status(self):
+        n = np.zeros(self.channels, dtype=np.int32)
+        self._ck(lib().span_b200_v29_tx_bank_status(self.h, n.ctypes.data))
+        return n
+
+    def sync(self):
+        self._ck(lib().span_b200_v29_tx_bank_sync(self.h))
+
+    def close(self):
+        if self.h:
+            lib().span_b200_v29_tx_bank_destroy(self.h)
+            self.h = None
+
+
+def v29_tx_tables():
+    t = np.zeros((10, 9), dtype=np.float32)
+    lib().span_b200_v29_tx_tables(t.ctypes.data)
+    return t
 
 
 def events_by_channel(ev, channels):

@@ -546,6 +546,94 @@ EXPORT int hostsim_awgn_run(int16_t *amp, int n, int seed, float level, int dbov
     return 0;
 }
 
+// tone_gen() with a full descriptor (same arguments as oracle/ref_harness_tx.c: ref_tone_gen_calls)
+EXPORT int hostsim_tone_gen_calls(int16_t *amp, const int32_t *max_lens, int ncalls, const int32_t *desc, int32_t *out_lens)
+{
+    static std::vector<float> sine;
+    if (sine.empty())
+    {
+        sine.resize(SBG_SINE_WORDS);
+        sbg::host_make_sine_table(sine.data());
+    }
+    sbg::ToneDesc d;
+    sbg::host_tone_descriptor(d, desc[0], desc[1], desc[2], desc[3], desc[4], desc[5], desc[6], desc[7], desc[8] != 0);
+    std::vector<int> state(sbg::T_COUNT, 0);
+    sbg::GenLoader ld = {state.data(), 1, 0};
+    sbg::GenStorer st = {state.data(), 1, 0};
+    sbg::ToneGen t;
+    t.sine = sine.data();
+    sbg::tone_gen_start(t, d);
+    int pos = 0;
+    for (int k = 0;  k < ncalls;  k++)
+    {
+        sbg::tone_gen_store(t, st);
+        sbg::tone_gen_load(t, ld);
+        sbg::RowOut out;
+        out.begin(amp + pos);
+        out_lens[k] = t.run(out, max_lens[k]);
+        out.flush();
+        pos += max_lens[k];
+    }
+    return 0;
+}
+
+// v29_tx() (same arguments as oracle/ref_harness_tx.c: ref_v29_tx_calls)
+EXPORT int hostsim_v29_tx_calls(int16_t *amp, const int32_t *max_lens, int ncalls, int bit_rate, int tep, float power_dbm0,
+                                int src_mode, uint32_t lfsr_seed, const uint8_t *bits, int nbits,
+                                int restart_before_call, int restart_rate, int restart_tep,
+                                int32_t *out_lens, int32_t *status)
+{
+    static std::vector<float> sine;
+    static std::vector<float> shaper;
+    if (sine.empty())
+    {
+        sine.resize(SBG_SINE_WORDS);
+        sbg::host_make_sine_table(sine.data());
+        sbm::make_tx_rrc(shaper, SBG_V29_TX_SETS, SBG_V29_TX_STEPS, 0.25);
+    }
+    if (bit_rate != 9600  &&  bit_rate != 7200  &&  bit_rate != 4800)
+        return -1;
+    std::vector<int> state(sbg::X_COUNT, 0);
+    sbg::GenLoader ld = {state.data(), 1, 0};
+    sbg::GenStorer st = {state.data(), 1, 0};
+    sbg::V29Tx t;
+    t.load(ld);
+    t.sine = sine.data();
+    t.shaper = shaper.data();
+    t.bits = bits;
+    t.carrier_phase_rate = sbg::host_dds_phase_ratef(1700.0f);
+    t.base_gain = powf(10.0f, (-14.0f - 3.14f)/20.0f)*32768.0f/1.000000f;
+    t.restart(bit_rate, tep);
+    t.base_gain = powf(10.0f, (power_dbm0 - 3.14f)/20.0f)*32768.0f/1.000000f;
+    t.set_working_gain();
+    t.src_mode = src_mode;
+    t.lfsr = (lfsr_seed & 0x7FFFFF)  ?  (lfsr_seed & 0x7FFFFF)  :  1;
+    t.bit_pos = 0;
+    t.bit_count = nbits;
+    int pos = 0;
+    for (int k = 0;  k < ncalls;  k++)
+    {
+        if (k == restart_before_call)
+            t.restart(restart_rate, restart_tep);
+        t.store(st);
+        t.load(ld);
+        sbg::RowOut out;
+        out.begin(amp + pos);
+        out_lens[k] = t.tx(out, max_lens[k]);
+        out.flush();
+        pos += max_lens[k];
+    }
+    *status = t.status;
+    return 0;
+}
+
+EXPORT void hostsim_v29_tx_tables(float *shaper)
+{
+    std::vector<float> t;
+    sbm::make_tx_rrc(t, SBG_V29_TX_SETS, SBG_V29_TX_STEPS, 0.25);
+    memcpy(shaper, t.data(), sizeof(float)*t.size());
+}
+
 EXPORT void hostsim_gen_tables(float *sine)
 {
     sbg::host_make_sine_table(sine);

@@ -141,3 +141,45 @@ def sig_run(amp, tone_type, chunk=160, lens=None, modes=((0, 0x40),)):
     if rc != 0 or nev.value > cap:
         raise RuntimeError("hostsim sig run failed")
     return {"out": out, "ev": ev[:nev.value].copy(), "final": fin}
+
+def tone_gen_calls(max_lens, desc, fill=0x5555):
+    """tone_gen() with descriptor desc = (f1, l1, f2, l2, d1, d2, d3, d4, repeat): len(max_lens) calls.
+    Returns (amp with `fill` where nothing was written, lens returned)."""
+    max_lens = np.asarray(max_lens, dtype=np.int32)
+    d = np.asarray(desc, dtype=np.int32)
+    assert d.shape == (9,)
+    amp = np.full(int(max_lens.sum()), fill, dtype=np.int16)
+    out_lens = np.zeros(len(max_lens), dtype=np.int32)
+    fn = lib().hostsim_tone_gen_calls
+    fn.restype = C.c_int
+    if fn(C.c_void_p(amp.ctypes.data), C.c_void_p(max_lens.ctypes.data), C.c_int(len(max_lens)), C.c_void_p(d.ctypes.data),
+          C.c_void_p(out_lens.ctypes.data)) != 0:
+        raise RuntimeError("tone_gen_calls failed")
+    return amp, out_lens
+
+
+def v29_tx_calls(max_lens, bit_rate=9600, tep=False, power_dbm0=-14.0, lfsr_seed=None, bits=None, nbits=0, restart=(-1, 9600, False),
+                 fill=0x5555):
+    """v29_tx(): len(max_lens) calls.  Data: the 23-bit sequence seeded lfsr_seed, or `bits` (uint8, LSB first, nbits of
+    them, then end of data).  restart = (before call, bit rate, tep).  Returns (amp, lens returned, status bits)."""
+    max_lens = np.asarray(max_lens, dtype=np.int32)
+    amp = np.full(int(max_lens.sum()), fill, dtype=np.int16)
+    out_lens = np.zeros(len(max_lens), dtype=np.int32)
+    status = C.c_int32(0)
+    b = None if bits is None else np.ascontiguousarray(bits, dtype=np.uint8)
+    fn = lib().hostsim_v29_tx_calls
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(amp.ctypes.data), C.c_void_p(max_lens.ctypes.data), C.c_int(len(max_lens)), C.c_int(bit_rate), C.c_int(int(tep)),
+            C.c_float(power_dbm0), C.c_int(0 if bits is None else 1), C.c_uint32(1 if lfsr_seed is None else lfsr_seed),
+            C.c_void_p(None if b is None else b.ctypes.data), C.c_int(nbits),
+            C.c_int(restart[0]), C.c_int(restart[1]), C.c_int(int(restart[2])),
+            C.c_void_p(out_lens.ctypes.data), C.byref(status))
+    if rc != 0:
+        raise RuntimeError("v29_tx_calls failed")
+    return amp, out_lens, status.value
+
+
+def v29_tx_tables():
+    t = np.zeros((10, 9), dtype=np.float32)
+    lib().hostsim_v29_tx_tables(C.c_void_p(t.ctypes.data))
+    return t

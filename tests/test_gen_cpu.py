@@ -43,6 +43,30 @@ def test_awgn_golden():
     assert g["add_out"].max() == 32767 and g["add_out"].min() == -32768
 
 
+def test_tone_gen_golden():
+    g = np.load(GOLD)
+    mk = cases()
+    for k, (desc, calls) in enumerate(mk.TONE_CASES):
+        amp, lens = hs.tone_gen_calls(calls, desc)
+        assert (lens == g["tone_lens%d" % k]).all(), k
+        assert (amp == g["tone_amp%d" % k]).all(), k
+    # the once-only cadence stops after 250 + 250 + 100 + 1000 ms = 12 800 samples, short of what the calls asked for
+    assert int(g["tone_lens1"].sum()) == 12800 < sum(mk.TONE_CASES[1][1])
+
+
+def test_v29_tx_golden():
+    g = np.load(GOLD)
+    mk = cases()
+    assert (hs.v29_tx_tables().view(np.int32) == g["v29tx_shaper"].view(np.int32)).all()
+    for k, c in enumerate(mk.V29_TX_CASES):
+        amp, lens, status = hs.v29_tx_calls(**mk.v29_tx_kwargs(c))
+        assert (lens == g["v29tx_lens%d" % k]).all(), k
+        assert status == int(g["v29tx_status%d" % k]), k
+        assert (amp == g["v29tx_amp%d" % k]).all(), k
+    # the transmitter whose data ran out reported end of data and shutdown, and went silent (v29_tx() returns 0)
+    assert int(g["v29tx_status4"]) == 3 and int(g["v29tx_lens4"][-1]) == 0
+
+
 def test_gen_tables(engine_lib):
     """The library's float DDS table equals the reference's literals (src/dds_float.c:51-2101) bit for bit."""
     g = np.load(GOLD)
@@ -65,6 +89,12 @@ def test_golden_matches_compiled_reference(oracles):
     t = po.gen_tables(S)
     for name, v in t.items():
         assert (v.view(np.int32) == g["tab_" + name].view(np.int32)).all(), name
+    for k, (desc, calls) in enumerate(mk.TONE_CASES):
+        amp, lens = po.tone_gen_calls(S, calls, desc)
+        assert (amp == g["tone_amp%d" % k]).all() and (lens == g["tone_lens%d" % k]).all()
+    for k, c in enumerate(mk.V29_TX_CASES):
+        amp, lens, status = po.v29_tx_calls(S, **mk.v29_tx_kwargs(c))
+        assert (amp == g["v29tx_amp%d" % k]).all() and (lens == g["v29tx_lens%d" % k]).all() and status == int(g["v29tx_status%d" % k])
 
 
 def test_random_vs_reference(oracles):
@@ -82,6 +112,24 @@ def test_random_vs_reference(oracles):
         a = po.dtmf_tx_calls(S, calls, digits, level=level, timing=timing)
         b = hs.dtmf_tx_calls(calls, digits, level=level, timing=timing)
         assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all(), k
+    for k in range(20):
+        desc = (int(rng.integers(300, 3000)), int(rng.integers(-30, 1)), int(rng.integers(0, 3000)) if k % 3 else 0, int(rng.integers(-30, 1)),
+                int(rng.integers(1, 600)), int(rng.integers(0, 600)), int(rng.integers(0, 300)) if k & 1 else 0, int(rng.integers(0, 900)), k & 2)
+        calls = [int(x) for x in rng.integers(1, 4000, int(rng.integers(1, 12)))]
+        a = po.tone_gen_calls(S, calls, desc)
+        b = hs.tone_gen_calls(calls, desc)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), desc
+    for k in range(20):
+        kw = dict(max_lens=[int(x) for x in rng.integers(1, 6000, int(rng.integers(1, 8)))], bit_rate=(9600, 7200, 4800)[k % 3], tep=bool(k & 1),
+                  power_dbm0=float(rng.integers(-30, -5)))
+        if k % 4 == 3:
+            kw["nbits"] = int(rng.integers(0, 4000))
+            kw["bits"] = rng.integers(0, 256, (kw["nbits"] + 7)//8 + 1, dtype=np.uint8)
+        else:
+            kw["lfsr_seed"] = int(rng.integers(1, 2**23))
+        a = po.v29_tx_calls(S, **kw)
+        b = hs.v29_tx_calls(**kw)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2], kw
     for k in range(10):
         seed = int(rng.integers(-2**31 + 1, 2**31 - 1))
         level = float(rng.uniform(-60, 3))
