@@ -63,6 +63,24 @@ typedef struct
     int32_t c;
 } span_b200_event_t;
 
+/* Compact 12-byte form of the same record, used where records travel: the multi-GPU gather (NCCL) and the host
+   read-back of large banks.  channel is the GLOBAL channel number (the bank's channel_base + the channel inside
+   the bank); block_kind = block index in bits 0-13 and the kind in bits 14-15 (1 = DIGIT, 2 = TONE, 3 = SEGMENT);
+   a and b are the 24-byte record's a and b as signed bytes (digit / code character, tone id, level in dB, segment
+   frequency indices: all within -128..127), c its c.  One rx call may hold at most 16384 blocks in this form. */
+typedef struct
+{
+    uint32_t channel;
+    int32_t c;
+    uint16_t block_kind;
+    int8_t a;
+    int8_t b;
+} span_b200_wire_event_t;
+
+#define SPAN_B200_WIRE_BLOCK(r)     ((int) ((r).block_kind & 0x3FFF))
+#define SPAN_B200_WIRE_KIND(r)      ((((r).block_kind >> 14) == 3)  ?  SPAN_B200_EV_SEGMENT  :  (int) ((r).block_kind >> 14))
+#define SPAN_B200_WIRE_MAX_BLOCKS   16384
+
 /* Flattened supervisory tone descriptor: what super_tone_rx_add_tone()/add_element()
    (src/super_tone_rx.c:125-161) were called with. */
 typedef struct
@@ -83,6 +101,13 @@ int span_b200_abi_version(void);
 const char *span_b200_last_error(void);
 int span_b200_ctx_device(const span_b200_ctx_t *ctx);
 int span_b200_ctx_sm_count(const span_b200_ctx_t *ctx);
+/* NUMA node the context's GPU is attached to (-1: unknown).  span_b200_host_alloc() returns pinned host memory placed
+   on that node where the OS allows it - the staging memory for *_rx_host(): with several GPUs in a box the host
+   interface runs at PCIe speed only if each GPU's buffers live on its own socket.  Free with span_b200_host_free()
+   (or implicitly with the context). */
+int span_b200_ctx_numa_node(const span_b200_ctx_t *ctx);
+void *span_b200_host_alloc(span_b200_ctx_t *ctx, size_t bytes);
+void span_b200_host_free(span_b200_ctx_t *ctx, void *p);
 
 /* ---- banks ------------------------------------------------------------------------------ */
 
@@ -160,6 +185,56 @@ const span_b200_event_t *span_b200_bank_events_device(span_b200_bank_t *bank);
 int64_t span_b200_bank_events_to_device(span_b200_bank_t *bank, span_b200_event_t *d_out, int64_t max, void *stream);
 /* Override the event buffer capacity (events per rx call).  0 = size for the worst case. */
 int span_b200_bank_set_event_capacity(span_b200_bank_t *bank, int64_t events);
+
+/* ---- compact records and the multi-GPU gather -------------------------------------- */
+
+/* Switch a bank to 12-byte wire records (on != 0): from the next rx call on, the emit pass writes
+   span_b200_wire_event_t records - into one of two buffers used alternately, so that the records of call k can
+   still be read (or travel) while call k + 1 runs - and span_b200_bank_events() / _events_device() /
+   _events_to_device() are refused; span_b200_bank_event_count() keeps working.  channel_base is added to every
+   channel number (the first global channel of this bank's shard). */
+int span_b200_bank_set_wire(span_b200_bank_t *bank, int on, uint32_t channel_base);
+/* Copy up to max wire records of the last rx call to host memory.  Returns the number copied. */
+int64_t span_b200_bank_events_wire(span_b200_bank_t *bank, span_b200_wire_event_t *out, int64_t max);
+/* Host helper: wire records -> 24-byte records (channel numbers are reduced by channel_base). */
+void span_b200_wire_expand(const span_b200_wire_event_t *in, span_b200_event_t *out, int64_t n, uint32_t channel_base);
+
+/* One communicator per process / GPU; all ranks of a job create it with the same id.  The id is made by
+   span_b200_comm_unique_id() on one rank and handed to the others by whatever out-of-band channel the application
+   has (the benchmark broadcasts it with torch.distributed).  It is an NCCL communicator (ncclCommInitRankConfig);
+   libnccl.so.2 is looked up at run time, the library does not link against it.  max_ctas > 0 caps the thread
+   blocks NCCL may use per operation (the filter kernels are compute-bound: NCCL should stay small). */
+typedef struct span_b200_comm_s span_b200_comm_t;
+#define SPAN_B200_COMM_ID_BYTES     128
+int span_b200_comm_unique_id(unsigned char id[SPAN_B200_COMM_ID_BYTES]);
+span_b200_comm_t *span_b200_comm_create(span_b200_ctx_t *ctx, const unsigned char id[SPAN_B200_COMM_ID_BYTES], int nranks, int rank,
+                                        int max_ctas);
+void span_b200_comm_destroy(span_b200_comm_t *comm);
+int span_b200_comm_rank(const span_b200_comm_t *comm);
+int span_b200_comm_nranks(const span_b200_comm_t *comm);
+
+/* Attach a bank (in wire mode) to a communicator: its records will be gathered to rank `root`.  On the root the
+   emit pass writes the root's own records straight into the gather buffer (no copy). */
+int span_b200_bank_attach_comm(span_b200_bank_t *bank, span_b200_comm_t *comm, int root);
+/* The gather of the records of the bank's last rx call, in two halves so that it can overlap the next call:
+     _begin: (collective, asynchronous) all ranks exchange their record counts (ncclAllGather on the communicator's
+             own stream, ordered after the rx call by an event);
+     _end:   (collective) waits on the HOST for those counts, then enqueues the transfer: every rank sends exactly its
+             own records to the root (ncclSend), the root receives each rank's records behind its own, in rank order
+             (ncclRecv with the exact counts, one group).  Returns the total number of records (all ranks), or -1;
+             counts (may be NULL) receives the nranks per-rank counts.
+   Pipelined use (what the benchmark does): rx(k); _end(k-1); _begin(k); ... which lets the records of call k-1
+   travel while the kernels of call k run.  Two record buffers are in flight; a third rx call waits (on the device)
+   for the transfer that still reads the buffer it is about to overwrite. */
+int span_b200_bank_gather_begin(span_b200_bank_t *bank);
+int64_t span_b200_bank_gather_end(span_b200_bank_t *bank, int64_t *counts);
+/* Root only: wait for the transfer started by the last _gather_end and return its records (device memory, valid until
+   the rx call after next) / copy them to the host.  Order: the root's records, then the other ranks' in rank order;
+   inside a rank as in the bank's own buffer. */
+int64_t span_b200_bank_gathered(span_b200_bank_t *bank, const span_b200_wire_event_t **d_records);
+int64_t span_b200_bank_gathered_host(span_b200_bank_t *bank, span_b200_wire_event_t *out, int64_t max);
+/* Wait for everything the communicator's stream holds */
+int span_b200_comm_sync(span_b200_comm_t *comm);
 
 /* Per-block diagnostics of the last rx call (tests, tuning): the [block][channel] decision
    codes and, for DTMF, the block energies of blocks whose decision was a hit. */

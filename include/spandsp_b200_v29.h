@@ -56,6 +56,9 @@ int span_b200_v29_bank_rx_host(span_b200_v29_bank_t *bank, const int16_t *h_amp,
 /* Results of the last rx call.  counts: per channel number of put_bit calls / qam reports. */
 int span_b200_v29_bank_counts(span_b200_v29_bank_t *bank, int32_t *nbits, int32_t *nsyms);
 int64_t span_b200_v29_bank_bits(span_b200_v29_bank_t *bank, int channel, int8_t *out, int64_t max);
+/* The put_bit streams of every channel in one transfer: out + c*out_stride receives the first
+   min(count, out_stride) entries of channel c, nbits (may be NULL) the per-channel counts.  Returns the largest count. */
+int64_t span_b200_v29_bank_bits_all(span_b200_v29_bank_t *bank, int8_t *out, int64_t out_stride, int32_t *nbits);
 int64_t span_b200_v29_bank_symbols(span_b200_v29_bank_t *bank, int channel, span_b200_v29_symbol_t *out, int64_t max);
 /* Device-side layout of the result buffers ([channel][capacity]) for callers that consume them on the GPU. */
 int span_b200_v29_bank_output_layout(span_b200_v29_bank_t *bank, const int8_t **d_bits, int64_t *bits_cap,

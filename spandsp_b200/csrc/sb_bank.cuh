@@ -37,7 +37,9 @@ struct BankArgs
     const int16_t *amp;             // [channel][sample], row stride in samples
     long long stride;
     int n;                          // samples per channel in this call
-    int channels;
+    int channels;                   // channels this launch covers (all pointers already point at its first channel)
+    int cstride;                    // channels of the whole bank: the row pitch of the [row][channel] state / code arrays
+    int blk0;                       // index of the first block decision this launch writes (0 unless a call is run in pieces)
     int cs0;                        // uniform block phase at entry (samples already in the open block)
     int slice_blocks;               // blocks per time slice (staged kernel)
     int nslices;
@@ -76,7 +78,7 @@ struct Runner
     int cs;                         // samples in the open block
     int blk;                        // index of the next block decision to write
     int c;                          // channel
-    int channels;
+    int channels;                   // row pitch of the [row][channel] arrays (BankArgs::cstride)
     bool active;
     bool filt;
     typename DET::Local loc;
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     const int end = (int) s1;
 
     Runner<DET, NPACK> r;
-    r.channels = a.channels;
+    r.channels = a.cstride;
     r.c = group*32 + lane;
     r.active = (r.c < a.channels);
     if (!r.active)
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
         // the constant bank (LDCU + MOV) in every unrolled vector, 10 extra issue slots per 8 samples.
         asm volatile("" : "+f"(r.fac[p].x), "+f"(r.fac[p].y));
     }
-    r.blk = slice*a.slice_blocks;
+    r.blk = a.blk0 + slice*a.slice_blocks;
     r.filt = false;
     if (slice == 0  &&  a.cs0 > 0)
     {
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     if (any_filter)
     {
         r.filt = DET::filter_on(a.det, r.c);
-        DET::load_filter(a.det, r.c, a.channels, r.z);
+        DET::load_filter(a.det, r.c, a.cstride, r.z);
     }
 
     // ---- staging geometry ----
@@ -676,7 +678,7 @@ __global__ void __launch_bounds__(WARPS*32, MINB) bank_kernel_staged(const BankA
     {
         r.store_carry(a);
         if (DET::FILTER  &&  any_filter  &&  r.active)
-            DET::store_filter(a.det, r.c, a.channels, r.z);
+            DET::store_filter(a.det, r.c, a.cstride, r.z);
     }
 }
 
@@ -691,14 +693,14 @@ __global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
         return;
 
     Runner<DET, NPACK> r;
-    r.channels = a.channels;
+    r.channels = a.cstride;
     r.c = c;
     r.active = true;
     DET::load_local(a.det, c, r.loc);
 #pragma unroll
     for (int p = 0;  p < DET::NPAIRS;  p++)
         r.fac[p] = DET::fac(a.det, p);
-    r.blk = 0;
+    r.blk = a.blk0;
     r.cs = (DET::RAW)  ?  0  :  a.cs[c];
     if (r.cs > 0)
         r.load_carry(a);
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
     if (DET::FILTER)
     {
         r.filt = DET::filter_on(a.det, c);
-        DET::load_filter(a.det, c, a.channels, r.z);
+        DET::load_filter(a.det, c, a.cstride, r.z);
     }
     const int16_t *row = a.amp + (long long) c*a.stride;
     const unsigned char *row8 = (const unsigned char *) a.amp + (long long) c*a.stride;
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(128) bank_kernel_direct(const BankArgs<DET> a)
                 r.zero_after_block();
             }
         }
-        DET::store_filter(a.det, c, a.channels, r.z);
+        DET::store_filter(a.det, c, a.cstride, r.z);
     }
     else
     {

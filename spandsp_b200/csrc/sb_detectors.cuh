@@ -24,7 +24,9 @@ struct SeqCommon
     int *cs;                    // [channels] block phase, advanced by the emit pass
     const unsigned int *offsets;    // exclusive scan of the per-warp counts (emit pass)
     unsigned int *counts;       // per-warp (32 channels) event counts (count pass)
-    span_b200_event_t *events;
+    span_b200_event_t *events;  // 24-byte records, or
+    span_b200_wire_event_t *wire;   // 12-byte wire records (multi-GPU gather, compact host read-back); one of the two is NULL
+    unsigned int channel_base;  // wire records carry the global channel number
     long long capacity;
 };
 
@@ -32,14 +34,40 @@ __device__ __forceinline__ void put_event(const SeqCommon &q, unsigned int pos, 
 {
     if ((long long) pos < q.capacity)
     {
-        span_b200_event_t e;
-        e.channel = c;
-        e.block = blk;
-        e.kind = kind;
-        e.a = a;
-        e.b = b;
-        e.c = cc;
-        q.events[pos] = e;
+        if (q.wire)
+        {
+            // kind 1 / 2 / 5 -> 1 / 2 / 3 in the top two bits of block_kind (include/spandsp_b200.h)
+            span_b200_wire_event_t w;
+            w.channel = q.channel_base + (unsigned int) c;
+            w.c = cc;
+            w.block_kind = (unsigned short) ((blk & 0x3FFF) | (((kind == SPAN_B200_EV_SEGMENT)  ?  3  :  kind) << 14));
+            w.a = (signed char) a;
+            w.b = (signed char) b;
+            q.wire[pos] = w;
+        }
+        else
+        {
+            span_b200_event_t e;
+            e.channel = c;
+            e.block = blk;
+            e.kind = kind;
+            e.a = a;
+            e.b = b;
+            e.c = cc;
+            q.events[pos] = e;
+        }
+    }
+}
+
+// Fill in field b of a record written earlier (the deferred DTMF level)
+__device__ __forceinline__ void set_event_b(const SeqCommon &q, unsigned int pos, int b)
+{
+    if ((long long) pos < q.capacity)
+    {
+        if (q.wire)
+            q.wire[pos].b = (signed char) b;
+        else
+            q.events[pos].b = b;
     }
 }
 
@@ -377,9 +405,9 @@ __global__ void __launch_bounds__(128) dtmf_sequencer(const DtmfSeqArgs s)
                         q_row[qn][threadIdx.x] = (unsigned short) row;
                         qn++;
                     }
-                    else if ((long long) pos < s.q.capacity)
+                    else
                     {
-                        s.q.events[pos].b = dtmf_level_tab(lvl_tab, s.level_n, s.level_min, s.eout[(size_t) b*s.q.channels + c]);
+                        set_event_b(s.q, pos, dtmf_level_tab(lvl_tab, s.level_n, s.level_min, s.eout[(size_t) b*s.q.channels + c]));
                     }
                 }
             }
@@ -396,9 +424,7 @@ __global__ void __launch_bounds__(128) dtmf_sequencer(const DtmfSeqArgs s)
                 {
                     if (i < qn)
                     {
-                        const unsigned int pos = q_pos[i][threadIdx.x];
-                        if ((long long) pos < s.q.capacity)
-                            s.q.events[pos].b = dtmf_level_tab(lvl_tab, s.level_n, s.level_min, en[i]);
+                        set_event_b(s.q, q_pos[i][threadIdx.x], dtmf_level_tab(lvl_tab, s.level_n, s.level_min, en[i]));
                     }
                 }
                 qn = 0;

@@ -129,6 +129,7 @@ static size_t state_size(int det)
 
 static int alloc_stage(span_b200_group_s *g, int max_samples)
 {
+    sb_device_guard sb_dg_((g)  ?  span_b200_ctx_device(g->ctx)  :  -1);
     int16_t *p = NULL;
     if (cudaMallocHost(&p, sizeof(int16_t)*(size_t) g->members*max_samples) != cudaSuccess)
     {
@@ -267,6 +268,7 @@ extern "C" void *span_b200_group_member(span_b200_group_t *g, int index)
 
 extern "C" void span_b200_group_destroy(span_b200_group_t *g)
 {
+    sb_device_guard sb_dg_((g)  ?  span_b200_ctx_device(g->ctx)  :  -1);
     std::lock_guard<std::recursive_mutex> lk(g_lock);
     if (g == NULL)
         return;
@@ -883,6 +885,7 @@ extern "C" int goertzel_update(goertzel_state_t *s, const int16_t amp[], int sam
         sb_set_error("goertzel_update: no CUDA device (there is no CPU fallback)");
         return 0;
     }
+    sb_device_guard sb_dg_(span_b200_ctx_device(span_b200_default_ctx()));
     cudaStream_t st = (cudaStream_t) sb_ctx_stream(span_b200_default_ctx());
     const float h[3] = {s->v2, s->v3, s->fac};
     cudaMemcpyAsync(g_gz_state, h, sizeof(h), cudaMemcpyHostToDevice, st);
@@ -909,6 +912,7 @@ extern "C" float goertzel_result(goertzel_state_t *s)
         sb_set_error("goertzel_result: no CUDA device (there is no CPU fallback)");
         return 0.0f;
     }
+    sb_device_guard sb_dg_(span_b200_ctx_device(span_b200_default_ctx()));
     cudaStream_t st = (cudaStream_t) sb_ctx_stream(span_b200_default_ctx());
     const float h[3] = {s->v2, s->v3, s->fac};
     cudaMemcpyAsync(g_gz_state, h, sizeof(h), cudaMemcpyHostToDevice, st);

@@ -7,10 +7,17 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <dlfcn.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <ctype.h>
+#include <nccl.h>             // types and prototypes only: libnccl.so.2 is resolved at run time (dlopen), never linked
 
 #include <algorithm>
 #include <vector>
 #include <mutex>
+#include <map>
 
 #include "sb_engine.h"
 #include "sb_detectors.cuh"
@@ -173,6 +180,9 @@ struct span_b200_ctx_s
     int level_n;
     int level_min;
     float *d_g711_lut;              // [2][256]: u-law, A-law expansion as float
+    int numa_node;                  // NUMA node the GPU hangs off (-1: unknown / single node)
+    std::mutex host_lock;
+    std::map<void *, size_t> host_blocks;   // span_b200_host_alloc() blocks
 };
 
 static int upload_constants(int device)
@@ -205,6 +215,8 @@ static int upload_constants(int device)
     return 0;
 }
 
+static int gpu_numa_node(int device);
+
 extern "C" span_b200_ctx_t *span_b200_ctx_create(int device)
 {
     int count = 0;
@@ -234,6 +246,7 @@ extern "C" span_b200_ctx_t *span_b200_ctx_create(int device)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int) prop.sharedMemPerBlockOptin;
+    ctx->numa_node = gpu_numa_node(device);
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     if (upload_constants(device) != 0)
     {
@@ -267,12 +280,100 @@ extern "C" void span_b200_ctx_destroy(span_b200_ctx_t *ctx)
     cudaFree(ctx->d_g711_lut);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
+    for (std::map<void *, size_t>::iterator it = ctx->host_blocks.begin();  it != ctx->host_blocks.end();  ++it)
+    {
+        cudaHostUnregister(it->first);
+        munmap(it->first, it->second);
+    }
     delete ctx;
 }
 
 extern "C" int span_b200_ctx_device(const span_b200_ctx_t *ctx)
 {
     return ctx->device;
+}
+
+// ---- NUMA-local pinned host memory --------------------------------------------------------------
+// The end-to-end rate of the host interface is the PCIe rate, and with several GPUs per box what limits that is where
+// the staging memory lives: a buffer on the other socket crosses the inter-socket link on every DMA.  A block from
+// span_b200_host_alloc() is placed on the NUMA node of the context's GPU (mbind, preferred policy: it degrades to
+// any node where the container's cpuset does not allow that one) and pinned (cudaHostRegister).
+static int gpu_numa_node(int device)
+{
+    char id[64];
+    if (cudaDeviceGetPCIBusId(id, sizeof(id), device) != cudaSuccess)
+        return -1;
+    for (char *p = id;  *p;  p++)
+        *p = (char) tolower(*p);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", id);
+    FILE *f = fopen(path, "r");
+    if (f == NULL)
+        return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1)
+        node = -1;
+    fclose(f);
+    return node;
+}
+
+extern "C" int span_b200_ctx_numa_node(const span_b200_ctx_t *ctx)
+{
+    return ctx->numa_node;
+}
+
+extern "C" void *span_b200_host_alloc(span_b200_ctx_t *ctx, size_t bytes)
+{
+    if (ctx == NULL  ||  bytes == 0)
+    {
+        sb_set_error("bad host allocation arguments");
+        return NULL;
+    }
+    SB_DEVICE_CKP(ctx->device);
+    const size_t page = 2u << 20;
+    const size_t len = (bytes + page - 1)/page*page;
+    void *p = mmap(NULL, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED)
+    {
+        sb_set_error("mmap of %zu bytes failed", len);
+        return NULL;
+    }
+    if (ctx->numa_node >= 0  &&  ctx->numa_node < 1024)
+    {
+        unsigned long mask[16];
+        memset(mask, 0, sizeof(mask));
+        mask[ctx->numa_node/(8*sizeof(unsigned long))] |= 1ul << (ctx->numa_node%(8*sizeof(unsigned long)));
+        // MPOL_PREFERRED = 1: pages come from this node while it has room and the cpuset allows it
+        (void) syscall(SYS_mbind, p, len, 1, mask, (unsigned long) (8*sizeof(mask)), 0u);
+    }
+    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterDefault);
+    if (e != cudaSuccess)
+    {
+        sb_set_error("cudaHostRegister of %zu bytes failed: %s", len, cudaGetErrorString(e));
+        munmap(p, len);
+        return NULL;
+    }
+    std::lock_guard<std::mutex> lk(ctx->host_lock);
+    ctx->host_blocks[p] = len;
+    return p;
+}
+
+extern "C" void span_b200_host_free(span_b200_ctx_t *ctx, void *p)
+{
+    if (ctx == NULL  ||  p == NULL)
+        return;
+    sb_device_guard sb_dg_(ctx->device);
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> lk(ctx->host_lock);
+        std::map<void *, size_t>::iterator it = ctx->host_blocks.find(p);
+        if (it == ctx->host_blocks.end())
+            return;
+        len = it->second;
+        ctx->host_blocks.erase(it);
+    }
+    cudaHostUnregister(p);
+    munmap(p, len);
 }
 
 extern "C" int span_b200_ctx_sm_count(const span_b200_ctx_t *ctx)
@@ -284,6 +385,30 @@ void *sb_ctx_stream(span_b200_ctx_t *ctx)
 {
     return (void *) ctx->stream;
 }
+
+// ------------------------------------------------------------------------------------------
+// communicator (multi-GPU gather of the event records); functions further down
+struct span_b200_comm_s
+{
+    span_b200_ctx_t *ctx;
+    int nranks;
+    int rank;
+    ncclComm_t nccl;
+    cudaStream_t stream;
+    // root: the gathered records of the two buffers in flight
+    span_b200_wire_event_t *gather[2];
+    long long gather_cap[2];
+    unsigned long long *d_counts[2];        // [nranks] all-gathered record counts
+    unsigned long long *h_counts[2];        // pinned
+    cudaEvent_t counts_ready[2];
+    cudaEvent_t done[2];                    // the transfer that read / filled buffer i has finished
+    bool done_valid[2];
+    int begun_slot;                         // slot of the last _gather_begin without _gather_end, or -1
+    int ended_slot;                         // slot of the last _gather_end, or -1
+    long long total[2];
+};
+
+static int comm_gather_reserve(span_b200_comm_t *cm, int slot, long long records, cudaStream_t st, long long keep);
 
 // ------------------------------------------------------------------------------------------
 // bank
@@ -338,13 +463,26 @@ struct span_b200_bank_s
     size_t eout_bytes;
     unsigned int *counts;
     unsigned int *offsets;
-    unsigned long long *d_total;
-    unsigned long long *h_total;
+    unsigned long long *d_total;            // [2]: one per record buffer (wire mode alternates; else slot 0)
+    unsigned long long *h_total;            // [2], pinned
     span_b200_event_t *events;
     long long ev_cap;
     long long ev_cap_user;
     int16_t *d_in;
     size_t d_in_bytes;
+    cudaStream_t copy_stream;       // rx_host: the H2D copies run beside the filter-bank kernels
+    cudaEvent_t copied[8];
+    cudaEvent_t in_free;
+
+    // wire mode (12-byte records, two buffers used alternately) and the multi-GPU gather
+    int wire_on;
+    unsigned int channel_base;
+    span_b200_wire_event_t *wire[2];
+    long long wire_cap[2];
+    int slot;                       // buffer of the last rx call
+    cudaEvent_t emitted[2];         // the emit pass that filled buffer i has finished
+    span_b200_comm_t *comm;
+    int root;
 
     int uniform_cs;                 // common block phase of all channels, -1 if they differ
     int last_nb;
@@ -419,9 +557,9 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
     CKB(cudaMalloc(&b->cs, sizeof(int)*C));
     CKB(cudaMalloc(&b->counts, sizeof(unsigned int)*((C + 31)/32 + 1)));
     CKB(cudaMalloc(&b->offsets, sizeof(unsigned int)*((C + 31)/32 + 1)));
-    CKB(cudaMalloc(&b->d_total, sizeof(unsigned long long)));
-    CKB(cudaMallocHost(&b->h_total, sizeof(unsigned long long)));
-    b->h_total[0] = 0;
+    CKB(cudaMalloc(&b->d_total, 2*sizeof(unsigned long long)));
+    CKB(cudaMallocHost(&b->h_total, 2*sizeof(unsigned long long)));
+    b->h_total[0] = b->h_total[1] = 0;
     return b;
 }
 
@@ -497,6 +635,7 @@ extern "C" int span_b200_bank_reset(span_b200_bank_t *b, int first, int count)
 
 extern "C" span_b200_bank_t *span_b200_dtmf_bank_create(span_b200_ctx_t *ctx, int channels)
 {
+    sb_device_guard sb_dg_(span_b200_ctx_device(ctx));
     span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_DTMF, channels, 102, 8);
     if (b == NULL)
         return NULL;
@@ -524,6 +663,7 @@ extern "C" span_b200_bank_t *span_b200_dtmf_bank_create(span_b200_ctx_t *ctx, in
 
 extern "C" span_b200_bank_t *span_b200_bell_mf_bank_create(span_b200_ctx_t *ctx, int channels)
 {
+    sb_device_guard sb_dg_(span_b200_ctx_device(ctx));
     span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_BELL_MF, channels, 120, 6);
     if (b == NULL)
         return NULL;
@@ -538,6 +678,7 @@ extern "C" span_b200_bank_t *span_b200_bell_mf_bank_create(span_b200_ctx_t *ctx,
 
 extern "C" span_b200_bank_t *span_b200_r2_mf_bank_create(span_b200_ctx_t *ctx, int channels, int fwd)
 {
+    sb_device_guard sb_dg_(span_b200_ctx_device(ctx));
     span_b200_bank_t *b = bank_alloc(ctx, SPAN_B200_DET_R2_MF, channels, 133, 6);
     if (b == NULL)
         return NULL;
@@ -703,6 +844,24 @@ extern "C" void span_b200_bank_destroy(span_b200_bank_t *b)
     cudaFree(b->offsets);
     cudaFree(b->d_total);
     cudaFreeHost(b->h_total);
+    if (b->copy_stream)
+    {
+        cudaStreamSynchronize(b->copy_stream);
+        cudaStreamDestroy(b->copy_stream);
+        for (int i = 0;  i < 8;  i++)
+        {
+            if (b->copied[i])
+                cudaEventDestroy(b->copied[i]);
+        }
+        if (b->in_free)
+            cudaEventDestroy(b->in_free);
+    }
+    for (int i = 0;  i < 2;  i++)
+    {
+        cudaFree(b->wire[i]);
+        if (b->emitted[i])
+            cudaEventDestroy(b->emitted[i]);
+    }
     cudaFree(b->events);
     cudaFree(b->d_in);
     for (size_t i = 0;  i < b->ev_pool.size();  i++)
@@ -985,6 +1144,7 @@ static int launch_variant(const BankArgs<DET> &a, bool filter, cudaStream_t st, 
 template <class DET>
 static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g, cudaStream_t st, bool all_variants)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     const bool filter = (b->det == SPAN_B200_DET_DTMF  &&  b->n_filter > 0);
     if (a.lut)
     {
@@ -1041,28 +1201,32 @@ static int launch_st(span_b200_bank_t *b, BankArgs<SuperToneDet<NP> > &a, const 
     return launch_bank<SuperToneDet<NP> >(b, a, g, st, false);
 }
 
+// One launch covers the channels [c0, c0 + count) of the bank: every per-channel pointer is advanced to c0, the
+// arrays keep the whole bank's row pitch.  d_amp is the row of channel c0 (bytes per sample: 2, or 1 for G.711).
 template <class DET>
-static void fill_common(span_b200_bank_t *b, BankArgs<DET> &a, const int16_t *d_amp, int64_t stride, int n)
+static void fill_common(span_b200_bank_t *b, BankArgs<DET> &a, const int16_t *d_amp, int64_t stride, int n, int c0, int count)
 {
     memset(&a, 0, sizeof(a));
     a.amp = d_amp;
     a.stride = stride;
     a.n = n;
-    a.channels = b->channels;
-    a.v2 = b->v2;
-    a.v3 = b->v3;
-    a.energy = b->energy;
-    a.cs = b->cs;
-    a.code = (typename DET::code_t *) b->code;
-    a.eout = b->eout;
+    a.channels = count;
+    a.cstride = b->channels;
+    a.v2 = b->v2 + c0;
+    a.v3 = b->v3 + c0;
+    a.energy = b->energy + c0;
+    a.cs = b->cs + c0;
+    a.code = (typename DET::code_t *) b->code + c0;
+    a.eout = (b->eout)  ?  (b->eout + c0)  :  NULL;
     a.block_rt = b->block;
 }
 
 template <int NP>
-static int run_st(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, const Geometry &g, cudaStream_t st, const float *lut)
+static int run_st(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, const Geometry &g, cudaStream_t st, const float *lut,
+                  int c0, int count)
 {
     BankArgs<SuperToneDet<NP> > a;
-    fill_common(b, a, d_amp, stride, n);
+    fill_common(b, a, d_amp, stride, n, c0, count);
     a.lut = lut;
     a.det = b->stp;
     return launch_st<NP>(b, a, g, st);
@@ -1087,24 +1251,41 @@ static long long worst_case_events(const span_b200_bank_t *b, int nb)
     }
 }
 
-// law: -1 = int16 linear samples; 0 = u-law bytes; 1 = A-law bytes (stride in samples either way)
-static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, void *stream, int law)
+// One rx call = prepare (geometry, scratch, record buffers) + the filter-bank kernel over all channels - in one launch,
+// or one launch per channel range when the samples arrive in pieces (rx_host) - + finish (the sequencers).
+struct RxCall
+{
+    Geometry g;
+    int n;
+    int law;                        // -1 = int16 linear samples; 0 = u-law bytes; 1 = A-law bytes (stride in samples either way)
+    const float *lut;
+    cudaStream_t st;
+    int slot;
+    span_b200_wire_event_t *wire_out;
+    long long out_cap;
+    cudaEvent_t t1;
+};
+
+static int rx_prepare(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, void *stream, int law, RxCall &rc)
 {
     if (b == NULL  ||  n < 0  ||  (n > 0  &&  d_amp == NULL))
     {
         sb_set_error("bad rx arguments");
         return -1;
     }
-    SB_DEVICE_CK(b->ctx->device);
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
     const int B = b->block;
-    Geometry g;
+    Geometry &g = rc.g;
+    rc.n = n;
+    rc.law = law;
+    rc.st = st;
+    rc.t1 = NULL;
     g.cs0 = b->uniform_cs;
     const bool aligned = ((((uintptr_t) d_amp) & 15) == 0)  &&  ((stride & ((law >= 0)  ?  15  :  7)) == 0);
     g.staged = (g.cs0 >= 0)  &&  aligned  &&  !b->tune_direct  &&  n > 0;
-    const float *lut = (law >= 0)  ?  (b->ctx->d_g711_lut + 256*law)  :  NULL;
+    rc.lut = (law >= 0)  ?  (b->ctx->d_g711_lut + 256*law)  :  NULL;
     g.nb = (g.cs0 >= 0)  ?  (g.cs0 + n)/B  :  (B - 1 + n)/B;
     // ---- time slicing ----
     g.nslices = 1;
@@ -1143,19 +1324,66 @@ static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, in
     long long want_ev = (b->ev_cap_user > 0)  ?  b->ev_cap_user  :  worst_case_events(b, g.nb);
     if (want_ev < 1)
         want_ev = 1;
-    if (b->ev_cap < want_ev  ||  (b->ev_cap_user > 0  &&  b->ev_cap != want_ev))
+    span_b200_wire_event_t *wire_out = NULL;
+    long long out_cap = 0;
+    int slot = 0;
+    if (b->wire_on)
     {
-        if (b->events)
-            CK(cudaFree(b->events));
-        b->events = NULL;
-        b->ev_cap = 0;
-        CK(cudaMalloc(&b->events, sizeof(span_b200_event_t)*(size_t) want_ev));
-        b->ev_cap = want_ev;
+        if (g.nb > SPAN_B200_WIRE_MAX_BLOCKS)
+        {
+            sb_set_error("wire records hold block numbers below %d; this call has %d blocks per channel", SPAN_B200_WIRE_MAX_BLOCKS, g.nb);
+            return -1;
+        }
+        slot = b->slot ^ 1;
+        const bool to_gather = (b->comm != NULL  &&  b->comm->rank == b->root);
+        if (b->comm  &&  b->comm->done_valid[slot])
+        {
+            // the transfer that read this buffer two calls ago must be over before the emit pass overwrites it
+            CK(cudaStreamWaitEvent(st, b->comm->done[slot], 0));
+        }
+        if (to_gather)
+        {
+            // root: emit straight into the gather buffer; room for every rank's worst case (grown on demand later)
+            if (comm_gather_reserve(b->comm, slot, want_ev*b->comm->nranks, st, 0) != 0)
+                return -1;
+            wire_out = b->comm->gather[slot];
+            out_cap = want_ev;
+        }
+        else
+        {
+            if (b->wire_cap[slot] < want_ev  ||  (b->ev_cap_user > 0  &&  b->wire_cap[slot] != want_ev))
+            {
+                if (b->wire[slot])
+                    CK(cudaFree(b->wire[slot]));
+                b->wire[slot] = NULL;
+                b->wire_cap[slot] = 0;
+                CK(cudaMalloc(&b->wire[slot], sizeof(span_b200_wire_event_t)*(size_t) want_ev));
+                b->wire_cap[slot] = want_ev;
+            }
+            wire_out = b->wire[slot];
+            out_cap = b->wire_cap[slot];
+        }
+        if (b->emitted[slot] == NULL)
+            CK(cudaEventCreateWithFlags(&b->emitted[slot], cudaEventDisableTiming));
     }
+    else
+    {
+        if (b->ev_cap < want_ev  ||  (b->ev_cap_user > 0  &&  b->ev_cap != want_ev))
+        {
+            if (b->events)
+                CK(cudaFree(b->events));
+            b->events = NULL;
+            b->ev_cap = 0;
+            CK(cudaMalloc(&b->events, sizeof(span_b200_event_t)*(size_t) want_ev));
+            b->ev_cap = want_ev;
+        }
+        out_cap = b->ev_cap;
+    }
+    rc.slot = slot;
+    rc.wire_out = wire_out;
+    rc.out_cap = out_cap;
     b->last_launches = 0;
-    // ---- bank kernel ----
-    cudaEvent_t t0 = NULL;
-    cudaEvent_t t1 = NULL;
+    b->last_path = "empty";
     if (b->tune_timing  &&  n > 0)
     {
         while ((int) b->ev_pool.size() < b->ev_used + 2)
@@ -1164,85 +1392,100 @@ static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, in
             CK(cudaEventCreate(&e));
             b->ev_pool.push_back(e);
         }
-        t0 = b->ev_pool[b->ev_used++];
-        t1 = b->ev_pool[b->ev_used++];
+        cudaEvent_t t0 = b->ev_pool[b->ev_used++];
+        rc.t1 = b->ev_pool[b->ev_used++];
         CK(cudaEventRecord(t0, st));
     }
-    if (n > 0)
+    return 0;
+}
+
+// The filter-bank kernel for channels [c0, c0 + count); d_amp = the row of channel c0
+static int rx_bank_launch(span_b200_bank_t *b, const RxCall &rc, const int16_t *d_amp, int64_t stride, int c0, int count)
+{
+    if (rc.n <= 0  ||  count <= 0)
+        return 0;
+    const Geometry &g = rc.g;
+    cudaStream_t st = rc.st;
+    const float *lut = rc.lut;
+    const int n = rc.n;
+    int rcode = 0;
+    switch (b->det)
     {
-        int rc = 0;
-        switch (b->det)
+    case SPAN_B200_DET_DTMF:
         {
-        case SPAN_B200_DET_DTMF:
-            {
-                BankArgs<DtmfDet> a;
-                fill_common(b, a, d_amp, stride, n);
-                a.lut = lut;
-                a.det.threshold = b->thr;
-                a.det.normal_twist = b->ntw;
-                a.det.reverse_twist = b->rtw;
-                a.det.flags = b->flags;
-                a.det.z = b->z;
-                rc = launch_bank<DtmfDet>(b, a, g, st, true);
-            }
-            break;
-        case SPAN_B200_DET_BELL_MF:
-            {
-                BankArgs<BellMfDet> a;
-                fill_common(b, a, d_amp, stride, n);
-                a.lut = lut;
-                rc = launch_bank<BellMfDet>(b, a, g, st, false);
-            }
-            break;
-        case SPAN_B200_DET_R2_MF:
-            {
-                BankArgs<R2MfDet> a;
-                fill_common(b, a, d_amp, stride, n);
-                a.lut = lut;
-                a.det.fwd = b->fwd;
-                rc = launch_bank<R2MfDet>(b, a, g, st, false);
-            }
-            break;
-        case SPAN_B200_DET_SUPER_TONE:
-            if (b->npairs <= 1)
-                rc = run_st<1>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 2)
-                rc = run_st<2>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 3)
-                rc = run_st<3>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 4)
-                rc = run_st<4>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 5)
-                rc = run_st<5>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 6)
-                rc = run_st<6>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 8)
-                rc = run_st<8>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 10)
-                rc = run_st<10>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 12)
-                rc = run_st<12>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 16)
-                rc = run_st<16>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 20)
-                rc = run_st<20>(b, d_amp, stride, n, g, st, lut);
-            else if (b->npairs <= 24)
-                rc = run_st<24>(b, d_amp, stride, n, g, st, lut);
-            else
-                rc = run_st<32>(b, d_amp, stride, n, g, st, lut);
-            break;
+            BankArgs<DtmfDet> a;
+            fill_common(b, a, d_amp, stride, n, c0, count);
+            a.lut = lut;
+            a.det.threshold = b->thr + c0;
+            a.det.normal_twist = b->ntw + c0;
+            a.det.reverse_twist = b->rtw + c0;
+            a.det.flags = b->flags + c0;
+            a.det.z = b->z + c0;
+            rcode = launch_bank<DtmfDet>(b, a, g, st, true);
         }
-        if (rc != 0)
-            return -1;
-        b->last_launches++;
-        if (t1)
-            CK(cudaEventRecord(t1, st));
+        break;
+    case SPAN_B200_DET_BELL_MF:
+        {
+            BankArgs<BellMfDet> a;
+            fill_common(b, a, d_amp, stride, n, c0, count);
+            a.lut = lut;
+            rcode = launch_bank<BellMfDet>(b, a, g, st, false);
+        }
+        break;
+    case SPAN_B200_DET_R2_MF:
+        {
+            BankArgs<R2MfDet> a;
+            fill_common(b, a, d_amp, stride, n, c0, count);
+            a.lut = lut;
+            a.det.fwd = b->fwd;
+            rcode = launch_bank<R2MfDet>(b, a, g, st, false);
+        }
+        break;
+    case SPAN_B200_DET_SUPER_TONE:
+        if (b->npairs <= 1)
+            rcode = run_st<1>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 2)
+            rcode = run_st<2>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 3)
+            rcode = run_st<3>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 4)
+            rcode = run_st<4>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 5)
+            rcode = run_st<5>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 6)
+            rcode = run_st<6>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 8)
+            rcode = run_st<8>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 10)
+            rcode = run_st<10>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 12)
+            rcode = run_st<12>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 16)
+            rcode = run_st<16>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 20)
+            rcode = run_st<20>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else if (b->npairs <= 24)
+            rcode = run_st<24>(b, d_amp, stride, n, g, st, lut, c0, count);
+        else
+            rcode = run_st<32>(b, d_amp, stride, n, g, st, lut, c0, count);
+        break;
     }
-    else
-    {
-        b->last_path = "empty";
-    }
-    // ---- sequencer: count, scan, emit ----
+    if (rcode != 0)
+        return -1;
+    b->last_launches++;
+    return 0;
+}
+
+// The sequencers: count, scan, emit
+static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
+{
+    const Geometry &g = rc.g;
+    cudaStream_t st = rc.st;
+    const int n = rc.n;
+    const int B = b->block;
+    const int slot = rc.slot;
+    if (rc.t1)
+        CK(cudaEventRecord(rc.t1, st));
     SeqCommon q;
     q.channels = b->channels;
     q.n = n;
@@ -1250,8 +1493,10 @@ static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, in
     q.cs = b->cs;
     q.offsets = b->offsets;
     q.counts = b->counts;
-    q.events = b->events;
-    q.capacity = b->ev_cap;
+    q.events = (b->wire_on)  ?  NULL  :  b->events;
+    q.wire = rc.wire_out;
+    q.channel_base = b->channel_base;
+    q.capacity = rc.out_cap;
     const int sgrid = (b->channels + 127)/128;
     for (int pass = 0;  pass < 2;  pass++)
     {
@@ -1324,11 +1569,16 @@ static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, in
         b->last_launches++;
         if (pass == 0)
         {
-            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, (b->channels + 31)/32, b->d_total);
+            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, (b->channels + 31)/32, b->d_total + slot);
             CK(cudaGetLastError());
             b->last_launches++;
-            CK(cudaMemcpyAsync(b->h_total, b->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(b->h_total + slot, b->d_total + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         }
+    }
+    if (b->wire_on)
+    {
+        CK(cudaEventRecord(b->emitted[slot], st));
+        b->slot = slot;
     }
     if (g.cs0 >= 0)
         b->uniform_cs = (g.cs0 + n) % B;
@@ -1336,6 +1586,22 @@ static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, in
     b->last_stream = st;
     b->have_last = true;
     return 0;
+}
+
+static int rx_core(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, void *stream, int law)
+{
+    if (b == NULL)
+    {
+        sb_set_error("bad rx arguments");
+        return -1;
+    }
+    SB_DEVICE_CK(b->ctx->device);
+    RxCall rc;
+    if (rx_prepare(b, d_amp, stride, n, stream, law, rc) != 0)
+        return -1;
+    if (rx_bank_launch(b, rc, d_amp, stride, 0, b->channels) != 0)
+        return -1;
+    return rx_finish(b, rc);
 }
 
 extern "C" int span_b200_bank_rx_device(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
@@ -1350,8 +1616,12 @@ extern "C" int span_b200_bank_rx_device_g711(span_b200_bank_t *b, const uint8_t 
     return rx_core(b, (const int16_t *) d_data, stride, n, stream, (alaw)  ?  1  :  0);
 }
 
-extern "C" int span_b200_bank_rx_host_g711(span_b200_bank_t *b, const uint8_t *h_data, int64_t stride,
-                                           int n, int alaw, void *stream)
+// Host samples.  The copy and the filter bank are pipelined over channel ranges: the rows of range k + 1 cross PCIe
+// (on the bank's copy stream) while the filter-bank kernel of range k runs; the sequencers follow once, over all
+// channels.  Pinned host memory makes the copies asynchronous; pageable memory works, serialised by the driver.
+#define SB_RX_HOST_PIECES   8
+
+static int rx_host_core(span_b200_bank_t *b, const void *h_data, int64_t stride, int n, void *stream, int law)
 {
     if (b == NULL  ||  n < 0  ||  (n > 0  &&  h_data == NULL))
     {
@@ -1362,49 +1632,70 @@ extern "C" int span_b200_bank_rx_host_g711(span_b200_bank_t *b, const uint8_t *h
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
-    const int64_t dstride = (n + 15) & ~15LL;
-    if (ensure((void **) &b->d_in, &b->d_in_bytes, (size_t) dstride*b->channels + 16) != 0)
+    const int bps = (law >= 0)  ?  1  :  2;
+    // Device rows are padded to a multiple of 16 bytes so that the staged kernel applies.
+    const int64_t dstride = (law >= 0)  ?  ((n + 15) & ~15LL)  :  ((n + 7) & ~7LL);
+    if (ensure((void **) &b->d_in, &b->d_in_bytes, (size_t) bps*(size_t) dstride*b->channels + 16) != 0)
+        return -1;
+    RxCall rc;
+    if (rx_prepare(b, b->d_in, dstride, n, (void *) st, law, rc) != 0)
         return -1;
     if (n > 0)
     {
-        if (stride == n  &&  dstride == n)
-            CK(cudaMemcpyAsync(b->d_in, h_data, (size_t) n*b->channels, cudaMemcpyHostToDevice, st));
-        else
-            CK(cudaMemcpy2DAsync(b->d_in, (size_t) dstride, h_data, (size_t) stride, (size_t) n, b->channels, cudaMemcpyHostToDevice, st));
+        if (b->copy_stream == NULL)
+        {
+            CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0;  i < SB_RX_HOST_PIECES;  i++)
+                CK(cudaEventCreateWithFlags(&b->copied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&b->in_free, cudaEventDisableTiming));
+        }
+        // the previous call's kernels (on st) may still read d_in
+        CK(cudaEventRecord(b->in_free, st));
+        CK(cudaStreamWaitEvent(b->copy_stream, b->in_free, 0));
+        // pieces of whole 32-channel groups; small banks go in one piece
+        int pieces = SB_RX_HOST_PIECES;
+        while (pieces > 1  &&  (long long) b->channels*n < (long long) pieces*(4 << 20))
+            pieces >>= 1;
+        const int groups = (b->channels + 31)/32;
+        for (int k = 0;  k < pieces;  k++)
+        {
+            const int c0 = (int) ((long long) groups*k/pieces)*32;
+            int c1 = (int) ((long long) groups*(k + 1)/pieces)*32;
+            if (c1 > b->channels)
+                c1 = b->channels;
+            if (c1 <= c0)
+                continue;
+            const char *src = (const char *) h_data + (size_t) c0*(size_t) stride*bps;
+            char *dst = (char *) b->d_in + (size_t) c0*(size_t) dstride*bps;
+            if (stride == n  &&  dstride == n)
+            {
+                // contiguous on both sides: one flat copy (measured 55 GB/s vs ~50 GB/s for the pitched form)
+                CK(cudaMemcpyAsync(dst, src, (size_t) bps*(size_t) n*(size_t) (c1 - c0), cudaMemcpyHostToDevice, b->copy_stream));
+            }
+            else
+            {
+                CK(cudaMemcpy2DAsync(dst, (size_t) bps*dstride, src, (size_t) bps*stride, (size_t) bps*n, (size_t) (c1 - c0),
+                                     cudaMemcpyHostToDevice, b->copy_stream));
+            }
+            CK(cudaEventRecord(b->copied[k], b->copy_stream));
+            CK(cudaStreamWaitEvent(st, b->copied[k], 0));
+            if (rx_bank_launch(b, rc, (const int16_t *) dst, dstride, c0, c1 - c0) != 0)
+                return -1;
+        }
     }
-    return rx_core(b, b->d_in, dstride, n, (void *) st, (alaw)  ?  1  :  0);
+    return rx_finish(b, rc);
+}
+
+extern "C" int span_b200_bank_rx_host_g711(span_b200_bank_t *b, const uint8_t *h_data, int64_t stride,
+                                           int n, int alaw, void *stream)
+{
+    return rx_host_core(b, h_data, stride, n, stream, (alaw)  ?  1  :  0);
 }
 
 extern "C" int span_b200_bank_rx_host(span_b200_bank_t *b, const int16_t *h_amp, int64_t stride,
                                       int n, void *stream)
 {
-    if (b == NULL  ||  n < 0  ||  (n > 0  &&  h_amp == NULL))
-    {
-        sb_set_error("bad rx arguments");
-        return -1;
-    }
-    SB_DEVICE_CK(b->ctx->device);
-    cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  b->ctx->stream;
-    if (b->have_last  &&  b->last_stream != st)
-        CK(cudaStreamSynchronize(b->last_stream));
-    // Device rows are padded to a multiple of 8 samples so that the staged kernel applies.
-    const int64_t dstride = (n + 7) & ~7LL;
-    if (ensure((void **) &b->d_in, &b->d_in_bytes, sizeof(int16_t)*(size_t) dstride*b->channels + 16) != 0)
-        return -1;
-    if (n > 0)
-    {
-        if (stride == n  &&  dstride == n)
-        {
-            // contiguous on both sides: one flat copy (measured 55 GB/s vs ~50 GB/s for the pitched form)
-            CK(cudaMemcpyAsync(b->d_in, h_amp, sizeof(int16_t)*(size_t) n*b->channels, cudaMemcpyHostToDevice, st));
-        }
-        else
-        {
-            CK(cudaMemcpy2DAsync(b->d_in, sizeof(int16_t)*dstride, h_amp, sizeof(int16_t)*stride,
-                                 sizeof(int16_t)*(size_t) n, b->channels, cudaMemcpyHostToDevice, st));
-        }
-    }
-    return span_b200_bank_rx_device(b, b->d_in, dstride, n, (void *) st);
+    return rx_host_core(b, h_amp, stride, n, stream, -1);
 }
 
 extern "C" int64_t span_b200_bank_event_count(span_b200_bank_t *b, int *overflow)
@@ -1415,18 +1706,35 @@ extern "C" int64_t span_b200_bank_event_count(span_b200_bank_t *b, int *overflow
         return 0;
     SB_DEVICE_CK(b->ctx->device);
     CK(cudaStreamSynchronize(b->last_stream));
-    long long total = (long long) b->h_total[0];
-    if (total > b->ev_cap)
+    const int slot = (b->wire_on)  ?  b->slot  :  0;
+    long long total = (long long) b->h_total[slot];
+    long long cap = b->ev_cap;
+    if (b->wire_on)
+        cap = (b->comm  &&  b->comm->rank == b->root)  ?  (b->comm->gather_cap[slot]/b->comm->nranks)  :  b->wire_cap[slot];
+    if (total > cap)
     {
         if (overflow)
             *overflow = 1;
-        total = b->ev_cap;
+        total = cap;
     }
     return total;
 }
 
+static int not_in_wire_mode(const span_b200_bank_t *b)
+{
+    if (b->wire_on)
+    {
+        sb_set_error("the bank is in wire mode: use span_b200_bank_events_wire() / the gather calls");
+        return 0;
+    }
+    return 1;
+}
+
 extern "C" int64_t span_b200_bank_events(span_b200_bank_t *b, span_b200_event_t *out, int64_t max)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
+    if (!not_in_wire_mode(b))
+        return -1;
     int64_t total = span_b200_bank_event_count(b, NULL);
     if (total < 0)
         return -1;
@@ -1439,6 +1747,9 @@ extern "C" int64_t span_b200_bank_events(span_b200_bank_t *b, span_b200_event_t 
 
 extern "C" int64_t span_b200_bank_events_to_device(span_b200_bank_t *b, span_b200_event_t *d_out, int64_t max, void *stream)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
+    if (!not_in_wire_mode(b))
+        return -1;
     int64_t total = span_b200_bank_event_count(b, NULL);
     if (total < 0)
         return -1;
@@ -1474,7 +1785,7 @@ extern "C" double span_b200_bank_kernel_ms(span_b200_bank_t *b, int *launches)
 
 extern "C" const span_b200_event_t *span_b200_bank_events_device(span_b200_bank_t *b)
 {
-    return b->events;
+    return (b->wire_on)  ?  NULL  :  b->events;
 }
 
 extern "C" int span_b200_bank_block_codes(span_b200_bank_t *b, uint16_t *codes, int64_t max)
@@ -1516,6 +1827,7 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
     a.block_rt = block_len;
     a.raw = d_out;
     a.raw_capacity = cap;
+    a.cstride = channels;
     a.det.bins = bins;
     for (int i = 0;  i < bins;  i++)
         a.det.fac[i] = fac[i];
@@ -1571,4 +1883,398 @@ extern "C" int span_b200_goertzel_blocks_device(span_b200_ctx_t *ctx, const floa
     if (rc != 0)
         return -1;
     return n/block_len;
+}
+
+// ------------------------------------------------------------------------------------------
+// wire records and the multi-GPU gather: channels shard over ranks with no exchange on the filter
+// path; the only traffic is the detected-digit / tone records on their way to the rank that replays the callbacks.
+
+extern "C" int span_b200_bank_set_wire(span_b200_bank_t *b, int on, uint32_t channel_base)
+{
+    if (b == NULL)
+        return -1;
+    SB_DEVICE_CK(b->ctx->device);
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    if (!on  &&  b->comm)
+    {
+        sb_set_error("the bank is attached to a communicator; it stays in wire mode");
+        return -1;
+    }
+    b->wire_on = (on != 0);
+    b->channel_base = channel_base;
+    b->h_total[0] = b->h_total[1] = 0;
+    b->slot = 0;
+    return 0;
+}
+
+extern "C" int64_t span_b200_bank_events_wire(span_b200_bank_t *b, span_b200_wire_event_t *out, int64_t max)
+{
+    if (b == NULL  ||  !b->wire_on)
+    {
+        sb_set_error("the bank is not in wire mode");
+        return -1;
+    }
+    int64_t total = span_b200_bank_event_count(b, NULL);
+    if (total < 0)
+        return -1;
+    if (total > max)
+        total = max;
+    SB_DEVICE_CK(b->ctx->device);
+    const span_b200_wire_event_t *src = (b->comm  &&  b->comm->rank == b->root)  ?  b->comm->gather[b->slot]  :  b->wire[b->slot];
+    if (total > 0)
+        CK(cudaMemcpy(out, src, sizeof(span_b200_wire_event_t)*(size_t) total, cudaMemcpyDeviceToHost));
+    return total;
+}
+
+extern "C" void span_b200_wire_expand(const span_b200_wire_event_t *in, span_b200_event_t *out, int64_t n, uint32_t channel_base)
+{
+    for (int64_t i = 0;  i < n;  i++)
+    {
+        out[i].channel = (int32_t) (in[i].channel - channel_base);
+        out[i].block = SPAN_B200_WIRE_BLOCK(in[i]);
+        out[i].kind = SPAN_B200_WIRE_KIND(in[i]);
+        out[i].a = in[i].a;
+        out[i].b = in[i].b;
+        out[i].c = in[i].c;
+    }
+}
+
+// ---- NCCL, resolved at run time ----------------------------------------------------------------
+struct nccl_api_t
+{
+    void *handle;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    const char *(*GetErrorString)(ncclResult_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
+    ncclResult_t (*GetVersion)(int *);
+};
+
+static nccl_api_t g_nccl;
+static std::mutex g_nccl_lock;
+
+static const nccl_api_t *nccl_api()
+{
+    std::lock_guard<std::mutex> lk(g_nccl_lock);
+    if (g_nccl.handle)
+        return &g_nccl;
+    // The copy the process already has (a host application that brought its own NCCL - PyTorch does), else the system's
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (h == NULL)
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == NULL)
+    {
+        sb_set_error("libnccl.so.2 not found (%s); the multi-GPU gather needs NCCL", dlerror());
+        return NULL;
+    }
+    nccl_api_t a;
+    memset(&a, 0, sizeof(a));
+    a.GetUniqueId = (decltype(a.GetUniqueId)) dlsym(h, "ncclGetUniqueId");
+    a.CommInitRankConfig = (decltype(a.CommInitRankConfig)) dlsym(h, "ncclCommInitRankConfig");
+    a.CommInitRank = (decltype(a.CommInitRank)) dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy)) dlsym(h, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString)) dlsym(h, "ncclGetErrorString");
+    a.AllGather = (decltype(a.AllGather)) dlsym(h, "ncclAllGather");
+    a.Send = (decltype(a.Send)) dlsym(h, "ncclSend");
+    a.Recv = (decltype(a.Recv)) dlsym(h, "ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart)) dlsym(h, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd)) dlsym(h, "ncclGroupEnd");
+    a.GetVersion = (decltype(a.GetVersion)) dlsym(h, "ncclGetVersion");
+    if (!a.GetUniqueId  ||  !a.CommInitRank  ||  !a.CommDestroy  ||  !a.GetErrorString  ||  !a.AllGather  ||  !a.Send  ||  !a.Recv
+        ||  !a.GroupStart  ||  !a.GroupEnd)
+    {
+        sb_set_error("libnccl.so.2 lacks a required entry point");
+        return NULL;
+    }
+    a.handle = h;
+    g_nccl = a;
+    return &g_nccl;
+}
+
+#define NK(call) \
+    do \
+    { \
+        ncclResult_t r_ = (call); \
+        if (r_ != ncclSuccess) \
+        { \
+            sb_set_error("%s failed: %s (%s:%d)", #call, nc->GetErrorString(r_), __FILE__, __LINE__); \
+            return -1; \
+        } \
+    } \
+    while (0)
+
+extern "C" int span_b200_comm_unique_id(unsigned char id[SPAN_B200_COMM_ID_BYTES])
+{
+    static_assert(sizeof(ncclUniqueId) == SPAN_B200_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    const nccl_api_t *nc = nccl_api();
+    if (nc == NULL)
+        return -1;
+    ncclUniqueId u;
+    NK(nc->GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+extern "C" void span_b200_comm_destroy(span_b200_comm_t *cm)
+{
+    if (cm == NULL)
+        return;
+    sb_device_guard sb_dg_(cm->ctx->device);
+    if (cm->stream)
+        cudaStreamSynchronize(cm->stream);
+    if (cm->nccl  &&  g_nccl.handle)
+        g_nccl.CommDestroy(cm->nccl);
+    for (int i = 0;  i < 2;  i++)
+    {
+        cudaFree(cm->gather[i]);
+        cudaFree(cm->d_counts[i]);
+        if (cm->h_counts[i])
+            cudaFreeHost(cm->h_counts[i]);
+        if (cm->counts_ready[i])
+            cudaEventDestroy(cm->counts_ready[i]);
+        if (cm->done[i])
+            cudaEventDestroy(cm->done[i]);
+    }
+    if (cm->stream)
+        cudaStreamDestroy(cm->stream);
+    delete cm;
+}
+
+extern "C" span_b200_comm_t *span_b200_comm_create(span_b200_ctx_t *ctx, const unsigned char id[SPAN_B200_COMM_ID_BYTES], int nranks, int rank,
+                                                   int max_ctas)
+{
+    if (ctx == NULL  ||  id == NULL  ||  nranks < 1  ||  rank < 0  ||  rank >= nranks)
+    {
+        sb_set_error("bad communicator arguments");
+        return NULL;
+    }
+    const nccl_api_t *nc = nccl_api();
+    if (nc == NULL)
+        return NULL;
+    SB_DEVICE_CKP(ctx->device);
+    span_b200_comm_t *cm = new span_b200_comm_s();
+    cm->ctx = ctx;
+    cm->nranks = nranks;
+    cm->rank = rank;
+    cm->begun_slot = -1;
+    cm->ended_slot = -1;
+    bool ok = cudaStreamCreateWithFlags(&cm->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0;  ok  &&  i < 2;  i++)
+    {
+        ok = cudaMalloc(&cm->d_counts[i], sizeof(unsigned long long)*nranks) == cudaSuccess
+             &&  cudaMallocHost(&cm->h_counts[i], sizeof(unsigned long long)*nranks) == cudaSuccess
+             &&  cudaEventCreateWithFlags(&cm->counts_ready[i], cudaEventDisableTiming) == cudaSuccess
+             &&  cudaEventCreateWithFlags(&cm->done[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok)
+    {
+        sb_set_error("communicator allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        span_b200_comm_destroy(cm);
+        return NULL;
+    }
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclResult_t r;
+    if (nc->CommInitRankConfig)
+    {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.blocking = 1;
+        if (max_ctas > 0)
+        {
+            cfg.minCTAs = 1;
+            cfg.maxCTAs = max_ctas;
+        }
+        r = nc->CommInitRankConfig(&cm->nccl, nranks, u, rank, &cfg);
+    }
+    else
+    {
+        r = nc->CommInitRank(&cm->nccl, nranks, u, rank);
+    }
+    if (r != ncclSuccess)
+    {
+        sb_set_error("ncclCommInitRank failed: %s", nc->GetErrorString(r));
+        cm->nccl = NULL;
+        span_b200_comm_destroy(cm);
+        return NULL;
+    }
+    return cm;
+}
+
+extern "C" int span_b200_comm_rank(const span_b200_comm_t *cm) { return cm->rank; }
+extern "C" int span_b200_comm_nranks(const span_b200_comm_t *cm) { return cm->nranks; }
+
+extern "C" int span_b200_comm_sync(span_b200_comm_t *cm)
+{
+    if (cm == NULL)
+        return -1;
+    SB_DEVICE_CK(cm->ctx->device);
+    CK(cudaStreamSynchronize(cm->stream));
+    return 0;
+}
+
+// Root: make gather[slot] hold `records` records.  keep > 0: the first `keep` records (the root's own, already
+// written by the emit pass on stream `st`) survive a re-allocation.
+static int comm_gather_reserve(span_b200_comm_t *cm, int slot, long long records, cudaStream_t st, long long keep)
+{
+    if (cm->gather_cap[slot] >= records)
+        return 0;
+    span_b200_wire_event_t *p = NULL;
+    CK(cudaMalloc(&p, sizeof(span_b200_wire_event_t)*(size_t) records));
+    if (cm->gather[slot])
+    {
+        if (keep > 0)
+        {
+            CK(cudaMemcpyAsync(p, cm->gather[slot], sizeof(span_b200_wire_event_t)*(size_t) keep, cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        CK(cudaStreamSynchronize(cm->stream));
+        CK(cudaFree(cm->gather[slot]));
+    }
+    cm->gather[slot] = p;
+    cm->gather_cap[slot] = records;
+    return 0;
+}
+
+extern "C" int span_b200_bank_attach_comm(span_b200_bank_t *b, span_b200_comm_t *cm, int root)
+{
+    if (b == NULL  ||  cm == NULL  ||  root < 0  ||  root >= cm->nranks  ||  cm->ctx != b->ctx)
+    {
+        sb_set_error("bad attach arguments (bank and communicator must share a context)");
+        return -1;
+    }
+    if (!b->wire_on)
+    {
+        sb_set_error("switch the bank to wire records first (span_b200_bank_set_wire)");
+        return -1;
+    }
+    SB_DEVICE_CK(b->ctx->device);
+    if (b->have_last)
+        CK(cudaStreamSynchronize(b->last_stream));
+    b->comm = cm;
+    b->root = root;
+    return 0;
+}
+
+extern "C" int span_b200_bank_gather_begin(span_b200_bank_t *b)
+{
+    if (b == NULL  ||  b->comm == NULL  ||  !b->have_last)
+    {
+        sb_set_error("gather: no communicator attached, or no rx call yet");
+        return -1;
+    }
+    span_b200_comm_t *cm = b->comm;
+    const nccl_api_t *nc = nccl_api();
+    if (nc == NULL)
+        return -1;
+    if (cm->begun_slot >= 0)
+    {
+        sb_set_error("gather: the previous _gather_begin has not been completed by _gather_end");
+        return -1;
+    }
+    SB_DEVICE_CK(b->ctx->device);
+    const int slot = b->slot;
+    CK(cudaStreamWaitEvent(cm->stream, b->emitted[slot], 0));
+    NK(nc->AllGather(b->d_total + slot, cm->d_counts[slot], 1, ncclUint64, cm->nccl, cm->stream));
+    CK(cudaMemcpyAsync(cm->h_counts[slot], cm->d_counts[slot], sizeof(unsigned long long)*cm->nranks, cudaMemcpyDeviceToHost, cm->stream));
+    CK(cudaEventRecord(cm->counts_ready[slot], cm->stream));
+    cm->begun_slot = slot;
+    return 0;
+}
+
+extern "C" int64_t span_b200_bank_gather_end(span_b200_bank_t *b, int64_t *counts)
+{
+    if (b == NULL  ||  b->comm == NULL  ||  b->comm->begun_slot < 0)
+    {
+        sb_set_error("gather: _gather_end without _gather_begin");
+        return -1;
+    }
+    span_b200_comm_t *cm = b->comm;
+    const nccl_api_t *nc = nccl_api();
+    if (nc == NULL)
+        return -1;
+    SB_DEVICE_CK(b->ctx->device);
+    const int slot = cm->begun_slot;
+    CK(cudaEventSynchronize(cm->counts_ready[slot]));
+    long long total = 0;
+    // a rank whose buffer overflowed sends what its buffer holds
+    const long long own_cap = (cm->rank == b->root)  ?  (cm->gather_cap[slot]/cm->nranks)  :  b->wire_cap[slot];
+    for (int r = 0;  r < cm->nranks;  r++)
+    {
+        if (counts)
+            counts[r] = (int64_t) cm->h_counts[slot][r];
+        total += (long long) cm->h_counts[slot][r];
+    }
+    long long own = (long long) cm->h_counts[slot][cm->rank];
+    if (own > own_cap)
+    {
+        sb_set_error("gather: this rank's record buffer overflowed (%lld records, room for %lld)", own, own_cap);
+        return -1;
+    }
+    if (cm->rank == b->root)
+    {
+        if (comm_gather_reserve(cm, slot, total, b->last_stream, own) != 0)
+            return -1;
+        long long off = own;
+        NK(nc->GroupStart());
+        for (int r = 0;  r < cm->nranks;  r++)
+        {
+            const long long n = (long long) cm->h_counts[slot][r];
+            if (r == cm->rank  ||  n == 0)
+                continue;
+            NK(nc->Recv(cm->gather[slot] + off, (size_t) n*sizeof(span_b200_wire_event_t), ncclUint8, r, cm->nccl, cm->stream));
+            off += n;
+        }
+        NK(nc->GroupEnd());
+    }
+    else if (own > 0)
+    {
+        NK(nc->GroupStart());
+        NK(nc->Send(b->wire[slot], (size_t) own*sizeof(span_b200_wire_event_t), ncclUint8, b->root, cm->nccl, cm->stream));
+        NK(nc->GroupEnd());
+    }
+    CK(cudaEventRecord(cm->done[slot], cm->stream));
+    cm->done_valid[slot] = true;
+    cm->total[slot] = total;
+    cm->ended_slot = slot;
+    cm->begun_slot = -1;
+    return total;
+}
+
+extern "C" int64_t span_b200_bank_gathered(span_b200_bank_t *b, const span_b200_wire_event_t **d_records)
+{
+    if (b == NULL  ||  b->comm == NULL  ||  b->comm->ended_slot < 0)
+    {
+        sb_set_error("gather: nothing gathered yet");
+        return -1;
+    }
+    span_b200_comm_t *cm = b->comm;
+    SB_DEVICE_CK(b->ctx->device);
+    const int slot = cm->ended_slot;
+    CK(cudaEventSynchronize(cm->done[slot]));
+    if (d_records)
+        *d_records = (cm->rank == b->root)  ?  cm->gather[slot]  :  NULL;
+    return cm->total[slot];
+}
+
+extern "C" int64_t span_b200_bank_gathered_host(span_b200_bank_t *b, span_b200_wire_event_t *out, int64_t max)
+{
+    const span_b200_wire_event_t *d = NULL;
+    int64_t total = span_b200_bank_gathered(b, &d);
+    if (total < 0)
+        return -1;
+    if (d == NULL)
+        return 0;
+    if (total > max)
+        total = max;
+    SB_DEVICE_CK(b->ctx->device);
+    if (total > 0)
+        CK(cudaMemcpy(out, d, sizeof(span_b200_wire_event_t)*(size_t) total, cudaMemcpyDeviceToHost));
+    return total;
 }

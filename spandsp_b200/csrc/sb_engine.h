@@ -19,6 +19,8 @@ struct sb_device_guard
     bool good;
     explicit sb_device_guard(int device) : prev(-1), want(device), good(true)
     {
+        if (want < 0)
+            return;                     // no object to act on: the caller's own argument check reports it
         if (cudaGetDevice(&prev) != cudaSuccess)
             prev = -1;
         if (prev != want)
@@ -26,7 +28,7 @@ struct sb_device_guard
     }
     ~sb_device_guard()
     {
-        if (prev >= 0  &&  prev != want)
+        if (want >= 0  &&  prev >= 0  &&  prev != want)
             cudaSetDevice(prev);
     }
     bool ok() const { return good; }

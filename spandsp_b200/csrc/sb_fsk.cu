@@ -110,6 +110,7 @@ static int fsk_range_ok(span_b200_fsk_bank_t *b, int first, int count)
 
 static int fsk_configure(span_b200_fsk_bank_t *b)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!b->configured)
     {
         CK(cudaFuncSetAttribute(fsk_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsk_smem_bytes(SBF_MAX_WINDOW)));
@@ -121,6 +122,7 @@ static int fsk_configure(span_b200_fsk_bank_t *b)
 
 static int fsk_ctl(span_b200_fsk_bank_t *b, int first, int count, int mode, const FskSetup &su, int aux)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (count <= 0)
         return 0;
     if (fsk_quiesce(b) != 0  ||  fsk_configure(b) != 0)
@@ -163,7 +165,7 @@ extern "C" void span_b200_fsk_bank_destroy(span_b200_fsk_bank_t *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->state);
@@ -230,6 +232,7 @@ extern "C" int span_b200_fsk_bank_restart(span_b200_fsk_bank_t *b, int first, in
 
 extern "C" int span_b200_fsk_bank_set_signal_cutoff(span_b200_fsk_bank_t *b, int first, int count, float cutoff)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!fsk_range_ok(b, first, count))
         return -1;
     if (fsk_quiesce(b) != 0)
@@ -337,6 +340,7 @@ extern "C" int span_b200_fsk_bank_rx_host(span_b200_fsk_bank_t *b, const int16_t
 
 extern "C" int span_b200_fsk_bank_counts(span_b200_fsk_bank_t *b, int32_t *nout)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (fsk_quiesce(b) != 0)
         return -1;
     CK(cudaMemcpy(nout, b->nout, sizeof(int)*(size_t) b->channels, cudaMemcpyDeviceToHost));
@@ -345,6 +349,7 @@ extern "C" int span_b200_fsk_bank_counts(span_b200_fsk_bank_t *b, int32_t *nout)
 
 extern "C" int64_t span_b200_fsk_bank_output(span_b200_fsk_bank_t *b, int channel, int16_t *out, int64_t max)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (channel < 0  ||  channel >= b->channels)
         return -1;
     if (fsk_quiesce(b) != 0)
@@ -374,6 +379,7 @@ extern "C" int span_b200_fsk_bank_output_layout(span_b200_fsk_bank_t *b, const i
 
 extern "C" int span_b200_fsk_bank_errors(span_b200_fsk_bank_t *b, int channel, int32_t *parity_errors, int32_t *framing_errors, int reset)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (channel < 0  ||  channel >= b->channels)
         return -1;
     if (fsk_quiesce(b) != 0)
@@ -397,6 +403,7 @@ extern "C" int span_b200_fsk_bank_errors(span_b200_fsk_bank_t *b, int channel, i
 
 extern "C" float span_b200_fsk_bank_signal_power(span_b200_fsk_bank_t *b, int channel)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     int reading = 0;
     if (channel < 0  ||  channel >= b->channels  ||  fsk_quiesce(b) != 0)
         return -96.329f + (3.14f + 3.02f);
@@ -410,6 +417,7 @@ extern "C" float span_b200_fsk_bank_signal_power(span_b200_fsk_bank_t *b, int ch
 
 extern "C" int span_b200_fsk_bank_channel_state(span_b200_fsk_bank_t *b, int channel, int32_t *info, int32_t *window)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (channel < 0  ||  channel >= b->channels)
         return -1;
     if (fsk_quiesce(b) != 0)

@@ -92,6 +92,7 @@ static int tx_range_ok(span_b200_dtmf_tx_bank_t *b, int first, int count)
 
 static int tx_ctl(span_b200_dtmf_tx_bank_t *b, int first, int count, int mode, float ga, float gb, int ia, int ib)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!tx_range_ok(b, first, count))
         return -1;
     if (count == 0)
@@ -126,7 +127,7 @@ extern "C" void span_b200_dtmf_tx_bank_destroy(span_b200_dtmf_tx_bank_t *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->state);
@@ -194,6 +195,7 @@ static int gen_realloc(void **p, size_t bytes)
 
 static int tx_put(span_b200_dtmf_tx_bank_t *b, int first, int count, const char *digits, int64_t stride, const int32_t *lens, int len_all)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!tx_range_ok(b, first, count)  ||  digits == NULL)
     {
         sb_set_error("bad put arguments");
@@ -295,6 +297,7 @@ extern "C" int span_b200_dtmf_tx_bank_tx_device(span_b200_dtmf_tx_bank_t *b, int
 
 extern "C" int span_b200_dtmf_tx_bank_tx_host(span_b200_dtmf_tx_bank_t *b, int16_t *h_amp, int64_t stride, int max_samples, int zero_fill)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b == NULL  ||  max_samples < 0  ||  (max_samples > 0  &&  h_amp == NULL))
     {
         sb_set_error("bad tx arguments");
@@ -328,6 +331,7 @@ extern "C" int span_b200_dtmf_tx_bank_tx_host(span_b200_dtmf_tx_bank_t *b, int16
 
 extern "C" int span_b200_dtmf_tx_bank_lens(span_b200_dtmf_tx_bank_t *b, int32_t *lens)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b == NULL  ||  lens == NULL)
         return -1;
     if (tx_quiesce(b) != 0)
@@ -406,7 +410,7 @@ extern "C" void span_b200_awgn_bank_destroy(span_b200_awgn_bank_t *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->istate);
@@ -522,6 +526,7 @@ static int gen_range_ok(const gen_bank_base *b, int first, int count)
 
 static bool gen_base_alloc(gen_bank_base *b, span_b200_ctx_t *ctx, int channels, int fields)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     b->ctx = ctx;
     b->channels = channels;
     std::vector<float> t(SBG_SINE_WORDS);
@@ -537,6 +542,7 @@ static bool gen_base_alloc(gen_bank_base *b, span_b200_ctx_t *ctx, int channels,
 
 static void gen_base_free(gen_bank_base *b)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->state);
@@ -581,7 +587,7 @@ extern "C" void span_b200_tone_gen_bank_destroy(span_b200_tone_gen_bank_t *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     gen_base_free(b);
     cudaFree(b->d_descs);
     delete b;
@@ -756,7 +762,7 @@ extern "C" void span_b200_v29_tx_bank_destroy(span_b200_v29_tx_bank_t *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     gen_base_free(b);
     cudaFree(b->shaper);
     cudaFree(b->bits);

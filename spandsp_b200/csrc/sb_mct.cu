@@ -100,6 +100,7 @@ static FskSetup mct_v21_setup(void)
 
 extern "C" int span_b200_mct_bank_init(span_b200_mct_bank_t *b, int first, int count, int tone_type)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!mct_range_ok(b, first, count))
         return -1;
     if (count == 0)
@@ -118,7 +119,7 @@ extern "C" void span_b200_mct_bank_destroy(span_b200_mct_bank_t *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->state);
@@ -248,6 +249,7 @@ extern "C" int span_b200_mct_bank_rx_host(span_b200_mct_bank_t *b, const int16_t
 
 extern "C" int64_t span_b200_mct_bank_events(span_b200_mct_bank_t *b, span_b200_mct_event_t *events, int64_t max)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b == NULL)
         return -1;
     if (mct_quiesce(b) != 0)
@@ -292,6 +294,7 @@ extern "C" int64_t span_b200_mct_bank_events(span_b200_mct_bank_t *b, span_b200_
 
 extern "C" int span_b200_mct_bank_get(span_b200_mct_bank_t *b, int first, int count, int32_t *hits)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!mct_range_ok(b, first, count))
         return -1;
     if (count == 0)
@@ -307,6 +310,7 @@ extern "C" int span_b200_mct_bank_get(span_b200_mct_bank_t *b, int first, int co
 
 extern "C" int span_b200_mct_bank_channel_state(span_b200_mct_bank_t *b, int channel, int32_t *info, int32_t *fsk_info)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b == NULL  ||  channel < 0  ||  channel >= b->channels)
         return -1;
     if (mct_quiesce(b) != 0)

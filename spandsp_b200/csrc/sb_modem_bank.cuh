@@ -181,6 +181,7 @@ static int modem_init_channels(ModemBank<RX> *b, int first, int count, int bit_r
 template <class RX>
 static int modem_alloc_state(ModemBank<RX> *b)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     const size_t C = b->channels;
     CK(cudaMalloc(&b->fstate, sizeof(float)*RX::F_COUNT*C));
     CK(cudaMalloc(&b->istate, sizeof(int)*RX::I_COUNT*C));
@@ -198,7 +199,7 @@ static void modem_destroy(ModemBank<RX> *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->fstate);
@@ -237,6 +238,7 @@ static int modem_range_ok(ModemBank<RX> *b, int first, int count)
 template <class RX>
 static int modem_set_signal_cutoff(ModemBank<RX> *b, int first, int count, float cutoff)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!modem_range_ok(b, first, count))
         return -1;
     if (modem_quiesce(b) != 0)
@@ -260,6 +262,7 @@ static int modem_set_signal_cutoff(ModemBank<RX> *b, int first, int count, float
 template <class RX>
 static int modem_fillin(ModemBank<RX> *b, int first, int count, int samples)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (!modem_range_ok(b, first, count)  ||  samples < 0)
     {
         sb_set_error("bad fillin arguments");
@@ -375,6 +378,7 @@ static int modem_rx_host(ModemBank<RX> *b, const int16_t *h_amp, int64_t stride,
 template <class RX>
 static int modem_counts(ModemBank<RX> *b, int32_t *nbits, int32_t *nsyms)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (modem_quiesce(b) != 0)
         return -1;
     if (nbits)
@@ -387,6 +391,7 @@ static int modem_counts(ModemBank<RX> *b, int32_t *nbits, int32_t *nsyms)
 template <class RX>
 static int64_t modem_bits(ModemBank<RX> *b, int channel, int8_t *out, int64_t max)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (channel < 0  ||  channel >= b->channels)
         return -1;
     if (modem_quiesce(b) != 0)
@@ -403,9 +408,43 @@ static int64_t modem_bits(ModemBank<RX> *b, int channel, int8_t *out, int64_t ma
     return k;
 }
 
+// The put_bit streams of all channels in one transfer: out[c*out_stride ..] receives the first min(count, out_stride)
+// entries of channel c; nbits (may be NULL) the per-channel counts.  Returns the largest count.
+template <class RX>
+static int64_t modem_bits_all(ModemBank<RX> *b, int8_t *out, int64_t out_stride, int32_t *nbits)
+{
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
+    if (b == NULL  ||  out == NULL  ||  out_stride < 0)
+    {
+        sb_set_error("bad arguments");
+        return -1;
+    }
+    if (modem_quiesce(b) != 0)
+        return -1;
+    std::vector<int> n((size_t) b->channels);
+    CK(cudaMemcpy(n.data(), b->nbits, sizeof(int)*(size_t) b->channels, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int c = 0;  c < b->channels;  c++)
+    {
+        if (nbits)
+            nbits[c] = n[c];
+        if (n[c] > mx)
+            mx = n[c];
+    }
+    long long w = mx;
+    if (w > b->bits_cap)
+        w = b->bits_cap;
+    if (w > out_stride)
+        w = out_stride;
+    if (w > 0)
+        CK(cudaMemcpy2D(out, (size_t) out_stride, b->bits, (size_t) b->bits_cap, (size_t) w, (size_t) b->channels, cudaMemcpyDeviceToHost));
+    return mx;
+}
+
 template <class RX>
 static int64_t modem_symbols(ModemBank<RX> *b, int channel, span_b200_v29_symbol_t *out, int64_t max)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (channel < 0  ||  channel >= b->channels  ||  !b->want_symbols)
         return -1;
     if (modem_quiesce(b) != 0)

@@ -63,6 +63,7 @@ static int sig_quiesce(span_b200_sig_bank_t *b)
 
 static int sig_ctl(span_b200_sig_bank_t *b, int first, int count, int mode, int ia, int ib, int ic, int id)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b == NULL  ||  first < 0  ||  count < 0  ||  first + count > b->channels)
     {
         sb_set_error("channel range out of bounds");
@@ -101,7 +102,7 @@ extern "C" void span_b200_sig_bank_destroy(span_b200_sig_bank_t *b)
 {
     if (b == NULL)
         return;
-    sb_device_guard sb_dg_(span_b200_ctx_device(b->ctx));
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b->have_last)
         cudaStreamSynchronize(b->last_stream);
     cudaFree(b->state);
@@ -224,6 +225,7 @@ extern "C" int span_b200_sig_bank_rx_host(span_b200_sig_bank_t *b, int16_t *h_am
 
 extern "C" int64_t span_b200_sig_bank_events(span_b200_sig_bank_t *b, span_b200_sig_event_t *events, int64_t max)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b == NULL)
         return -1;
     if (sig_quiesce(b) != 0)
@@ -268,6 +270,7 @@ extern "C" int64_t span_b200_sig_bank_events(span_b200_sig_bank_t *b, span_b200_
 
 extern "C" int span_b200_sig_bank_channel_state(span_b200_sig_bank_t *b, int channel, int32_t *info)
 {
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
     if (b == NULL  ||  channel < 0  ||  channel >= b->channels  ||  info == NULL)
         return -1;
     if (sig_quiesce(b) != 0)

@@ -144,6 +144,11 @@ extern "C" int64_t span_b200_v29_bank_bits(span_b200_v29_bank_t *b, int channel,
     return modem_bits(b, channel, out, max);
 }
 
+extern "C" int64_t span_b200_v29_bank_bits_all(span_b200_v29_bank_t *b, int8_t *out, int64_t out_stride, int32_t *nbits)
+{
+    return modem_bits_all(b, out, out_stride, nbits);
+}
+
 extern "C" int64_t span_b200_v29_bank_symbols(span_b200_v29_bank_t *b, int channel, span_b200_v29_symbol_t *out, int64_t max)
 {
     return modem_symbols(b, channel, out, max);

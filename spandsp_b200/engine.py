@@ -18,6 +18,8 @@ EV_DIGIT, EV_TONE, EV_SEGMENT = 1, 2, 5
 
 EVENT_DTYPE = np.dtype([("channel", "<i4"), ("block", "<i4"), ("kind", "<i4"),
                         ("a", "<i4"), ("b", "<i4"), ("c", "<i4")])
+WIRE_DTYPE = np.dtype([("channel", "<u4"), ("c", "<i4"), ("block_kind", "<u2"), ("a", "i1"), ("b", "i1")])
+assert WIRE_DTYPE.itemsize == 12
 
 
 class SuperToneDesc(C.Structure):
@@ -69,6 +71,23 @@ def lib():
         "span_b200_bank_set_event_capacity": (i32, [vp, i64]),
         "span_b200_bank_events_to_device": (i64, [vp, vp, i64, vp]),
         "span_b200_bank_kernel_ms": (C.c_double, [vp, C.POINTER(i32)]),
+        "span_b200_bank_set_wire": (i32, [vp, i32, C.c_uint32]),
+        "span_b200_bank_events_wire": (i64, [vp, vp, i64]),
+        "span_b200_wire_expand": (None, [vp, vp, i64, C.c_uint32]),
+        "span_b200_comm_unique_id": (i32, [vp]),
+        "span_b200_comm_create": (vp, [vp, vp, i32, i32, i32]),
+        "span_b200_comm_destroy": (None, [vp]),
+        "span_b200_comm_rank": (i32, [vp]),
+        "span_b200_comm_nranks": (i32, [vp]),
+        "span_b200_comm_sync": (i32, [vp]),
+        "span_b200_bank_attach_comm": (i32, [vp, vp, i32]),
+        "span_b200_bank_gather_begin": (i32, [vp]),
+        "span_b200_bank_gather_end": (i64, [vp, vp]),
+        "span_b200_bank_gathered": (i64, [vp, vp]),
+        "span_b200_bank_gathered_host": (i64, [vp, vp, i64]),
+        "span_b200_ctx_numa_node": (i32, [vp]),
+        "span_b200_host_alloc": (vp, [vp, C.c_size_t]),
+        "span_b200_host_free": (None, [vp, vp]),
         "span_b200_bank_last_blocks": (i32, [vp]),
         "span_b200_bank_block_codes": (i32, [vp, vp, i64]),
         "span_b200_bank_tune": (i32, [vp, i32, i32]),
@@ -86,6 +105,7 @@ def lib():
         "span_b200_v29_bank_counts": (i32, [vp, vp, vp]),
         "span_b200_v29_bank_bits": (i64, [vp, i32, vp, i64]),
         "span_b200_v29_bank_symbols": (i64, [vp, i32, vp, i64]),
+        "span_b200_v29_bank_bits_all": (i64, [vp, vp, i64, vp]),
         "span_b200_v29_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_v29_tables": (i32, [vp, vp, vp, vp, vp, vp]),
         "span_b200_v29_bank_restart_ex": (i32, [vp, i32, i32, i32, i32]),
@@ -227,6 +247,28 @@ class Context:
         if self.h:
             lib().span_b200_ctx_destroy(self.h)
             self.h = None
+
+    @property
+    def numa_node(self):
+        return lib().span_b200_ctx_numa_node(self.h)
+
+    def host_alloc(self, shape, dtype):
+        """Pinned host memory on the GPU's NUMA node (span_b200_host_alloc) as a numpy array; free with host_free()."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = lib().span_b200_host_alloc(self.h, n)
+        if not p:
+            raise EngineError(_err())
+        buf = (C.c_char * n).from_address(p)
+        arr = np.frombuffer(buf, dtype=dt).reshape(shape)
+        self._host = getattr(self, "_host", {})
+        self._host[arr.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr):
+        p = getattr(self, "_host", {}).pop(arr.ctypes.data, None)
+        if p:
+            lib().span_b200_host_free(self.h, p)
 
     # raw Goertzel bank -------------------------------------------------------------------
     def goertzel_blocks(self, fac, block_len, d_amp_ptr, stride, channels, samples, d_out_ptr, out_capacity, stream=None):
@@ -383,6 +425,53 @@ class Bank:
             raise EngineError(_err())
         return n
 
+    # wire records and the multi-GPU gather ------------------------------------------------
+    def set_wire(self, on=True, channel_base=0):
+        self._ck(lib().span_b200_bank_set_wire(self.h, int(on), channel_base))
+
+    def events_wire(self, out=None):
+        n, overflow = self.event_count()
+        if overflow:
+            raise EngineError("event buffer overflow")
+        if out is None:
+            out = np.zeros(n, dtype=WIRE_DTYPE)
+        got = lib().span_b200_bank_events_wire(self.h, out.ctypes.data, len(out))
+        if got < 0:
+            raise EngineError(_err())
+        return out[:got]
+
+    def attach_comm(self, comm, root=0):
+        self._ck(lib().span_b200_bank_attach_comm(self.h, comm.h, root))
+        self._comm = comm
+
+    def gather_begin(self):
+        self._ck(lib().span_b200_bank_gather_begin(self.h))
+
+    def gather_end(self):
+        """Returns (total records over all ranks, per-rank counts)."""
+        counts = np.zeros(self._comm.nranks, dtype=np.int64)
+        total = lib().span_b200_bank_gather_end(self.h, counts.ctypes.data)
+        if total < 0:
+            raise EngineError(_err())
+        return total, counts
+
+    def gathered(self):
+        """Root: (total, device pointer) of the last completed gather (waits for it)."""
+        p = C.c_void_p(0)
+        total = lib().span_b200_bank_gathered(self.h, C.byref(p))
+        if total < 0:
+            raise EngineError(_err())
+        return total, p.value
+
+    def gathered_host(self, out=None):
+        total, _ = self.gathered()
+        if out is None:
+            out = np.zeros(total, dtype=WIRE_DTYPE)
+        got = lib().span_b200_bank_gathered_host(self.h, out.ctypes.data, len(out))
+        if got < 0:
+            raise EngineError(_err())
+        return out[:got]
+
     def kernel_ms(self):
         """(summed filter-bank kernel time in ms, launches) since the last query; needs tune(4, 1)."""
         k = C.c_int(0)
@@ -406,6 +495,43 @@ class Bank:
         if self.h:
             lib().span_b200_bank_destroy(self.h)
             self.h = None
+
+
+class Comm:
+    """One rank of a multi-GPU job (span_b200_comm_create): an NCCL communicator the library resolves at run time."""
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        if lib().span_b200_comm_unique_id(buf.ctypes.data) != 0:
+            raise EngineError(_err())
+        return buf
+
+    def __init__(self, ctx, unique_id, nranks, rank, max_ctas=0):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        self.h = lib().span_b200_comm_create(ctx.h, uid.ctypes.data, nranks, rank, max_ctas)
+        if not self.h:
+            raise EngineError(_err())
+        self.nranks = nranks
+        self.rank = rank
+
+    def sync(self):
+        if lib().span_b200_comm_sync(self.h) != 0:
+            raise EngineError(_err())
+
+    def close(self):
+        if self.h:
+            lib().span_b200_comm_destroy(self.h)
+            self.h = None
+
+
+def wire_unpack(w):
+    """Wire records -> (channel, block, kind, a, b, c) int64 columns."""
+    bk = w["block_kind"].astype(np.int64)
+    kind = bk >> 14
+    kind = np.where(kind == 3, 5, kind)
+    return (w["channel"].astype(np.int64), bk & 0x3FFF, kind, w["a"].astype(np.int64), w["b"].astype(np.int64), w["c"].astype(np.int64))
 
 
 V29_SYMBOL_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4"), ("state", "<i4"), ("bit_pos", "<i4")])
