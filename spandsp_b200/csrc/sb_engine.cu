@@ -290,7 +290,7 @@ extern "C" void span_b200_ctx_destroy(span_b200_ctx_t *ctx)
 
 extern "C" int span_b200_ctx_device(const span_b200_ctx_t *ctx)
 {
-    return ctx->device;
+    return (ctx)  ?  ctx->device  :  -1;
 }
 
 // ---- NUMA-local pinned host memory --------------------------------------------------------------

@@ -526,7 +526,7 @@ static int gen_range_ok(const gen_bank_base *b, int first, int count)
 
 static bool gen_base_alloc(gen_bank_base *b, span_b200_ctx_t *ctx, int channels, int fields)
 {
-    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
+    sb_device_guard sb_dg_(span_b200_ctx_device(ctx));
     b->ctx = ctx;
     b->channels = channels;
     std::vector<float> t(SBG_SINE_WORDS);

@@ -3,8 +3,8 @@
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r02_topo.txt 2>&1
 (nproc; lscpu | head -30; ls /sys/devices/system/node/ 2>/dev/null; for d in /sys/bus/pci/devices/*; do if [ -f $d/numa_node ] && grep -qi 0x10de $d/vendor 2>/dev/null; then echo $d $(cat $d/numa_node) $(cat $d/class); fi; done; free -g | head -2; cat /proc/self/status | grep -i allowed) >> gpurun_out/r02_topo.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -5 gpurun_out/r02_pytest_gpu.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_a.json 2> gpurun_out/r02_bench_a.err; tail -3 gpurun_out/r02_bench_a.err
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -5 gpurun_out/r02_pytest_gpu.log
+timeout 900 python -X faulthandler bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_a.json 2> gpurun_out/r02_bench_a.err; tail -3 gpurun_out/r02_bench_a.err
 python - <<'PY'
 import json
 try:
