@@ -551,23 +551,27 @@ def run_cfg4(torch, engine, ctx, dev, work_stream, args, peaks, peak_src):
     out["parity_check"] = pc
     if not args.no_e2e:
         h_amp, h_arr = pinned_like(torch, ctx, d_amp, args.numa)
-        bcap = int(nbits.max()) + 64
-        h_bits = torch.empty((C_, bcap), dtype=torch.int8, pin_memory=True)
+        wcap = (int(nbits.max()) + 31) // 32 + 2
+        scap = 64
+        h_words = torch.empty((C_, wcap), dtype=torch.int32, pin_memory=True)       # the packed put_bit streams of every channel
+        h_status = torch.empty((C_, scap, 2), dtype=torch.int32, pin_memory=True)
         h_n = np.zeros(C_, dtype=np.int32)
-        fn = engine.lib().span_b200_v29_bank_bits_all
+        h_ns = np.zeros(C_, dtype=np.int32)
+        fn = engine.lib().span_b200_v29_bank_output_packed
 
         def step_host():
             bank.restart(9600)
             bank.rx_host((h_amp.data_ptr(), T), stream, samples=T)
-            return fn(bank.h, h_bits.data_ptr(), bcap, h_n.ctypes.data)
+            return fn(bank.h, h_words.data_ptr(), wcap, h_n.ctypes.data, h_status.data_ptr(), scap, h_ns.ctypes.data)
 
         for _ in range(2):
             step_host()
         e2e_steps = max(2, min(args.steps, 5))
         ems, mx = time_steps_host(torch, step_host, e2e_steps, barrier)
         out["e2e"] = {"value": C_ * T * e2e_steps / (ems / 1e3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(C_ * T * 2),
-                      "d2h_bytes_per_step": int(C_ * min(int(mx), bcap) + 4 * C_), "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
-                      "path": "span_b200_v29_bank_rx_host (pinned int16) + span_b200_v29_bank_bits_all (every channel's put_bit stream)"}
+                      "d2h_bytes_per_step": int(C_ * (4 * ((int(mx) + 31) // 32) + 8 * int(h_ns.max()) + 8)), "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
+                      "path": "span_b200_v29_bank_rx_host (pinned int16) + span_b200_v29_bank_output_packed (every channel's put_bit stream: "
+                              "data bits 32 to a word + status reports)"}
         del h_amp
         if h_arr is not None:
             ctx.host_free(h_arr)

@@ -50,11 +50,23 @@ int span_b200_v17_bank_rx_host(span_b200_v17_bank_t *bank, const int16_t *h_amp,
 /* Results of the last rx call.  counts: per channel number of put_bit calls / qam reports. */
 int span_b200_v17_bank_counts(span_b200_v17_bank_t *bank, int32_t *nbits, int32_t *nsyms);
 int64_t span_b200_v17_bank_bits(span_b200_v17_bank_t *bank, int channel, int8_t *out, int64_t max);
+/* The put_bit sequences of every channel as bytes: out + c*out_stride receives the first min(count, out_stride)
+   entries of channel c, nbits (may be NULL) the per-channel counts.  Returns the largest count. */
+int64_t span_b200_v17_bank_bits_all(span_b200_v17_bank_t *bank, int8_t *out, int64_t out_stride, int32_t *nbits);
 int64_t span_b200_v17_bank_symbols(span_b200_v17_bank_t *bank, int channel, span_b200_v17_symbol_t *out, int64_t max);
-/* Device-side layout of the result buffers ([channel][capacity]) for callers that consume them on the GPU. */
-int span_b200_v17_bank_output_layout(span_b200_v17_bank_t *bank, const int8_t **d_bits, int64_t *bits_cap,
-                                     const int32_t **d_nbits, const span_b200_v17_symbol_t **d_syms,
-                                     int64_t *sym_cap, const int32_t **d_nsyms);
+/* The output of the last rx call in the form the kernel writes it, for every channel, one transfer per array:
+     words   [channels][words_stride]      the data bits, 32 to a word, first bit = bit 0
+     status  [channels][status_stride][2]  the status reports: {position in the put_bit sequence, SIG_STATUS_* value}
+     nbits / nstatus [channels]            put_bit calls (bits + reports) / reports
+   Rows are cut to the strides given; words / status may be NULL.  Returns the largest nbits, or -1.  This is the bulk
+   read-back (1 bit per data bit over PCIe); *_bank_bits() and *_bank_bits_all() rebuild the byte-per-call sequence
+   from it on the host. */
+int64_t span_b200_v17_bank_output_packed(span_b200_v17_bank_t *bank, uint32_t *words, int64_t words_stride, int32_t *nbits,
+                                        int32_t *status, int64_t status_stride, int32_t *nstatus);
+/* Device-side layout of those buffers ([channel][capacity]) for callers that consume them on the GPU. */
+int span_b200_v17_bank_output_layout(span_b200_v17_bank_t *bank, const uint32_t **d_words, int64_t *words_cap, const int32_t **d_nbits,
+                                     const int32_t **d_status, int64_t *status_cap, const int32_t **d_nstatus,
+                                     const span_b200_v29_symbol_t **d_syms, int64_t *sym_cap, const int32_t **d_nsyms);
 /* eq_coeff: 33 complex taps (v17_rx_equalizer_state, src/v17rx.c:192-204); info[12] =
    {training_stage, carrier_phase_rate, eq_put_step, signal_present, agc_scaling (float bits),
     total_baud_timing_correction, diff, carrier_phase, power meter reading, bit_rate, short_train, trellis_ptr}. */

@@ -441,9 +441,15 @@ struct ModemArgs
     int channels;
     float *fstate;
     int *istate;
-    signed char *bits;                  // [channel][bits_cap]: 0/1 data bits and negative status codes
-    long long bits_cap;
+    // The put_bit stream of a call, per channel: the data bits packed 32 to a word (first bit = bit 0), the status
+    // reports (negative SIG_STATUS_* values through put_bit, src/v29rx.c:171-178) as {position in the put_bit
+    // sequence, value} pairs beside them.  nbits = put_bit calls (bits + reports), nstatus = reports.
+    unsigned int *words;                // [channel][words_cap]
+    long long words_cap;
+    int *status;                        // [channel][status_cap][2]
+    long long status_cap;
     int *nbits;                         // [channel]
+    int *nstatus;                       // [channel]
     span_b200_v29_symbol_t *syms;       // [channel][sym_cap], or NULL
     long long sym_cap;
     int *nsyms;
@@ -476,11 +482,26 @@ struct StateStorer
 // One receiver.  Scalars live in registers; the per-channel arrays live in shared memory,
 // lane-interleaved (element e of lane l at [e*32 + l]) so that any per-lane index is conflict-free.
 // D is the concrete receiver (CRTP): it supplies restart_after_carrier_down() and process_baud().
-template <class D, int COEFF_SETS, int EQ_LEN = SBM_EQ_LEN>
+// LPC = lanes per channel.  1: one thread runs one receiver (every receiver; also the host build).  4: four lanes
+// share one receiver - the scalar part of the receiver runs replicated on all four (same inputs, same arithmetic,
+// same results), the three loops that carry the flops are split between them:
+//   * the RRC FIR pair: lanes {real, imaginary} x {first, second segment of the reference's circular dot product};
+//   * the complex equalizer dot product: the same four roles (real / imaginary accumulator x segment);
+//   * the LMS update: taps i = lane, lane + 4, ...
+// The segment split is exact: vec_circular_dot_prodf() sums the taps before and after the ring's physical wrap in two
+// separate chains and adds the two sums, so the chains are independent.  To keep all lanes on one instruction
+// stream whatever the ring position, the rings are stored between two zero areas, [zeros | ring | zeros]: a lane
+// that owns the first segment reads the ring from the current position on and runs into the trailing zeros, a lane
+// that owns the second segment starts in the leading zeros and runs into the ring - every lane executes all N taps,
+// and a product with a zero sample is +-0, which leaves a sum that started at +0 unchanged (x + (+-0) = x, and
+// (+0) + (-0) = +0), so each chain has exactly the value the reference's shorter loop gives.
+template <class D, int COEFF_SETS, int EQ_LEN = SBM_EQ_LEN, int LPC = 1>
 struct RxCore
 {
     static const int SETS = COEFF_SETS;
     static const int EQ_TAPS = EQ_LEN;      // equalizer length (33: V.29, V.17; 32: V.27ter); arrays are sized for 33
+    static const int LANES = LPC;
+    static const int LS = 32/LPC;           // receivers per warp = element pitch of the per-receiver arrays in shared memory
     // Symbol clock of xxx_rx_fillin(): coefficient-set steps per sample and per T/2 (a receiver with several
     // baud rates overrides these)
     static int fillin_sets(int) { return COEFF_SETS; }
@@ -504,12 +525,24 @@ struct RxCore
     const unsigned short *sqrt_tab; // [193] fixed_sqrt table (shared memory copy)
     int *diff_angles;       // [16]
     float2 *eq_coeff;       // [33]
-    float2 *eq_buf;         // [66]: ring of 33, doubled
-    float *rrc;             // [54]: ring of 27, doubled
-    // outputs
+    float2 *eq_buf;         // LPC 1: [66], ring of 33 kept twice.  LPC 4: the ring, with 33 zeros before and after it
+    float *rrc;             // LPC 1: [54], ring of 27 kept twice.  LPC 4: the ring, with 27 zeros before and after it
+    float2 *eq_coef_re;     // LPC 4: (yr, -yi) per tap: what the lanes of the real accumulator multiply with
+    float2 *eq_coef_im;     // LPC 4: (yi, yr) per tap: the imaginary accumulator's
+    int sub;                // LPC 4: this lane's role, 0 = real / first segment, 1 = real / second, 2 = imag / first, 3 = imag / second
+    unsigned int gmask;     // LPC 4: the four lanes of this receiver
+    // outputs.  Device kernels pack the data bits (words / status); the host build writes one byte per put_bit call.
     signed char *bits;
     int nbits;
     int bits_cap;
+    unsigned int *words;
+    int words_cap;
+    int nwords;
+    unsigned int bit_acc;
+    int bit_fill;
+    int *status;
+    int status_cap;
+    int nstatus;
     span_b200_v29_symbol_t *syms;
     int nsyms;
     int sym_cap;
@@ -520,16 +553,75 @@ struct RxCore
 
     SB_HD D &self() { return *static_cast<D *>(this); }
 
-    static const int CORE_LANE_WORDS = 2*SBM_EQ_LEN + 4*SBM_EQ_LEN + 2*SBM_FILTER_STEPS + 16;
-    static const int IN_RING_WORDS = SBM_IN_RING/2;     // per lane, contiguous (not interleaved): cp.async needs 16 bytes in a row
+    // words per receiver of the lane-interleaved block
+    static const int CORE_LANE_WORDS = (LPC == 1)  ?  (2*SBM_EQ_LEN + 4*SBM_EQ_LEN + 2*SBM_FILTER_STEPS + 16)
+                                                   :  (6*SBM_EQ_LEN + 6*SBM_EQ_LEN + 3*SBM_FILTER_STEPS + 16 + 1);
+    static const int IN_RING_WORDS = SBM_IN_RING/2;     // per receiver, contiguous (not interleaved): cp.async needs 16 bytes in a row
 
-    // lane_base: this lane's float2 column of the lane-interleaved block (block base + 2*lane words)
+    // block: the warp's lane-interleaved area (element e of receiver r at [e*LS + r])
     SB_HD void bind_core(float *block, int lane)
     {
-        eq_coeff = ((float2 *) block) + lane;
-        eq_buf = ((float2 *) (block + (2*SBM_EQ_LEN)*32)) + lane;
-        rrc = block + (6*SBM_EQ_LEN)*32 + lane;
-        diff_angles = (int *) (block + (6*SBM_EQ_LEN + 2*SBM_FILTER_STEPS)*32) + lane;
+        if (LPC == 1)
+        {
+            eq_coeff = ((float2 *) block) + lane;
+            eq_buf = ((float2 *) (block + (2*SBM_EQ_LEN)*32)) + lane;
+            rrc = block + (6*SBM_EQ_LEN)*32 + lane;
+            diff_angles = (int *) (block + (6*SBM_EQ_LEN + 2*SBM_FILTER_STEPS)*32) + lane;
+            eq_coef_re = eq_coef_im = NULL;
+            sub = 0;
+            gmask = 0xFFFFFFFFu;
+        }
+        else
+        {
+            const int r = lane/LPC;
+            float2 *p2 = (float2 *) block;
+            eq_coeff = p2 + r;
+            eq_coef_re = p2 + SBM_EQ_LEN*LS + r;
+            eq_coef_im = p2 + 2*SBM_EQ_LEN*LS + r;
+            eq_buf = p2 + 3*SBM_EQ_LEN*LS + EQ_LEN*LS + r;              // the ring; EQ_LEN zeros on either side
+            float *pf = block + 12*SBM_EQ_LEN*LS;
+            rrc = pf + SBM_FILTER_STEPS*LS + r;                          // the ring; 27 zeros on either side
+            diff_angles = (int *) (pf + 3*SBM_FILTER_STEPS*LS) + r;
+            sub = lane%LPC;
+            gmask = ((1u << LPC) - 1u) << (lane - sub);
+        }
+    }
+
+    // LPC 4: the zero areas around the two rings (written once per launch)
+    SB_HD void zero_pads()
+    {
+        if (LPC > 1)
+        {
+            for (int k = 0;  k < EQ_LEN;  k++)
+            {
+                eq_buf[(k - EQ_LEN)*LS] = make_float2(0.0f, 0.0f);
+                eq_buf[(k + EQ_LEN)*LS] = make_float2(0.0f, 0.0f);
+            }
+            for (int k = 0;  k < SBM_FILTER_STEPS;  k++)
+            {
+                rrc[(k - SBM_FILTER_STEPS)*LS] = 0.0f;
+                rrc[(k + SBM_FILTER_STEPS)*LS] = 0.0f;
+            }
+        }
+    }
+
+    // One equalizer coefficient, in every form that is kept of it
+    SB_HD void set_coef(int i, float yr, float yi)
+    {
+        eq_coeff[i*LS] = make_float2(yr, yi);
+        if (LPC > 1)
+        {
+            eq_coef_re[i*LS] = make_float2(yr, -yi);
+            eq_coef_im[i*LS] = make_float2(yi, yr);
+        }
+    }
+
+    SB_HD void group_sync()
+    {
+#if defined(__CUDA_ARCH__)
+        if (LPC > 1)
+            __syncwarp(gmask);
+#endif
     }
 
     template <class V> SB_HD void visit_core(V &v)
@@ -549,13 +641,13 @@ struct RxCore
         v.f(F_BAUD_PHASE, baud_phase);
         for (int k = 0;  k < EQ_LEN;  k++)
         {
-            v.f(F_EQ_COEFF + 2*k, eq_coeff[k*32].x);
-            v.f(F_EQ_COEFF + 2*k + 1, eq_coeff[k*32].y);
-            v.f(F_EQ_BUF + 2*k, eq_buf[k*32].x);
-            v.f(F_EQ_BUF + 2*k + 1, eq_buf[k*32].y);
+            v.f(F_EQ_COEFF + 2*k, eq_coeff[k*LS].x);
+            v.f(F_EQ_COEFF + 2*k + 1, eq_coeff[k*LS].y);
+            v.f(F_EQ_BUF + 2*k, eq_buf[k*LS].x);
+            v.f(F_EQ_BUF + 2*k + 1, eq_buf[k*LS].y);
         }
         for (int k = 0;  k < SBM_FILTER_STEPS;  k++)
-            v.f(F_RRC + k, rrc[k*32]);
+            v.f(F_RRC + k, rrc[k*LS]);
         v.i(I_BIT_RATE, bit_rate);
         v.i(I_RRC_STEP, rrc_step);
         v.u(I_SCRAMBLE, scramble_reg);
@@ -580,30 +672,79 @@ struct RxCore
         v.i(I_LAST_ANGLE1, last_angle1);
         v.i(I_TOTAL_TIMING, total_timing);
         for (int k = 0;  k < 16;  k++)
-            v.i(I_DIFF_ANGLES + k, diff_angles[k*32]);
+            v.i(I_DIFF_ANGLES + k, diff_angles[k*LS]);
     }
 
-    // After loading: fill the second copy of the two rings
+    // After loading: LPC 1 fills the second copy of the two rings; LPC 4 derives the two extra forms of the coefficients
     SB_HD void mirror_rings()
     {
-        for (int k = 0;  k < EQ_LEN;  k++)
-            eq_buf[(k + EQ_LEN)*32] = eq_buf[k*32];
-        for (int k = 0;  k < SBM_FILTER_STEPS;  k++)
-            rrc[(k + SBM_FILTER_STEPS)*32] = rrc[k*32];
+        if (LPC == 1)
+        {
+            for (int k = 0;  k < EQ_LEN;  k++)
+                eq_buf[(k + EQ_LEN)*LS] = eq_buf[k*LS];
+            for (int k = 0;  k < SBM_FILTER_STEPS;  k++)
+                rrc[(k + SBM_FILTER_STEPS)*LS] = rrc[k*LS];
+        }
+        else
+        {
+            for (int k = 0;  k < EQ_LEN;  k++)
+            {
+                const float2 y = eq_coeff[k*LS];
+                set_coef(k, y.x, y.y);
+            }
+        }
     }
 
     SB_HD void rrc_clear()
     {
-        for (int i = 0;  i < 2*SBM_FILTER_STEPS;  i++)
-            rrc[i*32] = 0.0f;
+        for (int i = 0;  i < ((LPC == 1)  ?  2  :  1)*SBM_FILTER_STEPS;  i++)
+            rrc[i*LS] = 0.0f;
         rrc_step = 0;
     }
 
+    // One put_bit() call of the reference: a data bit, or (negative) a status report
     SB_HD void out_bit(int v)
     {
-        if (nbits < bits_cap)
-            bits[nbits] = (signed char) v;
+        if (words == NULL)
+        {
+            if (nbits < bits_cap)
+                bits[nbits] = (signed char) v;
+        }
+        else if (v < 0)
+        {
+            if (sub == 0  &&  nstatus < status_cap)
+            {
+                status[2*nstatus] = nbits;
+                status[2*nstatus + 1] = v;
+            }
+            nstatus++;
+        }
+        else
+        {
+            bit_acc |= (unsigned int) (v & 1) << bit_fill;
+            if (++bit_fill == 32)
+            {
+                if (sub == 0  &&  nwords < words_cap)
+                    words[nwords] = bit_acc;
+                nwords++;
+                bit_acc = 0;
+                bit_fill = 0;
+            }
+        }
         nbits++;
+    }
+
+    // End of a call: the bits of an unfinished word
+    SB_HD void out_flush()
+    {
+        if (words != NULL  &&  bit_fill > 0)
+        {
+            if (sub == 0  &&  nwords < words_cap)
+                words[nwords] = bit_acc;
+            nwords++;
+            bit_acc = 0;
+            bit_fill = 0;
+        }
     }
 
     // src/v29rx.c:171-178, src/v17rx.c:181-189: without a status handler the status goes through put_bit
@@ -616,7 +757,7 @@ struct RxCore
     {
         if (syms)
         {
-            if (nsyms < sym_cap)
+            if (sub == 0  &&  nsyms < sym_cap)
             {
                 span_b200_v29_symbol_t s;
                 s.re = zre;
@@ -632,13 +773,14 @@ struct RxCore
     }
 
     // src/v29rx.c:214-258, src/v17rx.c:219-264
+    // (with LPC 4 all lanes of a receiver write the same values to the same places: harmless)
     SB_HD void equalizer_reset()
     {
         for (int i = 0;  i < EQ_LEN;  i++)
-            eq_coeff[i*32] = make_float2(0.0f, 0.0f);
-        for (int i = 0;  i < 2*EQ_LEN;  i++)
-            eq_buf[i*32] = make_float2(0.0f, 0.0f);
-        eq_coeff[SBM_EQ_PRE_LEN*32] = make_float2(3.0f, 0.0f);
+            set_coef(i, 0.0f, 0.0f);
+        for (int i = 0;  i < ((LPC == 1)  ?  2  :  1)*EQ_LEN;  i++)
+            eq_buf[i*LS] = make_float2(0.0f, 0.0f);
+        set_coef(SBM_EQ_PRE_LEN, 3.0f, 0.0f);
         eq_put_step = COEFF_SETS*10/(3*2) - 1;
         eq_step = 0;
     }
@@ -647,22 +789,26 @@ struct RxCore
     {
         for (int i = 0;  i < EQ_LEN;  i++)
         {
-            eq_coeff[i*32] = make_float2(fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c],
-                                         fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i + 1)*channels + c]);
+            set_coef(i, fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c],
+                        fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i + 1)*channels + c]);
         }
-        for (int i = 0;  i < 2*EQ_LEN;  i++)
-            eq_buf[i*32] = make_float2(0.0f, 0.0f);
+        for (int i = 0;  i < ((LPC == 1)  ?  2  :  1)*EQ_LEN;  i++)
+            eq_buf[i*LS] = make_float2(0.0f, 0.0f);
         eq_put_step = COEFF_SETS*10/(3*2) - 1;
         eq_step = 0;
     }
 
     SB_HD void equalizer_save()
     {
-        for (int i = 0;  i < EQ_LEN;  i++)
+        group_sync();                       // the last LMS update was made by four lanes
+        if (sub == 0)
         {
-            const float2 y = eq_coeff[i*32];
-            fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c] = y.x;
-            fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i + 1)*channels + c] = y.y;
+            for (int i = 0;  i < EQ_LEN;  i++)
+            {
+                const float2 y = eq_coeff[i*LS];
+                fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i)*channels + c] = y.x;
+                fstate[(size_t) (F_EQ_COEFF_SAVE + 2*i + 1)*channels + c] = y.y;
+            }
         }
     }
 
@@ -680,9 +826,39 @@ struct RxCore
     // sample; coefficient rows are padded to 28 floats so that they load as float4.
     SB_HD void rrc_dot2(const float *row_re, const float *row_im, float &v_re, float &v_im)
     {
+#if defined(__CUDA_ARCH__)
+        if (LPC > 1)
+        {
+            // Four lanes, four chains: {real, imaginary} x {first, second segment}.  A lane of the first segment reads
+            // the ring from rrc_step on and runs into the zeros behind it; a lane of the second segment starts in the
+            // zeros before the ring (see the note at the top of RxCore).
+            const float *x = rrc + (rrc_step + ((sub & 1)  ?  -SBM_FILTER_STEPS  :  0))*LS;
+            const float4 *c4 = (const float4 *) ((sub & 2)  ?  row_im  :  row_re);
+            float z = 0.0f;
+#pragma unroll
+            for (int q = 0;  q < 7;  q++)
+            {
+                const float4 cc = c4[q];
+                const float cs[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                for (int e = 0;  e < 4;  e++)
+                {
+                    const int i = 4*q + e;
+                    if (i < SBM_FILTER_STEPS)
+                        z = fadd(z, fmul(x[i*LS], cs[e]));
+                }
+            }
+            // first + second segment (the partner lane holds the other one; addition commutes)
+            z = fadd(z, __shfl_xor_sync(gmask, z, 1));
+            const int base = (threadIdx.x & 31) - sub;
+            v_re = __shfl_sync(gmask, z, base);
+            v_im = __shfl_sync(gmask, z, base + 2);
+            return;
+        }
+#endif
         float zar = 0.0f, zbr = 0.0f, zai = 0.0f, zbi = 0.0f;
         const int first = SBM_FILTER_STEPS - rrc_step;      // taps in the first segment
-        const float *x = rrc + rrc_step*32;
+        const float *x = rrc + rrc_step*LS;
         const float4 *cr4 = (const float4 *) row_re;
         const float4 *ci4 = (const float4 *) row_im;
 #pragma unroll
@@ -698,7 +874,7 @@ struct RxCore
                 const int i = 4*q + e;
                 if (i < SBM_FILTER_STEPS)
                 {
-                    const float xv = x[i*32];
+                    const float xv = x[i*LS];
                     const float pr = fmul(xv, crs[e]);
                     const float pi = fmul(xv, cis[e]);
                     if (i < first)
@@ -721,14 +897,36 @@ struct RxCore
     // src/complex_vector_float.c:137-150,187-196
     SB_HD void equalizer_get(float &zre, float &zim)
     {
+#if defined(__CUDA_ARCH__)
+        if (LPC > 1)
+        {
+            // The same four roles.  The real lanes multiply with (yr, -yi): xr*yr + xi*(-yi) is xr*yr - xi*yi with the
+            // same two roundings (negation is exact); the imaginary lanes with (yi, yr): xr*yi + xi*yr.
+            const float2 *xb = eq_buf + (eq_step + ((sub & 1)  ?  -EQ_LEN  :  0))*LS;
+            const float2 *yb = (sub & 2)  ?  eq_coef_im  :  eq_coef_re;
+            float z = 0.0f;
+#pragma unroll
+            for (int i = 0;  i < EQ_LEN;  i++)
+            {
+                const float2 x = xb[i*LS];
+                const float2 y = yb[i*LS];
+                z = fadd(z, fadd(fmul(x.x, y.x), fmul(x.y, y.y)));
+            }
+            z = fadd(z, __shfl_xor_sync(gmask, z, 1));
+            const int base = (threadIdx.x & 31) - sub;
+            zre = __shfl_sync(gmask, z, base);
+            zim = __shfl_sync(gmask, z, base + 2);
+            return;
+        }
+#endif
         float are = 0.0f, aim = 0.0f, bre = 0.0f, bim = 0.0f;
         const int first = EQ_LEN - eq_step;
-        const float2 *xb = eq_buf + eq_step*32;
+        const float2 *xb = eq_buf + eq_step*LS;
 #pragma unroll
         for (int i = 0;  i < EQ_LEN;  i++)
         {
-            const float2 x = xb[i*32];
-            const float2 y = eq_coeff[i*32];
+            const float2 x = xb[i*LS];
+            const float2 y = eq_coeff[i*LS];
             const float pr = fsub(fmul(x.x, y.x), fmul(x.y, y.y));
             const float pi = fadd(fmul(x.x, y.y), fmul(x.y, y.x));
             if (i < first)
@@ -751,29 +949,55 @@ struct RxCore
     {
         const float ere = fmul(fsub(tre, zre), eq_delta);
         const float eim = fmul(fsub(tim, zim), eq_delta);
-        const float2 *xb = eq_buf + eq_step*32;
+        if (LPC > 1)
+        {
+            // taps sub, sub + LPC, ...: the updates are independent of each other
+#pragma unroll
+            for (int k = 0;  k < (EQ_LEN + LPC - 1)/LPC;  k++)
+            {
+                const int i = k*LPC + sub;
+                if (i < EQ_LEN)
+                {
+                    int p = eq_step + i;
+                    if (p >= EQ_LEN)
+                        p -= EQ_LEN;
+                    const float2 x = eq_buf[p*LS];
+                    const float2 y = eq_coeff[i*LS];
+                    set_coef(i, fadd(fmul(y.x, 0.9999f), fadd(fmul(x.y, eim), fmul(x.x, ere))),
+                                fadd(fmul(y.y, 0.9999f), fsub(fmul(x.x, eim), fmul(x.y, ere))));
+                }
+            }
+            group_sync();
+            return;
+        }
+        const float2 *xb = eq_buf + eq_step*LS;
 #pragma unroll
         for (int i = 0;  i < EQ_LEN;  i++)
         {
-            const float2 x = xb[i*32];
-            float2 y = eq_coeff[i*32];
+            const float2 x = xb[i*LS];
+            float2 y = eq_coeff[i*LS];
             y.x = fadd(fmul(y.x, 0.9999f), fadd(fmul(x.y, eim), fmul(x.x, ere)));
             y.y = fadd(fmul(y.y, 0.9999f), fsub(fmul(x.x, eim), fmul(x.y, ere)));
-            eq_coeff[i*32] = y;
+            eq_coeff[i*LS] = y;
         }
     }
 
-    // The equalizer "spin" (src/v29rx.c:618-625, src/v17rx.c:707-713,784-790); both ring copies
+    // The equalizer "spin" (src/v29rx.c:618-625, src/v17rx.c:707-713,784-790); LPC 1: both ring copies
     SB_HD void spin_equalizer_buffer(unsigned int phase_step)
     {
         const float p = phase_to_radians(phase_step);
         const float cr = host_cosf(p);
         const float ci = -host_sinf(p);
-        for (int q = 0;  q < 2*EQ_LEN;  q++)
+        group_sync();                       // a read-modify-write of shared data: one lane does it
+        if (sub == 0)
         {
-            const float2 x = eq_buf[q*32];
-            eq_buf[q*32] = make_float2(fsub(fmul(x.x, cr), fmul(x.y, ci)), fadd(fmul(x.x, ci), fmul(x.y, cr)));
+            for (int q = 0;  q < ((LPC == 1)  ?  2  :  1)*EQ_LEN;  q++)
+            {
+                const float2 x = eq_buf[q*LS];
+                eq_buf[q*LS] = make_float2(fsub(fmul(x.x, cr), fmul(x.y, ci)), fadd(fmul(x.x, ci), fmul(x.y, cr)));
+            }
         }
+        group_sync();
     }
 
     // src/v29rx.c:297-331, src/v17rx.c:313-338
@@ -880,8 +1104,9 @@ struct RxCore
     template <class K> SB_HD bool front(const K &k, const float *s_rrc_re, const float *s_rrc_im, short amp)
     {
         const float xv = (float) amp;
-        rrc[rrc_step*32] = xv;
-        rrc[(rrc_step + SBM_FILTER_STEPS)*32] = xv;
+        rrc[rrc_step*LS] = xv;
+        if (LPC == 1)
+            rrc[(rrc_step + SBM_FILTER_STEPS)*LS] = xv;
         if (++rrc_step >= SBM_FILTER_STEPS)
             rrc_step = 0;
         const int pw = signal_detect(k, amp);
@@ -937,8 +1162,9 @@ struct RxCore
         const float zzim = fsub(fmul(-h_sre, zi), fmul(sim, zr));
         eq_put_step += COEFF_SETS*10/(3*2);
         // process_half_baud, first part (src/v29rx.c:516-525, src/v17rx.c:638-647)
-        eq_buf[eq_step*32] = make_float2(zzre, zzim);
-        eq_buf[(eq_step + EQ_LEN)*32] = make_float2(zzre, zzim);
+        eq_buf[eq_step*LS] = make_float2(zzre, zzim);
+        if (LPC == 1)
+            eq_buf[(eq_step + EQ_LEN)*LS] = make_float2(zzre, zzim);
         if (++eq_step >= EQ_LEN)
             eq_step = 0;
         if ((baud_half ^= 1))
@@ -1090,12 +1316,23 @@ struct KernelArgs
     typename RX::Consts k;
 };
 
-// Shared memory: [rrc_re | rrc_im | RX tables | lane-interleaved per-channel arrays]
-template <class RX> constexpr int modem_smem_words()
+// Shared memory: [rrc_re | rrc_im | sine | sqrt | RX tables | per warp: lane-interleaved per-receiver arrays, input rings]
+template <class RX> __host__ __device__ constexpr int modem_table_words()
 {
-    return 2*RX::SETS*SBM_RRC_ROW + SBM_SINE_WORDS + SBM_SQRT_WORDS + RX::TABLE_WORDS + (RX::LANE_WORDS + RX::IN_RING_WORDS)*32;
+    return 2*RX::SETS*SBM_RRC_ROW + SBM_SINE_WORDS + SBM_SQRT_WORDS + RX::TABLE_WORDS;
 }
 
+template <class RX> __host__ __device__ constexpr int modem_warp_words()
+{
+    return (RX::LANE_WORDS + RX::IN_RING_WORDS)*RX::LS;
+}
+
+template <class RX> __host__ __device__ constexpr int modem_smem_words(int warps = 1)
+{
+    return modem_table_words<RX>() + warps*modem_warp_words<RX>();
+}
+
+// The CTA's tables (all threads), then this thread's receiver bound to its warp's area
 template <class RX>
 __device__ __forceinline__ void modem_bind(RX &r, const KernelArgs<RX> &ka, float *smem, int lane, int c,
                                            const float *&s_rrc_re, const float *&s_rrc_im)
@@ -1105,20 +1342,22 @@ __device__ __forceinline__ void modem_bind(RX &r, const KernelArgs<RX> &ka, floa
     float *w_sine = smem + 2*RX::SETS*SBM_RRC_ROW;
     unsigned int *w_sqrt = (unsigned int *) (w_sine + SBM_SINE_WORDS);
     float *tables = w_sine + SBM_SINE_WORDS + SBM_SQRT_WORDS;
-    float *lane_block = tables + RX::TABLE_WORDS;
-    for (int i = lane;  i < SBM_SINE_WORDS;  i += 32)
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    for (int i = tid;  i < SBM_SINE_WORDS;  i += nthr)
         w_sine[i] = ka.k.sine[i];
-    for (int i = lane;  i < 97;  i += 32)
+    for (int i = tid;  i < 97;  i += nthr)
         w_sqrt[i] = (unsigned int) ka.k.sqrt_tab[2*i] | ((2*i + 1 < 193)  ?  ((unsigned int) ka.k.sqrt_tab[2*i + 1] << 16)  :  0u);
-    for (int i = lane;  i < RX::SETS*SBM_RRC_ROW;  i += 32)
+    for (int i = tid;  i < RX::SETS*SBM_RRC_ROW;  i += nthr)
     {
         const int row = i/SBM_RRC_ROW;
         const int tap = i - row*SBM_RRC_ROW;
         w_rrc_re[i] = (tap < SBM_FILTER_STEPS)  ?  ka.k.rrc_re[row*SBM_FILTER_STEPS + tap]  :  0.0f;
         w_rrc_im[i] = (tap < SBM_FILTER_STEPS)  ?  ka.k.rrc_im[row*SBM_FILTER_STEPS + tap]  :  0.0f;
     }
-    RX::fill_tables(tables, ka.k, lane, 32);
-    __syncwarp();
+    RX::fill_tables(tables, ka.k, tid, nthr);
+    __syncthreads();
+    float *lane_block = smem + modem_table_words<RX>() + (tid >> 5)*modem_warp_words<RX>();
     s_rrc_re = w_rrc_re;
     s_rrc_im = w_rrc_im;
     r.c = c;
@@ -1126,38 +1365,56 @@ __device__ __forceinline__ void modem_bind(RX &r, const KernelArgs<RX> &ka, floa
     r.fstate = ka.a.fstate;
     r.sine = w_sine;
     r.sqrt_tab = (const unsigned short *) w_sqrt;
-    r.in_ring = (short *) (lane_block + RX::LANE_WORDS*32) + lane*SBM_IN_RING;
+    r.in_ring = (short *) (lane_block + RX::LANE_WORDS*RX::LS) + (lane/RX::LANES)*SBM_IN_RING;
     r.bind(tables, lane_block, lane);
 }
 
-// 32 channels per CTA (one warp): few channels exist (thousands), so spread them over all SMs.
-template <class RX>
-__global__ void __launch_bounds__(32) modem_rx_kernel(const KernelArgs<RX> ka)
+// A warp runs 32/RX::LANES receivers; WARPS warps per CTA share one copy of the tables.  Few channels exist
+// (thousands): with one lane per receiver a CTA is one warp so that they spread over all SMs; with four lanes per
+// receiver there are four times the warps and two of them share a CTA's tables.
+template <class RX, int WARPS>
+__global__ void __launch_bounds__(WARPS*32) modem_rx_kernel(const KernelArgs<RX> ka)
 {
     extern __shared__ float smem[];
-    const int lane = threadIdx.x;
-    const int c = blockIdx.x*32 + lane;
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x*WARPS + (threadIdx.x >> 5))*RX::LS + lane/RX::LANES;
     RX r;
     const float *s_rrc_re;
     const float *s_rrc_im;
     modem_bind(r, ka, smem, lane, (c < ka.a.channels)  ?  c  :  0, s_rrc_re, s_rrc_im);
     if (c >= ka.a.channels)
         return;
+    r.zero_pads();
     StateLoader ld = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
     r.visit(ld);
     r.mirror_rings();
-    r.bits = ka.a.bits + (size_t) c*ka.a.bits_cap;
-    r.bits_cap = (int) ka.a.bits_cap;
+    r.bits = NULL;
+    r.bits_cap = 0;
     r.nbits = 0;
+    r.words = ka.a.words + (size_t) c*ka.a.words_cap;
+    r.words_cap = (int) ka.a.words_cap;
+    r.nwords = 0;
+    r.bit_acc = 0;
+    r.bit_fill = 0;
+    r.status = ka.a.status + (size_t) c*ka.a.status_cap*2;
+    r.status_cap = (int) ka.a.status_cap;
+    r.nstatus = 0;
     r.syms = (ka.a.syms)  ?  (ka.a.syms + (size_t) c*ka.a.sym_cap)  :  NULL;
     r.sym_cap = (int) ka.a.sym_cap;
     r.nsyms = 0;
+    r.group_sync();
     r.run(ka.k, s_rrc_re, s_rrc_im, ka.a.amp + (long long) c*ka.a.stride, ka.a.n);
-    StateStorer st = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
-    r.visit(st);
-    ka.a.nbits[c] = r.nbits;
-    if (ka.a.nsyms)
-        ka.a.nsyms[c] = r.nsyms;
+    r.out_flush();
+    r.group_sync();
+    if (r.sub == 0)
+    {
+        StateStorer st = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
+        r.visit(st);
+        ka.a.nbits[c] = r.nbits;
+        ka.a.nstatus[c] = r.nstatus;
+        if (ka.a.nsyms)
+            ka.a.nsyms[c] = r.nsyms;
+    }
 }
 
 // xxx_rx_init() (mode < 0: all state zeroed first, then init with `mode` = -1 - restart argument) or
@@ -1177,9 +1434,18 @@ __global__ void __launch_bounds__(32) modem_init_kernel(const KernelArgs<RX> ka,
     modem_bind(r, ka, smem, lane, (idx < count)  ?  c  :  first, s_rrc_re, s_rrc_im);
     if (idx >= count)
         return;
+    r.zero_pads();
     r.bits = NULL;
     r.bits_cap = 0;
     r.nbits = 0;
+    r.words = NULL;
+    r.words_cap = 0;
+    r.nwords = 0;
+    r.bit_acc = 0;
+    r.bit_fill = 0;
+    r.status = NULL;
+    r.status_cap = 0;
+    r.nstatus = 0;
     r.syms = NULL;
     r.sym_cap = 0;
     r.nsyms = 0;

@@ -34,6 +34,14 @@
 
 namespace sbm {
 
+// The kernel a bank's rx call runs: by default the receiver itself, one thread per receiver, one warp per CTA
+template <class RX>
+struct RxKernel
+{
+    typedef RX type;
+    static const int WARPS = 1;
+};
+
 template <class RX>
 struct ModemBank
 {
@@ -44,9 +52,12 @@ struct ModemBank
     int *istate;
     std::vector<void *> owned;          // device allocations holding the constant tables
     typename RX::Consts k;
-    signed char *bits;
-    long long bits_cap;
+    unsigned int *words;                // packed data bits, [channel][words_cap]
+    long long words_cap;
+    int *status;                        // status reports, [channel][status_cap][2]
+    long long status_cap;
     int *nbits;
+    int *nstatus;
     span_b200_v29_symbol_t *syms;
     long long sym_cap;
     int *nsyms;
@@ -122,24 +133,34 @@ static int modem_core_tables(ModemBank<RX> *b, double carrier_hz, double godard_
     return 0;
 }
 
-template <class RX>
-static KernelArgs<RX> modem_args(ModemBank<RX> *b, const int16_t *d_amp, int64_t stride, int n)
+// KRX: the receiver type of the kernel the arguments are for (RX itself, or its RxKernel<RX>::type)
+template <class KRX, class RX>
+static KernelArgs<KRX> modem_args_for(ModemBank<RX> *b, const int16_t *d_amp, int64_t stride, int n)
 {
-    KernelArgs<RX> ka;
+    KernelArgs<KRX> ka;
     ka.a.amp = d_amp;
     ka.a.stride = stride;
     ka.a.n = n;
     ka.a.channels = b->channels;
     ka.a.fstate = b->fstate;
     ka.a.istate = b->istate;
-    ka.a.bits = b->bits;
-    ka.a.bits_cap = b->bits_cap;
+    ka.a.words = b->words;
+    ka.a.words_cap = b->words_cap;
+    ka.a.status = b->status;
+    ka.a.status_cap = b->status_cap;
     ka.a.nbits = b->nbits;
+    ka.a.nstatus = b->nstatus;
     ka.a.syms = (b->want_symbols)  ?  b->syms  :  NULL;
     ka.a.sym_cap = b->sym_cap;
     ka.a.nsyms = b->nsyms;
     ka.k = b->k;
     return ka;
+}
+
+template <class RX>
+static KernelArgs<RX> modem_args(ModemBank<RX> *b, const int16_t *d_amp, int64_t stride, int n)
+{
+    return modem_args_for<RX, RX>(b, d_amp, stride, n);
 }
 
 template <class RX>
@@ -151,8 +172,10 @@ static int modem_configure()
     CK(cudaGetDevice(&dev));
     if (dev < 0  ||  dev >= 64  ||  !configured[dev])
     {
+        typedef typename RxKernel<RX>::type KRX;
         const int smem = (int) sizeof(float)*modem_smem_words<RX>();
-        CK(cudaFuncSetAttribute(modem_rx_kernel<RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int ksmem = (int) sizeof(float)*modem_smem_words<KRX>(RxKernel<RX>::WARPS);
+        CK(cudaFuncSetAttribute(modem_rx_kernel<KRX, RxKernel<RX>::WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ksmem));
         CK(cudaFuncSetAttribute(modem_init_kernel<RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (dev >= 0  &&  dev < 64)
             configured[dev] = true;
@@ -188,8 +211,10 @@ static int modem_alloc_state(ModemBank<RX> *b)
     CK(cudaMemset(b->fstate, 0, sizeof(float)*RX::F_COUNT*C));
     CK(cudaMemset(b->istate, 0, sizeof(int)*RX::I_COUNT*C));
     CK(cudaMalloc(&b->nbits, sizeof(int)*C));
+    CK(cudaMalloc(&b->nstatus, sizeof(int)*C));
     CK(cudaMalloc(&b->nsyms, sizeof(int)*C));
     CK(cudaMemset(b->nbits, 0, sizeof(int)*C));
+    CK(cudaMemset(b->nstatus, 0, sizeof(int)*C));
     CK(cudaMemset(b->nsyms, 0, sizeof(int)*C));
     return 0;
 }
@@ -206,8 +231,10 @@ static void modem_destroy(ModemBank<RX> *b)
     cudaFree(b->istate);
     for (size_t i = 0;  i < b->owned.size();  i++)
         cudaFree(b->owned[i]);
-    cudaFree(b->bits);
+    cudaFree(b->words);
+    cudaFree(b->status);
     cudaFree(b->nbits);
+    cudaFree(b->nstatus);
     cudaFree(b->syms);
     cudaFree(b->nsyms);
     cudaFree(b->d_in);
@@ -318,15 +345,25 @@ static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t strid
     cudaStream_t st = (stream)  ?  (cudaStream_t) stream  :  (cudaStream_t) sb_ctx_stream(b->ctx);
     if (b->have_last  &&  b->last_stream != st)
         CK(cudaStreamSynchronize(b->last_stream));
-    // Worst case: bits per baud at 2400 baud/8000 Hz plus timing drift, plus status reports.
-    const long long want_bits = (long long) n*b->bits_per_sample_x2/2 + 64;
-    if (b->bits_cap < want_bits)
+    // Worst case: bits per baud at 2400 baud/8000 Hz plus timing drift; status reports: a carrier cycle (up, training,
+    // result, down) takes hundreds of samples.
+    const long long want_words = ((long long) n*b->bits_per_sample_x2/2 + 64 + 31)/32 + 1;
+    if (b->words_cap < want_words)
     {
         if (b->have_last)
             CK(cudaStreamSynchronize(b->last_stream));
-        if (modem_realloc((void **) &b->bits, (size_t) want_bits*b->channels) != 0)
+        if (modem_realloc((void **) &b->words, sizeof(unsigned int)*(size_t) want_words*b->channels) != 0)
             return -1;
-        b->bits_cap = want_bits;
+        b->words_cap = want_words;
+    }
+    const long long want_status = (long long) n/64 + 16;
+    if (b->status_cap < want_status)
+    {
+        if (b->have_last)
+            CK(cudaStreamSynchronize(b->last_stream));
+        if (modem_realloc((void **) &b->status, sizeof(int)*2*(size_t) want_status*b->channels) != 0)
+            return -1;
+        b->status_cap = want_status;
     }
     const long long want_syms = (long long) n*2/5 + 16;
     if (b->want_symbols  &&  b->sym_cap < want_syms)
@@ -339,9 +376,12 @@ static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t strid
     }
     if (modem_configure<RX>() != 0)
         return -1;
-    KernelArgs<RX> ka = modem_args(b, d_amp, stride, n);
-    const int smem = (int) sizeof(float)*modem_smem_words<RX>();
-    modem_rx_kernel<RX><<<(b->channels + 31)/32, 32, smem, st>>>(ka);
+    typedef typename RxKernel<RX>::type KRX;
+    const int warps = RxKernel<RX>::WARPS;
+    KernelArgs<KRX> ka = modem_args_for<KRX>(b, d_amp, stride, n);
+    const int smem = (int) sizeof(float)*modem_smem_words<KRX>(warps);
+    const int per_cta = warps*KRX::LS;                  // receivers per CTA
+    modem_rx_kernel<KRX, RxKernel<RX>::WARPS><<<(b->channels + per_cta - 1)/per_cta, warps*32, smem, st>>>(ka);
     CK(cudaGetLastError());
     b->last_stream = st;
     b->have_last = true;
@@ -388,6 +428,34 @@ static int modem_counts(ModemBank<RX> *b, int32_t *nbits, int32_t *nsyms)
     return 0;
 }
 
+// The put_bit sequence of one channel as the reference's callback would have seen it - 0 / 1 and the negative status
+// values in their places - rebuilt from the packed data bits and the status list.  Returns the number of entries.
+static inline long long modem_unpack(const unsigned int *words, long long words_cap, const int *status, long long status_cap,
+                                     int nbits, int nstatus, int8_t *out, long long max)
+{
+    long long ns = nstatus;
+    if (ns > status_cap)
+        ns = status_cap;
+    long long k = 0;            // position in the put_bit sequence
+    long long d = 0;            // data bits consumed
+    long long si = 0;
+    const long long total = (nbits < max)  ?  nbits  :  max;
+    while (k < total)
+    {
+        if (si < ns  &&  status[2*si] == k)
+        {
+            out[k++] = (int8_t) status[2*si + 1];
+            si++;
+            continue;
+        }
+        if ((d >> 5) >= words_cap)
+            break;
+        out[k++] = (int8_t) ((words[d >> 5] >> (d & 31)) & 1u);
+        d++;
+    }
+    return k;
+}
+
 template <class RX>
 static int64_t modem_bits(ModemBank<RX> *b, int channel, int8_t *out, int64_t max)
 {
@@ -397,19 +465,73 @@ static int64_t modem_bits(ModemBank<RX> *b, int channel, int8_t *out, int64_t ma
     if (modem_quiesce(b) != 0)
         return -1;
     int n = 0;
+    int ns = 0;
     CK(cudaMemcpy(&n, b->nbits + channel, sizeof(int), cudaMemcpyDeviceToHost));
-    long long k = n;
-    if (k > b->bits_cap)
-        k = b->bits_cap;
-    if (k > max)
-        k = max;
-    if (k > 0)
-        CK(cudaMemcpy(out, b->bits + (size_t) channel*b->bits_cap, (size_t) k, cudaMemcpyDeviceToHost));
-    return k;
+    CK(cudaMemcpy(&ns, b->nstatus + channel, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n <= 0  ||  b->words == NULL)
+        return 0;
+    long long nw = ((long long) n + 31)/32;
+    if (nw > b->words_cap)
+        nw = b->words_cap;
+    long long nst = (ns < b->status_cap)  ?  ns  :  b->status_cap;
+    std::vector<unsigned int> w((size_t) nw + 1);
+    std::vector<int> s2((size_t) 2*nst + 2);
+    CK(cudaMemcpy(w.data(), b->words + (size_t) channel*b->words_cap, sizeof(unsigned int)*(size_t) nw, cudaMemcpyDeviceToHost));
+    if (nst > 0)
+        CK(cudaMemcpy(s2.data(), b->status + (size_t) channel*b->status_cap*2, sizeof(int)*2*(size_t) nst, cudaMemcpyDeviceToHost));
+    return modem_unpack(w.data(), nw, s2.data(), nst, n, ns, out, max);
 }
 
-// The put_bit streams of all channels in one transfer: out[c*out_stride ..] receives the first min(count, out_stride)
-// entries of channel c; nbits (may be NULL) the per-channel counts.  Returns the largest count.
+// Every channel's output in the packed form the kernel writes, one transfer per array (the bulk read-back):
+//   words  [channels][words_stride]   the data bits, 32 to a word, first bit = bit 0 (row c holds channel c's)
+//   status [channels][status_stride][2]  {position in the put_bit sequence, negative SIG_STATUS_* value}
+//   nbits / nstatus [channels]        put_bit calls (bits + reports) / reports of each channel
+// Rows are cut to the strides given.  Returns the largest nbits, or -1.
+template <class RX>
+static int64_t modem_output_packed(ModemBank<RX> *b, uint32_t *words, int64_t words_stride, int32_t *nbits,
+                                   int32_t *status, int64_t status_stride, int32_t *nstatus)
+{
+    sb_device_guard sb_dg_((b)  ?  span_b200_ctx_device(b->ctx)  :  -1);
+    if (b == NULL  ||  nbits == NULL  ||  nstatus == NULL  ||  words_stride < 0  ||  status_stride < 0)
+    {
+        sb_set_error("bad arguments");
+        return -1;
+    }
+    if (modem_quiesce(b) != 0)
+        return -1;
+    const size_t C = (size_t) b->channels;
+    CK(cudaMemcpy(nbits, b->nbits, sizeof(int)*C, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nstatus, b->nstatus, sizeof(int)*C, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    long long ms = 0;
+    for (size_t c = 0;  c < C;  c++)
+    {
+        if (nbits[c] > mx)
+            mx = nbits[c];
+        if (nstatus[c] > ms)
+            ms = nstatus[c];
+    }
+    long long w = (mx + 31)/32;
+    if (w > b->words_cap)
+        w = b->words_cap;
+    if (w > words_stride)
+        w = words_stride;
+    if (words  &&  w > 0)
+        CK(cudaMemcpy2D(words, sizeof(uint32_t)*(size_t) words_stride, b->words, sizeof(unsigned int)*(size_t) b->words_cap,
+                        sizeof(uint32_t)*(size_t) w, C, cudaMemcpyDeviceToHost));
+    if (ms > b->status_cap)
+        ms = b->status_cap;
+    if (ms > status_stride)
+        ms = status_stride;
+    if (status  &&  ms > 0)
+        CK(cudaMemcpy2D(status, sizeof(int32_t)*2*(size_t) status_stride, b->status, sizeof(int)*2*(size_t) b->status_cap,
+                        sizeof(int32_t)*2*(size_t) ms, C, cudaMemcpyDeviceToHost));
+    return mx;
+}
+
+// The put_bit sequences of all channels as bytes: out[c*out_stride ..] receives the first min(count, out_stride) entries
+// of channel c; nbits (may be NULL) the per-channel counts.  A convenience over modem_output_packed (the unpacking runs
+// on the host).  Returns the largest count.
 template <class RX>
 static int64_t modem_bits_all(ModemBank<RX> *b, int8_t *out, int64_t out_stride, int32_t *nbits)
 {
@@ -419,25 +541,22 @@ static int64_t modem_bits_all(ModemBank<RX> *b, int8_t *out, int64_t out_stride,
         sb_set_error("bad arguments");
         return -1;
     }
-    if (modem_quiesce(b) != 0)
+    const size_t C = (size_t) b->channels;
+    std::vector<int32_t> n(C);
+    std::vector<int32_t> ns(C);
+    const long long wcap = (b->words_cap > 0)  ?  b->words_cap  :  1;
+    const long long scap = (b->status_cap > 0)  ?  b->status_cap  :  1;
+    std::vector<uint32_t> w(C*(size_t) wcap);
+    std::vector<int32_t> st(C*(size_t) scap*2);
+    const int64_t mx = modem_output_packed(b, w.data(), wcap, n.data(), st.data(), scap, ns.data());
+    if (mx < 0)
         return -1;
-    std::vector<int> n((size_t) b->channels);
-    CK(cudaMemcpy(n.data(), b->nbits, sizeof(int)*(size_t) b->channels, cudaMemcpyDeviceToHost));
-    long long mx = 0;
-    for (int c = 0;  c < b->channels;  c++)
+    for (size_t c = 0;  c < C;  c++)
     {
         if (nbits)
             nbits[c] = n[c];
-        if (n[c] > mx)
-            mx = n[c];
+        modem_unpack(&w[c*(size_t) wcap], wcap, &st[c*(size_t) scap*2], scap, n[c], ns[c], out + c*(size_t) out_stride, out_stride);
     }
-    long long w = mx;
-    if (w > b->bits_cap)
-        w = b->bits_cap;
-    if (w > out_stride)
-        w = out_stride;
-    if (w > 0)
-        CK(cudaMemcpy2D(out, (size_t) out_stride, b->bits, (size_t) b->bits_cap, (size_t) w, (size_t) b->channels, cudaMemcpyDeviceToHost));
     return mx;
 }
 
@@ -462,15 +581,22 @@ static int64_t modem_symbols(ModemBank<RX> *b, int channel, span_b200_v29_symbol
 }
 
 template <class RX>
-static int modem_output_layout(ModemBank<RX> *b, const int8_t **d_bits, int64_t *bits_cap, const int32_t **d_nbits,
+static int modem_output_layout(ModemBank<RX> *b, const uint32_t **d_words, int64_t *words_cap, const int32_t **d_nbits,
+                               const int32_t **d_status, int64_t *status_cap, const int32_t **d_nstatus,
                                const span_b200_v29_symbol_t **d_syms, int64_t *sym_cap, const int32_t **d_nsyms)
 {
-    if (d_bits)
-        *d_bits = (const int8_t *) b->bits;
-    if (bits_cap)
-        *bits_cap = b->bits_cap;
+    if (d_words)
+        *d_words = (const uint32_t *) b->words;
+    if (words_cap)
+        *words_cap = b->words_cap;
     if (d_nbits)
         *d_nbits = b->nbits;
+    if (d_status)
+        *d_status = b->status;
+    if (status_cap)
+        *status_cap = b->status_cap;
+    if (d_nstatus)
+        *d_nstatus = b->nstatus;
     if (d_syms)
         *d_syms = b->syms;
     if (sym_cap)

@@ -130,16 +130,27 @@ extern "C" int64_t span_b200_v27ter_bank_bits(span_b200_v27ter_bank_t *b, int ch
     return modem_bits(b, channel, out, max);
 }
 
+extern "C" int64_t span_b200_v27ter_bank_bits_all(span_b200_v27ter_bank_t *b, int8_t *out, int64_t out_stride, int32_t *nbits)
+{
+    return modem_bits_all(b, out, out_stride, nbits);
+}
+
 extern "C" int64_t span_b200_v27ter_bank_symbols(span_b200_v27ter_bank_t *b, int channel, span_b200_v27ter_symbol_t *out, int64_t max)
 {
     return modem_symbols(b, channel, out, max);
 }
 
-extern "C" int span_b200_v27ter_bank_output_layout(span_b200_v27ter_bank_t *b, const int8_t **d_bits, int64_t *bits_cap,
-                                                   const int32_t **d_nbits, const span_b200_v27ter_symbol_t **d_syms,
-                                                   int64_t *sym_cap, const int32_t **d_nsyms)
+extern "C" int span_b200_v27ter_bank_output_layout(span_b200_v27ter_bank_t *b, const uint32_t **d_words, int64_t *words_cap, const int32_t **d_nbits,
+                                                const int32_t **d_status, int64_t *status_cap, const int32_t **d_nstatus,
+                                                const span_b200_v29_symbol_t **d_syms, int64_t *sym_cap, const int32_t **d_nsyms)
 {
-    return modem_output_layout(b, d_bits, bits_cap, d_nbits, d_syms, sym_cap, d_nsyms);
+    return modem_output_layout(b, d_words, words_cap, d_nbits, d_status, status_cap, d_nstatus, d_syms, sym_cap, d_nsyms);
+}
+
+extern "C" int64_t span_b200_v27ter_bank_output_packed(span_b200_v27ter_bank_t *b, uint32_t *words, int64_t words_stride, int32_t *nbits,
+                                                   int32_t *status, int64_t status_stride, int32_t *nstatus)
+{
+    return modem_output_packed(b, words, words_stride, nbits, status, status_stride, nstatus);
 }
 
 extern "C" int span_b200_v27ter_bank_channel_state(span_b200_v27ter_bank_t *b, int channel, float *eq_coeff, int32_t *info)

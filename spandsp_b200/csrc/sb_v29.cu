@@ -4,6 +4,18 @@
 #include "sb_modem_bank.cuh"
 #include "sb_v29_rx.cuh"
 
+namespace sbm {
+
+// V.29 banks run the four-lanes-per-receiver form of the receiver, two warps per CTA (same state arrays, same results)
+template <>
+struct RxKernel<RxV29>
+{
+    typedef RxV29x4 type;
+    static const int WARPS = 2;
+};
+
+}  // namespace sbm
+
 using namespace sbm;
 
 struct span_b200_v29_bank_s : ModemBank<RxV29>
@@ -154,11 +166,17 @@ extern "C" int64_t span_b200_v29_bank_symbols(span_b200_v29_bank_t *b, int chann
     return modem_symbols(b, channel, out, max);
 }
 
-extern "C" int span_b200_v29_bank_output_layout(span_b200_v29_bank_t *b, const int8_t **d_bits, int64_t *bits_cap,
-                                                const int32_t **d_nbits, const span_b200_v29_symbol_t **d_syms,
-                                                int64_t *sym_cap, const int32_t **d_nsyms)
+extern "C" int span_b200_v29_bank_output_layout(span_b200_v29_bank_t *b, const uint32_t **d_words, int64_t *words_cap, const int32_t **d_nbits,
+                                                const int32_t **d_status, int64_t *status_cap, const int32_t **d_nstatus,
+                                                const span_b200_v29_symbol_t **d_syms, int64_t *sym_cap, const int32_t **d_nsyms)
 {
-    return modem_output_layout(b, d_bits, bits_cap, d_nbits, d_syms, sym_cap, d_nsyms);
+    return modem_output_layout(b, d_words, words_cap, d_nbits, d_status, status_cap, d_nstatus, d_syms, sym_cap, d_nsyms);
+}
+
+extern "C" int64_t span_b200_v29_bank_output_packed(span_b200_v29_bank_t *b, uint32_t *words, int64_t words_stride, int32_t *nbits,
+                                                   int32_t *status, int64_t status_stride, int32_t *nstatus)
+{
+    return modem_output_packed(b, words, words_stride, nbits, status, status_stride, nstatus);
 }
 
 // Receiver status of one channel: v29_rx_equalizer_state / carrier_frequency / symbol_timing_correction /

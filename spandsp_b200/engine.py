@@ -105,6 +105,8 @@ def lib():
         "span_b200_v29_bank_counts": (i32, [vp, vp, vp]),
         "span_b200_v29_bank_bits": (i64, [vp, i32, vp, i64]),
         "span_b200_v29_bank_symbols": (i64, [vp, i32, vp, i64]),
+        "span_b200_v29_bank_output_packed": (i64, [vp, vp, i64, vp, vp, i64, vp]),
+        "span_b200_v29_bank_output_layout": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "span_b200_v29_bank_bits_all": (i64, [vp, vp, i64, vp]),
         "span_b200_v29_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_v29_tables": (i32, [vp, vp, vp, vp, vp, vp]),
@@ -120,6 +122,9 @@ def lib():
         "span_b200_v17_bank_counts": (i32, [vp, vp, vp]),
         "span_b200_v17_bank_bits": (i64, [vp, i32, vp, i64]),
         "span_b200_v17_bank_symbols": (i64, [vp, i32, vp, i64]),
+        "span_b200_v17_bank_bits_all": (i64, [vp, vp, i64, vp]),
+        "span_b200_v17_bank_output_packed": (i64, [vp, vp, i64, vp, vp, i64, vp]),
+        "span_b200_v17_bank_output_layout": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "span_b200_v17_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_v17_tables": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "span_b200_v27ter_bank_create": (vp, [vp, i32, i32, i32]),
@@ -133,6 +138,9 @@ def lib():
         "span_b200_v27ter_bank_counts": (i32, [vp, vp, vp]),
         "span_b200_v27ter_bank_bits": (i64, [vp, i32, vp, i64]),
         "span_b200_v27ter_bank_symbols": (i64, [vp, i32, vp, i64]),
+        "span_b200_v27ter_bank_bits_all": (i64, [vp, vp, i64, vp]),
+        "span_b200_v27ter_bank_output_packed": (i64, [vp, vp, i64, vp, vp, i64, vp]),
+        "span_b200_v27ter_bank_output_layout": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "span_b200_v27ter_bank_channel_state": (i32, [vp, i32, vp, vp]),
         "span_b200_v27ter_tables": (i32, [vp, vp, vp, vp, vp]),
         "span_b200_fsk_preset": (vp, [i32]),
@@ -574,7 +582,12 @@ class V29Bank:
     def rx_device(self, d_ptr, stride, samples, stream=None):
         self._ck(self._fn("rx_device")(self.h, d_ptr, stride, samples, stream))
 
-    def rx_host(self, amp, stream=None):
+    def rx_host(self, amp, stream=None, samples=None):
+        """amp: int16 numpy array [channels, n] (rows contiguous) or a (ptr, stride) pair with samples."""
+        if isinstance(amp, tuple):
+            ptr, stride = amp
+            self._ck(self._fn("rx_host")(self.h, ptr, stride, samples, stream))
+            return
         assert amp.dtype == np.int16 and amp.ndim == 2 and amp.shape[0] == self.channels and amp.strides[1] == 2
         self._ck(self._fn("rx_host")(self.h, amp.ctypes.data, amp.strides[0] // 2, amp.shape[1], stream))
 
@@ -583,6 +596,21 @@ class V29Bank:
         ns = np.zeros(self.channels, dtype=np.int32)
         self._ck(self._fn("counts")(self.h, nb.ctypes.data, ns.ctypes.data))
         return nb, ns
+
+    def output_packed(self, words=None, status=None):
+        """The bulk read-back: (words uint32 [C][W], nbits [C], status int32 [C][S][2], nstatus [C]); pass pre-allocated
+        (pinned) arrays to avoid the allocation."""
+        nb = np.zeros(self.channels, dtype=np.int32)
+        ns = np.zeros(self.channels, dtype=np.int32)
+        if words is None:
+            cnt, _ = self.counts()
+            words = np.zeros((self.channels, (int(cnt.max()) + 31) // 32 + 1), dtype=np.uint32)
+        if status is None:
+            status = np.zeros((self.channels, 64, 2), dtype=np.int32)
+        mx = self._fn("output_packed")(self.h, words.ctypes.data, words.shape[1], nb.ctypes.data, status.ctypes.data, status.shape[1], ns.ctypes.data)
+        if mx < 0:
+            raise EngineError(_err())
+        return words, nb, status, ns
 
     def bits(self, channel, cap=1 << 22):
         out = np.zeros(cap, dtype=np.int8)

@@ -14,7 +14,7 @@ SYM_DTYPE = np.dtype([("re", "<f4"), ("im", "<f4"), ("tre", "<f4"), ("tim", "<f4
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh", "sb_mct_rx.cuh", "sb_gen.cuh", "sb_sig_rx.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("sb_modem.cuh", "sb_v29_rx.cuh", "sb_v29_rx_body.cuh", "sb_v17_rx.cuh", "sb_v27ter_rx.cuh", "sb_fsk_rx.cuh", "sb_mct_rx.cuh", "sb_gen.cuh", "sb_sig_rx.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     subprocess.run([os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
