@@ -1,0 +1,11 @@
+/*
+ * spandsp/fsk.h - so that a caller written against the reference compiles unchanged with -I<this repo>/include:
+ * what src/spandsp/fsk.h: fsk_rx_*, preset_fsk_specs declares is declared, for the paths this library
+ * replaces, by spandsp_b200_dropin.h.
+ */
+#if !defined(_SPANDSP_B200_FWD_FSK_H_)
+#define _SPANDSP_B200_FWD_FSK_H_
+
+#include "../spandsp_b200_dropin.h"
+
+#endif

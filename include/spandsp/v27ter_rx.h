@@ -1,0 +1,11 @@
+/*
+ * spandsp/v27ter_rx.h - so that a caller written against the reference compiles unchanged with -I<this repo>/include:
+ * what src/spandsp/v27ter_rx.h: v27ter_rx_* declares is declared, for the paths this library
+ * replaces, by spandsp_b200_dropin.h.
+ */
+#if !defined(_SPANDSP_B200_FWD_V27TER_RX_H_)
+#define _SPANDSP_B200_FWD_V27TER_RX_H_
+
+#include "../spandsp_b200_dropin.h"
+
+#endif

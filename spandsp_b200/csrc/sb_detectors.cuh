@@ -476,6 +476,47 @@ __global__ void __launch_bounds__(128) dtmf_sequencer(const DtmfSeqArgs s)
     }
 }
 
+// The staged walk of dtmf_sequencer as a helper for the detectors without a per-tile epilogue: the CTA's 128 channels
+// step through all nbu block rows of 8-bit decision codes, tile by tile (16-byte cp.async, double buffered); f(block,
+// code) is called by all threads together for every row.  Needs a uniform block phase and channels % 16 == 0.
+template <class F>
+__device__ __forceinline__ void walk_codes8(const unsigned char *code, int channels, int nbu, unsigned char (*tile)[SB_SEQ_TILE*128], F f)
+{
+    const int ntiles = (nbu + SB_SEQ_TILE - 1)/SB_SEQ_TILE;
+    const int c0 = blockIdx.x*128;
+    auto issue = [&](int t)
+    {
+        if (t < ntiles)
+        {
+            const uint32_t dst0 = (uint32_t) __cvta_generic_to_shared(tile[t & 1]);
+            for (int k = threadIdx.x;  k < SB_SEQ_TILE*8;  k += 128)
+            {
+                const int row = k >> 3;
+                const int piece = k & 7;
+                const int b = t*SB_SEQ_TILE + row;
+                const bool ok = (b < nbu  &&  c0 + 16*piece < channels);
+                const unsigned char *src = (ok)  ?  (code + (size_t) b*channels + c0 + 16*piece)  :  code;
+                cp_async_16(dst0 + row*128 + piece*16, src, (ok)  ?  16  :  0);
+            }
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    for (int t = 0;  t < ntiles;  t++)
+    {
+        issue(t + 1);
+        cp_async_wait<1>();
+        __syncthreads();
+        const unsigned char *col = tile[t & 1] + threadIdx.x;
+        const int rows = (nbu - t*SB_SEQ_TILE < SB_SEQ_TILE)  ?  (nbu - t*SB_SEQ_TILE)  :  SB_SEQ_TILE;
+#pragma unroll 4
+        for (int row = 0;  row < rows;  row++)
+            f(t*SB_SEQ_TILE + row, (int) col[row*128]);
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
 // ==========================================================================================
 // Bell MF and MFC/R2  (reference: src/bell_r2_mf.c)
 __constant__ float c_bell_mf_fac[6];    // 700 ... 1700 Hz   (src/bell_r2_mf.c:251-254)
@@ -638,34 +679,45 @@ __global__ void __launch_bounds__(128) bell_mf_sequencer(const MfSeqArgs s)
     int h4 = s.hits[4*C + c];
     EventSink<EMIT> sink(s.q, wg);
 
-    constexpr int G = 16;
-    for (int b0 = 0;  b0 < nb_max;  b0 += G)
+    auto one_block = [&](int b, bool run, int hit)
     {
-        unsigned char codes[G];
-#pragma unroll
-        for (int i = 0;  i < G;  i++)
-            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned char) 0;
-#pragma unroll
-        for (int i = 0;  i < G;  i++)
+        bool ev = false;
+        if (run)
         {
-            const int b = b0 + i;
-            bool ev = false;
-            const int hit = codes[i];
-            if (b < nb)
+            ev = hit
+                 &&  hit == h4  &&  hit == h3
+                 &&  ((hit != '*'  &&  hit != h2  &&  hit != h1)
+                      ||
+                      (hit == '*'  &&  hit == h2  &&  hit != h1  &&  hit != h0));
+            h0 = h1;
+            h1 = h2;
+            h2 = h3;
+            h3 = h4;
+            h4 = hit;
+        }
+        sink.push(ev, c, b, SPAN_B200_EV_DIGIT, hit, 0, 0);
+    };
+
+    if (s.q.cs0 >= 0  &&  (s.q.channels & 15) == 0)
+    {
+        __shared__ __align__(16) unsigned char tile[2][SB_SEQ_TILE*128];
+        walk_codes8(s.code, s.q.channels, (s.q.cs0 + s.q.n)/B, tile, [&](int b, int hit) { one_block(b, live, hit); });
+    }
+    else
+    {
+        constexpr int G = 16;
+        for (int b0 = 0;  b0 < nb_max;  b0 += G)
+        {
+            unsigned char codes[G];
+#pragma unroll
+            for (int i = 0;  i < G;  i++)
+                codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned char) 0;
+#pragma unroll
+            for (int i = 0;  i < G;  i++)
             {
-                ev = hit
-                     &&  hit == h4  &&  hit == h3
-                     &&  ((hit != '*'  &&  hit != h2  &&  hit != h1)
-                          ||
-                          (hit == '*'  &&  hit == h2  &&  hit != h1  &&  hit != h0));
-                h0 = h1;
-                h1 = h2;
-                h2 = h3;
-                h3 = h4;
-                h4 = hit;
+                if (b0 + i < nb_max)
+                    one_block(b0 + i, b0 + i < nb, codes[i]);
             }
-            if (b < nb_max)
-                sink.push(ev, c, b, SPAN_B200_EV_DIGIT, hit, 0, 0);
         }
     }
     sink.finish(wg);
@@ -696,26 +748,37 @@ __global__ void __launch_bounds__(128) r2_mf_sequencer(const MfSeqArgs s)
     int current = s.hits[c];
     EventSink<EMIT> sink(s.q, wg);
 
-    constexpr int G = 16;
-    for (int b0 = 0;  b0 < nb_max;  b0 += G)
+    auto one_block = [&](int b, bool run, int hit)
     {
-        unsigned char codes[G];
-#pragma unroll
-        for (int i = 0;  i < G;  i++)
-            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned char) 0;
-#pragma unroll
-        for (int i = 0;  i < G;  i++)
+        bool ev = false;
+        if (run)
         {
-            const int b = b0 + i;
-            bool ev = false;
-            const int hit = codes[i];
-            if (b < nb)
+            ev = (hit != current);
+            current = hit;
+        }
+        sink.push(ev, c, b, SPAN_B200_EV_TONE, hit, (hit)  ?  -10  :  -99, 0);
+    };
+
+    if (s.q.cs0 >= 0  &&  (s.q.channels & 15) == 0)
+    {
+        __shared__ __align__(16) unsigned char tile[2][SB_SEQ_TILE*128];
+        walk_codes8(s.code, s.q.channels, (s.q.cs0 + s.q.n)/B, tile, [&](int b, int hit) { one_block(b, live, hit); });
+    }
+    else
+    {
+        constexpr int G = 16;
+        for (int b0 = 0;  b0 < nb_max;  b0 += G)
+        {
+            unsigned char codes[G];
+#pragma unroll
+            for (int i = 0;  i < G;  i++)
+                codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned char) 0;
+#pragma unroll
+            for (int i = 0;  i < G;  i++)
             {
-                ev = (hit != current);
-                current = hit;
+                if (b0 + i < nb_max)
+                    one_block(b0 + i, b0 + i < nb, codes[i]);
             }
-            if (b < nb_max)
-                sink.push(ev, c, b, SPAN_B200_EV_TONE, hit, (hit)  ?  -10  :  -99, 0);
         }
     }
     sink.finish(wg);
@@ -874,6 +937,7 @@ struct StTemplates
     const int *tone_segs;               // [tones]
     const int *tone_first;              // [tones] index of the tone's first element in `elements`
     const int4 *elements;               // {f1, f2, min_duration, max_duration} in samples
+    int total_elements;
 };
 
 struct StSeqArgs
@@ -888,15 +952,20 @@ struct StSeqArgs
     int want_segments;
 };
 
+// The eleven segment slots of one channel (src/spandsp/private/super_tone_rx.h:57: segments[11]); slot 10 holds the
+// block pair seen last, slot 9 the segment in progress.  Kept in shared memory, [field][thread]: the cadence tests index
+// them with run-time positions, which registers cannot do.
 struct StSegs
 {
-    int f1[11];
-    int f2[11];
-    int dur[11];
+    int *base;                          // this thread's column of int [33][128]
+
+    __device__ __forceinline__ int &f1(int i) const { return base[(3*i)*128]; }
+    __device__ __forceinline__ int &f2(int i) const { return base[(3*i + 1)*128]; }
+    __device__ __forceinline__ int &dur(int i) const { return base[(3*i + 2)*128]; }
 };
 
 // src/super_tone_rx.c:164-228
-__device__ inline int st_test_cadence(const int4 *pattern, int steps, const StSegs &t, int rotation)
+__device__ __forceinline__ int st_test_cadence(const int4 *pattern, int steps, const StSegs &t, int rotation)
 {
     int j;
 
@@ -907,16 +976,18 @@ __device__ inline int st_test_cadence(const int4 *pattern, int steps, const StSe
         {
             steps = -steps;
             j = (rotation + steps - 2)%steps;
-            if (pattern[j].x != t.f1[8]  ||  pattern[j].y != t.f2[8])
+            const int4 p = pattern[j];
+            if (p.x != t.f1(8)  ||  p.y != t.f2(8))
                 return 0;
-            if (pattern[j].z > t.dur[8]*128  ||  pattern[j].w < t.dur[8]*128)
+            if (p.z > t.dur(8)*128  ||  p.w < t.dur(8)*128)
                 return 0;
         }
         if (steps)
             j = (rotation + steps - 1)%steps;
-        if (pattern[j].x != t.f1[9]  ||  pattern[j].y != t.f2[9])
+        const int4 p = pattern[j];
+        if (p.x != t.f1(9)  ||  p.y != t.f2(9))
             return 0;
-        if (pattern[j].w < t.dur[9]*128)
+        if (p.w < t.dur(9)*128)
             return 0;
     }
     else
@@ -924,19 +995,31 @@ __device__ inline int st_test_cadence(const int4 *pattern, int steps, const StSe
         for (int i = 0;  i < steps;  i++)
         {
             j = i + 10 - steps;
-            if (pattern[i].x != t.f1[j]  ||  pattern[i].y != t.f2[j])
+            const int4 p = pattern[i];
+            if (p.x != t.f1(j)  ||  p.y != t.f2(j))
                 return 0;
-            if (pattern[i].z > t.dur[j]*128  ||  pattern[i].w < t.dur[j]*128)
+            if (p.z > t.dur(j)*128  ||  p.w < t.dur(j)*128)
                 return 0;
         }
     }
     return 1;
 }
 
-// src/super_tone_rx.c:366-448
+#define SB_ST_TILE          48          // block rows of decisions staged per tile (16-bit codes: 256 bytes per row and CTA)
+#define SB_ST_SMEM_ELEMENTS 160         // cadence template elements kept in shared memory (larger descriptors read them from global memory)
+#define SB_ST_SMEM_TONES    64
+
+// src/super_tone_rx.c:366-448.  Thread per channel; the per-channel history, the cadence templates and - where the bank
+// has one block phase and the rows are 16-byte aligned - tiles of the decision codes live in shared memory, so the
+// serial walk over the blocks pays shared-memory latency instead of one or more global round trips per block.
 template <bool EMIT>
 __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
 {
+    __shared__ int seg[33*128];
+    __shared__ __align__(16) unsigned short tile[2][SB_ST_TILE*128];
+    __shared__ int4 s_elements[SB_ST_SMEM_ELEMENTS];
+    __shared__ int s_tone_segs[SB_ST_SMEM_TONES];
+    __shared__ int s_tone_first[SB_ST_SMEM_TONES];
     const int gc = blockIdx.x*blockDim.x + threadIdx.x;
     const int wg = gc >> 5;
     const bool live = (gc < s.q.channels);
@@ -945,14 +1028,27 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     const size_t C = s.q.channels;
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
     const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
-    const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
     StSegs t;
-    for (int i = 0;  i < 11;  i++)
+    t.base = seg + threadIdx.x;
+    for (int i = 0;  i < 33;  i++)
+        seg[i*128 + threadIdx.x] = s.segments[(size_t) i*C + c];
+    // templates: shared memory copies where they fit
+    const bool small = (s.t.tones <= SB_ST_SMEM_TONES  &&  s.t.total_elements <= SB_ST_SMEM_ELEMENTS);
+    if (small)
     {
-        t.f1[i] = s.segments[(size_t) (3*i)*C + c];
-        t.f2[i] = s.segments[(size_t) (3*i + 1)*C + c];
-        t.dur[i] = s.segments[(size_t) (3*i + 2)*C + c];
+        for (int i = threadIdx.x;  i < s.t.total_elements;  i += 128)
+            s_elements[i] = s.t.elements[i];
+        for (int i = threadIdx.x;  i < s.t.tones;  i += 128)
+        {
+            s_tone_segs[i] = s.t.tone_segs[i];
+            s_tone_first[i] = s.t.tone_first[i];
+        }
     }
+    __syncthreads();
+    const int4 *elements = (small)  ?  s_elements  :  s.t.elements;
+    const int *tone_segs = (small)  ?  s_tone_segs  :  s.t.tone_segs;
+    const int *tone_first = (small)  ?  s_tone_first  :  s.t.tone_first;
+    const int ntones = s.t.tones;
     int detected = s.detected_tone[c];
     int rotation = s.rotation[c];
     int pending = s.pending[c];
@@ -976,17 +1072,17 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         seg_f1 = seg_f2 = seg_ms = found_id = 0;
         if (!run)
             return;
-        if (k1 != t.f1[10]  ||  k2 != t.f2[10])
+        if (k1 != t.f1(10)  ||  k2 != t.f2(10))
         {
-            t.f1[10] = k1;
-            t.f2[10] = k2;
-            t.dur[9]++;
+            t.f1(10) = k1;
+            t.f2(10) = k2;
+            t.dur(9)++;
         }
-        else if (k1 != t.f1[9]  ||  k2 != t.f2[9])
+        else if (k1 != t.f1(9)  ||  k2 != t.f2(9))
         {
             if (detected >= 0)
             {
-                if (!st_test_cadence(s.t.elements + s.t.tone_first[detected], -s.t.tone_segs[detected], t, rotation++))
+                if (!st_test_cadence(elements + tone_first[detected], -tone_segs[detected], t, rotation++))
                 {
                     detected = -1;
                     e_lost = true;
@@ -995,37 +1091,37 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             if (s.want_segments)
             {
                 e_seg = true;
-                seg_f1 = t.f1[9];
-                seg_f2 = t.f2[9];
-                seg_ms = t.dur[9]*128/8;
+                seg_f1 = t.f1(9);
+                seg_f2 = t.f2(9);
+                seg_ms = t.dur(9)*128/8;
             }
             for (int i = 0;  i < 9;  i++)
             {
-                t.f1[i] = t.f1[i + 1];
-                t.f2[i] = t.f2[i + 1];
-                t.dur[i] = t.dur[i + 1];
+                t.f1(i) = t.f1(i + 1);
+                t.f2(i) = t.f2(i + 1);
+                t.dur(i) = t.dur(i + 1);
             }
-            t.f1[9] = k1;
-            t.f2[9] = k2;
-            t.dur[9] = 1;
+            t.f1(9) = k1;
+            t.f2(9) = k2;
+            t.dur(9) = 1;
         }
         else
         {
             if (detected >= 0)
             {
-                if (!st_test_cadence(s.t.elements + s.t.tone_first[detected], s.t.tone_segs[detected], t, rotation))
+                if (!st_test_cadence(elements + tone_first[detected], tone_segs[detected], t, rotation))
                 {
                     detected = -1;
                     e_lost = true;
                 }
             }
-            t.dur[9]++;
+            t.dur(9)++;
         }
         if (detected < 0)
         {
-            for (int j = 0;  j < s.t.tones;  j++)
+            for (int j = 0;  j < ntones;  j++)
             {
-                if (st_test_cadence(s.t.elements + s.t.tone_first[j], s.t.tone_segs[j], t, -1))
+                if (st_test_cadence(elements + tone_first[j], tone_segs[j], t, -1))
                 {
                     detected = j;
                     rotation = 0;
@@ -1044,6 +1140,25 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         sink.push(e_found, c, blk, SPAN_B200_EV_TONE, found_id, -10, 0);
     };
 
+    const long long consumed_at_end = (long long) cs_old + s.q.n;
+    // one decision code through the reference's block logic, including the one-bin quirk
+    auto one_block = [&](int b, bool run, int code)
+    {
+        chunk(run, (code & 0x7F) - 1, ((code >> 7) & 0x7F) - 1);
+        flush(b);
+        const bool quirk = run  &&  (code & SB_ST_QUIRK);
+        if (__any_sync(0xFFFFFFFFu, quirk))
+        {
+            // The reference loops straight back into super_tone_chunk with zero energy unless the
+            // block ended exactly at the end of the caller's buffer (src/super_tone_rx.c:466-486).
+            const bool again = quirk  &&  ((long long) (b + 1)*B < consumed_at_end);
+            chunk(again, -1, -1);
+            flush(b);
+            if (quirk  &&  !again)
+                pending = 1;
+        }
+    };
+
     // A zero-energy re-chunk owed from the previous call (one-bin descriptors only).
     {
         const bool owe = live  &&  pending  &&  s.q.n > 0;
@@ -1055,49 +1170,59 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         if (owe)
             pending = 0;
     }
-    const long long consumed_at_end = (long long) cs_old + s.q.n;
-    constexpr int G = 16;
-    for (int b0 = 0;  b0 < nb_max;  b0 += G)
+    if (s.q.cs0 >= 0  &&  (s.q.channels & 7) == 0)
     {
-        unsigned short codes[G];
-#pragma unroll
-        for (int i = 0;  i < G;  i++)
-            codes[i] = (b0 + i < nb)  ?  s.code[(size_t) (b0 + i)*C + c]  :  (unsigned short) 0;
-#pragma unroll 1
-        for (int i = 0;  i < G;  i++)
+        const int nbu = (s.q.cs0 + s.q.n)/B;                // the same for every channel
+        const int ntiles = (nbu + SB_ST_TILE - 1)/SB_ST_TILE;
+        const int c0 = blockIdx.x*128;
+        auto issue = [&](int tl)
         {
-            const int b = b0 + i;
-            if (b >= nb_max)
-                break;
-            const bool run = (b < nb);
-            int code = 0;
-#pragma unroll
-            for (int q = 0;  q < G;  q++)
-                code = (q == i)  ?  (int) codes[q]  :  code;
-            chunk(run, (code & 0x7F) - 1, ((code >> 7) & 0x7F) - 1);
-            flush(b);
-            const bool quirk = run  &&  (code & SB_ST_QUIRK);
-            if (__any_sync(0xFFFFFFFFu, quirk))
+            if (tl < ntiles)
             {
-                // The reference loops straight back into super_tone_chunk with zero energy unless the
-                // block ended exactly at the end of the caller's buffer (src/super_tone_rx.c:466-486).
-                const bool again = quirk  &&  ((long long) (b + 1)*B < consumed_at_end);
-                chunk(again, -1, -1);
-                flush(b);
-                if (quirk  &&  !again)
-                    pending = 1;
+                const uint32_t dst0 = (uint32_t) __cvta_generic_to_shared(tile[tl & 1]);
+                for (int k = threadIdx.x;  k < SB_ST_TILE*16;  k += 128)
+                {
+                    const int row = k >> 4;
+                    const int piece = k & 15;
+                    const int b = tl*SB_ST_TILE + row;
+                    const bool ok = (b < nbu  &&  c0 + 8*piece < s.q.channels);
+                    const unsigned short *src = (ok)  ?  (s.code + (size_t) b*C + c0 + 8*piece)  :  s.code;
+                    cp_async_16(dst0 + row*256 + piece*16, src, (ok)  ?  16  :  0);
+                }
             }
+            cp_async_commit();
+        };
+        issue(0);
+        for (int tl = 0;  tl < ntiles;  tl++)
+        {
+            issue(tl + 1);
+            cp_async_wait<1>();
+            __syncthreads();
+            const unsigned short *col = tile[tl & 1] + threadIdx.x;
+            const int rows = (nbu - tl*SB_ST_TILE < SB_ST_TILE)  ?  (nbu - tl*SB_ST_TILE)  :  SB_ST_TILE;
+#pragma unroll 1
+            for (int row = 0;  row < rows;  row++)
+                one_block(tl*SB_ST_TILE + row, live, (int) col[row*128]);
+            __syncthreads();
+        }
+        cp_async_wait<0>();
+    }
+    else
+    {
+        const int nb_max = __reduce_max_sync(0xFFFFFFFFu, nb);
+#pragma unroll 1
+        for (int b = 0;  b < nb_max;  b++)
+        {
+            const bool run = (b < nb);
+            const int code = (run)  ?  (int) s.code[(size_t) b*C + c]  :  0;
+            one_block(b, run, code);
         }
     }
     sink.finish(wg);
     if (EMIT  &&  live)
     {
-        for (int i = 0;  i < 11;  i++)
-        {
-            s.segments[(size_t) (3*i)*C + c] = t.f1[i];
-            s.segments[(size_t) (3*i + 1)*C + c] = t.f2[i];
-            s.segments[(size_t) (3*i + 2)*C + c] = t.dur[i];
-        }
+        for (int i = 0;  i < 33;  i++)
+            s.segments[(size_t) i*C + c] = seg[i*128 + threadIdx.x];
         s.detected_tone[c] = detected;
         s.rotation[c] = rotation;
         s.pending[c] = (unsigned char) pending;

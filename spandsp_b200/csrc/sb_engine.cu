@@ -454,6 +454,7 @@ struct span_b200_bank_s
     int *d_tone_first;
     int4 *d_elements;
     int tones;
+    int total_elements;
     std::vector<float> h_fac;
 
     // per-call scratch
@@ -788,6 +789,7 @@ extern "C" span_b200_bank_t *span_b200_super_tone_bank_create(span_b200_ctx_t *c
         b->stp.fac[i] = bd.fac[i];
     b->h_fac.assign(bd.fac, bd.fac + bd.monitored);
     b->tones = desc->tones;
+    b->total_elements = (int) elements.size();
     const size_t C = channels;
     CKB(cudaMalloc(&b->segments, sizeof(int)*33*C));
     CKB(cudaMalloc(&b->detected, sizeof(int)*C));
@@ -1553,6 +1555,7 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
                 s.t.tone_segs = b->d_tone_segs;
                 s.t.tone_first = b->d_tone_first;
                 s.t.elements = b->d_elements;
+                s.t.total_elements = b->total_elements;
                 s.segments = b->segments;
                 s.detected_tone = b->detected;
                 s.rotation = b->rotation;

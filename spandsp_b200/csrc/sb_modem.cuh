@@ -40,6 +40,7 @@
 #define SBM_SQRT_WORDS      100     // 193 uint16 of the fixed_sqrt table, padded to keep 16-byte alignment
 #define SBM_IN_RING         32      // samples per lane in the input staging ring (power of two)
 #define SBM_RRC_ROW         28      // coefficient rows in shared memory, padded from 27 so that they load as float4
+#define SBM_RRC_SKEW        16      // words between the real and the imaginary table: row r of the two then sits 16 banks apart
 
 #define SIG_STATUS_CARRIER_DOWN             (-1)    // src/spandsp/async.h:66-103
 #define SIG_STATUS_CARRIER_UP               (-2)
@@ -529,6 +530,12 @@ struct RxCore
     float *rrc;             // LPC 1: [54], ring of 27 kept twice.  LPC 4: the ring, with 27 zeros before and after it
     float2 *eq_coef_re;     // LPC 4: (yr, -yi) per tap: what the lanes of the real accumulator multiply with
     float2 *eq_coef_im;     // LPC 4: (yi, yr) per tap: the imaginary accumulator's
+    int lms_pending;        // LPC 4: an LMS update / a save of the coefficients is owed for this baud (done by run())
+    int save_pending;
+    float lms_ere;
+    float lms_eim;
+    float h_zre;            // LPC 4: the equalizer output of this baud, computed by run() with the warp converged
+    float h_zim;
     int sub;                // LPC 4: this lane's role, 0 = real / first segment, 1 = real / second, 2 = imag / first, 3 = imag / second
     unsigned int gmask;     // LPC 4: the four lanes of this receiver
     // outputs.  Device kernels pack the data bits (words / status); the host build writes one byte per put_bit call.
@@ -800,7 +807,16 @@ struct RxCore
 
     SB_HD void equalizer_save()
     {
-        group_sync();                       // the last LMS update was made by four lanes
+        if (LPC > 1)
+        {
+            save_pending = 1;               // after the deferred LMS update of this baud (run())
+            return;
+        }
+        equalizer_save_now();
+    }
+
+    SB_HD void equalizer_save_now()
+    {
         if (sub == 0)
         {
             for (int i = 0;  i < EQ_LEN;  i++)
@@ -848,11 +864,13 @@ struct RxCore
                         z = fadd(z, fmul(x[i*LS], cs[e]));
                 }
             }
-            // first + second segment (the partner lane holds the other one; addition commutes)
-            z = fadd(z, __shfl_xor_sync(gmask, z, 1));
-            const int base = (threadIdx.x & 31) - sub;
-            v_re = __shfl_sync(gmask, z, base);
-            v_im = __shfl_sync(gmask, z, base + 2);
+            // first + second segment (the partner lane holds the other one; addition commutes), then the other
+            // component from the lane two further on.  Every lane of the warp is here (run() keeps the warp converged
+            // around this call), so the shuffles take the full mask.
+            z = fadd(z, __shfl_xor_sync(0xFFFFFFFFu, z, 1));
+            const float o = __shfl_xor_sync(0xFFFFFFFFu, z, 2);
+            v_re = (sub & 2)  ?  o  :  z;
+            v_im = (sub & 2)  ?  z  :  o;
             return;
         }
 #endif
@@ -912,10 +930,10 @@ struct RxCore
                 const float2 y = yb[i*LS];
                 z = fadd(z, fadd(fmul(x.x, y.x), fmul(x.y, y.y)));
             }
-            z = fadd(z, __shfl_xor_sync(gmask, z, 1));
-            const int base = (threadIdx.x & 31) - sub;
-            zre = __shfl_sync(gmask, z, base);
-            zim = __shfl_sync(gmask, z, base + 2);
+            z = fadd(z, __shfl_xor_sync(0xFFFFFFFFu, z, 1));
+            const float o = __shfl_xor_sync(0xFFFFFFFFu, z, 2);
+            zre = (sub & 2)  ?  o  :  z;
+            zim = (sub & 2)  ?  z  :  o;
             return;
         }
 #endif
@@ -951,23 +969,12 @@ struct RxCore
         const float eim = fmul(fsub(tim, zim), eq_delta);
         if (LPC > 1)
         {
-            // taps sub, sub + LPC, ...: the updates are independent of each other
-#pragma unroll
-            for (int k = 0;  k < (EQ_LEN + LPC - 1)/LPC;  k++)
-            {
-                const int i = k*LPC + sub;
-                if (i < EQ_LEN)
-                {
-                    int p = eq_step + i;
-                    if (p >= EQ_LEN)
-                        p -= EQ_LEN;
-                    const float2 x = eq_buf[p*LS];
-                    const float2 y = eq_coeff[i*LS];
-                    set_coef(i, fadd(fmul(y.x, 0.9999f), fadd(fmul(x.y, eim), fmul(x.x, ere))),
-                                fadd(fmul(y.y, 0.9999f), fsub(fmul(x.x, eim), fmul(x.y, ere))));
-                }
-            }
-            group_sync();
+            // Deferred: run() does the update with the whole warp once the per-baud work of all receivers is through
+            // (each receiver adapts every tenth baud in data mode, at its own bauds: a warp would otherwise walk the
+            // 33 taps with four lanes almost every baud).
+            lms_pending = 1;
+            lms_ere = ere;
+            lms_eim = eim;
             return;
         }
         const float2 *xb = eq_buf + eq_step*LS;
@@ -1266,8 +1273,159 @@ struct RxCore
         return cur;
     }
 
+    // The first part of front(): the sample into the ring
+    SB_HD void front_insert(short amp)
+    {
+        rrc[rrc_step*LS] = (float) amp;
+        if (++rrc_step >= SBM_FILTER_STEPS)
+            rrc_step = 0;
+    }
+
+    // The coefficient set front() will use for the next sample (eq_put_step after its decrement)
+    SB_HD int front_step() const
+    {
+        int step = -(eq_put_step - COEFF_SETS);
+        if (step < 0)
+            step += COEFF_SETS;
+        if (step < 0)
+            step = 0;
+        else if (step > COEFF_SETS - 1)
+            step = COEFF_SETS - 1;
+        return step;
+    }
+
+    // The rest of front(), given the FIR pair of the sample just inserted
+    template <class K> SB_HD bool front_rest(const K &k, short amp, float v, float vim)
+    {
+        const int pw = signal_detect(k, amp);
+        if (pw == 0)
+            return false;
+        if (training_stage == D::STAGE_PARKED)
+            return false;
+        eq_put_step -= COEFF_SETS;
+        h_vim = vim;
+        const float sre = fmul(v, agc_scaling);
+        {
+            float t = fadd(fadd(fmul(lbe0, k.g_low[0]), fmul(lbe1, k.g_low[1])), sre);
+            lbe1 = lbe0;
+            lbe0 = t;
+            t = fadd(fadd(fmul(hbe0, k.g_high[0]), fmul(hbe1, k.g_high[1])), sre);
+            hbe1 = hbe0;
+            hbe0 = t;
+        }
+        if (eq_put_step <= 0)
+        {
+            h_pw = pw;
+            h_sre = sre;
+            return true;
+        }
+        carrier_phase += (unsigned int) phase_rate;
+        return false;
+    }
+
+#if defined(__CUDA_ARCH__)
+    // The deferred LMS updates of this baud, the whole warp on one receiver at a time: lane i takes tap i (lane 0 also
+    // tap 32).  Same arithmetic per tap as the one-lane form; the taps are independent of each other.
+    SB_HD void warp_lms()
+    {
+        const int lane = threadIdx.x & 31;
+        unsigned int need = __ballot_sync(0xFFFFFFFFu, lms_pending != 0  &&  sub == 0);
+        while (need)
+        {
+            const int src = __ffs((int) need) - 1;
+            need &= need - 1;
+            const float ere = __shfl_sync(0xFFFFFFFFu, lms_ere, src);
+            const float eim = __shfl_sync(0xFFFFFFFFu, lms_eim, src);
+            const int es = __shfl_sync(0xFFFFFFFFu, eq_step, src);
+            const int shift = src/LPC - lane/LPC;               // that receiver's column relative to mine
+#pragma unroll
+            for (int rep = 0;  rep < 2;  rep++)
+            {
+                const int i = lane + 32*rep;
+                if (i < EQ_LEN)
+                {
+                    int p = es + i;
+                    if (p >= EQ_LEN)
+                        p -= EQ_LEN;
+                    const float2 x = eq_buf[p*LS + shift];
+                    const float2 y = eq_coeff[i*LS + shift];
+                    const float yr = fadd(fmul(y.x, 0.9999f), fadd(fmul(x.y, eim), fmul(x.x, ere)));
+                    const float yi = fadd(fmul(y.y, 0.9999f), fsub(fmul(x.x, eim), fmul(x.y, ere)));
+                    eq_coeff[i*LS + shift] = make_float2(yr, yi);
+                    eq_coef_re[i*LS + shift] = make_float2(yr, -yi);
+                    eq_coef_im[i*LS + shift] = make_float2(yi, yr);
+                }
+            }
+        }
+        lms_pending = 0;
+        __syncwarp();
+        if (__any_sync(0xFFFFFFFFu, save_pending != 0))
+        {
+            if (save_pending)
+                equalizer_save_now();
+            save_pending = 0;
+        }
+    }
+#endif
+
+    // Four lanes per receiver: the same walk, but the warp stays converged around the three cooperative pieces - the
+    // FIR pair is evaluated by every lane in every round (for a receiver that takes no sample in a round it is
+    // evaluated on whatever the ring holds and discarded: the instruction stream costs the same), the equalizer
+    // once per trip, the LMS updates after it.
+    template <class K> SB_HD void run_group(const K &k, const float *s_rrc_re, const float *s_rrc_im, const int16_t *row, int n)
+    {
+#if defined(__CUDA_ARCH__)
+        int pos = 0;
+        feed_open(row, n);
+        lms_pending = 0;
+        save_pending = 0;
+#pragma unroll 1
+        while (__any_sync(0xFFFFFFFFu, pos < n))
+        {
+            unsigned long long cur = feed_peek4(pos);
+            bool whole = false;
+#pragma unroll
+            for (int h = 0;  h < 2;  h++)
+            {
+                const bool on = !(h == 0  &&  baud_half);
+                bool due = false;
+#pragma unroll
+                for (int q = 0;  q < 2;  q++)
+                {
+                    const bool take = on  &&  pos < n  &&  !due;
+                    const short amp = (short) (cur & 0xFFFFu);
+                    if (take)
+                    {
+                        cur >>= 16;
+                        front_insert(amp);
+                        pos++;
+                    }
+                    const int step = front_step();
+                    float v;
+                    float vim;
+                    rrc_dot2(s_rrc_re + step*SBM_RRC_ROW, s_rrc_im + step*SBM_RRC_ROW, v, vim);
+                    if (take)
+                        due = front_rest(k, amp, v, vim);
+                }
+                if (due)
+                    whole = half(k);
+            }
+            // the equalizer on the buffer as it stands (for a receiver that completed a baud: with both T/2 samples in)
+            equalizer_get(h_zre, h_zim);
+            if (whole)
+                baud(k);
+            warp_lms();
+        }
+#endif
+    }
+
     template <class K> SB_HD void run(const K &k, const float *s_rrc_re, const float *s_rrc_im, const int16_t *row, int n)
     {
+        if (LPC > 1)
+        {
+            run_group(k, s_rrc_re, s_rrc_im, row, n);
+            return;
+        }
         int pos = 0;
         feed_open(row, n);
 #pragma unroll 1
@@ -1319,7 +1477,7 @@ struct KernelArgs
 // Shared memory: [rrc_re | rrc_im | sine | sqrt | RX tables | per warp: lane-interleaved per-receiver arrays, input rings]
 template <class RX> __host__ __device__ constexpr int modem_table_words()
 {
-    return 2*RX::SETS*SBM_RRC_ROW + SBM_SINE_WORDS + SBM_SQRT_WORDS + RX::TABLE_WORDS;
+    return 2*RX::SETS*SBM_RRC_ROW + SBM_RRC_SKEW + SBM_SINE_WORDS + SBM_SQRT_WORDS + RX::TABLE_WORDS;
 }
 
 template <class RX> __host__ __device__ constexpr int modem_warp_words()
@@ -1338,8 +1496,8 @@ __device__ __forceinline__ void modem_bind(RX &r, const KernelArgs<RX> &ka, floa
                                            const float *&s_rrc_re, const float *&s_rrc_im)
 {
     float *w_rrc_re = smem;
-    float *w_rrc_im = smem + RX::SETS*SBM_RRC_ROW;
-    float *w_sine = smem + 2*RX::SETS*SBM_RRC_ROW;
+    float *w_rrc_im = smem + RX::SETS*SBM_RRC_ROW + SBM_RRC_SKEW;
+    float *w_sine = smem + 2*RX::SETS*SBM_RRC_ROW + SBM_RRC_SKEW;
     unsigned int *w_sqrt = (unsigned int *) (w_sine + SBM_SINE_WORDS);
     float *tables = w_sine + SBM_SINE_WORDS + SBM_SQRT_WORDS;
     const int tid = threadIdx.x;
@@ -1381,32 +1539,37 @@ __global__ void __launch_bounds__(WARPS*32) modem_rx_kernel(const KernelArgs<RX>
     RX r;
     const float *s_rrc_re;
     const float *s_rrc_im;
-    modem_bind(r, ka, smem, lane, (c < ka.a.channels)  ?  c  :  0, s_rrc_re, s_rrc_im);
-    if (c >= ka.a.channels)
+    // Lanes beyond the last channel: with one lane per receiver they leave; with several lanes per receiver the warp
+    // has to stay whole for its shuffles, so they shadow the last channel (same input, same state, same arithmetic)
+    // and write nothing.
+    const bool live = (c < ka.a.channels);
+    const int cc = (live)  ?  c  :  (ka.a.channels - 1);
+    modem_bind(r, ka, smem, lane, cc, s_rrc_re, s_rrc_im);
+    if (!live  &&  RX::LANES == 1)
         return;
     r.zero_pads();
-    StateLoader ld = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
+    StateLoader ld = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) cc};
     r.visit(ld);
     r.mirror_rings();
     r.bits = NULL;
     r.bits_cap = 0;
     r.nbits = 0;
-    r.words = ka.a.words + (size_t) c*ka.a.words_cap;
-    r.words_cap = (int) ka.a.words_cap;
+    r.words = ka.a.words + (size_t) cc*ka.a.words_cap;
+    r.words_cap = (live)  ?  (int) ka.a.words_cap  :  0;
     r.nwords = 0;
     r.bit_acc = 0;
     r.bit_fill = 0;
-    r.status = ka.a.status + (size_t) c*ka.a.status_cap*2;
-    r.status_cap = (int) ka.a.status_cap;
+    r.status = ka.a.status + (size_t) cc*ka.a.status_cap*2;
+    r.status_cap = (live)  ?  (int) ka.a.status_cap  :  0;
     r.nstatus = 0;
-    r.syms = (ka.a.syms)  ?  (ka.a.syms + (size_t) c*ka.a.sym_cap)  :  NULL;
+    r.syms = (ka.a.syms  &&  live)  ?  (ka.a.syms + (size_t) cc*ka.a.sym_cap)  :  NULL;
     r.sym_cap = (int) ka.a.sym_cap;
     r.nsyms = 0;
     r.group_sync();
-    r.run(ka.k, s_rrc_re, s_rrc_im, ka.a.amp + (long long) c*ka.a.stride, ka.a.n);
+    r.run(ka.k, s_rrc_re, s_rrc_im, ka.a.amp + (long long) cc*ka.a.stride, ka.a.n);
     r.out_flush();
     r.group_sync();
-    if (r.sub == 0)
+    if (r.sub == 0  &&  live)
     {
         StateStorer st = {ka.a.fstate, ka.a.istate, (size_t) ka.a.channels, (size_t) c};
         r.visit(st);

@@ -191,7 +191,15 @@ struct SBM_V29_NAME : RxCore<SBM_V29_NAME, V29_COEFF_SETS, SBM_EQ_LEN, SBM_V29_L
         eq_put_step += godard_per_baud(k);
         float zre;
         float zim;
-        equalizer_get(zre, zim);
+        if (Core::LANES > 1)
+        {
+            zre = h_zre;                    // computed by run_group() with the warp converged
+            zim = h_zim;
+        }
+        else
+        {
+            equalizer_get(zre, zim);
+        }
         float tre = 0.0f;
         float tim = 0.0f;
 
