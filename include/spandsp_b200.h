@@ -263,6 +263,40 @@ int span_b200_goertzel_blocks_device(span_b200_ctx_t *ctx, const float *fac, int
                                      const int16_t *d_amp, int64_t stride, int channels, int samples,
                                      float *d_out, int64_t out_capacity, void *stream);
 
+/* The same with the block's total energy beside the bins: d_energy [block][channel] receives the sequential float sum of
+   x*x over each block - what the reference's remaining users of these primitives keep for their "fraction of total energy"
+   tests (src/ademco_contactid.c:901-931, src/v18.c:1560-1600). */
+int span_b200_goertzel_blocks_energy_device(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len,
+                                            const int16_t *d_amp, int64_t stride, int channels, int samples,
+                                            float *d_out, int64_t out_capacity, float *d_energy, void *stream);
+/* Those users' tone sets: frequencies (Hz) and block length.  Returns the number of frequencies. */
+enum
+{
+    SPAN_B200_TONE_SET_ADEMCO_CONTACTID = 0,    /* 1400 / 2300 Hz handshake, 55-sample blocks (src/ademco_contactid.c:446,1179-1180) */
+    SPAN_B200_TONE_SET_V18 = 1                  /* the nine V.18 probing tones, 102-sample blocks (src/v18.c:177,200-211) */
+};
+int span_b200_goertzel_tone_set(int which, float *freqs, int max, int *block_len);
+/* make_goertzel_descriptor()'s coefficient 2*cos(2*pi*f/8000) as the library computes it (src/tone_detect.c:60-68) */
+float span_b200_goertzel_coefficient(float freq);
+
+/* ---- RFC 4733 telephone-event payloads (the on-the-wire form of the digit reports) ------------ */
+
+/* DTMF digit character -> event code 0-15 ('0'-'9', '*', '#', 'A'-'D'); -1 for anything else */
+int span_b200_rfc4733_event_code(int digit);
+/* One 4-byte payload: event, E bit, volume (0..63 = -dBm0), duration in timestamp units (samples at 8 kHz), network order */
+void span_b200_rfc4733_pack(uint8_t out[4], int event, int end, int volume, int duration);
+/* A channel's formatter state: the event in progress (-1: none) and its volume.  Initialise event to -1. */
+typedef struct
+{
+    int32_t event;
+    int32_t volume;
+} span_b200_rfc4733_state_t;
+/* One realtime DTMF report (what dtmf_rx's realtime callback / a SPAN_B200_EV_TONE record carries: code = digit or 0,
+   level in dBm0, duration in samples since the previous report) -> the payloads it implies, 4 bytes each in out: the end
+   packet (E = 1, duration) of the digit in progress, then the first packet (E = 0, duration 0) of a new digit.
+   Returns how many (0, 1 or 2). */
+int span_b200_rfc4733_dtmf(span_b200_rfc4733_state_t *st, int code, int level, int duration, uint8_t out[8]);
+
 #if defined(__cplusplus)
 }
 #endif

@@ -132,6 +132,32 @@ void goertzel_reset(goertzel_state_t *s);
 int goertzel_update(goertzel_state_t *s, const int16_t amp[], int samples);
 float goertzel_result(goertzel_state_t *s);
 
+/* ---- what the modem receivers report through put_bit / the status handler: src/spandsp/async.h:62-103 ---- */
+enum
+{
+    SIG_STATUS_CARRIER_DOWN = -1,
+    SIG_STATUS_CARRIER_UP = -2,
+    SIG_STATUS_TRAINING_IN_PROGRESS = -3,
+    SIG_STATUS_TRAINING_SUCCEEDED = -4,
+    SIG_STATUS_TRAINING_FAILED = -5,
+    SIG_STATUS_FRAMING_OK = -6,
+    SIG_STATUS_END_OF_DATA = -7,
+    SIG_STATUS_ABORT = -8,
+    SIG_STATUS_BREAK = -9,
+    SIG_STATUS_SHUTDOWN_COMPLETE = -10,
+    SIG_STATUS_OCTET_REPORT = -11,
+    SIG_STATUS_POOR_SIGNAL_QUALITY = -12,
+    SIG_STATUS_MODEM_RETRAIN_OCCURRED = -13,
+    SIG_STATUS_LINK_CONNECTED = -14,
+    SIG_STATUS_LINK_DISCONNECTED = -15,
+    SIG_STATUS_LINK_ERROR = -16,
+    SIG_STATUS_LINK_IDLE = -17
+};
+
+#if !defined(SAMPLE_RATE)
+#define SAMPLE_RATE         8000    /* src/spandsp/telephony.h:45 */
+#endif
+
 /* ---- V.29 receiver: src/spandsp/v29rx.h:130-244, src/v29rx.c:145-195,867-1153 -------------------- */
 typedef struct
 {
@@ -307,6 +333,39 @@ int sig_tone_rx_release(sig_tone_rx_state_t *s);
 int sig_tone_rx_free(sig_tone_rx_state_t *s);
 int sig_tone_rx(sig_tone_rx_state_t *s, int16_t amp[], int len);
 void sig_tone_rx_set_mode(sig_tone_rx_state_t *s, int mode, int duration);
+
+/* ---- FAX receive front end: the fast modem beside the V.21 receiver until one of them has the signal ---------
+   src/fax_modems.c:177-333: fax_modems_v17_v21_rx() / fax_modems_v27ter_v21_rx() / fax_modems_v29_v21_rx() hand every
+   block of audio to the fast modem and to the V.21 channel 2 receiver; the first to produce something keeps the line:
+   the fast modem when it reports SIG_STATUS_TRAINING_SUCCEEDED (its status handler swaps the rx handler,
+   :197-209,244-256,291-303), V.21 when the HDLC layer above it has accepted a frame (rx_frame_received, :219-225,
+   :266-272,:313-319).  The HDLC framer itself stays with the caller (it is not part of this library): it tells the
+   front end through span_b200_fax_rx_frame_received(). */
+typedef struct span_b200_fax_rx_s span_b200_fax_rx_t;
+
+enum
+{
+    SPAN_B200_FAX_RX_BOTH = 0,      /* the race is on: both receivers get the audio */
+    SPAN_B200_FAX_RX_FAST = 1,      /* the fast modem trained: only it runs from here on */
+    SPAN_B200_FAX_RX_V21 = 2        /* a V.21 frame was accepted: only the V.21 receiver runs from here on */
+};
+
+/* fast_modem: 17, 27 or 29 (V.17, V.27ter, V.29) at bit_rate; fast_put_bit receives the fast modem's bits and status
+   reports exactly as fax_modems.c passes them on (the status also when the status handler consumed it, :304), v21_put_bit
+   those of the V.21 receiver (fsk_rx_init(&preset_fsk_specs[FSK_V21CH2], FSK_FRAME_MODE_SYNC, ...) with the -39.09 dBm0
+   cutoff of fax_modems_start_slow_modem(), :341-343).  NULL on a bad modem / rate or without a device. */
+span_b200_fax_rx_t *span_b200_fax_rx_init(int fast_modem, int bit_rate, int short_train,
+                                          span_put_bit_func_t fast_put_bit, void *fast_user_data,
+                                          span_put_bit_func_t v21_put_bit, void *v21_user_data);
+int span_b200_fax_rx_free(span_b200_fax_rx_t *s);
+/* fax_modems_vXX_v21_rx(): returns 0 */
+int span_b200_fax_rx(span_b200_fax_rx_t *s, const int16_t amp[], int len);
+/* fax_modems_vXX_v21_rx_fillin() */
+int span_b200_fax_rx_fillin(span_b200_fax_rx_t *s, int len);
+/* The caller's HDLC layer accepted a frame from the V.21 bit stream (s->rx_frame_received = true in the reference) */
+void span_b200_fax_rx_frame_received(span_b200_fax_rx_t *s);
+/* SPAN_B200_FAX_RX_* */
+int span_b200_fax_rx_current(const span_b200_fax_rx_t *s);
 
 #if defined(__cplusplus)
 }

@@ -201,6 +201,8 @@ struct Runner
                     if (i < loc.bins  &&  idx < a.raw_capacity)
                         a.raw[idx] = e[i];
                 }
+                if (DET::ENERGY  &&  a.eout)
+                    a.eout[(size_t) blk*channels + c] = energy;
             }
         }
         else

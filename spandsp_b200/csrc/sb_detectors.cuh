@@ -903,12 +903,14 @@ struct SuperToneDet
 
 // Raw Goertzel bank: arbitrary coefficients and block length, energies out
 // (goertzel_update()/goertzel_result(), src/tone_detect.c:123-205).
-template <int NP>
+// WITH_ENERGY: also the block's total energy (sequential float sum of x*x, as every caller of these primitives in the
+// reference keeps it beside its Goertzels: src/ademco_contactid.c:901-905, src/v18.c:1560-1566) -> eout[block][channel]
+template <int NP, bool WITH_ENERGY = false>
 struct RawDet
 {
     static constexpr int NPAIRS = NP;
     static constexpr int BLOCK = 0;                 // run-time block length
-    static constexpr bool ENERGY = false;
+    static constexpr bool ENERGY = WITH_ENERGY;
     static constexpr bool ENERGY_OUT = false;
     static constexpr bool FILTER = false;
     static constexpr bool RAW = true;

@@ -1934,3 +1934,190 @@ extern "C" int sig_tone_rx(sig_tone_rx_state_t *s, int16_t amp[], int len)
     }
     return len;                                             // src/sig_tone.c:663
 }
+
+// ------------------------------------------------------------------------------------------
+// FAX receive front end (src/fax_modems.c:177-333): host glue over the drop-in receivers above
+struct span_b200_fax_rx_s
+{
+    int fast_modem;
+    v29_rx_state_t *v29;
+    v17_rx_state_t *v17;
+    v27ter_rx_state_t *v27ter;
+    fsk_rx_state_t *v21;
+    span_put_bit_func_t fast_put_bit;
+    void *fast_user_data;
+    int current;
+    int rx_frame_received;
+};
+
+// v29_rx_status_handler() / v17_rx_status_handler() / v27ter_rx_status_handler() (src/fax_modems.c:197-209,244-256,291-303)
+static void fax_fast_status(void *user_data, int status)
+{
+    span_b200_fax_rx_t *s = (span_b200_fax_rx_t *) user_data;
+    if (status == SIG_STATUS_TRAINING_SUCCEEDED)
+    {
+        // "Switching from V.xx + V.21 to V.xx": the fast modem keeps the line, and its status goes through put_bit again
+        s->current = SPAN_B200_FAX_RX_FAST;
+        switch (s->fast_modem)
+        {
+        case 29:
+            v29_rx_set_modem_status_handler(s->v29, NULL, s);
+            break;
+        case 17:
+            v17_rx_set_modem_status_handler(s->v17, NULL, s);
+            break;
+        default:
+            v27ter_rx_set_modem_status_handler(s->v27ter, NULL, s);
+            break;
+        }
+    }
+    if (s->fast_put_bit)
+        s->fast_put_bit(s->fast_user_data, status);
+}
+
+extern "C" int span_b200_fax_rx_free(span_b200_fax_rx_t *s)
+{
+    if (s == NULL)
+        return 0;
+    if (s->v29)
+        v29_rx_free(s->v29);
+    if (s->v17)
+        v17_rx_free(s->v17);
+    if (s->v27ter)
+        v27ter_rx_free(s->v27ter);
+    if (s->v21)
+        fsk_rx_free(s->v21);
+    delete s;
+    return 0;
+}
+
+extern "C" span_b200_fax_rx_t *span_b200_fax_rx_init(int fast_modem, int bit_rate, int short_train,
+                                                     span_put_bit_func_t fast_put_bit, void *fast_user_data,
+                                                     span_put_bit_func_t v21_put_bit, void *v21_user_data)
+{
+    span_b200_fax_rx_t *s = new span_b200_fax_rx_s();
+    memset(s, 0, sizeof(*s));
+    s->fast_modem = fast_modem;
+    s->fast_put_bit = fast_put_bit;
+    s->fast_user_data = fast_user_data;
+    s->current = SPAN_B200_FAX_RX_BOTH;
+    bool ok = false;
+    switch (fast_modem)
+    {
+    case 29:
+        if ((s->v29 = v29_rx_init(NULL, bit_rate, fast_put_bit, fast_user_data)) != NULL)
+        {
+            v29_rx_set_modem_status_handler(s->v29, fax_fast_status, s);
+            ok = true;
+        }
+        break;
+    case 17:
+        if ((s->v17 = v17_rx_init(NULL, bit_rate, fast_put_bit, fast_user_data)) != NULL)
+        {
+            if (short_train)
+                v17_rx_restart(s->v17, bit_rate, short_train);
+            v17_rx_set_modem_status_handler(s->v17, fax_fast_status, s);
+            ok = true;
+        }
+        break;
+    case 27:
+        if ((s->v27ter = v27ter_rx_init(NULL, bit_rate, fast_put_bit, fast_user_data)) != NULL)
+        {
+            v27ter_rx_set_modem_status_handler(s->v27ter, fax_fast_status, s);
+            ok = true;
+        }
+        break;
+    default:
+        sb_set_error("fast modem %d (17, 27 or 29)", fast_modem);
+        break;
+    }
+    if (ok)
+    {
+        // fax_modems_start_slow_modem(FAX_MODEM_V21_RX), src/fax_modems.c:340-343
+        s->v21 = fsk_rx_init(NULL, &preset_fsk_specs[FSK_V21CH2], FSK_FRAME_MODE_SYNC, v21_put_bit, v21_user_data);
+        if (s->v21)
+            fsk_rx_set_signal_cutoff(s->v21, -39.09f);
+        else
+            ok = false;
+    }
+    if (!ok)
+    {
+        span_b200_fax_rx_free(s);
+        return NULL;
+    }
+    return s;
+}
+
+extern "C" void span_b200_fax_rx_frame_received(span_b200_fax_rx_t *s)
+{
+    s->rx_frame_received = 1;
+}
+
+extern "C" int span_b200_fax_rx_current(const span_b200_fax_rx_t *s)
+{
+    return s->current;
+}
+
+static void fax_fast_rx(span_b200_fax_rx_t *s, const int16_t amp[], int len)
+{
+    switch (s->fast_modem)
+    {
+    case 29:
+        v29_rx(s->v29, amp, len);
+        break;
+    case 17:
+        v17_rx(s->v17, amp, len);
+        break;
+    default:
+        v27ter_rx(s->v27ter, amp, len);
+        break;
+    }
+}
+
+// fax_modems_v29_v21_rx() and its two siblings (src/fax_modems.c:213-228,260-275,307-322) - and, once the handler has
+// been swapped, the plain receiver the reference's rx handler then points at
+extern "C" int span_b200_fax_rx(span_b200_fax_rx_t *s, const int16_t amp[], int len)
+{
+    switch (s->current)
+    {
+    case SPAN_B200_FAX_RX_FAST:
+        fax_fast_rx(s, amp, len);
+        return 0;
+    case SPAN_B200_FAX_RX_V21:
+        fsk_rx(s->v21, amp, len);
+        return 0;
+    }
+    // The status handler may swap to the fast modem in the middle of this call; the reference still runs fsk_rx() on
+    // this block (the swap only changes who gets the NEXT block)
+    fax_fast_rx(s, amp, len);
+    fsk_rx(s->v21, amp, len);
+    if (s->rx_frame_received)
+    {
+        // "We have received something, and the fast modem has not trained. We must be receiving valid V.21" - checked
+        // after both receivers have run, so V.21 also wins a tie inside one block (:313-319)
+        s->current = SPAN_B200_FAX_RX_V21;
+    }
+    return 0;
+}
+
+extern "C" int span_b200_fax_rx_fillin(span_b200_fax_rx_t *s, int len)
+{
+    if (s->current != SPAN_B200_FAX_RX_V21)
+    {
+        switch (s->fast_modem)
+        {
+        case 29:
+            v29_rx_fillin(s->v29, len);
+            break;
+        case 17:
+            v17_rx_fillin(s->v17, len);
+            break;
+        default:
+            v27ter_rx_fillin(s->v27ter, len);
+            break;
+        }
+    }
+    if (s->current != SPAN_B200_FAX_RX_FAST)
+        fsk_rx_fillin(s->v21, len);
+    return 0;
+}

@@ -1817,11 +1817,11 @@ extern "C" int span_b200_bank_block_codes(span_b200_bank_t *b, uint16_t *codes, 
 
 // ------------------------------------------------------------------------------------------
 // raw Goertzel banks
-template <int NP>
+template <int NP, bool E>
 static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len, const int16_t *d_amp,
-                   int64_t stride, int channels, int n, float *d_out, int64_t cap, cudaStream_t st)
+                   int64_t stride, int channels, int n, float *d_out, int64_t cap, float *d_energy, cudaStream_t st)
 {
-    BankArgs<RawDet<NP> > a;
+    BankArgs<RawDet<NP, E> > a;
     memset(&a, 0, sizeof(a));
     a.amp = d_amp;
     a.stride = stride;
@@ -1830,6 +1830,7 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
     a.block_rt = block_len;
     a.raw = d_out;
     a.raw_capacity = cap;
+    a.eout = d_energy;
     a.cstride = channels;
     a.det.bins = bins;
     for (int i = 0;  i < bins;  i++)
@@ -1853,16 +1854,16 @@ static int run_raw(span_b200_ctx_t *ctx, const float *fac, int bins, int block_l
             L = 16;
         a.slice_blocks = (nb > L)  ?  L  :  (nb + 1);
         a.nslices = (nb > L)  ?  ((nb + L - 1)/L)  :  1;
-        return launch_staged<RawDet<NP>, 8, 2, 4, 4, NP>(a, false, st);
+        return launch_staged<RawDet<NP, E>, 8, 2, 4, 4, NP>(a, false, st);
     }
-    bank_kernel_direct<RawDet<NP>, RawDet<NP>::NPAIRS + 1, false><<<(channels + 127)/128, 128, 0, st>>>(a);
+    bank_kernel_direct<RawDet<NP, E>, RawDet<NP, E>::NPAIRS + 1, false><<<(channels + 127)/128, 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int span_b200_goertzel_blocks_device(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len,
-                                                const int16_t *d_amp, int64_t stride, int channels, int n,
-                                                float *d_out, int64_t out_capacity, void *stream)
+template <bool E>
+static int goertzel_blocks(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len, const int16_t *d_amp, int64_t stride, int channels,
+                           int n, float *d_out, int64_t out_capacity, float *d_energy, void *stream)
 {
     if (ctx == NULL  ||  fac == NULL  ||  bins < 1  ||  bins > SB_RAW_MAX_BINS  ||  block_len < 1  ||  channels < 1  ||  n < 0)
     {
@@ -1874,19 +1875,135 @@ extern "C" int span_b200_goertzel_blocks_device(span_b200_ctx_t *ctx, const floa
     const int np = (bins + 1)/2;
     int rc;
     if (np <= 1)
-        rc = run_raw<1>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+        rc = run_raw<1, E>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, d_energy, st);
     else if (np <= 2)
-        rc = run_raw<2>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+        rc = run_raw<2, E>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, d_energy, st);
     else if (np <= 4)
-        rc = run_raw<4>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+        rc = run_raw<4, E>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, d_energy, st);
     else if (np <= 8)
-        rc = run_raw<8>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+        rc = run_raw<8, E>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, d_energy, st);
     else
-        rc = run_raw<16>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, st);
+        rc = run_raw<16, E>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, d_energy, st);
     if (rc != 0)
         return -1;
     return n/block_len;
 }
+
+extern "C" int span_b200_goertzel_blocks_device(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len,
+                                                const int16_t *d_amp, int64_t stride, int channels, int n,
+                                                float *d_out, int64_t out_capacity, void *stream)
+{
+    return goertzel_blocks<false>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, NULL, stream);
+}
+
+extern "C" int span_b200_goertzel_blocks_energy_device(span_b200_ctx_t *ctx, const float *fac, int bins, int block_len,
+                                                       const int16_t *d_amp, int64_t stride, int channels, int n,
+                                                       float *d_out, int64_t out_capacity, float *d_energy, void *stream)
+{
+    if (d_energy == NULL)
+    {
+        sb_set_error("no energy buffer");
+        return -1;
+    }
+    return goertzel_blocks<true>(ctx, fac, bins, block_len, d_amp, stride, channels, n, d_out, out_capacity, d_energy, stream);
+}
+
+// The two remaining users of the Goertzel primitives in the reference, as tone sets for the raw bank
+extern "C" int span_b200_goertzel_tone_set(int which, float *freqs, int max, int *block_len)
+{
+    static const float ademco[2] = {1400.0f, 2300.0f};                      // src/ademco_contactid.c:1179-1180, block 55 (:446)
+    static const float v18[9] = {390.0f, 980.0f, 1180.0f, 1270.0f, 1300.0f, 1400.0f, 1650.0f, 1800.0f, 2225.0f};    // src/v18.c:200-211, block 102 (:177)
+    const float *f;
+    int n;
+    int bl;
+    switch (which)
+    {
+    case SPAN_B200_TONE_SET_ADEMCO_CONTACTID:
+        f = ademco;
+        n = 2;
+        bl = 55;
+        break;
+    case SPAN_B200_TONE_SET_V18:
+        f = v18;
+        n = 9;
+        bl = 102;
+        break;
+    default:
+        sb_set_error("unknown tone set %d", which);
+        return -1;
+    }
+    if (block_len)
+        *block_len = bl;
+    for (int i = 0;  i < n  &&  i < max;  i++)
+        freqs[i] = f[i];
+    return n;
+}
+
+extern "C" float span_b200_goertzel_coefficient(float freq)
+{
+    return sb_goertzel_fac(freq);
+}
+
+// ------------------------------------------------------------------------------------------
+// RFC 4733 telephone-event payloads for the DTMF reports (the wire form of a detected digit)
+extern "C" int span_b200_rfc4733_event_code(int digit)
+{
+    if (digit >= '0'  &&  digit <= '9')
+        return digit - '0';
+    switch (digit)
+    {
+    case '*': return 10;
+    case '#': return 11;
+    case 'A': return 12;
+    case 'B': return 13;
+    case 'C': return 14;
+    case 'D': return 15;
+    }
+    return -1;
+}
+
+extern "C" void span_b200_rfc4733_pack(uint8_t out[4], int event, int end, int volume, int duration)
+{
+    if (volume < 0)
+        volume = 0;
+    if (volume > 63)
+        volume = 63;
+    if (duration < 0)
+        duration = 0;
+    if (duration > 0xFFFF)
+        duration = 0xFFFF;
+    out[0] = (uint8_t) event;
+    out[1] = (uint8_t) (((end)  ?  0x80  :  0) | volume);
+    out[2] = (uint8_t) (duration >> 8);
+    out[3] = (uint8_t) (duration & 0xFF);
+}
+
+extern "C" int span_b200_rfc4733_dtmf(span_b200_rfc4733_state_t *st, int code, int level, int duration, uint8_t out[8])
+{
+    int n = 0;
+    if (st->event >= 0)
+    {
+        // whatever the report says, the event in progress ends here; `duration` is how long it lasted
+        span_b200_rfc4733_pack(out, st->event, 1, st->volume, duration);
+        n++;
+        st->event = -1;
+    }
+    if (code != 0)
+    {
+        const int ev = span_b200_rfc4733_event_code(code);
+        if (ev >= 0)
+        {
+            st->event = ev;
+            st->volume = (level < 0)  ?  -level  :  0;          // "power level of the tone, expressed in dBm0 after dropping the sign"
+            if (st->volume > 63)
+                st->volume = 63;
+            span_b200_rfc4733_pack(out + 4*n, ev, 0, st->volume, 0);
+            n++;
+        }
+    }
+    return n;
+}
+
 
 // ------------------------------------------------------------------------------------------
 // wire records and the multi-GPU gather: channels shard over ranks with no exchange on the filter

@@ -1384,12 +1384,13 @@ struct RxCore
         {
             unsigned long long cur = feed_peek4(pos);
             bool whole = false;
-#pragma unroll
+            // (rolled: four copies of the sample path do not fit the instruction cache - measured, profiles/r02_ncu_v29_*)
+#pragma unroll 1
             for (int h = 0;  h < 2;  h++)
             {
                 const bool on = !(h == 0  &&  baud_half);
                 bool due = false;
-#pragma unroll
+#pragma unroll 1
                 for (int q = 0;  q < 2;  q++)
                 {
                     const bool take = on  &&  pos < n  &&  !due;

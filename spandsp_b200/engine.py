@@ -94,6 +94,12 @@ def lib():
         "span_b200_bank_last_path": (C.c_char_p, [vp]),
         "span_b200_bank_last_launches": (i32, [vp]),
         "span_b200_goertzel_blocks_device": (i32, [vp, vp, i32, i32, vp, i64, i32, i32, vp, i64, vp]),
+        "span_b200_goertzel_blocks_energy_device": (i32, [vp, vp, i32, i32, vp, i64, i32, i32, vp, i64, vp, vp]),
+        "span_b200_goertzel_tone_set": (i32, [i32, vp, i32, vp]),
+        "span_b200_goertzel_coefficient": (f32, [f32]),
+        "span_b200_rfc4733_event_code": (i32, [i32]),
+        "span_b200_rfc4733_pack": (None, [vp, i32, i32, i32, i32]),
+        "span_b200_rfc4733_dtmf": (i32, [vp, i32, i32, i32, vp]),
         "span_b200_v29_bank_create": (vp, [vp, i32, i32, i32]),
         "span_b200_v29_bank_destroy": (None, [vp]),
         "span_b200_v29_bank_channels": (i32, [vp]),
@@ -279,10 +285,14 @@ class Context:
             lib().span_b200_host_free(self.h, p)
 
     # raw Goertzel bank -------------------------------------------------------------------
-    def goertzel_blocks(self, fac, block_len, d_amp_ptr, stride, channels, samples, d_out_ptr, out_capacity, stream=None):
+    def goertzel_blocks(self, fac, block_len, d_amp_ptr, stride, channels, samples, d_out_ptr, out_capacity, stream=None, d_energy_ptr=None):
         fac = np.ascontiguousarray(fac, dtype=np.float32)
-        rc = lib().span_b200_goertzel_blocks_device(self.h, fac.ctypes.data, len(fac), block_len, d_amp_ptr, stride,
-                                                    channels, samples, d_out_ptr, out_capacity, stream)
+        if d_energy_ptr is not None:
+            rc = lib().span_b200_goertzel_blocks_energy_device(self.h, fac.ctypes.data, len(fac), block_len, d_amp_ptr, stride,
+                                                               channels, samples, d_out_ptr, out_capacity, d_energy_ptr, stream)
+        else:
+            rc = lib().span_b200_goertzel_blocks_device(self.h, fac.ctypes.data, len(fac), block_len, d_amp_ptr, stride,
+                                                        channels, samples, d_out_ptr, out_capacity, stream)
         if rc < 0:
             raise EngineError(_err())
         return rc

@@ -128,7 +128,19 @@ def test_c_program_links_against_dropin(tmp_path, engine_lib):
     src.write_text(r'''
 #include <stdio.h>
 #include <string.h>
-#include "spandsp_b200_dropin.h"
+/* the reference's own header names: a caller written against spandsp compiles with no source edit */
+#include <spandsp/telephony.h>
+#include <spandsp/async.h>
+#include <spandsp/dtmf.h>
+#include <spandsp/bell_r2_mf.h>
+#include <spandsp/super_tone_rx.h>
+#include <spandsp/tone_detect.h>
+#include <spandsp/v29rx.h>
+#include <spandsp/v17rx.h>
+#include <spandsp/v27ter_rx.h>
+#include <spandsp/fsk.h>
+#include <spandsp/modem_connect_tones.h>
+#include <spandsp/sig_tone.h>
 
 static void digits(void *user, const char *d, int len) { (void) user; (void) d; (void) len; }
 static void tone(void *user, int code, int level, int delay) { (void) user; (void) code; (void) level; (void) delay; }
@@ -142,6 +154,8 @@ int main(void)
     sig_tone_rx_state_t *g;
 
     memset(amp, 0, sizeof(amp));
+    if (SIG_STATUS_TRAINING_SUCCEEDED != -4  ||  SAMPLE_RATE != 8000)
+        return 5;
     s = dtmf_rx_init(NULL, digits, NULL);
     m = modem_connect_tones_rx_init(NULL, MODEM_CONNECT_TONES_FAX_CNG, tone, NULL);
     g = sig_tone_rx_init(NULL, SIG_TONE_2280HZ, tone, NULL);
