@@ -52,7 +52,8 @@ enum
 };
 
 /* 24-byte event record.  Within one rx call the events of any single channel appear in time
-   order; across channels the buffer is ordered by (group of 32 channels, block, channel). */
+   order; across channels the buffer is ordered by (group of channels, block, channel), the groups being runs of
+   32 consecutive channels (super-tone banks: 8). */
 typedef struct
 {
     int32_t channel;

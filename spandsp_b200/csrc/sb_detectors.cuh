@@ -83,10 +83,13 @@ struct EventSink
     unsigned int base;
     unsigned int lt;
 
-    __device__ __forceinline__ EventSink(const SeqCommon &qq, int warp_global) : q(qq)
+    int cpw;                        // channels per warp (32, or fewer where a sequencer spreads a bank over more warps)
+
+    __device__ __forceinline__ EventSink(const SeqCommon &qq, int warp_global, int channels_per_warp = 32) : q(qq)
     {
+        cpw = channels_per_warp;
         // (a CTA's trailing warps may lie wholly beyond the last channel: they have no slot in offsets[] / counts[])
-        base = (EMIT  &&  warp_global*32 < qq.channels)  ?  qq.offsets[warp_global]  :  0;
+        base = (EMIT  &&  warp_global*cpw < qq.channels)  ?  qq.offsets[warp_global]  :  0;
         lt = (1u << (threadIdx.x & 31)) - 1u;
     }
 
@@ -114,7 +117,7 @@ struct EventSink
         if (!EMIT)
         {
             const unsigned int total = __reduce_add_sync(0xFFFFFFFFu, base);
-            if ((threadIdx.x & 31) == 0  &&  warp_global*32 < q.channels)
+            if ((threadIdx.x & 31) == 0  &&  warp_global*cpw < q.channels)
                 q.counts[warp_global] = total;
         }
     }
@@ -1007,33 +1010,44 @@ __device__ __forceinline__ int st_test_cadence(const int4 *pattern, int steps, c
     return 1;
 }
 
-#define SB_ST_TILE          48          // block rows of decisions staged per tile (16-bit codes: 256 bytes per row and CTA)
+#define SB_ST_TILE          48          // block rows of decisions staged per tile
+#define SB_ST_CPW           8           // channels per warp
+#define SB_ST_CPC           (4*SB_ST_CPW)   // channels per CTA (four warps)
 #define SB_ST_SMEM_ELEMENTS 160         // cadence template elements kept in shared memory (larger descriptors read them from global memory)
 #define SB_ST_SMEM_TONES    64
 
-// src/super_tone_rx.c:366-448.  Thread per channel; the per-channel history, the cadence templates and - where the bank
-// has one block phase and the rows are 16-byte aligned - tiles of the decision codes live in shared memory, so the
-// serial walk over the blocks pays shared-memory latency instead of one or more global round trips per block.
+// src/super_tone_rx.c:366-448.  The cadence logic is a chain of dependent, data-dependent branches per block: what it
+// costs is latency, and a warp pays for every path any of its channels takes.  So a warp carries only SB_ST_CPW
+// channels (lanes 0..7; the bank then spreads over four times the warps, which is what hides the latency: there are
+// only tens of thousands of channels), the per-channel history, the cadence templates and - where the bank has one
+// block phase and the rows are 16-byte aligned - tiles of the decision codes live in shared memory.
+// Event order: (group of SB_ST_CPW channels, block, channel).
 template <bool EMIT>
 __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
 {
     __shared__ int seg[33*128];
-    __shared__ __align__(16) unsigned short tile[2][SB_ST_TILE*128];
+    __shared__ __align__(16) unsigned short tile[2][SB_ST_TILE*SB_ST_CPC];
     __shared__ int4 s_elements[SB_ST_SMEM_ELEMENTS];
     __shared__ int s_tone_segs[SB_ST_SMEM_TONES];
     __shared__ int s_tone_first[SB_ST_SMEM_TONES];
-    const int gc = blockIdx.x*blockDim.x + threadIdx.x;
-    const int wg = gc >> 5;
-    const bool live = (gc < s.q.channels);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wg = blockIdx.x*4 + warp;                         // group of SB_ST_CPW channels
+    const int gc = wg*SB_ST_CPW + lane;
+    const bool live = (lane < SB_ST_CPW  &&  gc < s.q.channels);
     const int c = (live)  ?  gc  :  (s.q.channels - 1);
+    const int col_in_cta = warp*SB_ST_CPW + ((lane < SB_ST_CPW)  ?  lane  :  0);
     const int B = 128;
     const size_t C = s.q.channels;
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
     const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
     StSegs t;
     t.base = seg + threadIdx.x;
-    for (int i = 0;  i < 33;  i++)
-        seg[i*128 + threadIdx.x] = s.segments[(size_t) i*C + c];
+    if (lane < SB_ST_CPW)
+    {
+        for (int i = 0;  i < 33;  i++)
+            seg[i*128 + threadIdx.x] = s.segments[(size_t) i*C + c];
+    }
     // templates: shared memory copies where they fit
     const bool small = (s.t.tones <= SB_ST_SMEM_TONES  &&  s.t.total_elements <= SB_ST_SMEM_ELEMENTS);
     if (small)
@@ -1054,7 +1068,7 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     int detected = s.detected_tone[c];
     int rotation = s.rotation[c];
     int pending = s.pending[c];
-    EventSink<EMIT> sink(s.q, wg);
+    EventSink<EMIT> sink(s.q, wg, SB_ST_CPW);
 
     // One super_tone_chunk() step.  It can raise up to three callbacks, in this order: tone lost,
     // segment report, tone found.  They are recorded here and pushed by all lanes together.
@@ -1137,9 +1151,13 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
 
     auto flush = [&](int blk)
     {
-        sink.push(e_lost, c, blk, SPAN_B200_EV_TONE, -1, -10, 0);
-        sink.push(e_seg, c, blk, SPAN_B200_EV_SEGMENT, seg_f1, seg_f2, seg_ms);
-        sink.push(e_found, c, blk, SPAN_B200_EV_TONE, found_id, -10, 0);
+        // (most blocks raise nothing in any channel of the warp: one vote instead of three)
+        if (__any_sync(0xFFFFFFFFu, e_lost  ||  e_seg  ||  e_found))
+        {
+            sink.push(e_lost, c, blk, SPAN_B200_EV_TONE, -1, -10, 0);
+            sink.push(e_seg, c, blk, SPAN_B200_EV_SEGMENT, seg_f1, seg_f2, seg_ms);
+            sink.push(e_found, c, blk, SPAN_B200_EV_TONE, found_id, -10, 0);
+        }
     };
 
     const long long consumed_at_end = (long long) cs_old + s.q.n;
@@ -1176,20 +1194,21 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     {
         const int nbu = (s.q.cs0 + s.q.n)/B;                // the same for every channel
         const int ntiles = (nbu + SB_ST_TILE - 1)/SB_ST_TILE;
-        const int c0 = blockIdx.x*128;
+        const int c0 = blockIdx.x*SB_ST_CPC;
+        constexpr int PIECES = SB_ST_CPC/8;                 // 16-byte pieces per row
         auto issue = [&](int tl)
         {
             if (tl < ntiles)
             {
                 const uint32_t dst0 = (uint32_t) __cvta_generic_to_shared(tile[tl & 1]);
-                for (int k = threadIdx.x;  k < SB_ST_TILE*16;  k += 128)
+                for (int k = threadIdx.x;  k < SB_ST_TILE*PIECES;  k += 128)
                 {
-                    const int row = k >> 4;
-                    const int piece = k & 15;
+                    const int row = k/PIECES;
+                    const int piece = k - row*PIECES;
                     const int b = tl*SB_ST_TILE + row;
                     const bool ok = (b < nbu  &&  c0 + 8*piece < s.q.channels);
                     const unsigned short *src = (ok)  ?  (s.code + (size_t) b*C + c0 + 8*piece)  :  s.code;
-                    cp_async_16(dst0 + row*256 + piece*16, src, (ok)  ?  16  :  0);
+                    cp_async_16(dst0 + row*(SB_ST_CPC*2) + piece*16, src, (ok)  ?  16  :  0);
                 }
             }
             cp_async_commit();
@@ -1200,11 +1219,11 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             issue(tl + 1);
             cp_async_wait<1>();
             __syncthreads();
-            const unsigned short *col = tile[tl & 1] + threadIdx.x;
+            const unsigned short *col = tile[tl & 1] + col_in_cta;
             const int rows = (nbu - tl*SB_ST_TILE < SB_ST_TILE)  ?  (nbu - tl*SB_ST_TILE)  :  SB_ST_TILE;
 #pragma unroll 1
             for (int row = 0;  row < rows;  row++)
-                one_block(tl*SB_ST_TILE + row, live, (int) col[row*128]);
+                one_block(tl*SB_ST_TILE + row, live, (int) col[row*SB_ST_CPC]);
             __syncthreads();
         }
         cp_async_wait<0>();

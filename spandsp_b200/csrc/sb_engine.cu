@@ -556,8 +556,9 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
     CKB(cudaMalloc(&b->v3, sizeof(float)*2*b->npairs*C));
     CKB(cudaMalloc(&b->energy, sizeof(float)*C));
     CKB(cudaMalloc(&b->cs, sizeof(int)*C));
-    CKB(cudaMalloc(&b->counts, sizeof(unsigned int)*((C + 31)/32 + 1)));
-    CKB(cudaMalloc(&b->offsets, sizeof(unsigned int)*((C + 31)/32 + 1)));
+    // one count / offset per group of channels that share a warp in the sequencer (32; the super-tone sequencer: SB_ST_CPW)
+    CKB(cudaMalloc(&b->counts, sizeof(unsigned int)*((C + SB_ST_CPW - 1)/SB_ST_CPW + 1)));
+    CKB(cudaMalloc(&b->offsets, sizeof(unsigned int)*((C + SB_ST_CPW - 1)/SB_ST_CPW + 1)));
     CKB(cudaMalloc(&b->d_total, 2*sizeof(unsigned long long)));
     CKB(cudaMallocHost(&b->h_total, 2*sizeof(unsigned long long)));
     b->h_total[0] = b->h_total[1] = 0;
@@ -1500,6 +1501,7 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
     q.channel_base = b->channel_base;
     q.capacity = rc.out_cap;
     const int sgrid = (b->channels + 127)/128;
+    const int cpw = (b->det == SPAN_B200_DET_SUPER_TONE)  ?  SB_ST_CPW  :  32;      // channels per sequencer warp
     for (int pass = 0;  pass < 2;  pass++)
     {
         switch (b->det)
@@ -1561,10 +1563,11 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
                 s.rotation = b->rotation;
                 s.pending = b->pending;
                 s.want_segments = b->want_segments;
+                const int stgrid = (b->channels + SB_ST_CPC - 1)/SB_ST_CPC;
                 if (pass == 0)
-                    super_tone_sequencer<false><<<sgrid, 128, 0, st>>>(s);
+                    super_tone_sequencer<false><<<stgrid, 128, 0, st>>>(s);
                 else
-                    super_tone_sequencer<true><<<sgrid, 128, 0, st>>>(s);
+                    super_tone_sequencer<true><<<stgrid, 128, 0, st>>>(s);
             }
             break;
         }
@@ -1572,7 +1575,7 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
         b->last_launches++;
         if (pass == 0)
         {
-            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, (b->channels + 31)/32, b->d_total + slot);
+            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, (b->channels + cpw - 1)/cpw, b->d_total + slot);
             CK(cudaGetLastError());
             b->last_launches++;
             CK(cudaMemcpyAsync(b->h_total + slot, b->d_total + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
