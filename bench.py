@@ -753,10 +753,11 @@ def main():
             sizes = [int(((ids >= r * C_) & (ids < (r + 1) * C_)).sum()) for r in range(world)]
             pad = torch.zeros((max(sizes), T), dtype=torch.int16, device=dev)
             pad[: rows_local.shape[0]] = rows_local
-            bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-            dist.gather(pad, bufs, dst=0)
+            pad8 = pad.view(torch.uint8)                    # (torch's NCCL binding has no int16)
+            bufs = [torch.empty_like(pad8) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad8, bufs, dst=0)
             if rank == 0:
-                rows = torch.cat([b[:n] for b, n in zip(bufs, sizes)]).cpu().numpy()
+                rows = torch.cat([b.view(torch.int16)[:n] for b, n in zip(bufs, sizes)]).cpu().numpy()
                 cols = engine.wire_unpack(bank.gathered_host())
         else:
             rows = rows_local.cpu().numpy()

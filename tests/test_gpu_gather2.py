@@ -64,27 +64,30 @@ def test_gather_two_ranks(tmp_path, engine_lib):
     mp.spawn(worker, args=(2, uid, str(tmp_path)), nprocs=2, join=True)
     gathered = np.load(os.path.join(str(tmp_path), "gathered.npy"))
     counts = np.load(os.path.join(str(tmp_path), "counts.npy"))
-    # reference: one bank over all channels on this process's GPU, call by call
+    # reference: the two shards as two banks on this process's GPU, call by call; the gathered buffer must hold the root's
+    # records and then rank 1's, each in its bank's own order, with global channel numbers
     amp, _ = synth.dtmf_channels(NCH*2, N, seed=6)
     ctx = engine_lib.Context(0)
-    ref = engine_lib.Bank.dtmf(ctx, NCH*2)
-    ref.dtmf_realtime(True)
-    d = torch.from_numpy(amp).cuda()
+    refs = []
+    for r in range(2):
+        b = engine_lib.Bank.dtmf(ctx, NCH)
+        b.dtmf_realtime(True)
+        refs.append((b, torch.from_numpy(np.ascontiguousarray(amp[r*NCH:(r + 1)*NCH])).cuda()))
     torch.cuda.synchronize()
     want = []
     k = 0
     for pos in range(0, N, CALL):
-        ref.rx_device(d.data_ptr() + 2*pos, N, CALL)
-        ev = ref.events()
-        ch = ev["channel"]
-        # rank order: the root's channels, then rank 1's; inside a rank the bank's own order (here both halves keep it)
-        for lo in (0, NCH):
-            part = ev[(ch >= lo) & (ch < lo + NCH)]
-            want.extend((int(e["channel"]), int(e["block"]), int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])) for e in part)
-        assert counts[k].tolist() == [int(((ch >= 0) & (ch < NCH)).sum()), int((ch >= NCH).sum())]
+        per_rank = []
+        for r, (b, d) in enumerate(refs):
+            b.rx_device(d.data_ptr() + 2*pos, N, CALL)
+            ev = b.events()
+            per_rank.append(len(ev))
+            want.extend((int(e["channel"]) + r*NCH, int(e["block"]), int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])) for e in ev)
+        assert counts[k].tolist() == per_rank
         k += 1
     cols = engine_lib.wire_unpack(gathered)
     have = [tuple(int(col[i]) for col in cols) for i in range(len(gathered))]
     assert have == want and len(want) > 100
-    ref.close()
+    for b, _ in refs:
+        b.close()
     ctx.close()
