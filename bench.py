@@ -617,6 +617,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--numa", type=int, default=1, help="1: staging memory of the e2e arm on the GPU's NUMA node (span_b200_host_alloc)")
     ap.add_argument("--nccl-ctas", type=int, default=4, help="cap on the thread blocks NCCL may use for the record gather")
+    ap.add_argument("--gather", default="peer_copy", choices=["peer_copy", "nccl"],
+                    help="how the records travel to rank 0: the root's copy engines over NVLink (CUDA IPC), or ncclSend/ncclRecv")
     ap.add_argument("--realtime", type=int, default=1, help="1: realtime (on/off + level) events, 0: digit events")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -672,6 +674,7 @@ def main():
         uid = torch.from_numpy(engine.Comm.unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).to(dev)
         dist.broadcast(uid, 0)
         comm = engine.Comm(ctx, uid.cpu().numpy(), world, rank, max_ctas=args.nccl_ctas)
+        comm.set_transport(args.gather)
         bank.attach_comm(comm, 0)
 
     state = {"k": 0, "total": 0}
@@ -890,8 +893,10 @@ def main():
                    "channels_per_gpu": C_, "events": "realtime (on/off, level, duration)" if args.realtime else "digits",
                    "events_per_step": int(total_events), "l2": "input %.1f GB per GPU per step, larger than L2" % (C_ * T * 2 / 1e9),
                    "kernel_path": kernel_path,
-                   "parallelism": "channels sharded x%d; records gathered to rank 0 by span_b200_bank_gather_* "
-                                  "(12-byte records, exact-count ncclSend/ncclRecv, NCCL capped at %d CTAs)" % (world, args.nccl_ctas)},
+                   "parallelism": "channels sharded x%d; records gathered to rank 0 by span_b200_bank_gather_* (12-byte records, "
+                                  "counts by ncclAllGather, records by %s, NCCL capped at %d CTAs)"
+                                  % (world, "the root's copy engines over NVLink (exact counts, CUDA IPC)" if args.gather == "peer_copy"
+                                     else "exact-count ncclSend/ncclRecv", args.nccl_ctas)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "parity_check": parity,
     }

@@ -211,6 +211,20 @@ int span_b200_comm_unique_id(unsigned char id[SPAN_B200_COMM_ID_BYTES]);
 span_b200_comm_t *span_b200_comm_create(span_b200_ctx_t *ctx, const unsigned char id[SPAN_B200_COMM_ID_BYTES], int nranks, int rank,
                                         int max_ctas);
 void span_b200_comm_destroy(span_b200_comm_t *comm);
+/* How the records travel to the root once the counts are known (all ranks must use the same):
+     SPAN_B200_GATHER_PEER_COPY (default)  the root reads exactly each rank's records out of that rank's buffer with its
+         copy engines over NVLink / NVSwitch (the buffers are shared through CUDA IPC handles that ride in the counts
+         exchange): no SM of any GPU is used, which matters because the filter kernels are compute-bound; the counts
+         and the completion are NCCL collectives;
+     SPAN_B200_GATHER_NCCL  exact-count ncclSend (ranks) / ncclRecv (root), one group.
+   The environment variable SPANDSP_B200_GATHER=nccl selects the second at creation. */
+enum
+{
+    SPAN_B200_GATHER_NCCL = 0,
+    SPAN_B200_GATHER_PEER_COPY = 1
+};
+int span_b200_comm_set_transport(span_b200_comm_t *comm, int transport);
+int span_b200_comm_transport(const span_b200_comm_t *comm);
 int span_b200_comm_rank(const span_b200_comm_t *comm);
 int span_b200_comm_nranks(const span_b200_comm_t *comm);
 
@@ -220,10 +234,10 @@ int span_b200_bank_attach_comm(span_b200_bank_t *bank, span_b200_comm_t *comm, i
 /* The gather of the records of the bank's last rx call, in two halves so that it can overlap the next call:
      _begin: (collective, asynchronous) all ranks exchange their record counts (ncclAllGather on the communicator's
              own stream, ordered after the rx call by an event);
-     _end:   (collective) waits on the HOST for those counts, then enqueues the transfer: every rank sends exactly its
-             own records to the root (ncclSend), the root receives each rank's records behind its own, in rank order
-             (ncclRecv with the exact counts, one group).  Returns the total number of records (all ranks), or -1;
-             counts (may be NULL) receives the nranks per-rank counts.
+     _end:   (collective) waits on the HOST for those counts, then enqueues the transfer of exactly each rank's records
+             to the root, which lays them out behind its own in rank order (peer copies or ncclSend / ncclRecv, see
+             span_b200_comm_set_transport).  Returns the total number of records (all ranks), or -1; counts (may be
+             NULL) receives the nranks per-rank counts.
    Pipelined use (what the benchmark does): rx(k); _end(k-1); _begin(k); ... which lets the records of call k-1
    travel while the kernels of call k run.  Two record buffers are in flight; a third rx call waits (on the device)
    for the transfer that still reads the buffer it is about to overwrite. */

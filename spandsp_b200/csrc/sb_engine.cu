@@ -398,8 +398,12 @@ struct span_b200_comm_s
     // root: the gathered records of the two buffers in flight
     span_b200_wire_event_t *gather[2];
     long long gather_cap[2];
-    unsigned long long *d_counts[2];        // [nranks] all-gathered record counts
+    unsigned long long *d_counts[2];        // [nranks][SB_META_WORDS] all-gathered {record count, buffer generation, IPC handle}
     unsigned long long *h_counts[2];        // pinned
+    unsigned long long *d_sync;             // [1 + nranks] completion collective of the peer-copy transport
+    int transport;                          // SPAN_B200_GATHER_*
+    void **peer_ptr[2];                     // [nranks] the ranks' record buffers as mapped here (root, peer-copy transport)
+    unsigned long long *peer_gen[2];        // [nranks] generation of the mapping
     cudaEvent_t counts_ready[2];
     cudaEvent_t done[2];                    // the transfer that read / filled buffer i has finished
     bool done_valid[2];
@@ -409,6 +413,10 @@ struct span_b200_comm_s
 };
 
 static int comm_gather_reserve(span_b200_comm_t *cm, int slot, long long records, cudaStream_t st, long long keep);
+
+// What a rank contributes to the counts exchange, per record buffer: [0] = records of the call (written by the scan
+// kernel), [1] = generation of the buffer (it changes when the buffer is re-allocated), [2..9] = its cudaIpcMemHandle_t
+#define SB_META_WORDS   10
 
 // ------------------------------------------------------------------------------------------
 // bank
@@ -464,8 +472,9 @@ struct span_b200_bank_s
     size_t eout_bytes;
     unsigned int *counts;
     unsigned int *offsets;
-    unsigned long long *d_total;            // [2]: one per record buffer (wire mode alternates; else slot 0)
-    unsigned long long *h_total;            // [2], pinned
+    unsigned long long *d_total;            // [2][SB_META_WORDS]: per record buffer (wire mode alternates; else slot 0), see SB_META_WORDS
+    unsigned long long *h_total;            // [2][SB_META_WORDS], pinned: [0] comes back from the device, [1..] go up
+    unsigned long long wire_gen;
     span_b200_event_t *events;
     long long ev_cap;
     long long ev_cap_user;
@@ -559,9 +568,10 @@ static span_b200_bank_t *bank_alloc(span_b200_ctx_t *ctx, int det, int channels,
     // one count / offset per group of channels that share a warp in the sequencer (32; the super-tone sequencer: SB_ST_CPW)
     CKB(cudaMalloc(&b->counts, sizeof(unsigned int)*((C + SB_ST_CPW - 1)/SB_ST_CPW + 1)));
     CKB(cudaMalloc(&b->offsets, sizeof(unsigned int)*((C + SB_ST_CPW - 1)/SB_ST_CPW + 1)));
-    CKB(cudaMalloc(&b->d_total, 2*sizeof(unsigned long long)));
-    CKB(cudaMallocHost(&b->h_total, 2*sizeof(unsigned long long)));
-    b->h_total[0] = b->h_total[1] = 0;
+    CKB(cudaMalloc(&b->d_total, 2*SB_META_WORDS*sizeof(unsigned long long)));
+    CKB(cudaMemset(b->d_total, 0, 2*SB_META_WORDS*sizeof(unsigned long long)));
+    CKB(cudaMallocHost(&b->h_total, 2*SB_META_WORDS*sizeof(unsigned long long)));
+    memset(b->h_total, 0, 2*SB_META_WORDS*sizeof(unsigned long long));
     return b;
 }
 
@@ -1362,6 +1372,23 @@ static int rx_prepare(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
                 b->wire_cap[slot] = 0;
                 CK(cudaMalloc(&b->wire[slot], sizeof(span_b200_wire_event_t)*(size_t) want_ev));
                 b->wire_cap[slot] = want_ev;
+                // what another rank needs to read this buffer over NVLink (peer-copy transport of the gather)
+                cudaIpcMemHandle_t h;
+                static_assert(sizeof(h) == 8*sizeof(unsigned long long), "cudaIpcMemHandle_t is 64 bytes");
+                unsigned long long *hm = b->h_total + slot*SB_META_WORDS;
+                if (cudaIpcGetMemHandle(&h, b->wire[slot]) == cudaSuccess)
+                {
+                    hm[1] = ++b->wire_gen;
+                    memcpy(&hm[2], &h, sizeof(h));
+                }
+                else
+                {
+                    cudaGetLastError();
+                    hm[1] = 0;                  // no handle: only the NCCL transport can move these records
+                    memset(&hm[2], 0, sizeof(h));
+                }
+                CK(cudaMemcpyAsync(b->d_total + slot*SB_META_WORDS + 1, hm + 1, (SB_META_WORDS - 1)*sizeof(unsigned long long),
+                                   cudaMemcpyHostToDevice, st));
             }
             wire_out = b->wire[slot];
             out_cap = b->wire_cap[slot];
@@ -1575,10 +1602,11 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
         b->last_launches++;
         if (pass == 0)
         {
-            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, (b->channels + cpw - 1)/cpw, b->d_total + slot);
+            scan_counts<<<1, 1024, 0, st>>>(b->counts, b->offsets, (b->channels + cpw - 1)/cpw, b->d_total + slot*SB_META_WORDS);
             CK(cudaGetLastError());
             b->last_launches++;
-            CK(cudaMemcpyAsync(b->h_total + slot, b->d_total + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(b->h_total + slot*SB_META_WORDS, b->d_total + slot*SB_META_WORDS, sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, st));
         }
     }
     if (b->wire_on)
@@ -1713,7 +1741,7 @@ extern "C" int64_t span_b200_bank_event_count(span_b200_bank_t *b, int *overflow
     SB_DEVICE_CK(b->ctx->device);
     CK(cudaStreamSynchronize(b->last_stream));
     const int slot = (b->wire_on)  ?  b->slot  :  0;
-    long long total = (long long) b->h_total[slot];
+    long long total = (long long) b->h_total[slot*SB_META_WORDS];
     long long cap = b->ev_cap;
     if (b->wire_on)
         cap = (b->comm  &&  b->comm->rank == b->root)  ?  (b->comm->gather_cap[slot]/b->comm->nranks)  :  b->wire_cap[slot];
@@ -2026,7 +2054,7 @@ extern "C" int span_b200_bank_set_wire(span_b200_bank_t *b, int on, uint32_t cha
     }
     b->wire_on = (on != 0);
     b->channel_base = channel_base;
-    b->h_total[0] = b->h_total[1] = 0;
+    b->h_total[0] = b->h_total[SB_META_WORDS] = 0;
     b->slot = 0;
     return 0;
 }
@@ -2154,8 +2182,19 @@ extern "C" void span_b200_comm_destroy(span_b200_comm_t *cm)
         cudaStreamSynchronize(cm->stream);
     if (cm->nccl  &&  g_nccl.handle)
         g_nccl.CommDestroy(cm->nccl);
+    cudaFree(cm->d_sync);
     for (int i = 0;  i < 2;  i++)
     {
+        if (cm->peer_ptr[i])
+        {
+            for (int r = 0;  r < cm->nranks;  r++)
+            {
+                if (cm->peer_ptr[i][r])
+                    cudaIpcCloseMemHandle(cm->peer_ptr[i][r]);
+            }
+            delete[] cm->peer_ptr[i];
+            delete[] cm->peer_gen[i];
+        }
         cudaFree(cm->gather[i]);
         cudaFree(cm->d_counts[i]);
         if (cm->h_counts[i])
@@ -2188,11 +2227,20 @@ extern "C" span_b200_comm_t *span_b200_comm_create(span_b200_ctx_t *ctx, const u
     cm->rank = rank;
     cm->begun_slot = -1;
     cm->ended_slot = -1;
-    bool ok = cudaStreamCreateWithFlags(&cm->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // How the records travel: by default the root pulls them out of the ranks' buffers with its copy engines over
+    // NVLink (no SM of any GPU is used, the filter kernels are compute-bound); SPANDSP_B200_GATHER=nccl selects
+    // exact-count ncclSend / ncclRecv instead.  The counts and the completion are NCCL collectives either way.
+    const char *tr = getenv("SPANDSP_B200_GATHER");
+    cm->transport = (tr  &&  strcmp(tr, "nccl") == 0)  ?  SPAN_B200_GATHER_NCCL  :  SPAN_B200_GATHER_PEER_COPY;
+    bool ok = cudaStreamCreateWithFlags(&cm->stream, cudaStreamNonBlocking) == cudaSuccess
+              &&  cudaMalloc(&cm->d_sync, sizeof(unsigned long long)*(1 + nranks)) == cudaSuccess
+              &&  cudaMemset(cm->d_sync, 0, sizeof(unsigned long long)*(1 + nranks)) == cudaSuccess;
     for (int i = 0;  ok  &&  i < 2;  i++)
     {
-        ok = cudaMalloc(&cm->d_counts[i], sizeof(unsigned long long)*nranks) == cudaSuccess
-             &&  cudaMallocHost(&cm->h_counts[i], sizeof(unsigned long long)*nranks) == cudaSuccess
+        cm->peer_ptr[i] = new void *[nranks]();
+        cm->peer_gen[i] = new unsigned long long[nranks]();
+        ok = cudaMalloc(&cm->d_counts[i], sizeof(unsigned long long)*SB_META_WORDS*nranks) == cudaSuccess
+             &&  cudaMallocHost(&cm->h_counts[i], sizeof(unsigned long long)*SB_META_WORDS*nranks) == cudaSuccess
              &&  cudaEventCreateWithFlags(&cm->counts_ready[i], cudaEventDisableTiming) == cudaSuccess
              &&  cudaEventCreateWithFlags(&cm->done[i], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -2229,6 +2277,19 @@ extern "C" span_b200_comm_t *span_b200_comm_create(span_b200_ctx_t *ctx, const u
     }
     return cm;
 }
+
+extern "C" int span_b200_comm_set_transport(span_b200_comm_t *cm, int transport)
+{
+    if (cm == NULL  ||  (transport != SPAN_B200_GATHER_NCCL  &&  transport != SPAN_B200_GATHER_PEER_COPY))
+    {
+        sb_set_error("bad transport");
+        return -1;
+    }
+    cm->transport = transport;
+    return 0;
+}
+
+extern "C" int span_b200_comm_transport(const span_b200_comm_t *cm) { return cm->transport; }
 
 extern "C" int span_b200_comm_rank(const span_b200_comm_t *cm) { return cm->rank; }
 extern "C" int span_b200_comm_nranks(const span_b200_comm_t *cm) { return cm->nranks; }
@@ -2304,8 +2365,9 @@ extern "C" int span_b200_bank_gather_begin(span_b200_bank_t *b)
     SB_DEVICE_CK(b->ctx->device);
     const int slot = b->slot;
     CK(cudaStreamWaitEvent(cm->stream, b->emitted[slot], 0));
-    NK(nc->AllGather(b->d_total + slot, cm->d_counts[slot], 1, ncclUint64, cm->nccl, cm->stream));
-    CK(cudaMemcpyAsync(cm->h_counts[slot], cm->d_counts[slot], sizeof(unsigned long long)*cm->nranks, cudaMemcpyDeviceToHost, cm->stream));
+    NK(nc->AllGather(b->d_total + slot*SB_META_WORDS, cm->d_counts[slot], SB_META_WORDS, ncclUint64, cm->nccl, cm->stream));
+    CK(cudaMemcpyAsync(cm->h_counts[slot], cm->d_counts[slot], sizeof(unsigned long long)*SB_META_WORDS*cm->nranks, cudaMemcpyDeviceToHost,
+                       cm->stream));
     CK(cudaEventRecord(cm->counts_ready[slot], cm->stream));
     cm->begun_slot = slot;
     return 0;
@@ -2326,21 +2388,60 @@ extern "C" int64_t span_b200_bank_gather_end(span_b200_bank_t *b, int64_t *count
     const int slot = cm->begun_slot;
     CK(cudaEventSynchronize(cm->counts_ready[slot]));
     long long total = 0;
-    // a rank whose buffer overflowed sends what its buffer holds
+    const unsigned long long *meta = cm->h_counts[slot];
     const long long own_cap = (cm->rank == b->root)  ?  (cm->gather_cap[slot]/cm->nranks)  :  b->wire_cap[slot];
     for (int r = 0;  r < cm->nranks;  r++)
     {
         if (counts)
-            counts[r] = (int64_t) cm->h_counts[slot][r];
-        total += (long long) cm->h_counts[slot][r];
+            counts[r] = (int64_t) meta[r*SB_META_WORDS];
+        total += (long long) meta[r*SB_META_WORDS];
     }
-    long long own = (long long) cm->h_counts[slot][cm->rank];
+    long long own = (long long) meta[cm->rank*SB_META_WORDS];
     if (own > own_cap)
     {
         sb_set_error("gather: this rank's record buffer overflowed (%lld records, room for %lld)", own, own_cap);
         return -1;
     }
-    if (cm->rank == b->root)
+    if (cm->transport == SPAN_B200_GATHER_PEER_COPY)
+    {
+        if (cm->rank == b->root)
+        {
+            if (comm_gather_reserve(cm, slot, total, b->last_stream, own) != 0)
+                return -1;
+            long long off = own;
+            for (int r = 0;  r < cm->nranks;  r++)
+            {
+                const long long n = (long long) meta[r*SB_META_WORDS];
+                if (r == cm->rank  ||  n == 0)
+                    continue;
+                const unsigned long long gen = meta[r*SB_META_WORDS + 1];
+                if (gen == 0)
+                {
+                    sb_set_error("gather: rank %d exported no memory handle; use SPANDSP_B200_GATHER=nccl", r);
+                    return -1;
+                }
+                if (cm->peer_gen[slot][r] != gen)
+                {
+                    // that rank (re-)allocated its buffer: map the new one
+                    if (cm->peer_ptr[slot][r])
+                        CK(cudaIpcCloseMemHandle(cm->peer_ptr[slot][r]));
+                    cm->peer_ptr[slot][r] = NULL;
+                    cudaIpcMemHandle_t h;
+                    memcpy(&h, &meta[r*SB_META_WORDS + 2], sizeof(h));
+                    CK(cudaIpcOpenMemHandle(&cm->peer_ptr[slot][r], h, cudaIpcMemLazyEnablePeerAccess));
+                    cm->peer_gen[slot][r] = gen;
+                }
+                // the root's copy engine reads the rank's records over NVLink: exactly n records, behind the previous rank's
+                CK(cudaMemcpyAsync(cm->gather[slot] + off, cm->peer_ptr[slot][r], (size_t) n*sizeof(span_b200_wire_event_t),
+                                   cudaMemcpyDefault, cm->stream));
+                off += n;
+            }
+        }
+        // completion: a tiny collective behind the copies on the root's stream - a rank's buffer is free again when
+        // this has completed on that rank, because the root takes part only after its copies have finished
+        NK(nc->AllGather(cm->d_sync, cm->d_sync + 1, 1, ncclUint64, cm->nccl, cm->stream));
+    }
+    else if (cm->rank == b->root)
     {
         if (comm_gather_reserve(cm, slot, total, b->last_stream, own) != 0)
             return -1;
@@ -2348,7 +2449,7 @@ extern "C" int64_t span_b200_bank_gather_end(span_b200_bank_t *b, int64_t *count
         NK(nc->GroupStart());
         for (int r = 0;  r < cm->nranks;  r++)
         {
-            const long long n = (long long) cm->h_counts[slot][r];
+            const long long n = (long long) meta[r*SB_META_WORDS];
             if (r == cm->rank  ||  n == 0)
                 continue;
             NK(nc->Recv(cm->gather[slot] + off, (size_t) n*sizeof(span_b200_wire_event_t), ncclUint8, r, cm->nccl, cm->stream));

@@ -78,6 +78,8 @@ def lib():
         "span_b200_comm_create": (vp, [vp, vp, i32, i32, i32]),
         "span_b200_comm_destroy": (None, [vp]),
         "span_b200_comm_rank": (i32, [vp]),
+        "span_b200_comm_set_transport": (i32, [vp, i32]),
+        "span_b200_comm_transport": (i32, [vp]),
         "span_b200_comm_nranks": (i32, [vp]),
         "span_b200_comm_sync": (i32, [vp]),
         "span_b200_bank_attach_comm": (i32, [vp, vp, i32]),
@@ -537,6 +539,15 @@ class Comm:
     def sync(self):
         if lib().span_b200_comm_sync(self.h) != 0:
             raise EngineError(_err())
+
+    def set_transport(self, which):
+        """'peer_copy' (the root's copy engines pull the records over NVLink) or 'nccl' (exact-count send / recv)."""
+        if lib().span_b200_comm_set_transport(self.h, {"nccl": 0, "peer_copy": 1}[which]) != 0:
+            raise EngineError(_err())
+
+    @property
+    def transport(self):
+        return ("nccl", "peer_copy")[lib().span_b200_comm_transport(self.h)]
 
     def close(self):
         if self.h:

@@ -13,7 +13,7 @@ N = 16320
 CALL = 4080
 
 
-def worker(rank, world, uid, tmp):
+def worker(rank, world, uid, tmp, transport):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -27,6 +27,8 @@ def worker(rank, world, uid, tmp):
     bank.dtmf_realtime(True)
     bank.set_wire(True, rank*NCH)
     comm = engine.Comm(ctx, uid, world, rank, max_ctas=2)
+    comm.set_transport(transport)
+    assert comm.transport == transport
     bank.attach_comm(comm, 0)
     d = torch.from_numpy(mine).cuda()
     torch.cuda.synchronize()
@@ -54,14 +56,16 @@ def worker(rank, world, uid, tmp):
     ctx.close()
 
 
-def test_gather_two_ranks(tmp_path, engine_lib):
+@pytest.mark.parametrize("transport", ["peer_copy", "nccl"])
+def test_gather_two_ranks(tmp_path, engine_lib, transport):
+    """peer_copy: the root's copy engines read each rank's records over NVLink (CUDA IPC); nccl: exact-count send / recv."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     import synth
     uid = engine_lib.Comm.unique_id()
-    mp.spawn(worker, args=(2, uid, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(worker, args=(2, uid, str(tmp_path), transport), nprocs=2, join=True)
     gathered = np.load(os.path.join(str(tmp_path), "gathered.npy"))
     counts = np.load(os.path.join(str(tmp_path), "counts.npy"))
     # reference: the two shards as two banks on this process's GPU, call by call; the gathered buffer must hold the root's

@@ -1,0 +1,25 @@
+#!/bin/bash
+# two GPUs: both transports of the in-library gather (test), bench at N = 2 with each
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_gather2.py -x -q -m gpu 2>&1 | tail -5
+for mode in "peer_copy 4" "nccl 16" ; do
+set -- $mode
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --gather $1 --nccl-ctas $2 --no-e2e --no-cpu > gpurun_out/r02_bench_n2_$1.json 2> gpurun_out/r02_bench_n2_$1.err; tail -3 gpurun_out/r02_bench_n2_$1.err
+python - $1 <<'PY'
+import json, sys
+try:
+    d=json.loads(open('gpurun_out/r02_bench_n2_%s.json' % sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], 'N2 value', d['value'], 'ms', d['ms_per_step'], 'kern', d['roofline']['kernel_ms'], 'parity', d['parity_check']['mismatches'], d['parity_check']['events'])
+except Exception as e:
+    print('bench parse failed', e)
+PY
+done
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; tail -3 gpurun_out/r02_bench_n2.err
+python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/r02_bench_n2.json').read().strip().splitlines()[-1])
+    print('full N2 value', d['value'], 'ms', d['ms_per_step'], 'kern', d['roofline']['kernel_ms'], 'e2e', d['e2e']['value'], 'parity', d['parity_check'])
+except Exception as e:
+    print('bench parse failed', e)
+PY
