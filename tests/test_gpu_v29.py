@@ -138,3 +138,38 @@ def test_v29_old_train_restart(gpu_ctx, engine_lib, oracles):
     assert len(bits) == len(r["bits"]) and (bits == r["bits"]).all()
     assert len(syms) == len(r["syms"]) and close(syms["re"], r["syms"]["re"]) and close(syms["im"], r["syms"]["im"])
     bank.close()
+
+
+def test_v29_packed_output(gpu_ctx, engine_lib):
+    """The bulk read-back (data bits 32 to a word + status reports as {position, value}) holds exactly the put_bit
+    sequence that span_b200_v29_bank_bits() rebuilds, for every channel of a bank whose channels are at different points
+    (signal, noise only, carrier drop); and the four-lane kernel equals the golden vectors on a channel count that
+    leaves lanes without a channel (shadow lanes)."""
+    import torch
+    g = np.load(GOLD)
+    rows = [np.ascontiguousarray(g["amp%d" % k]) for k in (1, 0, 1)]
+    n = min(len(r) for r in rows)
+    nch = 13                                   # 13 receivers: one full group of 8 and a partial one
+    amp = np.stack([rows[c % 3][:n] for c in range(nch)])
+    amp[5] = (np.random.default_rng(1).normal(0, 30, n)).astype(np.int16)        # noise only
+    amp[7, n//2:] = 0                                                             # carrier drops half way
+    bank = engine_lib.V29Bank(gpu_ctx, nch, 9600)
+    d = torch.from_numpy(amp).cuda()
+    torch.cuda.synchronize()
+    bank.rx_device(d.data_ptr(), n, n)
+    words, nb, status, ns = bank.output_packed()
+    for c in range(nch):
+        seq = bank.bits(c)
+        assert len(seq) == nb[c]
+        st = [(int(status[c, i, 0]), int(status[c, i, 1])) for i in range(ns[c])]
+        assert st == [(i, int(v)) for i, v in enumerate(seq) if v < 0], c
+        data = seq[seq >= 0]
+        w = words[c]
+        unpacked = ((w[np.arange(len(data)) >> 5] >> (np.arange(len(data)) & 31).astype(np.uint32)) & 1).astype(np.int8)
+        assert (unpacked == data).all(), c
+    assert -1 in bank.bits(7) and len(bank.bits(5)) == 0
+    for c in (0, 3, 12):
+        k = (1, 0, 1)[c % 3]
+        if len(rows[c % 3]) == n:
+            assert (bank.bits(c) == g["bits%d" % k]).all(), c
+    bank.close()
