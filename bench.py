@@ -771,69 +771,85 @@ def main():
         barrier()
 
     # ---- end-to-end arm: pinned host input through span_b200_bank_rx_host ----------------------
+    def all_ok(ok):
+        """Every rank managed (a failed allocation on one rank must not leave the others waiting in a collective)."""
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     e2e = None
     if not args.no_e2e:
         if comm is not None:
             comm.sync()
-        h_amp, h_arr = pinned_like(torch, ctx, d_amp, args.numa)
         nev_cap = C_ * (T // 102 // 2 + 1)
-        h_events_t = torch.empty((nev_cap, 3), dtype=torch.int32, pin_memory=True)      # pinned: D2H at link speed
-        h_events = h_events_t.numpy().view(engine.WIRE_DTYPE).reshape(-1)
-        bank.reset()
-        if args.realtime:
-            bank.dtmf_realtime(True)
-        e2e_steps = max(2, min(args.steps, 5))
-
-        def step_host():
-            bank.rx_host((h_amp.data_ptr(), T), stream, samples=T)
-            return len(bank.events_wire(out=h_events))
-
-        for _ in range(2):
-            nev = step_host()
-        ems, nev = time_steps_host(torch, step_host, e2e_steps, barrier)
-        t = torch.tensor([ems], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ems = float(t.item())
-        e2e = {"value": C_ * world * T * e2e_steps / (ems / 1e3) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(C_ * T * 2), "d2h_bytes_per_step": int(nev * 12 + 8),
-               "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
-               "path": "span_b200_bank_rx_host (pinned int16 [channel][sample], copy pipelined with the kernels over channel ranges) "
-                       "+ span_b200_bank_events_wire (12-byte records)",
-               "numa": {"gpu_node": ctx.numa_node, "staging": "span_b200_host_alloc (GPU's node)" if h_arr is not None else "cudaHostAlloc (default policy)"}}
-        del h_amp
-        if h_arr is not None:
-            ctx.host_free(h_arr)
-        # ---- same, with 8-bit u-law input (G.711 expand fused into the kernel load).
-        # Reported beside e2e, not instead of it: the reference API takes int16.
-        gpath = os.path.join(ROOT, "tests", "golden", "g711_golden.npz")
-        if os.path.exists(gpath) and not args.no_g711:
-            enc = torch.from_numpy(np.load(gpath)["encode_ulaw"]).to(dev)
-            h_u8 = torch.empty((C_, T), dtype=torch.uint8, pin_memory=True)
-            for c0 in range(0, C_, 2048):
-                c1 = min(C_, c0 + 2048)
-                h_u8[c0:c1].copy_(enc[(d_amp[c0:c1].to(torch.int32) + 32768).long()])
-            torch.cuda.synchronize()
-            del enc
+        h_amp = h_arr = h_events = None
+        err = None
+        try:
+            h_amp, h_arr = pinned_like(torch, ctx, d_amp, args.numa)
+            h_events_t = torch.empty((nev_cap, 3), dtype=torch.int32, pin_memory=True)      # pinned: D2H at link speed
+            h_events = h_events_t.numpy().view(engine.WIRE_DTYPE).reshape(-1)
+        except Exception as e:  # noqa: BLE001
+            err = "%s: %s" % (type(e).__name__, str(e).splitlines()[0])
+        if not all_ok(err is None):
+            e2e = {"error": "pinned host staging could not be allocated on every rank (%s)" % (err or "another rank")}
+        else:
             bank.reset()
             if args.realtime:
                 bank.dtmf_realtime(True)
+            e2e_steps = max(2, min(args.steps, 5))
 
-            def step_host_g711():
-                bank.rx_host_g711((h_u8.data_ptr(), T), False, stream, samples=T)
+            def step_host():
+                bank.rx_host((h_amp.data_ptr(), T), stream, samples=T)
                 return len(bank.events_wire(out=h_events))
 
             for _ in range(2):
-                nev8 = step_host_g711()
-            gms, nev8 = time_steps_host(torch, step_host_g711, e2e_steps, barrier)
-            t = torch.tensor([gms], dtype=torch.float64, device=dev)
+                nev = step_host()
+            ems, nev = time_steps_host(torch, step_host, e2e_steps, barrier)
+            t = torch.tensor([ems], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            gms = float(t.item())
-            e2e["g711_ulaw"] = {"value": C_ * world * T * e2e_steps / (gms / 1e3) / 1e6, "unit": "Msamples/s",
-                                "h2d_bytes_per_step": int(C_ * T), "d2h_bytes_per_step": int(nev8 * 12 + 8),
-                                "ms_per_step": gms / e2e_steps, "path": "span_b200_bank_rx_host_g711 (pinned u-law bytes)"}
-            del h_u8
+            ems = float(t.item())
+            e2e = {"value": C_ * world * T * e2e_steps / (ems / 1e3) / 1e6, "unit": "Msamples/s",
+                   "h2d_bytes_per_step": int(C_ * T * 2), "d2h_bytes_per_step": int(nev * 12 + 8),
+                   "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
+                   "path": "span_b200_bank_rx_host (pinned int16 [channel][sample], copy pipelined with the kernels over channel ranges) "
+                           "+ span_b200_bank_events_wire (12-byte records)",
+                   "numa": {"gpu_node": ctx.numa_node, "staging": "span_b200_host_alloc (GPU's node)" if h_arr is not None else "cudaHostAlloc (default policy)"}}
+            # ---- same, with 8-bit u-law input (G.711 expand fused into the kernel load; SURVEY 8f rank 1).
+            # Reported beside e2e, not instead of it: the reference API takes int16.  The u-law bytes go into the first half
+            # of the staging buffer the int16 arm used (no second pinned allocation).
+            gpath = os.path.join(ROOT, "tests", "golden", "g711_golden.npz")
+            if os.path.exists(gpath) and not args.no_g711:
+                enc = torch.from_numpy(np.load(gpath)["encode_ulaw"]).to(dev)
+                h_u8 = h_amp.view(torch.uint8).reshape(-1)[: C_ * T].view(C_, T)
+                for c0 in range(0, C_, 2048):
+                    c1 = min(C_, c0 + 2048)
+                    h_u8[c0:c1].copy_(enc[(d_amp[c0:c1].to(torch.int32) + 32768).long()])
+                torch.cuda.synchronize()
+                del enc
+                bank.reset()
+                if args.realtime:
+                    bank.dtmf_realtime(True)
+
+                def step_host_g711():
+                    bank.rx_host_g711((h_u8.data_ptr(), T), False, stream, samples=T)
+                    return len(bank.events_wire(out=h_events))
+
+                for _ in range(2):
+                    nev8 = step_host_g711()
+                gms, nev8 = time_steps_host(torch, step_host_g711, e2e_steps, barrier)
+                t = torch.tensor([gms], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                gms = float(t.item())
+                e2e["g711_ulaw"] = {"value": C_ * world * T * e2e_steps / (gms / 1e3) / 1e6, "unit": "Msamples/s",
+                                    "h2d_bytes_per_step": int(C_ * T), "d2h_bytes_per_step": int(nev8 * 12 + 8),
+                                    "ms_per_step": gms / e2e_steps, "path": "span_b200_bank_rx_host_g711 (pinned u-law bytes)"}
+                del h_u8
+        del h_amp
+        if h_arr is not None:
+            ctx.host_free(h_arr)
 
     if rank != 0:
         if comm is not None:
