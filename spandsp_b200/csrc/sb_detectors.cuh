@@ -955,58 +955,46 @@ struct StSeqArgs
     int *rotation;
     unsigned char *pending;             // one-bin quirk: a zero-energy re-chunk is owed at the next call
     int want_segments;
+    void *log;                          // [groups][SB_ST_LOG] records kept by the count pass (wire or 24-byte, as the call asks), or NULL
 };
 
-// The eleven segment slots of one channel (src/spandsp/private/super_tone_rx.h:57: segments[11]); slot 10 holds the
-// block pair seen last, slot 9 the segment in progress.  Kept in shared memory, [field][thread]: the cadence tests index
-// them with run-time positions, which registers cannot do.
+// The segment history of one channel (src/spandsp/private/super_tone_rx.h:57: segments[11]); slot 10 holds the block
+// pair seen last, slot 9 the segment in progress - those two live in registers in the sequencer - and slots 0..8 the
+// finished segments.  Slots 0..9 are kept in shared memory, [field][thread], as a ring of 16: the cadence tests index
+// them with run-time positions, which registers cannot do, and the reference's "shift everything down by one" becomes
+// a step of the ring's head.
 struct StSegs
 {
-    int *base;                          // this thread's column of int [33][128]
+    int *base;                          // this thread's column of int [48][128]
+    int head;
 
-    __device__ __forceinline__ int &f1(int i) const { return base[(3*i)*128]; }
-    __device__ __forceinline__ int &f2(int i) const { return base[(3*i + 1)*128]; }
-    __device__ __forceinline__ int &dur(int i) const { return base[(3*i + 2)*128]; }
+    __device__ __forceinline__ int &f1(int i) const { return base[(3*((head + i) & 15))*128]; }
+    __device__ __forceinline__ int &f2(int i) const { return base[(3*((head + i) & 15) + 1)*128]; }
+    __device__ __forceinline__ int &dur(int i) const { return base[(3*((head + i) & 15) + 2)*128]; }
 };
 
-// src/super_tone_rx.c:164-228
+// src/super_tone_rx.c:164-228, the two forms a tone in progress is tested with (rotation >= 0)
 __device__ __forceinline__ int st_test_cadence(const int4 *pattern, int steps, const StSegs &t, int rotation)
 {
-    int j;
+    int j = 0;
 
-    if (rotation >= 0)
+    if (steps < 0)
     {
-        j = 0;
-        if (steps < 0)
-        {
-            steps = -steps;
-            j = (rotation + steps - 2)%steps;
-            const int4 p = pattern[j];
-            if (p.x != t.f1(8)  ||  p.y != t.f2(8))
-                return 0;
-            if (p.z > t.dur(8)*128  ||  p.w < t.dur(8)*128)
-                return 0;
-        }
-        if (steps)
-            j = (rotation + steps - 1)%steps;
+        steps = -steps;
+        j = (rotation + steps - 2)%steps;
         const int4 p = pattern[j];
-        if (p.x != t.f1(9)  ||  p.y != t.f2(9))
+        if (p.x != t.f1(8)  ||  p.y != t.f2(8))
             return 0;
-        if (p.w < t.dur(9)*128)
+        if (p.z > t.dur(8)*128  ||  p.w < t.dur(8)*128)
             return 0;
     }
-    else
-    {
-        for (int i = 0;  i < steps;  i++)
-        {
-            j = i + 10 - steps;
-            const int4 p = pattern[i];
-            if (p.x != t.f1(j)  ||  p.y != t.f2(j))
-                return 0;
-            if (p.z > t.dur(j)*128  ||  p.w < t.dur(j)*128)
-                return 0;
-        }
-    }
+    if (steps)
+        j = (rotation + steps - 1)%steps;
+    const int4 p = pattern[j];
+    if (p.x != t.f1(9)  ||  p.y != t.f2(9))
+        return 0;
+    if (p.w < t.dur(9)*128)
+        return 0;
     return 1;
 }
 
@@ -1015,17 +1003,24 @@ __device__ __forceinline__ int st_test_cadence(const int4 *pattern, int steps, c
 #define SB_ST_CPC           (4*SB_ST_CPW)   // channels per CTA (four warps)
 #define SB_ST_SMEM_ELEMENTS 160         // cadence template elements kept in shared memory (larger descriptors read them from global memory)
 #define SB_ST_SMEM_TONES    64
+#define SB_ST_LOG           (32*SB_ST_CPW)  // records per group of SB_ST_CPW channels the count pass keeps for the emit pass
 
 // src/super_tone_rx.c:366-448.  The cadence logic is a chain of dependent, data-dependent branches per block: what it
-// costs is latency, and a warp pays for every path any of its channels takes.  So a warp carries only SB_ST_CPW
-// channels (lanes 0..7; the bank then spreads over four times the warps, which is what hides the latency: there are
-// only tens of thousands of channels), the per-channel history, the cadence templates and - where the bank has one
-// block phase and the rows are 16-byte aligned - tiles of the decision codes live in shared memory.
+// costs is latency, and a warp pays for every path any of its channels takes.  So
+// - a warp carries only SB_ST_CPW channels (lanes 0..7; the bank then spreads over four times the warps, which is what
+//   hides the latency: there are only tens of thousands of channels);
+// - the per-channel history, the cadence templates and - where the bank has one block phase and the rows are 16-byte
+//   aligned - tiles of the decision codes live in shared memory;
+// - the cadence tests, which the reference runs every block, are run only at the blocks where their outcome can change
+//   (see keep_until / scan_at below);
+// - the count pass keeps the records it counts (up to SB_ST_LOG per group, in s.log) and, when they all fitted, commits
+//   the channel state itself; the emit pass then only moves those records to their final places.  A group with more
+//   records than that is walked again by the emit pass, from the untouched state, as in the other sequencers.
 // Event order: (group of SB_ST_CPW channels, block, channel).
 template <bool EMIT>
 __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
 {
-    __shared__ int seg[33*128];
+    __shared__ int seg[48*128];
     __shared__ __align__(16) unsigned short tile[2][SB_ST_TILE*SB_ST_CPC];
     __shared__ int4 s_elements[SB_ST_SMEM_ELEMENTS];
     __shared__ int s_tone_segs[SB_ST_SMEM_TONES];
@@ -1034,8 +1029,31 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     const int warp = threadIdx.x >> 5;
     const int wg = blockIdx.x*4 + warp;                         // group of SB_ST_CPW channels
     const int gc = wg*SB_ST_CPW + lane;
-    const bool live = (lane < SB_ST_CPW  &&  gc < s.q.channels);
-    const int c = (live)  ?  gc  :  (s.q.channels - 1);
+    const bool group_there = (wg*SB_ST_CPW < s.q.channels);
+    const size_t record = (s.q.wire)  ?  sizeof(span_b200_wire_event_t)  :  sizeof(span_b200_event_t);
+    bool walk = true;
+    if (EMIT  &&  s.log)
+    {
+        // Groups whose records the count pass kept: move them.  The CTA walks only if one of its groups overflowed
+        // (its barriers need all four warps), and then only that group's lanes are live.
+        const unsigned int count = (group_there)  ?  s.q.counts[wg]  :  0;
+        walk = (count > SB_ST_LOG);
+        if (!walk  &&  count)
+        {
+            const unsigned int base = s.q.offsets[wg];
+            const unsigned int *src = (const unsigned int *) ((const char *) s.log + (size_t) wg*SB_ST_LOG*record);
+            unsigned int *dst = (s.q.wire)  ?  (unsigned int *) (s.q.wire + base)  :  (unsigned int *) (s.q.events + base);
+            const unsigned int words_per = (unsigned int) (record/4);
+            const long long room = s.q.capacity - (long long) base;
+            const unsigned int fit = (room <= 0)  ?  0  :  ((room < (long long) count)  ?  (unsigned int) room  :  count);
+            for (unsigned int k = lane;  k < fit*words_per;  k += 32)
+                dst[k] = src[k];
+        }
+        if (!__syncthreads_or(walk))
+            return;
+    }
+    const bool live = (walk  &&  lane < SB_ST_CPW  &&  gc < s.q.channels);
+    const int c = (lane < SB_ST_CPW  &&  gc < s.q.channels)  ?  gc  :  (s.q.channels - 1);
     const int col_in_cta = warp*SB_ST_CPW + ((lane < SB_ST_CPW)  ?  lane  :  0);
     const int B = 128;
     const size_t C = s.q.channels;
@@ -1043,10 +1061,22 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
     StSegs t;
     t.base = seg + threadIdx.x;
+    t.head = 0;
+    // slots 9 (segment in progress) and 10 (pair seen last) are touched by every block: registers
+    int f1_9 = 0;
+    int f2_9 = 0;
+    int dur_9 = 0;
+    int f1_10 = 0;
+    int f2_10 = 0;
     if (lane < SB_ST_CPW)
     {
-        for (int i = 0;  i < 33;  i++)
+        for (int i = 0;  i < 27;  i++)
             seg[i*128 + threadIdx.x] = s.segments[(size_t) i*C + c];
+        f1_9 = s.segments[(size_t) 27*C + c];
+        f2_9 = s.segments[(size_t) 28*C + c];
+        dur_9 = s.segments[(size_t) 29*C + c];
+        f1_10 = s.segments[(size_t) 30*C + c];
+        f2_10 = s.segments[(size_t) 31*C + c];
     }
     // templates: shared memory copies where they fit
     const bool small = (s.t.tones <= SB_ST_SMEM_TONES  &&  s.t.total_elements <= SB_ST_SMEM_ELEMENTS);
@@ -1068,7 +1098,49 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     int detected = s.detected_tone[c];
     int rotation = s.rotation[c];
     int pending = s.pending[c];
+
+    // Record output.  Emit pass: the usual warp-aggregated sink.  Count pass: the same aggregation, into the group's
+    // piece of the log, so that the records already lie in their final order.
     EventSink<EMIT> sink(s.q, wg, SB_ST_CPW);
+    SeqCommon lq = s.q;
+    if (!EMIT)
+    {
+        lq.capacity = (s.log)  ?  SB_ST_LOG  :  0;
+        if (s.q.wire)
+            lq.wire = (span_b200_wire_event_t *) s.log + (size_t) wg*SB_ST_LOG;
+        else
+            lq.events = (span_b200_event_t *) s.log + (size_t) wg*SB_ST_LOG;
+    }
+    unsigned int logged = 0;
+    const unsigned int lt = (1u << lane) - 1u;
+    auto push = [&](bool has, int blk, int kind, int a, int b, int cc)
+    {
+        if (EMIT)
+        {
+            sink.push(has, c, blk, kind, a, b, cc);
+        }
+        else
+        {
+            const unsigned int m = __ballot_sync(0xFFFFFFFFu, has);
+            if (has)
+                put_event(lq, logged + __popc(m & lt), c, blk, kind, a, b, cc);
+            logged += __popc(m);
+        }
+    };
+
+    auto spill = [&]()
+    {
+        t.f1(9) = f1_9;
+        t.f2(9) = f2_9;
+        t.dur(9) = dur_9;
+    };
+    // While a block only lengthens the segment in progress, the outcome of the cadence tests is a function of that
+    // one duration.  keep_until: the largest duration for which the detected tone's test still passes (-1: not
+    // worked out yet); scan_at: the smallest duration at which the search over all tones can succeed at all.  Both
+    // are recomputed whenever the history shifts, a tone is found or lost, and at the start of every call, so the
+    // tests the reference runs every block are run here only at the blocks where their result can change.
+    int keep_until = -1;
+    int scan_at = 0;
 
     // One super_tone_chunk() step.  It can raise up to three callbacks, in this order: tone lost,
     // segment report, tone found.  They are recorded here and pushed by all lanes together.
@@ -1088,16 +1160,17 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         seg_f1 = seg_f2 = seg_ms = found_id = 0;
         if (!run)
             return;
-        if (k1 != t.f1(10)  ||  k2 != t.f2(10))
+        if (k1 != f1_10  ||  k2 != f2_10)
         {
-            t.f1(10) = k1;
-            t.f2(10) = k2;
-            t.dur(9)++;
+            f1_10 = k1;
+            f2_10 = k2;
+            dur_9++;
         }
-        else if (k1 != t.f1(9)  ||  k2 != t.f2(9))
+        else if (k1 != f1_9  ||  k2 != f2_9)
         {
             if (detected >= 0)
             {
+                spill();
                 if (!st_test_cadence(elements + tone_first[detected], -tone_segs[detected], t, rotation++))
                 {
                     detected = -1;
@@ -1107,45 +1180,93 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             if (s.want_segments)
             {
                 e_seg = true;
-                seg_f1 = t.f1(9);
-                seg_f2 = t.f2(9);
-                seg_ms = t.dur(9)*128/8;
+                seg_f1 = f1_9;
+                seg_f2 = f2_9;
+                seg_ms = dur_9*128/8;
             }
-            for (int i = 0;  i < 9;  i++)
-            {
-                t.f1(i) = t.f1(i + 1);
-                t.f2(i) = t.f2(i + 1);
-                t.dur(i) = t.dur(i + 1);
-            }
-            t.f1(9) = k1;
-            t.f2(9) = k2;
-            t.dur(9) = 1;
+            // segments[i] = segments[i + 1] for i = 0..8 (src/super_tone_rx.c:409-410): the ring steps, the finished
+            // segment becomes slot 8
+            t.head = (t.head + 1) & 15;
+            t.f1(8) = f1_9;
+            t.f2(8) = f2_9;
+            t.dur(8) = dur_9;
+            f1_9 = k1;
+            f2_9 = k2;
+            dur_9 = 1;
+            keep_until = -1;
+            scan_at = 0;
         }
         else
         {
             if (detected >= 0)
             {
-                if (!st_test_cadence(elements + tone_first[detected], tone_segs[detected], t, rotation))
+                if (keep_until < 0)
+                {
+                    // st_test_cadence(pattern, steps > 0, rotation >= 0) (src/super_tone_rx.c:187-196) as a bound
+                    const int steps = tone_segs[detected];
+                    const int j = (steps)  ?  ((rotation + steps - 1)%steps)  :  0;
+                    const int4 p = elements[tone_first[detected] + j];
+                    keep_until = (p.x != f1_9  ||  p.y != f2_9  ||  p.w < 0)  ?  0  :  (p.w >> 7);
+                }
+                if (dur_9 > keep_until)
                 {
                     detected = -1;
                     e_lost = true;
+                    scan_at = 0;
                 }
             }
-            t.dur(9)++;
+            dur_9++;
         }
-        if (detected < 0)
+        if (detected < 0  &&  dur_9 >= scan_at)
         {
+            // The search of src/super_tone_rx.c:425-437 (st_test_cadence with rotation < 0, src/super_tone_rx.c:
+            // 198-212), tones in order, first match wins.  The newest segment is compared first (it is the one that
+            // rules most tones out; the test is a conjunction, so the order does not matter).  A tone whose only
+            // failing check is "segment in progress still too short" names the duration at which to look again.
+            spill();
+            int next = 0x7FFFFFFF;
             for (int j = 0;  j < ntones;  j++)
             {
-                if (st_test_cadence(elements + tone_first[j], tone_segs[j], t, -1))
+                const int4 *pattern = elements + tone_first[j];
+                const int steps = tone_segs[j];
+                bool ok = true;
+                bool short_yet = false;
+                int need = 0;
+                for (int i = steps - 1;  i >= 0  &&  ok;  i--)
+                {
+                    const int k = i + 10 - steps;
+                    const int4 p = pattern[i];
+                    const int d = t.dur(k)*128;
+                    if (p.x != t.f1(k)  ||  p.y != t.f2(k)  ||  p.w < d)
+                    {
+                        ok = false;
+                    }
+                    else if (p.z > d)
+                    {
+                        if (k == 9)
+                        {
+                            short_yet = true;
+                            need = (p.z + 127) >> 7;
+                        }
+                        else
+                        {
+                            ok = false;
+                        }
+                    }
+                }
+                if (ok  &&  !short_yet)
                 {
                     detected = j;
                     rotation = 0;
                     e_found = true;
                     found_id = j;
+                    keep_until = -1;
                     break;
                 }
+                if (ok  &&  need < next)
+                    next = need;
             }
+            scan_at = next;
         }
     };
 
@@ -1154,9 +1275,9 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         // (most blocks raise nothing in any channel of the warp: one vote instead of three)
         if (__any_sync(0xFFFFFFFFu, e_lost  ||  e_seg  ||  e_found))
         {
-            sink.push(e_lost, c, blk, SPAN_B200_EV_TONE, -1, -10, 0);
-            sink.push(e_seg, c, blk, SPAN_B200_EV_SEGMENT, seg_f1, seg_f2, seg_ms);
-            sink.push(e_found, c, blk, SPAN_B200_EV_TONE, found_id, -10, 0);
+            push(e_lost, blk, SPAN_B200_EV_TONE, -1, -10, 0);
+            push(e_seg, blk, SPAN_B200_EV_SEGMENT, seg_f1, seg_f2, seg_ms);
+            push(e_found, blk, SPAN_B200_EV_TONE, found_id, -10, 0);
         }
     };
 
@@ -1239,11 +1360,26 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             one_block(b, run, code);
         }
     }
-    sink.finish(wg);
-    if (EMIT  &&  live)
+    bool commit = EMIT;
+    if (!EMIT)
     {
-        for (int i = 0;  i < 33;  i++)
-            s.segments[(size_t) i*C + c] = seg[i*128 + threadIdx.x];
+        if (lane == 0  &&  group_there)
+            s.q.counts[wg] = logged;
+        commit = (s.log != NULL  &&  logged <= SB_ST_LOG);
+    }
+    if (commit  &&  live)
+    {
+        for (int i = 0;  i < 9;  i++)
+        {
+            s.segments[(size_t) (3*i)*C + c] = t.f1(i);
+            s.segments[(size_t) (3*i + 1)*C + c] = t.f2(i);
+            s.segments[(size_t) (3*i + 2)*C + c] = t.dur(i);
+        }
+        s.segments[(size_t) 27*C + c] = f1_9;
+        s.segments[(size_t) 28*C + c] = f2_9;
+        s.segments[(size_t) 29*C + c] = dur_9;
+        s.segments[(size_t) 30*C + c] = f1_10;
+        s.segments[(size_t) 31*C + c] = f2_10;
         s.detected_tone[c] = detected;
         s.rotation[c] = rotation;
         s.pending[c] = (unsigned char) pending;

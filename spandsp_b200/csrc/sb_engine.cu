@@ -458,6 +458,7 @@ struct span_b200_bank_s
     int *detected;
     int *rotation;
     unsigned char *pending;
+    void *st_log;                       // [groups][SB_ST_LOG] records the super-tone count pass keeps for the emit pass
     int *d_tone_segs;
     int *d_tone_first;
     int4 *d_elements;
@@ -806,6 +807,7 @@ extern "C" span_b200_bank_t *span_b200_super_tone_bank_create(span_b200_ctx_t *c
     CKB(cudaMalloc(&b->detected, sizeof(int)*C));
     CKB(cudaMalloc(&b->rotation, sizeof(int)*C));
     CKB(cudaMalloc(&b->pending, C));
+    CKB(cudaMalloc(&b->st_log, (size_t) ((C + SB_ST_CPW - 1)/SB_ST_CPW)*SB_ST_LOG*sizeof(span_b200_event_t)));
     CKB(cudaMalloc(&b->d_tone_segs, sizeof(int)*(desc->tones + 1)));
     CKB(cudaMalloc(&b->d_tone_first, sizeof(int)*(desc->tones + 1)));
     CKB(cudaMalloc(&b->d_elements, sizeof(int4)*(elements.size() + 1)));
@@ -848,6 +850,7 @@ extern "C" void span_b200_bank_destroy(span_b200_bank_t *b)
     cudaFree(b->detected);
     cudaFree(b->rotation);
     cudaFree(b->pending);
+    cudaFree(b->st_log);
     cudaFree(b->d_tone_segs);
     cudaFree(b->d_tone_first);
     cudaFree(b->d_elements);
@@ -1590,6 +1593,7 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
                 s.rotation = b->rotation;
                 s.pending = b->pending;
                 s.want_segments = b->want_segments;
+                s.log = b->st_log;
                 const int stgrid = (b->channels + SB_ST_CPC - 1)/SB_ST_CPC;
                 if (pass == 0)
                     super_tone_sequencer<false><<<stgrid, 128, 0, st>>>(s);

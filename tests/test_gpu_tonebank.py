@@ -353,3 +353,39 @@ def test_large_roundtrip_properties(gpu_ctx, engine_lib, torch_mod):
     order = np.argsort(first[:, 0], kind="stable")      # engine order is (group of 32, block, channel)
     assert [tuple(r) for r in first[order].tolist()] == got
     bank.close()
+
+
+@pytest.mark.parametrize("wire", [False, True])
+def test_super_tone_dense_events(gpu_ctx, engine_lib, torch_mod, port, wire):
+    """Many records per call: the super-tone count pass keeps up to SB_ST_LOG (256) records per group of 8 channels
+    for the emit pass; groups with more are walked again.  Channels 8..15 and 29..36 change segment every 40 ms
+    (hundreds of segment reports in one call), the others follow ordinary cadences - so one CTA holds both kinds of
+    group - and everything must still equal the reference record for record, across two calls (state carried)."""
+    torch = torch_mod
+    rng = np.random.default_rng(77)
+    tones = synth.random_tones(rng, nfreqs=6, ntones=6)
+    freqs = sorted({e[0] for t in tones for e in t if e[0]})
+    slow = [[(e[0], e[1], -12, (e[2] + e[3]) // 2) for e in t] for t in tones]
+    fast = [[(freqs[0], 0, -12, 40), (0, 0, -12, 40), (freqs[1], freqs[2], -12, 48), (0, 0, -12, 32)]]
+    amp = synth.cadence_channels(37, 48000, slow, seed=3)
+    dense = synth.cadence_channels(16, 48000, fast, seed=4)
+    amp[8:16] = dense[:8]
+    amp[29:37] = dense[8:]
+    p = po.make_params(po.DET_SUPER_TONE, po.MODE_SEGMENTS, 24000, tones=tones)
+    ev, fin, _ = port.run(p, amp)
+    assert max(len(e) for e in ev[8:16]) > 100
+    bank = engine_lib.Bank.super_tone(gpu_ctx, 37, tones, want_segments=True)
+    if not wire:
+        check(bank, amp, 24000, oracle_rows(ev, False), torch)
+    else:
+        bank.set_wire(True, 0)
+        d = torch.from_numpy(amp).cuda()
+        rows = []
+        for pos in (0, 24000):
+            bank.rx_device(d.data_ptr() + 2*pos, 48000, 24000)
+            ch, blk, kind, a, b, c = engine_lib.wire_unpack(bank.events_wire())
+            rows += [(int(ch[i]), int(kind[i]), int(a[i]), int(b[i]), int(c[i])) for i in range(len(ch))]
+        exp = [(c, int(e["kind"]), int(e["a"]), int(e["b"]), int(e["c"])) for c, evs in enumerate(ev) for e in evs]
+        assert [[r for r in rows if r[0] == c] for c in range(37)] == [[r for r in exp if r[0] == c] for c in range(37)]
+    assert (bank.status() == fin["status"]).all()
+    bank.close()
