@@ -958,49 +958,25 @@ struct StSeqArgs
     void *log;                          // [groups][SB_ST_LOG] records kept by the count pass (wire or 24-byte, as the call asks), or NULL
 };
 
+#define SB_ST_TILE          48          // block rows of decisions staged per tile
+#define SB_ST_CPW           8           // channels per warp
+#define SB_ST_CPC           (4*SB_ST_CPW)   // channels per CTA (four warps)
+
 // The segment history of one channel (src/spandsp/private/super_tone_rx.h:57: segments[11]); slot 10 holds the block
 // pair seen last, slot 9 the segment in progress - those two live in registers in the sequencer - and slots 0..8 the
-// finished segments.  Slots 0..9 are kept in shared memory, [field][thread], as a ring of 16: the cadence tests index
+// finished segments.  Slots 0..8 are kept in shared memory, [field][channel], as a ring of 16: the cadence tests index
 // them with run-time positions, which registers cannot do, and the reference's "shift everything down by one" becomes
 // a step of the ring's head.
 struct StSegs
 {
-    int *base;                          // this thread's column of int [48][128]
+    int *base;                          // this channel's column of int [48][SB_ST_CPC]
     int head;
 
-    __device__ __forceinline__ int &f1(int i) const { return base[(3*((head + i) & 15))*128]; }
-    __device__ __forceinline__ int &f2(int i) const { return base[(3*((head + i) & 15) + 1)*128]; }
-    __device__ __forceinline__ int &dur(int i) const { return base[(3*((head + i) & 15) + 2)*128]; }
+    __device__ __forceinline__ int &f1(int i) const { return base[(3*((head + i) & 15))*SB_ST_CPC]; }
+    __device__ __forceinline__ int &f2(int i) const { return base[(3*((head + i) & 15) + 1)*SB_ST_CPC]; }
+    __device__ __forceinline__ int &dur(int i) const { return base[(3*((head + i) & 15) + 2)*SB_ST_CPC]; }
 };
 
-// src/super_tone_rx.c:164-228, the two forms a tone in progress is tested with (rotation >= 0)
-__device__ __forceinline__ int st_test_cadence(const int4 *pattern, int steps, const StSegs &t, int rotation)
-{
-    int j = 0;
-
-    if (steps < 0)
-    {
-        steps = -steps;
-        j = (rotation + steps - 2)%steps;
-        const int4 p = pattern[j];
-        if (p.x != t.f1(8)  ||  p.y != t.f2(8))
-            return 0;
-        if (p.z > t.dur(8)*128  ||  p.w < t.dur(8)*128)
-            return 0;
-    }
-    if (steps)
-        j = (rotation + steps - 1)%steps;
-    const int4 p = pattern[j];
-    if (p.x != t.f1(9)  ||  p.y != t.f2(9))
-        return 0;
-    if (p.w < t.dur(9)*128)
-        return 0;
-    return 1;
-}
-
-#define SB_ST_TILE          48          // block rows of decisions staged per tile
-#define SB_ST_CPW           8           // channels per warp
-#define SB_ST_CPC           (4*SB_ST_CPW)   // channels per CTA (four warps)
 #define SB_ST_SMEM_ELEMENTS 160         // cadence template elements kept in shared memory (larger descriptors read them from global memory)
 #define SB_ST_SMEM_TONES    64
 #define SB_ST_LOG           (32*SB_ST_CPW)  // records per group of SB_ST_CPW channels the count pass keeps for the emit pass
@@ -1020,11 +996,12 @@ __device__ __forceinline__ int st_test_cadence(const int4 *pattern, int steps, c
 template <bool EMIT>
 __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
 {
-    __shared__ int seg[48*128];
+    __shared__ int seg[48*SB_ST_CPC];                       // (lanes beyond SB_ST_CPW never run a block: they share their warp's first column, untouched)
     __shared__ __align__(16) unsigned short tile[2][SB_ST_TILE*SB_ST_CPC];
     __shared__ int4 s_elements[SB_ST_SMEM_ELEMENTS];
     __shared__ int s_tone_segs[SB_ST_SMEM_TONES];
     __shared__ int s_tone_first[SB_ST_SMEM_TONES];
+    __shared__ int s_last_key[SB_ST_SMEM_TONES];                // the frequency pair of each tone's last step, as a decision code (-1: no steps)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wg = blockIdx.x*4 + warp;                         // group of SB_ST_CPW channels
@@ -1060,23 +1037,21 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     const int cs_old = (s.q.cs0 >= 0)  ?  s.q.cs0  :  s.q.cs[c];
     const int nb = (live)  ?  ((cs_old + s.q.n)/B)  :  0;
     StSegs t;
-    t.base = seg + threadIdx.x;
+    t.base = seg + col_in_cta;
     t.head = 0;
     // slots 9 (segment in progress) and 10 (pair seen last) are touched by every block: registers
     int f1_9 = 0;
     int f2_9 = 0;
     int dur_9 = 0;
-    int f1_10 = 0;
-    int f2_10 = 0;
+    int key10 = 0;                      // slot 10, in the form of the decision codes
     if (lane < SB_ST_CPW)
     {
         for (int i = 0;  i < 27;  i++)
-            seg[i*128 + threadIdx.x] = s.segments[(size_t) i*C + c];
+            seg[i*SB_ST_CPC + col_in_cta] = s.segments[(size_t) i*C + c];
         f1_9 = s.segments[(size_t) 27*C + c];
         f2_9 = s.segments[(size_t) 28*C + c];
         dur_9 = s.segments[(size_t) 29*C + c];
-        f1_10 = s.segments[(size_t) 30*C + c];
-        f2_10 = s.segments[(size_t) 31*C + c];
+        key10 = SB_ST_CODE(s.segments[(size_t) 30*C + c], s.segments[(size_t) 31*C + c]);
     }
     // templates: shared memory copies where they fit
     const bool small = (s.t.tones <= SB_ST_SMEM_TONES  &&  s.t.total_elements <= SB_ST_SMEM_ELEMENTS);
@@ -1086,8 +1061,17 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             s_elements[i] = s.t.elements[i];
         for (int i = threadIdx.x;  i < s.t.tones;  i += 128)
         {
-            s_tone_segs[i] = s.t.tone_segs[i];
-            s_tone_first[i] = s.t.tone_first[i];
+            const int steps = s.t.tone_segs[i];
+            const int first = s.t.tone_first[i];
+            s_tone_segs[i] = steps;
+            s_tone_first[i] = first;
+            s_last_key[i] = -1;
+            if (steps > 0)
+            {
+                const int4 p = s.t.elements[first + steps - 1];
+                // (a pair no decision code can carry never matches: any other non-negative value will do)
+                s_last_key[i] = (p.x >= -1  &&  p.x < 127  &&  p.y >= -1  &&  p.y < 127)  ?  (int) SB_ST_CODE(p.x, p.y)  :  0x4000;
+            }
         }
     }
     __syncthreads();
@@ -1128,19 +1112,21 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         }
     };
 
-    auto spill = [&]()
-    {
-        t.f1(9) = f1_9;
-        t.f2(9) = f2_9;
-        t.dur(9) = dur_9;
-    };
     // While a block only lengthens the segment in progress, the outcome of the cadence tests is a function of that
     // one duration.  keep_until: the largest duration for which the detected tone's test still passes (-1: not
     // worked out yet); scan_at: the smallest duration at which the search over all tones can succeed at all.  Both
     // are recomputed whenever the history shifts, a tone is found or lost, and at the start of every call, so the
     // tests the reference runs every block are run here only at the blocks where their result can change.
+    // repeat_until / differ_until fold the two into "the largest duration from which a repeat of the segment's pair /
+    // a pair other than the one seen last is a bare increment"; key9 is slot 9 in the form of the decision codes.
     int keep_until = -1;
     int scan_at = 0;
+    int repeat_until = -1;
+    int differ_until = -1;
+    int key9 = -1;
+    // rotation modulo the detected tone's step count, stepped with it (-1: not worked out yet): the reference's
+    // (rotation + steps - k) % steps without a division per test
+    int rmod = -1;
 
     // One super_tone_chunk() step.  It can raise up to three callbacks, in this order: tone lost,
     // segment report, tone found.  They are recorded here and pushed by all lanes together.
@@ -1160,18 +1146,44 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         seg_f1 = seg_f2 = seg_ms = found_id = 0;
         if (!run)
             return;
-        if (k1 != f1_10  ||  k2 != f2_10)
+        if ((int) SB_ST_CODE(k1, k2) != key10)
         {
-            f1_10 = k1;
-            f2_10 = k2;
+            key10 = SB_ST_CODE(k1, k2);
             dur_9++;
         }
         else if (k1 != f1_9  ||  k2 != f2_9)
         {
             if (detected >= 0)
             {
-                spill();
-                if (!st_test_cadence(elements + tone_first[detected], -tone_segs[detected], t, rotation++))
+                // st_test_cadence(pattern, -steps, rotation++) (src/super_tone_rx.c:172-196): the finished segment
+                // (slot 9, about to become slot 8... here still in registers) against the step it should have been,
+                // with both duration bounds; the one before it (slot 8) likewise
+                const int4 *pattern = elements + tone_first[detected];
+                const int steps = tone_segs[detected];
+                bool ok = true;
+                int j = 0;
+                if (steps > 0)
+                {
+                    if (rmod < 0)
+                        rmod = rotation%steps;
+                    const int x = rmod + steps - 2;
+                    j = (x < 0)  ?  0  :  ((x >= steps)  ?  (x - steps)  :  x);
+                    const int4 p = pattern[j];
+                    const int d8 = t.dur(8)*128;
+                    if (p.x != t.f1(8)  ||  p.y != t.f2(8)  ||  p.z > d8  ||  p.w < d8)
+                        ok = false;
+                    const int y = rmod + steps - 1;
+                    j = (y >= steps)  ?  (y - steps)  :  y;
+                    rmod = (rmod + 1 >= steps)  ?  0  :  (rmod + 1);
+                }
+                if (ok)
+                {
+                    const int4 p = pattern[j];
+                    if (p.x != f1_9  ||  p.y != f2_9  ||  p.w < dur_9*128)
+                        ok = false;
+                }
+                rotation++;
+                if (!ok)
                 {
                     detected = -1;
                     e_lost = true;
@@ -1204,7 +1216,14 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
                 {
                     // st_test_cadence(pattern, steps > 0, rotation >= 0) (src/super_tone_rx.c:187-196) as a bound
                     const int steps = tone_segs[detected];
-                    const int j = (steps)  ?  ((rotation + steps - 1)%steps)  :  0;
+                    int j = 0;
+                    if (steps > 0)
+                    {
+                        if (rmod < 0)
+                            rmod = rotation%steps;
+                        const int y = rmod + steps - 1;
+                        j = (y >= steps)  ?  (y - steps)  :  y;
+                    }
                     const int4 p = elements[tone_first[detected] + j];
                     keep_until = (p.x != f1_9  ||  p.y != f2_9  ||  p.w < 0)  ?  0  :  (p.w >> 7);
                 }
@@ -1221,43 +1240,51 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         {
             // The search of src/super_tone_rx.c:425-437 (st_test_cadence with rotation < 0, src/super_tone_rx.c:
             // 198-212), tones in order, first match wins.  The newest segment is compared first (it is the one that
-            // rules most tones out; the test is a conjunction, so the order does not matter).  A tone whose only
-            // failing check is "segment in progress still too short" names the duration at which to look again.
-            spill();
+            // rules most tones out - by its frequency pair alone, kept per tone in s_last_key; the test is a
+            // conjunction, so the order does not matter).  A tone whose only failing check is "segment in progress
+            // still too short" names the duration at which to look again.
+            const int mykey = SB_ST_CODE(f1_9, f2_9);
+            const int d9 = dur_9*128;
             int next = 0x7FFFFFFF;
             for (int j = 0;  j < ntones;  j++)
             {
+                if (small)
+                {
+                    const int key = s_last_key[j];
+                    if (key != mykey  &&  key >= 0)
+                        continue;
+                }
                 const int4 *pattern = elements + tone_first[j];
                 const int steps = tone_segs[j];
                 bool ok = true;
                 bool short_yet = false;
                 int need = 0;
-                for (int i = steps - 1;  i >= 0  &&  ok;  i--)
+                if (steps > 0)
+                {
+                    const int4 p = pattern[steps - 1];
+                    if (p.x != f1_9  ||  p.y != f2_9  ||  p.w < d9)
+                    {
+                        ok = false;
+                    }
+                    else if (p.z > d9)
+                    {
+                        short_yet = true;
+                        need = (p.z + 127) >> 7;
+                    }
+                }
+                for (int i = steps - 2;  i >= 0  &&  ok;  i--)
                 {
                     const int k = i + 10 - steps;
                     const int4 p = pattern[i];
                     const int d = t.dur(k)*128;
-                    if (p.x != t.f1(k)  ||  p.y != t.f2(k)  ||  p.w < d)
-                    {
+                    if (p.x != t.f1(k)  ||  p.y != t.f2(k)  ||  p.w < d  ||  p.z > d)
                         ok = false;
-                    }
-                    else if (p.z > d)
-                    {
-                        if (k == 9)
-                        {
-                            short_yet = true;
-                            need = (p.z + 127) >> 7;
-                        }
-                        else
-                        {
-                            ok = false;
-                        }
-                    }
                 }
                 if (ok  &&  !short_yet)
                 {
                     detected = j;
                     rotation = 0;
+                    rmod = 0;
                     e_found = true;
                     found_id = j;
                     keep_until = -1;
@@ -1268,6 +1295,10 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             }
             scan_at = next;
         }
+        key9 = SB_ST_CODE(f1_9, f2_9);
+        const int no_scan_until = (scan_at >= 2)  ?  (scan_at - 2)  :  -1;
+        repeat_until = (detected >= 0)  ?  keep_until  :  no_scan_until;
+        differ_until = (detected >= 0)  ?  0x7FFFFFFF  :  no_scan_until;      // (that branch tests nothing while a tone is held)
     };
 
     auto flush = [&](int blk)
@@ -1285,6 +1316,21 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     // one decision code through the reference's block logic, including the one-bin quirk
     auto one_block = [&](int b, bool run, int code)
     {
+        // Nearly always, in every channel of the warp: either the pair of the segment in progress again, or a pair
+        // that differs from the one seen last (two tones too close for a 16 ms block to separate beat, and the
+        // decision alternates: the reference then just notes the pair and lengthens the segment) - and no test due.
+        const bool same = (code == key10);
+        const bool fast = !run  ||  ((same)  ?  (key10 == key9  &&  dur_9 <= repeat_until)
+                                             :  (!(code & SB_ST_QUIRK)  &&  dur_9 <= differ_until));
+        if (__all_sync(0xFFFFFFFFu, fast))
+        {
+            if (run)
+            {
+                key10 = code;
+                dur_9++;
+            }
+            return;
+        }
         chunk(run, (code & 0x7F) - 1, ((code >> 7) & 0x7F) - 1);
         flush(b);
         const bool quirk = run  &&  (code & SB_ST_QUIRK);
@@ -1342,9 +1388,15 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             __syncthreads();
             const unsigned short *col = tile[tl & 1] + col_in_cta;
             const int rows = (nbu - tl*SB_ST_TILE < SB_ST_TILE)  ?  (nbu - tl*SB_ST_TILE)  :  SB_ST_TILE;
+            int code = (int) col[0];
 #pragma unroll 1
             for (int row = 0;  row < rows;  row++)
-                one_block(tl*SB_ST_TILE + row, live, (int) col[row*SB_ST_CPC]);
+            {
+                // (the next row's code is fetched before this row's chain of branches, not after it)
+                const int next = (int) col[((row + 1 < SB_ST_TILE)  ?  (row + 1)  :  row)*SB_ST_CPC];
+                one_block(tl*SB_ST_TILE + row, live, code);
+                code = next;
+            }
             __syncthreads();
         }
         cp_async_wait<0>();
@@ -1378,8 +1430,8 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         s.segments[(size_t) 27*C + c] = f1_9;
         s.segments[(size_t) 28*C + c] = f2_9;
         s.segments[(size_t) 29*C + c] = dur_9;
-        s.segments[(size_t) 30*C + c] = f1_10;
-        s.segments[(size_t) 31*C + c] = f2_10;
+        s.segments[(size_t) 30*C + c] = (key10 & 0x7F) - 1;
+        s.segments[(size_t) 31*C + c] = ((key10 >> 7) & 0x7F) - 1;
         s.detected_tone[c] = detected;
         s.rotation[c] = rotation;
         s.pending[c] = (unsigned char) pending;
