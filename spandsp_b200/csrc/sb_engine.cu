@@ -1137,7 +1137,7 @@ template <class DET, int NPACK>
 static int launch_variant(const BankArgs<DET> &a, bool filter, cudaStream_t st, int variant = 0)
 {
     // Occupancy experiments (DTMF only, tuning knob 1): more resident warps per SM at a lower register cap
-    if constexpr (std::is_same<DET, DtmfDet>::value  &&  NPACK == DET::NPAIRS)
+    if constexpr (std::is_same<DET, DtmfDet>::value  &&  (NPACK == DET::NPAIRS  ||  NPACK == DET::NPAIRS + 1))
     {
         if (variant == 1)
             return launch_staged<DET, 8, 2, 4, 6, NPACK>(a, filter, st);    // 24 warps/SM, <= 80 registers
@@ -1145,6 +1145,13 @@ static int launch_variant(const BankArgs<DET> &a, bool filter, cudaStream_t st, 
             return launch_staged<DET, 8, 2, 8, 3, NPACK>(a, filter, st);    // 24 warps/SM in 3 CTAs of 8 warps
         if (variant == 3)
             return launch_staged<DET, 8, 2, 2, 10, NPACK>(a, filter, st);   // 20 warps/SM in 10 CTAs of 2 warps
+        if constexpr (NPACK == DET::NPAIRS + 1)
+        {
+            if (variant == 4)
+                return launch_staged<DET, 8, 2, 4, 5, NPACK>(a, filter, st);    // 20 warps/SM, <= 96 registers
+            if (variant == 5)
+                return launch_staged<DET, 8, 3, 4, 4, NPACK>(a, filter, st);    // three stages in flight
+        }
     }
     // (row bytes per stage = SEG_VEC*16, stages, warps per CTA, min CTAs per SM).  The round-1 sweep
     // (profiles/r01_sweep_dtmf*.json) covered nine shapes; the fastest is kept: 128-byte row segments,
@@ -1196,8 +1203,10 @@ static int launch_bank(span_b200_bank_t *b, BankArgs<DET> &a, const Geometry &g,
         {
             if (all_variants  &&  b->tune_packed == 0)
                 return launch_variant<DET, 0>(a, filter, st);
-            if (all_variants  &&  (b->tune_packed == 4  ||  b->tune_variant != 0))
+            if (all_variants  &&  b->tune_packed == 4)
                 return launch_variant<DET, DET::NPAIRS>(a, filter, st, b->tune_variant);
+            if (all_variants  &&  b->tune_variant != 0)
+                return launch_variant<DET, DET::NPAIRS + 1>(a, filter, st, b->tune_variant);
         }
         return launch_variant<DET, DET::NPAIRS + 1>(a, filter, st);
     }

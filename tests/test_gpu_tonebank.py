@@ -134,7 +134,7 @@ def test_dtmf_staged_sequencer(gpu_ctx, engine_lib, torch_mod, port, chunk, mode
     bank.close()
 
 
-@pytest.mark.parametrize("knob", [("variant", 1), ("variant", 2), ("variant", 3), ("packed", 0), ("packed", 5),
+@pytest.mark.parametrize("knob", [("variant", 1), ("variant", 2), ("variant", 3), ("variant", 4), ("variant", 5), ("packed", 0), ("packed", 5),
                                   ("direct", 1), ("slice", 3), ("slice", 1)])
 def test_dtmf_kernel_variants(gpu_ctx, engine_lib, torch_mod, port, knob):
     """Every staging variant, the scalar-add build, the direct kernel and odd slice lengths give

@@ -17,7 +17,7 @@ slices = [int(x) for x in os.environ.get("SWEEP_SLICES", "0,16,64").split(",")]
 
 dev = torch.device("cuda", 0)
 ctx = engine.Context(0)
-d_amp = bench.synth_dtmf_torch(torch, C, T, 1234567, dev)
+d_amp = bench.make_dtmf_input(torch, engine, ctx, C, T, 0, dev, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 stream = torch.cuda.current_stream().cuda_stream
 rows = []
