@@ -388,6 +388,8 @@ void *sb_ctx_stream(span_b200_ctx_t *ctx)
 
 // ------------------------------------------------------------------------------------------
 // communicator (multi-GPU gather of the event records); functions further down
+#define SB_PULL_STREAMS 4
+
 struct span_b200_comm_s
 {
     span_b200_ctx_t *ctx;
@@ -406,6 +408,11 @@ struct span_b200_comm_s
     unsigned long long *peer_gen[2];        // [nranks] generation of the mapping
     cudaEvent_t counts_ready[2];
     cudaEvent_t done[2];                    // the transfer that read / filled buffer i has finished
+    // root, peer-copy transport: the ranks' records are pulled on several streams at once (one copy engine pulling
+    // over NVLink is latency-limited well below the link rate), forked from / joined to `stream` by events
+    cudaStream_t pull[SB_PULL_STREAMS];
+    cudaEvent_t fork;
+    cudaEvent_t joined[SB_PULL_STREAMS];
     bool done_valid[2];
     int begun_slot;                         // slot of the last _gather_begin without _gather_end, or -1
     int ended_slot;                         // slot of the last _gather_end, or -1
@@ -1289,6 +1296,7 @@ struct RxCall
     span_b200_wire_event_t *wire_out;
     long long out_cap;
     cudaEvent_t t1;
+    cudaEvent_t before_emit;        // the gather transfer that still reads the record buffer this call's emit pass overwrites, or NULL
 };
 
 static int rx_prepare(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride, int n, void *stream, int law, RxCall &rc)
@@ -1307,6 +1315,7 @@ static int rx_prepare(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
     rc.law = law;
     rc.st = st;
     rc.t1 = NULL;
+    rc.before_emit = NULL;
     g.cs0 = b->uniform_cs;
     const bool aligned = ((((uintptr_t) d_amp) & 15) == 0)  &&  ((stride & ((law >= 0)  ?  15  :  7)) == 0);
     g.staged = (g.cs0 >= 0)  &&  aligned  &&  !b->tune_direct  &&  n > 0;
@@ -1361,11 +1370,10 @@ static int rx_prepare(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
         }
         slot = b->slot ^ 1;
         const bool to_gather = (b->comm != NULL  &&  b->comm->rank == b->root);
-        if (b->comm  &&  b->comm->done_valid[slot])
-        {
-            // the transfer that read this buffer two calls ago must be over before the emit pass overwrites it
-            CK(cudaStreamWaitEvent(st, b->comm->done[slot], 0));
-        }
+        // the transfer that read this buffer two calls ago must be over before the emit pass overwrites it: the wait
+        // goes in front of the emit pass, not of the filter bank, so the transfer has this call's filter kernel to hide
+        // behind as well
+        rc.before_emit = (b->comm  &&  b->comm->done_valid[slot])  ?  b->comm->done[slot]  :  NULL;
         if (to_gather)
         {
             // root: emit straight into the gather buffer; room for every rank's worst case (grown on demand later)
@@ -1379,7 +1387,12 @@ static int rx_prepare(span_b200_bank_t *b, const int16_t *d_amp, int64_t stride,
             if (b->wire_cap[slot] < want_ev  ||  (b->ev_cap_user > 0  &&  b->wire_cap[slot] != want_ev))
             {
                 if (b->wire[slot])
+                {
+                    // (another rank may still be reading it)
+                    if (b->comm  &&  b->comm->done_valid[slot])
+                        CK(cudaEventSynchronize(b->comm->done[slot]));
                     CK(cudaFree(b->wire[slot]));
+                }
                 b->wire[slot] = NULL;
                 b->wire_cap[slot] = 0;
                 CK(cudaMalloc(&b->wire[slot], sizeof(span_b200_wire_event_t)*(size_t) want_ev));
@@ -1543,6 +1556,8 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
     const int cpw = (b->det == SPAN_B200_DET_SUPER_TONE)  ?  SB_ST_CPW  :  32;      // channels per sequencer warp
     for (int pass = 0;  pass < 2;  pass++)
     {
+        if (pass == 1  &&  rc.before_emit)
+            CK(cudaStreamWaitEvent(st, rc.before_emit, 0));
         switch (b->det)
         {
         case SPAN_B200_DET_DTMF:
@@ -2217,6 +2232,18 @@ extern "C" void span_b200_comm_destroy(span_b200_comm_t *cm)
         if (cm->done[i])
             cudaEventDestroy(cm->done[i]);
     }
+    for (int i = 0;  i < SB_PULL_STREAMS;  i++)
+    {
+        if (cm->pull[i])
+        {
+            cudaStreamSynchronize(cm->pull[i]);
+            cudaStreamDestroy(cm->pull[i]);
+        }
+        if (cm->joined[i])
+            cudaEventDestroy(cm->joined[i]);
+    }
+    if (cm->fork)
+        cudaEventDestroy(cm->fork);
     if (cm->stream)
         cudaStreamDestroy(cm->stream);
     delete cm;
@@ -2248,6 +2275,12 @@ extern "C" span_b200_comm_t *span_b200_comm_create(span_b200_ctx_t *ctx, const u
     bool ok = cudaStreamCreateWithFlags(&cm->stream, cudaStreamNonBlocking) == cudaSuccess
               &&  cudaMalloc(&cm->d_sync, sizeof(unsigned long long)*(1 + nranks)) == cudaSuccess
               &&  cudaMemset(cm->d_sync, 0, sizeof(unsigned long long)*(1 + nranks)) == cudaSuccess;
+    ok = ok  &&  cudaEventCreateWithFlags(&cm->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0;  ok  &&  i < SB_PULL_STREAMS;  i++)
+    {
+        ok = cudaStreamCreateWithFlags(&cm->pull[i], cudaStreamNonBlocking) == cudaSuccess
+             &&  cudaEventCreateWithFlags(&cm->joined[i], cudaEventDisableTiming) == cudaSuccess;
+    }
     for (int i = 0;  ok  &&  i < 2;  i++)
     {
         cm->peer_ptr[i] = new void *[nranks]();
@@ -2422,6 +2455,8 @@ extern "C" int64_t span_b200_bank_gather_end(span_b200_bank_t *b, int64_t *count
             if (comm_gather_reserve(cm, slot, total, b->last_stream, own) != 0)
                 return -1;
             long long off = own;
+            int pulls = 0;
+            CK(cudaEventRecord(cm->fork, cm->stream));
             for (int r = 0;  r < cm->nranks;  r++)
             {
                 const long long n = (long long) meta[r*SB_META_WORDS];
@@ -2445,9 +2480,18 @@ extern "C" int64_t span_b200_bank_gather_end(span_b200_bank_t *b, int64_t *count
                     cm->peer_gen[slot][r] = gen;
                 }
                 // the root's copy engine reads the rank's records over NVLink: exactly n records, behind the previous rank's
+                cudaStream_t ps = cm->pull[pulls % SB_PULL_STREAMS];
+                if (pulls < SB_PULL_STREAMS)
+                    CK(cudaStreamWaitEvent(ps, cm->fork, 0));
                 CK(cudaMemcpyAsync(cm->gather[slot] + off, cm->peer_ptr[slot][r], (size_t) n*sizeof(span_b200_wire_event_t),
-                                   cudaMemcpyDefault, cm->stream));
+                                   cudaMemcpyDefault, ps));
+                pulls++;
                 off += n;
+            }
+            for (int i = 0;  i < pulls  &&  i < SB_PULL_STREAMS;  i++)
+            {
+                CK(cudaEventRecord(cm->joined[i], cm->pull[i]));
+                CK(cudaStreamWaitEvent(cm->stream, cm->joined[i], 0));
             }
         }
         // completion: a tiny collective behind the copies on the root's stream - a rank's buffer is free again when
