@@ -389,3 +389,46 @@ def test_super_tone_dense_events(gpu_ctx, engine_lib, torch_mod, port, wire):
         assert [[r for r in rows if r[0] == c] for c in range(37)] == [[r for r in exp if r[0] == c] for c in range(37)]
     assert (bank.status() == fin["status"]).all()
     bank.close()
+
+
+@pytest.mark.parametrize("det", ["dtmf", "super_tone"])
+def test_event_capacity_overflow(gpu_ctx, engine_lib, torch_mod, det):
+    """A caller-set record capacity smaller than what a call produces: the call reports the overflow, hands back
+    exactly the first `capacity` records (in buffer order), and the channel state still advances as if nothing had
+    been dropped - the next call's records equal those of a bank that never overflowed.  For the super-tone bank this
+    also covers the emit pass placing the count pass's kept records against a short buffer."""
+    torch = torch_mod
+    if det == "dtmf":
+        amp, _ = synth.dtmf_channels(64, 24000, seed=21)
+        make = lambda: engine_lib.Bank.dtmf(gpu_ctx, 64)
+    else:
+        rng = np.random.default_rng(5)
+        tones = synth.random_tones(rng, nfreqs=5, ntones=5)
+        cads = [[(e[0], e[1], -12, (e[2] + e[3]) // 2) for e in t] for t in tones]
+        amp = synth.cadence_channels(64, 24000, cads, seed=6)
+        make = lambda: engine_lib.Bank.super_tone(gpu_ctx, 64, tones, want_segments=True)
+    d = torch.from_numpy(amp).cuda()
+    full, short = make(), make()
+    if det == "dtmf":
+        full.dtmf_realtime(True)
+        short.dtmf_realtime(True)
+    full.rx_device(d.data_ptr(), 24000, 12000)
+    ev1 = full.events().copy()
+    assert len(ev1) > 40
+    cap = len(ev1) // 2
+    short.set_event_capacity(cap)
+    short.rx_device(d.data_ptr(), 24000, 12000)
+    n, overflow = short.event_count()
+    assert overflow and n == cap
+    with pytest.raises(engine_lib.EngineError):
+        short.events()
+    out = np.zeros(cap + 8, dtype=engine_lib.EVENT_DTYPE)
+    got = engine_lib.lib().span_b200_bank_events(short.h, out.ctypes.data, len(out))
+    assert got == cap and (out[:cap] == ev1[:cap]).all()
+    short.set_event_capacity(0)
+    full.rx_device(d.data_ptr() + 2*12000, 24000, 12000)
+    short.rx_device(d.data_ptr() + 2*12000, 24000, 12000)
+    assert (short.events() == full.events()).all() and len(full.events()) > 0
+    assert (short.status() == full.status()).all()
+    full.close()
+    short.close()
