@@ -741,6 +741,29 @@ struct RxCore
         nbits++;
     }
 
+    // n (1..4) data bits at once, first bit in bit 0 of v
+    SB_HD void out_bits(unsigned int v, int n)
+    {
+        if (words == NULL)
+        {
+            for (int i = 0;  i < n;  i++)
+                out_bit((int) ((v >> i) & 1u));
+            return;
+        }
+        const unsigned long long acc = (unsigned long long) bit_acc | ((unsigned long long) v << bit_fill);
+        bit_fill += n;
+        bit_acc = (unsigned int) acc;
+        if (bit_fill >= 32)
+        {
+            if (sub == 0  &&  nwords < words_cap)
+                words[nwords] = bit_acc;
+            nwords++;
+            bit_acc = (unsigned int) (acc >> 32);
+            bit_fill -= 32;
+        }
+        nbits += n;
+    }
+
     // End of a call: the bits of an unfinished word
     SB_HD void out_flush()
     {
@@ -867,8 +890,12 @@ struct RxCore
             // first + second segment (the partner lane holds the other one; addition commutes), then the other
             // component from the lane two further on.  Every lane of the warp is here (run() keeps the warp converged
             // around this call), so the shuffles take the full mask.
-            z = fadd(z, __shfl_xor_sync(0xFFFFFFFFu, z, 1));
-            const float o = __shfl_xor_sync(0xFFFFFFFFu, z, 2);
+            // (three independent shuffles instead of two dependent butterfly steps: one shuffle latency, not two)
+            const float p1 = __shfl_xor_sync(0xFFFFFFFFu, z, 1);
+            const float p2 = __shfl_xor_sync(0xFFFFFFFFu, z, 2);
+            const float p3 = __shfl_xor_sync(0xFFFFFFFFu, z, 3);
+            z = fadd(z, p1);
+            const float o = fadd(p2, p3);
             v_re = (sub & 2)  ?  o  :  z;
             v_im = (sub & 2)  ?  z  :  o;
             return;
@@ -930,8 +957,11 @@ struct RxCore
                 const float2 y = yb[i*LS];
                 z = fadd(z, fadd(fmul(x.x, y.x), fmul(x.y, y.y)));
             }
-            z = fadd(z, __shfl_xor_sync(0xFFFFFFFFu, z, 1));
-            const float o = __shfl_xor_sync(0xFFFFFFFFu, z, 2);
+            const float p1 = __shfl_xor_sync(0xFFFFFFFFu, z, 1);
+            const float p2 = __shfl_xor_sync(0xFFFFFFFFu, z, 2);
+            const float p3 = __shfl_xor_sync(0xFFFFFFFFu, z, 3);
+            z = fadd(z, p1);
+            const float o = fadd(p2, p3);
             zre = (sub & 2)  ?  o  :  z;
             zim = (sub & 2)  ?  z  :  o;
             return;

@@ -134,6 +134,29 @@ struct SBM_V29_NAME : RxCore<SBM_V29_NAME, V29_COEFF_SETS, SBM_EQ_LEN, SBM_V29_L
             out_bit(out);
     }
 
+    // n (2..4) consecutive put_bit() calls at once, first bit in bit 0.  The descrambler's taps are 18 and 23 bits
+    // back, so the bits of one baud do not feed each other: bit i is b[i] ^ reg[17 - i] ^ reg[22 - i] of the register
+    // as it stood before the baud.
+    SB_HD static unsigned int rev4(unsigned int x)
+    {
+#if defined(__CUDA_ARCH__)
+        return __brev(x) >> 28;
+#else
+        return ((x & 1u) << 3) | ((x & 2u) << 1) | ((x & 4u) >> 1) | ((x & 8u) >> 3);
+#endif
+    }
+
+    SB_HD void put_bits(unsigned int b, int n)
+    {
+        const unsigned int mask = (1u << n) - 1u;
+        b &= mask;
+        const unsigned int taps = ((scramble_reg >> 14) ^ (scramble_reg >> 19)) & 0xFu;
+        const unsigned int out = (b ^ rev4(taps)) & mask;
+        scramble_reg = (scramble_reg << n) | (rev4(b) >> (4 - n));
+        if (training_stage == STAGE_NORMAL)
+            out_bits(out, n);
+    }
+
     // src/v29rx.c:402-480
     SB_HD void decode_baud(float zre, float zim)
     {
@@ -146,8 +169,7 @@ struct SBM_V29_NAME : RxCore<SBM_V29_NAME, V29_COEFF_SETS, SBM_EQ_LEN, SBM_V29_L
             const int b2 = (zim < -zre);
             nearest = ((b2 << 1) | (b1 ^ b2)) << 1;
             raw_bits = t->phase_steps_4800[((nearest - constellation_state) >> 1) & 3];
-            put_bit(raw_bits);
-            put_bit(raw_bits >> 1);
+            put_bits((unsigned int) raw_bits, 2);
         }
         else
         {
@@ -156,16 +178,14 @@ struct SBM_V29_NAME : RxCore<SBM_V29_NAME, V29_COEFF_SETS, SBM_EQ_LEN, SBM_V29_L
             re = (re > 19)  ?  19  :  (re < 0)  ?  0  :  re;
             im = (im > 19)  ?  19  :  (im < 0)  ?  0  :  im;
             nearest = t->space_map[re][im];
-            if (bit_rate == 9600)
-                put_bit(nearest >> 3);
-            else
+            const unsigned int amp_bit = (unsigned int) (nearest >> 3) & 1u;
+            if (bit_rate != 9600)
                 nearest &= 7;
             raw_bits = t->phase_steps_9600[(nearest - constellation_state) & 7];
-            for (int i = 0;  i < 3;  i++)
-            {
-                put_bit(raw_bits);
-                raw_bits >>= 1;
-            }
+            if (bit_rate == 9600)
+                put_bits(amp_bit | ((unsigned int) (raw_bits & 7) << 1), 4);
+            else
+                put_bits((unsigned int) raw_bits, 3);
         }
         const float tre = t->constellation[nearest][0];
         const float tim = t->constellation[nearest][1];
