@@ -570,7 +570,7 @@ def run_cfg4(torch, engine, ctx, dev, work_stream, args, peaks, peak_src):
         ems, mx = time_steps_host(torch, step_host, e2e_steps, barrier)
         out["e2e"] = {"value": C_ * T * e2e_steps / (ems / 1e3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(C_ * T * 2),
                       "d2h_bytes_per_step": int(C_ * (4 * ((int(mx) + 31) // 32) + 8 * int(h_ns.max()) + 8)), "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
-                      "path": "span_b200_v29_bank_rx_host (pinned int16) + span_b200_v29_bank_output_packed (every channel's put_bit stream: "
+                      "path": "span_b200_v29_bank_rx_host (pinned int16, fed in four pieces of time: the copy of a piece overlaps the kernel of the one before) + span_b200_v29_bank_output_packed (every channel's put_bit stream: "
                               "data bits 32 to a word + status reports)"}
         del h_amp
         if h_arr is not None:

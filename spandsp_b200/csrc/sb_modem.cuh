@@ -454,6 +454,8 @@ struct ModemArgs
     span_b200_v29_symbol_t *syms;       // [channel][sym_cap], or NULL
     long long sym_cap;
     int *nsyms;
+    int append;                         // the call continues the previous one's output (a long call fed in pieces): counts and
+                                        // the unfinished word are taken up where that call left them
 };
 
 // State visitors: one list of fields (visit()) serves loading and storing.  Every field is visited by
@@ -1596,6 +1598,17 @@ __global__ void __launch_bounds__(WARPS*32) modem_rx_kernel(const KernelArgs<RX>
     r.syms = (ka.a.syms  &&  live)  ?  (ka.a.syms + (size_t) cc*ka.a.sym_cap)  :  NULL;
     r.sym_cap = (int) ka.a.sym_cap;
     r.nsyms = 0;
+    if (ka.a.append)
+    {
+        r.nbits = ka.a.nbits[cc];
+        r.nstatus = ka.a.nstatus[cc];
+        const int data_bits = r.nbits - r.nstatus;
+        r.nwords = data_bits >> 5;
+        r.bit_fill = data_bits & 31;
+        r.bit_acc = (r.bit_fill != 0  &&  r.nwords < (int) ka.a.words_cap)  ?  r.words[r.nwords]  :  0u;
+        if (ka.a.nsyms)
+            r.nsyms = ka.a.nsyms[cc];
+    }
     r.group_sync();
     r.run(ka.k, s_rrc_re, s_rrc_im, ka.a.amp + (long long) cc*ka.a.stride, ka.a.n);
     r.out_flush();

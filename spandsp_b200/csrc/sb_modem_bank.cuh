@@ -42,6 +42,8 @@ struct RxKernel
     static const int WARPS = 1;
 };
 
+#define SBM_HOST_PIECES 4
+
 template <class RX>
 struct ModemBank
 {
@@ -64,6 +66,9 @@ struct ModemBank
     int want_symbols;
     int16_t *d_in;
     size_t d_in_bytes;
+    cudaStream_t copy_stream;           // rx_host: the pieces of a call cross PCIe here while the kernel of the piece before runs
+    cudaEvent_t copied[SBM_HOST_PIECES];
+    cudaEvent_t in_free;                // the kernels that read d_in have finished
     cudaStream_t last_stream;
     bool have_last;
     int on_power;
@@ -153,6 +158,7 @@ static KernelArgs<KRX> modem_args_for(ModemBank<RX> *b, const int16_t *d_amp, in
     ka.a.syms = (b->want_symbols)  ?  b->syms  :  NULL;
     ka.a.sym_cap = b->sym_cap;
     ka.a.nsyms = b->nsyms;
+    ka.a.append = 0;
     ka.k = b->k;
     return ka;
 }
@@ -238,6 +244,18 @@ static void modem_destroy(ModemBank<RX> *b)
     cudaFree(b->syms);
     cudaFree(b->nsyms);
     cudaFree(b->d_in);
+    if (b->copy_stream)
+    {
+        cudaStreamSynchronize(b->copy_stream);
+        cudaStreamDestroy(b->copy_stream);
+    }
+    for (int i = 0;  i < SBM_HOST_PIECES;  i++)
+    {
+        if (b->copied[i])
+            cudaEventDestroy(b->copied[i]);
+    }
+    if (b->in_free)
+        cudaEventDestroy(b->in_free);
     delete b;
 }
 
@@ -333,8 +351,10 @@ static inline int modem_realloc(void **p, size_t bytes)
     return 0;
 }
 
+// append: this call continues the output of the previous one (modem_rx_host feeds a long call in pieces); n_total: the
+// samples of the whole call, which the output buffers are sized for
 template <class RX>
-static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t stride, int n, void *stream)
+static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t stride, int n, void *stream, bool append = false, int n_total = -1)
 {
     if (b == NULL  ||  n < 0  ||  (n > 0  &&  d_amp == NULL))
     {
@@ -347,7 +367,9 @@ static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t strid
         CK(cudaStreamSynchronize(b->last_stream));
     // Worst case: bits per baud at 2400 baud/8000 Hz plus timing drift; status reports: a carrier cycle (up, training,
     // result, down) takes hundreds of samples.
-    const long long want_words = ((long long) n*b->bits_per_sample_x2/2 + 64 + 31)/32 + 1;
+    if (n_total < n)
+        n_total = n;
+    const long long want_words = ((long long) n_total*b->bits_per_sample_x2/2 + 64 + 31)/32 + 1;
     if (b->words_cap < want_words)
     {
         if (b->have_last)
@@ -356,7 +378,7 @@ static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t strid
             return -1;
         b->words_cap = want_words;
     }
-    const long long want_status = (long long) n/64 + 16;
+    const long long want_status = (long long) n_total/64 + 16;
     if (b->status_cap < want_status)
     {
         if (b->have_last)
@@ -365,7 +387,7 @@ static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t strid
             return -1;
         b->status_cap = want_status;
     }
-    const long long want_syms = (long long) n*2/5 + 16;
+    const long long want_syms = (long long) n_total*2/5 + 16;
     if (b->want_symbols  &&  b->sym_cap < want_syms)
     {
         if (b->have_last)
@@ -379,6 +401,7 @@ static int modem_rx_device(ModemBank<RX> *b, const int16_t *d_amp, int64_t strid
     typedef typename RxKernel<RX>::type KRX;
     const int warps = RxKernel<RX>::WARPS;
     KernelArgs<KRX> ka = modem_args_for<KRX>(b, d_amp, stride, n);
+    ka.a.append = (append)  ?  1  :  0;
     const int smem = (int) sizeof(float)*modem_smem_words<KRX>(warps);
     const int per_cta = warps*KRX::LS;                  // receivers per CTA
     modem_rx_kernel<KRX, RxKernel<RX>::WARPS><<<(b->channels + per_cta - 1)/per_cta, warps*32, smem, st>>>(ka);
@@ -409,10 +432,45 @@ static int modem_rx_host(ModemBank<RX> *b, const int16_t *h_amp, int64_t stride,
             return -1;
         b->d_in_bytes = want;
     }
-    if (n > 0)
-        CK(cudaMemcpy2DAsync(b->d_in, sizeof(int16_t)*(size_t) n, h_amp, sizeof(int16_t)*stride, sizeof(int16_t)*(size_t) n,
-                             b->channels, cudaMemcpyHostToDevice, st));
-    return modem_rx_device(b, b->d_in, n, n, (void *) st);
+    // A long call is fed in SBM_HOST_PIECES pieces of time: piece k + 1 crosses PCIe on the copy stream while the kernel
+    // of piece k runs (a receiver kernel lasts as long as its sample count whatever the channel count, so the split is
+    // over samples, not channels); the kernels of pieces 1.. continue the output of the one before.
+    const int piece = ((n + SBM_HOST_PIECES - 1)/SBM_HOST_PIECES + 7) & ~7;
+    if (n < 8000)
+    {
+        if (n > 0)
+            CK(cudaMemcpy2DAsync(b->d_in, sizeof(int16_t)*(size_t) n, h_amp, sizeof(int16_t)*stride, sizeof(int16_t)*(size_t) n,
+                                 b->channels, cudaMemcpyHostToDevice, st));
+        return modem_rx_device(b, b->d_in, n, n, (void *) st);
+    }
+    if (b->copy_stream == NULL)
+    {
+        CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0;  i < SBM_HOST_PIECES;  i++)
+            CK(cudaEventCreateWithFlags(&b->copied[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->in_free, cudaEventDisableTiming));
+    }
+    // the copies must not overtake what the caller's stream still does with d_in (the previous call's kernels), nor
+    // start before the work already queued on the caller's stream (its ordering is the caller's contract)
+    CK(cudaEventRecord(b->in_free, st));
+    CK(cudaStreamWaitEvent(b->copy_stream, b->in_free, 0));
+    int pieces = 0;
+    for (int s0 = 0;  s0 < n;  s0 += piece, pieces++)
+    {
+        const int len = (n - s0 < piece)  ?  (n - s0)  :  piece;
+        CK(cudaMemcpy2DAsync(b->d_in + s0, sizeof(int16_t)*(size_t) n, h_amp + s0, sizeof(int16_t)*stride, sizeof(int16_t)*(size_t) len,
+                             b->channels, cudaMemcpyHostToDevice, b->copy_stream));
+        CK(cudaEventRecord(b->copied[pieces], b->copy_stream));
+    }
+    pieces = 0;
+    for (int s0 = 0;  s0 < n;  s0 += piece, pieces++)
+    {
+        const int len = (n - s0 < piece)  ?  (n - s0)  :  piece;
+        CK(cudaStreamWaitEvent(st, b->copied[pieces], 0));
+        if (modem_rx_device(b, b->d_in + s0, n, len, (void *) st, pieces > 0, n) != 0)
+            return -1;
+    }
+    return 0;
 }
 
 template <class RX>

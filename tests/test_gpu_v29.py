@@ -173,3 +173,39 @@ def test_v29_packed_output(gpu_ctx, engine_lib):
         if len(rows[c % 3]) == n:
             assert (bank.bits(c) == g["bits%d" % k]).all(), c
     bank.close()
+
+
+def test_v29_rx_host_in_pieces(gpu_ctx, engine_lib):
+    """span_b200_v29_bank_rx_host() feeds a long call to the kernel in pieces of time (the copy of a piece overlaps the
+    kernel of the one before); the kernels continue each other's output.  The put_bit stream, its status reports, the
+    qam symbols and the receiver state afterwards must equal those of one rx_device() call on the whole buffer -
+    including a buffer length that is no multiple of the piece or of a packed word, and a second call after it."""
+    import torch
+    g = np.load(GOLD)
+    rows = [np.ascontiguousarray(g["amp%d" % k]) for k in (1, 0, 1)]
+    n0 = min(len(r) for r in rows)
+    nch = 11
+    one = np.stack([rows[c % 3][:n0] for c in range(nch)])
+    amp = np.concatenate([one, np.zeros((nch, 4000), np.int16), one], axis=1)       # two pages with a gap
+    amp[4] = (np.random.default_rng(2).normal(0, 30, amp.shape[1])).astype(np.int16)
+    whole = amp
+    # an odd length (pieces and rows off the 16-byte grid: the kernel's unaligned input path) and an aligned one
+    for n in (whole.shape[1] - 3, (whole.shape[1] // 32)*32):
+        assert n >= 8000
+        amp = np.ascontiguousarray(whole[:, :n])
+        a = engine_lib.V29Bank(gpu_ctx, nch, 9600, want_symbols=True)
+        b = engine_lib.V29Bank(gpu_ctx, nch, 9600, want_symbols=True)
+        d = torch.from_numpy(amp).cuda()
+        torch.cuda.synchronize()
+        for rep in range(2):
+            a.rx_device(d.data_ptr(), n, n)
+            b.rx_host(amp)
+            wa, nba, sa, nsa = a.output_packed()
+            wb, nbb, sb, nsb = b.output_packed()
+            assert (nba == nbb).all() and (nsa == nsb).all() and nba.max() > 1000
+            for c in range(nch):
+                assert (a.bits(c) == b.bits(c)).all(), (n, rep, c)
+                sya, syb = a.symbols(c), b.symbols(c)
+                assert len(sya) == len(syb) and sya.tobytes() == syb.tobytes(), (n, rep, c)
+        a.close()
+        b.close()
