@@ -993,11 +993,13 @@ struct StSegs
 //   the channel state itself; the emit pass then only moves those records to their final places.  A group with more
 //   records than that is walked again by the emit pass, from the untouched state, as in the other sequencers.
 // Event order: (group of SB_ST_CPW channels, block, channel).
-template <bool EMIT>
+// SMALL: the descriptor's templates fit the shared-memory copies (the usual case; a compile-time fact so that they are
+// read with shared-memory loads, not through generic pointers)
+template <bool EMIT, bool SMALL>
 __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
 {
     __shared__ int seg[48*SB_ST_CPC];                       // (lanes beyond SB_ST_CPW never run a block: they share their warp's first column, untouched)
-    __shared__ __align__(16) unsigned short tile[2][SB_ST_TILE*SB_ST_CPC];
+    __shared__ __align__(16) unsigned short tile[2][(SB_ST_TILE + 1)*SB_ST_CPC];
     __shared__ int4 s_elements[SB_ST_SMEM_ELEMENTS];
     __shared__ int s_tone_segs[SB_ST_SMEM_TONES];
     __shared__ int s_tone_first[SB_ST_SMEM_TONES];
@@ -1054,7 +1056,7 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         key10 = SB_ST_CODE(s.segments[(size_t) 30*C + c], s.segments[(size_t) 31*C + c]);
     }
     // templates: shared memory copies where they fit
-    const bool small = (s.t.tones <= SB_ST_SMEM_TONES  &&  s.t.total_elements <= SB_ST_SMEM_ELEMENTS);
+    constexpr bool small = SMALL;
     if (small)
     {
         for (int i = threadIdx.x;  i < s.t.total_elements;  i += 128)
@@ -1075,9 +1077,15 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
         }
     }
     __syncthreads();
-    const int4 *elements = (small)  ?  s_elements  :  s.t.elements;
-    const int *tone_segs = (small)  ?  s_tone_segs  :  s.t.tone_segs;
-    const int *tone_first = (small)  ?  s_tone_first  :  s.t.tone_first;
+    const int4 *elements = s.t.elements;
+    const int *tone_segs = s.t.tone_segs;
+    const int *tone_first = s.t.tone_first;
+    if constexpr (SMALL)
+    {
+        elements = s_elements;
+        tone_segs = s_tone_segs;
+        tone_first = s_tone_first;
+    }
     const int ntones = s.t.tones;
     int detected = s.detected_tone[c];
     int rotation = s.rotation[c];
@@ -1137,6 +1145,22 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
     int seg_f2;
     int seg_ms;
     int found_id;
+
+    // st_test_cadence(pattern, steps > 0, rotation >= 0) (src/super_tone_rx.c:187-196) as a bound on the duration
+    auto work_out_keep_until = [&]()
+    {
+        const int steps = tone_segs[detected];
+        int j = 0;
+        if (steps > 0)
+        {
+            if (rmod < 0)
+                rmod = rotation%steps;
+            const int y = rmod + steps - 1;
+            j = (y >= steps)  ?  (y - steps)  :  y;
+        }
+        const int4 p = elements[tone_first[detected] + j];
+        keep_until = (p.x != f1_9  ||  p.y != f2_9  ||  p.w < 0)  ?  0  :  (p.w >> 7);
+    };
 
     auto chunk = [&](bool run, int k1, int k2)
     {
@@ -1213,20 +1237,7 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             if (detected >= 0)
             {
                 if (keep_until < 0)
-                {
-                    // st_test_cadence(pattern, steps > 0, rotation >= 0) (src/super_tone_rx.c:187-196) as a bound
-                    const int steps = tone_segs[detected];
-                    int j = 0;
-                    if (steps > 0)
-                    {
-                        if (rmod < 0)
-                            rmod = rotation%steps;
-                        const int y = rmod + steps - 1;
-                        j = (y >= steps)  ?  (y - steps)  :  y;
-                    }
-                    const int4 p = elements[tone_first[detected] + j];
-                    keep_until = (p.x != f1_9  ||  p.y != f2_9  ||  p.w < 0)  ?  0  :  (p.w >> 7);
-                }
+                    work_out_keep_until();
                 if (dur_9 > keep_until)
                 {
                     detected = -1;
@@ -1295,6 +1306,9 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             }
             scan_at = next;
         }
+        // (worked out here, not at the next block, so that the next block can already take the fast path)
+        if (detected >= 0  &&  keep_until < 0)
+            work_out_keep_until();
         key9 = SB_ST_CODE(f1_9, f2_9);
         const int no_scan_until = (scan_at >= 2)  ?  (scan_at - 2)  :  -1;
         repeat_until = (detected >= 0)  ?  keep_until  :  no_scan_until;
@@ -1388,13 +1402,17 @@ __global__ void __launch_bounds__(128) super_tone_sequencer(const StSeqArgs s)
             __syncthreads();
             const unsigned short *col = tile[tl & 1] + col_in_cta;
             const int rows = (nbu - tl*SB_ST_TILE < SB_ST_TILE)  ?  (nbu - tl*SB_ST_TILE)  :  SB_ST_TILE;
+            // (the next row's code is fetched before this row's chain of branches, not after it; the tile has a spare
+            // row so that the fetch behind the last one stays inside it)
             int code = (int) col[0];
+            int blk = tl*SB_ST_TILE;
+            const int blk_end = blk + rows;
 #pragma unroll 1
-            for (int row = 0;  row < rows;  row++)
+            for (  ;  blk < blk_end;  blk++)
             {
-                // (the next row's code is fetched before this row's chain of branches, not after it)
-                const int next = (int) col[((row + 1 < SB_ST_TILE)  ?  (row + 1)  :  row)*SB_ST_CPC];
-                one_block(tl*SB_ST_TILE + row, live, code);
+                col += SB_ST_CPC;
+                const int next = (int) col[0];
+                one_block(blk, live, code);
                 code = next;
             }
             __syncthreads();

@@ -1619,10 +1619,21 @@ static int rx_finish(span_b200_bank_t *b, const RxCall &rc)
                 s.want_segments = b->want_segments;
                 s.log = b->st_log;
                 const int stgrid = (b->channels + SB_ST_CPC - 1)/SB_ST_CPC;
+                const bool small = (b->tones <= SB_ST_SMEM_TONES  &&  b->total_elements <= SB_ST_SMEM_ELEMENTS);
                 if (pass == 0)
-                    super_tone_sequencer<false><<<stgrid, 128, 0, st>>>(s);
+                {
+                    if (small)
+                        super_tone_sequencer<false, true><<<stgrid, 128, 0, st>>>(s);
+                    else
+                        super_tone_sequencer<false, false><<<stgrid, 128, 0, st>>>(s);
+                }
                 else
-                    super_tone_sequencer<true><<<stgrid, 128, 0, st>>>(s);
+                {
+                    if (small)
+                        super_tone_sequencer<true, true><<<stgrid, 128, 0, st>>>(s);
+                    else
+                        super_tone_sequencer<true, false><<<stgrid, 128, 0, st>>>(s);
+                }
             }
             break;
         }
