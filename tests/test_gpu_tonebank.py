@@ -432,3 +432,23 @@ def test_event_capacity_overflow(gpu_ctx, engine_lib, torch_mod, det):
     assert (short.status() == full.status()).all()
     full.close()
     short.close()
+
+
+def test_super_tone_large_descriptor(gpu_ctx, engine_lib, torch_mod, port):
+    """A descriptor with more tones (76) than the sequencer's shared-memory copies hold: the kernel instantiation that
+    reads the templates from global memory.  The oracle harness takes 32 tones, so the descriptor is a 6-tone one plus 70
+    tones on the same frequencies that can never match (a first segment of at least 60 s): the reference's reports for
+    it are those of the 6-tone descriptor."""
+    rng = np.random.default_rng(99)
+    tones = synth.random_tones(rng, nfreqs=6, ntones=6)
+    freqs = sorted({e[0] for t in tones for e in t if e[0]})
+    cads = [[(e[0], e[1], -12, (e[2] + e[3]) // 2) for e in t] for t in tones]
+    amp = synth.cadence_channels(24, 32000, cads, seed=9)
+    p = po.make_params(po.DET_SUPER_TONE, po.MODE_SEGMENTS, 8000, tones=tones)
+    ev, fin, _ = port.run(p, amp)
+    assert sum(len(e) for e in ev) > 100
+    big = tones + [[(freqs[i % len(freqs)], freqs[(i + 1) % len(freqs)] if i % 2 else 0, 60000, 0)] for i in range(70)]
+    bank = engine_lib.Bank.super_tone(gpu_ctx, 24, big, want_segments=True)
+    check(bank, amp, 8000, oracle_rows(ev, False), torch_mod)
+    assert (bank.status() == fin["status"]).all()
+    bank.close()
